@@ -1,0 +1,159 @@
+/* phendiff_b200 — C ABI of the B200-native DDIM inversion + regeneration hot path.
+ *
+ * The reference (thethomasboyer/PhenDiff) is pure Python and has no FFI of its own; its boundary for this path is
+ * the Python object protocol of SURVEY.md §8(b).  This header is the C-ABI a reference maintainer would bind
+ * with ctypes from those Python objects.  Every entry point cites the reference interface
+ * it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all tensors are raw DEVICE pointers unless the name says "host".
+ *   - the caller (PyTorch) allocates every buffer including the workspace; the library keeps no caller pointer
+ *     beyond a call, except the workspace registered with pd_unet_bind_workspace and the weights, which are
+ *     COPIED into library-owned, re-laid-out device buffers by pd_unet_load_weight / pd_unet_finalize.
+ *   - every compute call is asynchronous on the given cudaStream_t; no hidden synchronisation.
+ *   - return value: 0 = ok, non-zero = error; pd_last_error() gives the thread-local message.
+ *   - a handle is bound to the CUDA device that was current at pd_unet_create and is not thread-safe
+ *     (one process per GPU, like the reference).
+ *   - boundary tensors are NCHW fp32 contiguous (the reference's layout); inside, activations are NHWC
+ *     bf16 (PD_PREC_BF16) or NHWC fp32 (PD_PREC_FP32 validation mode).
+ */
+#ifndef PHENDIFF_B200_H
+#define PHENDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pd_unet pd_unet_t;
+typedef void* pd_stream_t; /* cudaStream_t */
+
+enum { PD_PREC_FP32 = 0, PD_PREC_BF16 = 1 };
+enum { PD_PRED_EPSILON = 0, PD_PRED_SAMPLE = 1, PD_PRED_V = 2 };
+#define PD_MAX_BLOCKS 8
+
+/* Constructor arguments of CustomCondUNet2DModel (reference: src/cond_unet_2d/cond_unet_2d.py:73-107), i.e. the
+ * keys of models_configs/denoiser/*.json.  Only the shipped option set is implemented natively
+ * (positional time embedding, class_embed_type None, act "silu", resnet_time_scale_shift "default"). */
+typedef struct pd_unet_config {
+    int32_t in_channels;
+    int32_t out_channels;
+    int32_t n_blocks;
+    int32_t block_out_channels[PD_MAX_BLOCKS];
+    int32_t down_attn[PD_MAX_BLOCKS]; /* 1: AttnDownBlock2D, 0: DownBlock2D */
+    int32_t up_attn[PD_MAX_BLOCKS];   /* 1: AttnUpBlock2D,   0: UpBlock2D   */
+    int32_t layers_per_block;
+    int32_t attention_head_dim;
+    int32_t norm_num_groups;
+    float norm_eps;
+    int32_t num_class_embeds; /* 0: no class embedding table */
+    int32_t flip_sin_to_cos;
+    float freq_shift;
+    int32_t downsample_padding;
+    float mid_block_scale_factor;
+    int32_t add_attention;
+    int32_t precision;       /* PD_PREC_* */
+    int32_t max_microbatch;  /* images processed per pass through the layer graph (0: library default) */
+    int32_t conv_impl;       /* 0: tcgen05 implicit GEMM where the shape allows (bf16 only), 1: force SIMT kernels */
+    int32_t attn_impl;       /* 0: tensor-core flash kernel (bf16 only), 1: force SIMT kernel */
+} pd_unet_config_t;
+
+/* One scheduler update, host-computed scalars (reference: diffusers DDIMScheduler.step /
+ * DDIMInverseScheduler.step as called at pipeline_conditionial_ddim.py:340-347 and utils_Img2Img.py:794-798;
+ * SURVEY.md Appendix A.3-A.5):
+ *   x0  = by prediction type from (x, m, sqrt_alpha, sqrt_beta);  eps likewise
+ *   x0  = clamp(x0, +-clip_range) if clip;   eps = (x - sqrt_alpha*x0)/sqrt_beta if use_clipped_model_output
+ *   out = sqrt_alpha_next * x0 + dir_coef * eps  (+ sigma * noise when noise != NULL)
+ * where dir_coef = sqrt(1 - alpha_next - sigma^2).  IEEE semantics are kept at alpha = 0 (x0 = +-inf/NaN -> clamp). */
+typedef struct pd_step_coeffs {
+    int32_t pred_type; /* PD_PRED_* */
+    int32_t clip;
+    int32_t use_clipped_model_output;
+    float clip_range;
+    float sqrt_alpha;
+    float sqrt_beta;
+    float sqrt_alpha_next;
+    float dir_coef;
+    float sigma;
+    float timestep; /* value fed to the UNet for this step (whole-path entry point only) */
+} pd_step_coeffs_t;
+
+const char* pd_last_error(void);
+int pd_version(void);
+
+/* ---- lifetime (replaces CustomCondUNet2DModel.__init__ / from_config / load_state_dict, cond_unet_2d.py:73-242,
+ *      utils_models.py:158-182) ---- */
+int pd_unet_create(const pd_unet_config_t* cfg, pd_unet_t** out);
+int pd_unet_destroy(pd_unet_t* h);
+/* parameter table in diffusers checkpoint naming */
+int pd_unet_num_params(pd_unet_t* h, int32_t* n);
+int pd_unet_param_info(pd_unet_t* h, int32_t idx, const char** name, int32_t* ndim, int64_t shape[4]);
+/* copy one fp32 tensor (host or device pointer, contiguous, OIHW / (out,in) as in the checkpoint) */
+int pd_unet_load_weight(pd_unet_t* h, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+/* re-layout weights for the kernels; fails if a parameter was never loaded */
+int pd_unet_finalize(pd_unet_t* h, pd_stream_t stream);
+int pd_unet_time_embed_dim(pd_unet_t* h, int32_t* dim);
+
+/* ---- planning: static buffer plan for (batch, H, W); the caller then provides the workspace ---- */
+int pd_unet_plan(pd_unet_t* h, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes);
+int pd_unet_bind_workspace(pd_unet_t* h, void* workspace, size_t bytes);
+
+/* ---- CustomCondUNet2DModel.forward(sample, timestep, class_labels, class_emb) (cond_unet_2d.py:244-362) ----
+ * sample, out: (B,C,H,W) fp32 NCHW.  timesteps: (B,) fp32 (already broadcast, cond_unet_2d.py:276-287).
+ * Exactly one of class_labels (B,) int64 / class_emb (B, time_embed_dim) fp32 is non-NULL when the model has a
+ * class table; both NULL otherwise. */
+int pd_unet_forward(pd_unet_t* h, const float* sample, const float* timesteps, const int64_t* class_labels,
+                    const float* class_emb, float* out, pd_stream_t stream);
+
+/* ---- DDIMScheduler.step / DDIMInverseScheduler.step on (n) elements ----
+ * x_out and x0_out may be NULL; x_out may alias x.  noise is NULL when eta == 0. */
+int pd_ddim_step(const pd_step_coeffs_t* c, const float* x, const float* model_output, const float* noise,
+                 float* x_out, float* x0_out, int64_t n, pd_stream_t stream);
+
+/* DDIMScheduler.add_noise / get_velocity: out = ca[b]*a + cb[b]*b per sample (per_sample elements each) */
+int pd_axpby_per_sample(const float* a, const float* b, const float* ca, const float* cb, float* out, int32_t batch,
+                        int64_t per_sample, pd_stream_t stream);
+
+/* classifier-free guidance combine (pipeline_conditionial_ddim.py:323-332): out = base + w[b]*(cond - uncond),
+ * base = uncond ("imagen", eqn 0) or cond ("CFG", eqn 1); w is a (B,) device vector */
+int pd_cfg_combine(const float* cond, const float* uncond, const float* w, int32_t eqn, float* out, int32_t batch,
+                   int64_t per_sample, pd_stream_t stream);
+
+/* pipeline post-processing (pipeline_conditionial_ddim.py:349-350): NCHW [-1,1] -> NHWC [0,1] */
+int pd_denorm_nhwc(const float* x, float* out, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                   pd_stream_t stream);
+
+/* ---- whole path: _ddib (utils_Img2Img.py:566-612) = _inversion (utils_Img2Img.py:763-800) + the pipeline loop
+ *      (pipeline_conditionial_ddim.py:286-347) with w = 0.  steps_host: n_inv inversion steps followed by n_gen
+ *      generation steps, in execution order.  x: (B,C,H,W) fp32, updated IN PLACE to the regenerated x_0'.
+ *      The scheduler update of every step is fused into the conv_out kernel, so x_t is read and written once. */
+int pd_ddib_transfer(pd_unet_t* h, float* x, const int64_t* src_labels, const int64_t* tgt_labels,
+                     const pd_step_coeffs_t* steps_host, int32_t n_inv, int32_t n_gen, pd_stream_t stream);
+
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int pd_unet_launch_count(pd_unet_t* h, int64_t* n);
+
+/* ---- unit-test entry points for individual kernels (used by tests/, not by the product path) ---- */
+/* generic NHWC convolution through the SIMT fp32 kernel or the tcgen05 kernel; activations bf16 when bf16 != 0.
+ * x1 (N,H,W,C1) and optional x2 (N,H,W,C2) are channel-concatenated; w is OIHW fp32 (O, C1+C2, k, k);
+ * optional sc_w (O, Csc1+Csc2) 1x1 shortcut over (sc1|sc2) accumulated into the same output;
+ * addvec (N,O) fp32, residual (N,Ho,Wo,O) optional.  out (N,Ho,Wo,O). */
+int pd_test_conv(int32_t use_tc, int32_t bf16, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2,
+                 int32_t cout, int32_t ksize, int32_t stride, int32_t pad, const void* x1, const void* x2,
+                 const float* weight, const float* bias, const float* addvec, const void* residual,
+                 const void* sc1, const void* sc2, int32_t csc1, int32_t csc2, const float* sc_w, float out_scale,
+                 void* out, pd_stream_t stream);
+/* GroupNorm(+SiLU) over NHWC, two concatenated sources */
+int pd_test_groupnorm(int32_t bf16, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+                      int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta,
+                      void* out, pd_stream_t stream);
+/* self-attention core on packed qkv (N, S, 3C) -> (N, S, C), head_dim d */
+int pd_test_attention(int32_t use_mma, int32_t bf16, int32_t n, int32_t s, int32_t c, int32_t d, const void* qkv,
+                      void* out, pd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHENDIFF_B200_H */

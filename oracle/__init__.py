@@ -1,0 +1,8 @@
+"""ORACLE — CPU restatement of the reference's hot path (test infrastructure only; PARITY UNPINNED).
+
+See oracle/unet.py, oracle/schedulers.py, oracle/pipeline.py for the per-function reference citations.
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline and --impl reference legs).
+"""
+from .pipeline import OraclePipeline, oracle_ddib, oracle_inversion
+from .schedulers import OracleDDIMInverseScheduler, OracleDDIMScheduler, rescale_zero_terminal_snr
+from .unet import OracleCondUNet2D

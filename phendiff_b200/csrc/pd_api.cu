@@ -1,0 +1,951 @@
+// phendiff_b200 — C ABI (include/phendiff_b200.h), model graph, static buffer planner and step executor.
+//
+// The layer graph mirrors what CustomCondUNet2DModel.__init__ builds (reference: src/cond_unet_2d/cond_unet_2d.py:126-242,
+// blocks per SURVEY Appendix A.1/A.2); forward order mirrors cond_unet_2d.py:244-362.  Parameter names are the diffusers
+// checkpoint keys (Appendix A.7).  The executor records the whole forward once per (micro-batch, H, W) as a flat list of
+// kernel launches over a statically planned workspace (no allocation, no host sync on the step path).
+#include "pd_kernels.h"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pd {
+
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// parameters and layers
+// ---------------------------------------------------------------------------------------------------------------------
+struct Param {
+    std::string name;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+    float* dev = nullptr;
+    bool loaded = false;
+};
+
+struct ConvL {
+    Param *w = nullptr, *b = nullptr;
+    int cin = 0, cout = 0, k = 3, stride = 1, pad = 1;
+    float* w_simt = nullptr;  // (k*k*cin, cout) fp32
+    bf16* w_tc = nullptr;     // (cout, k*k*cin) bf16
+};
+struct GNL { Param *g = nullptr, *b = nullptr; int C = 0; };
+struct ResL {
+    GNL n1, n2;
+    ConvL c1, c2, sc;
+    bool has_sc = false;
+    Param *tw = nullptr, *tb = nullptr;
+    int cin = 0, cout = 0, temb_off = 0;
+    float scale = 1.f;
+    bf16* w2sc_tc = nullptr;   // (cout, 9*cout + cin): conv2 and the 1x1 shortcut as ONE K-concatenated GEMM
+    float* b2sc = nullptr;     // conv2.bias + conv_shortcut.bias
+};
+struct AttnL {
+    GNL gn;
+    Param *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob;
+    int C = 0;
+    float rescale = 1.f;
+    float* wqkv_raw = nullptr;   // (3C, C) fp32, rows q|k|v
+    float* bqkv = nullptr;       // (3C)
+    float* wqkv_simt = nullptr;  // (C, 3C)
+    bf16* wqkv_tc = nullptr;     // (3C, C)
+    float* wo_simt = nullptr;    // (C, C) transposed
+    bf16* wo_tc = nullptr;       // (C, C)
+};
+struct DownB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_down = false; ConvL down; };
+struct UpB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_up = false; ConvL up; };
+
+struct Arena {
+    bool dry = true;
+    uint8_t* base = nullptr;
+    size_t peak = 0;
+    std::vector<std::pair<size_t, size_t>> freel;  // (offset, size), sorted by offset
+    void reset(bool d, uint8_t* b) { dry = d; base = b; peak = 0; freel.clear(); freel.push_back({0, (size_t)1 << 60}); }
+    size_t alloc(size_t bytes) {
+        bytes = (bytes + 1023) & ~(size_t)1023;
+        for (size_t i = 0; i < freel.size(); ++i) {
+            if (freel[i].second >= bytes) {
+                size_t off = freel[i].first;
+                freel[i].first += bytes;
+                freel[i].second -= bytes;
+                if (freel[i].second == 0) freel.erase(freel.begin() + i);
+                peak = std::max(peak, off + bytes);
+                return off;
+            }
+        }
+        return (size_t)-1;
+    }
+    void release(size_t off, size_t bytes) {
+        bytes = (bytes + 1023) & ~(size_t)1023;
+        auto it = std::lower_bound(freel.begin(), freel.end(), std::make_pair(off, (size_t)0));
+        it = freel.insert(it, {off, bytes});
+        if (it + 1 != freel.end() && it->first + it->second == (it + 1)->first) {
+            it->second += (it + 1)->second;
+            freel.erase(it + 1);
+        }
+        if (it != freel.begin() && (it - 1)->first + (it - 1)->second == it->first) {
+            (it - 1)->second += it->second;
+            freel.erase(it);
+        }
+    }
+};
+
+struct Tensor {   // NHWC activation of the current micro-batch
+    size_t off = 0, bytes = 0;
+    int C = 0, H = 0, W = 0, refs = 0;
+};
+
+struct Ctx {   // per-call inputs of the recorded program
+    const float* x = nullptr;          // (mb, Cin, H, W) sample
+    const float* timesteps = nullptr;  // (mb) or null -> t_scalar
+    float t_scalar = 0.f;
+    const int64_t* labels = nullptr;
+    const float* class_emb = nullptr;
+    float* model_out = nullptr;        // (mb, Cout, H, W) or null
+    float* x_update = nullptr;         // x_t updated in place by the fused conv_out epilogue, or null
+    const pd_step_coeffs_t* step = nullptr;
+};
+
+typedef std::function<int(const Ctx&, cudaStream_t)> Op;
+
+}  // namespace pd
+
+using namespace pd;
+
+struct pd_unet {
+    pd_unet_config_t cfg;
+    int device = 0;
+    bool bf = false;
+    int D = 0;  // time_embed_dim
+    int J = 0;  // total time_emb_proj outputs
+    std::vector<std::unique_ptr<Param>> params;
+    std::map<std::string, Param*> by_name;
+    std::map<std::string, std::string> alias;
+    // layers
+    ConvL conv_in, conv_out;
+    Param *te_w1, *te_b1, *te_w2, *te_b2, *cls = nullptr;
+    std::vector<DownB> down;
+    ResL mid_r0, mid_r1;
+    AttnL mid_attn;
+    bool mid_has_attn = true;
+    std::vector<UpB> up;
+    GNL norm_out;
+    float* wcat = nullptr;      // (J, D)
+    float* bcat = nullptr;      // (J)  time_emb_proj.bias + conv1.bias
+    float* w_in = nullptr;      // (9*Cin, C0)
+    float* w_out = nullptr;     // (9, C0, 4)
+    bool finalized = false;
+    std::vector<void*> owned;   // derived device buffers
+    // plan
+    int B = 0, H = 0, W = 0, mb = 0;
+    size_t ws_bytes = 0;
+    Arena arena;
+    std::vector<Op> ops;
+    std::vector<ConvTcPlan*> tc_plans;
+    std::vector<std::unique_ptr<Tensor>> tensors;
+    bool bound = false;
+    int n_gn = 0;
+    size_t stats_off = 0, stats_bytes = 0, emb_off = 0, temb_off = 0;
+    int64_t launches = 0;
+    int tc_layers = 0, simt_layers = 0;
+};
+
+namespace pd {
+
+static Param* add_param(pd_unet* m, const std::string& name, std::vector<int64_t> shape) {
+    auto p = std::make_unique<Param>();
+    p->name = name;
+    p->shape = shape;
+    p->numel = 1;
+    for (auto s : shape) p->numel *= (size_t)s;
+    Param* r = p.get();
+    m->by_name[name] = r;
+    m->params.push_back(std::move(p));
+    return r;
+}
+static void make_conv(pd_unet* m, ConvL& c, const std::string& pfx, int cin, int cout, int k, int stride, int pad) {
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad;
+    c.w = add_param(m, pfx + ".weight", {cout, cin, k, k});
+    c.b = add_param(m, pfx + ".bias", {cout});
+}
+static void make_gn(pd_unet* m, GNL& g, const std::string& pfx, int C) {
+    g.C = C;
+    g.g = add_param(m, pfx + ".weight", {C});
+    g.b = add_param(m, pfx + ".bias", {C});
+}
+static void make_res(pd_unet* m, ResL& r, const std::string& pfx, int cin, int cout, float scale) {
+    r.cin = cin; r.cout = cout; r.scale = scale;
+    make_gn(m, r.n1, pfx + ".norm1", cin);
+    make_conv(m, r.c1, pfx + ".conv1", cin, cout, 3, 1, 1);
+    r.tw = add_param(m, pfx + ".time_emb_proj.weight", {cout, m->D});
+    r.tb = add_param(m, pfx + ".time_emb_proj.bias", {cout});
+    make_gn(m, r.n2, pfx + ".norm2", cout);
+    make_conv(m, r.c2, pfx + ".conv2", cout, cout, 3, 1, 1);
+    r.has_sc = cin != cout;
+    if (r.has_sc) make_conv(m, r.sc, pfx + ".conv_shortcut", cin, cout, 1, 1, 0);
+    r.temb_off = m->J;
+    m->J += cout;
+}
+static void make_attn(pd_unet* m, AttnL& a, const std::string& pfx, int C, float rescale) {
+    a.C = C; a.rescale = rescale;
+    make_gn(m, a.gn, pfx + ".group_norm", C);
+    const char* names[4] = {"to_q", "to_k", "to_v", "to_out.0"};
+    const char* old[4] = {"query", "key", "value", "proj_attn"};   // A.7: deprecated spellings accepted on load
+    Param** ws[4] = {&a.qw, &a.kw, &a.vw, &a.ow};
+    Param** bs[4] = {&a.qb, &a.kb, &a.vb, &a.ob};
+    for (int i = 0; i < 4; ++i) {
+        *ws[i] = add_param(m, pfx + "." + names[i] + ".weight", {C, C});
+        *bs[i] = add_param(m, pfx + "." + names[i] + ".bias", {C});
+        m->alias[pfx + "." + old[i] + ".weight"] = pfx + "." + names[i] + ".weight";
+        m->alias[pfx + "." + old[i] + ".bias"] = pfx + "." + names[i] + ".bias";
+    }
+}
+
+static int build_graph(pd_unet* m) {
+    const pd_unet_config_t& c = m->cfg;
+    const int nb = c.n_blocks;
+    const int* boc = c.block_out_channels;
+    m->D = boc[0] * 4;   // cond_unet_2d.py:111
+    m->J = 0;
+    make_conv(m, m->conv_in, "conv_in", c.in_channels, boc[0], 3, 1, 1);
+    m->te_w1 = add_param(m, "time_embedding.linear_1.weight", {m->D, boc[0]});
+    m->te_b1 = add_param(m, "time_embedding.linear_1.bias", {m->D});
+    m->te_w2 = add_param(m, "time_embedding.linear_2.weight", {m->D, m->D});
+    m->te_b2 = add_param(m, "time_embedding.linear_2.bias", {m->D});
+    if (c.num_class_embeds > 0) m->cls = add_param(m, "class_embedding.weight", {c.num_class_embeds, m->D});
+    // down (cond_unet_2d.py:159-182)
+    int out = boc[0];
+    m->down.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+        int cin = out;
+        out = boc[i];
+        DownB& d = m->down[i];
+        d.has_attn = c.down_attn[i] != 0;
+        d.has_down = i != nb - 1;
+        d.res.resize(c.layers_per_block);
+        if (d.has_attn) d.attn.resize(c.layers_per_block);
+        std::string pfx = "down_blocks." + std::to_string(i);
+        for (int j = 0; j < c.layers_per_block; ++j) {
+            make_res(m, d.res[j], pfx + ".resnets." + std::to_string(j), j == 0 ? cin : out, out, 1.f);
+            if (d.has_attn) make_attn(m, d.attn[j], pfx + ".attentions." + std::to_string(j), out, 1.f);
+        }
+        if (d.has_down) make_conv(m, d.down, pfx + ".downsamplers.0.conv", out, out, 3, 2, c.downsample_padding);
+    }
+    // mid (cond_unet_2d.py:184-197)
+    m->mid_has_attn = c.add_attention != 0;
+    make_res(m, m->mid_r0, "mid_block.resnets.0", boc[nb - 1], boc[nb - 1], c.mid_block_scale_factor);
+    if (m->mid_has_attn) make_attn(m, m->mid_attn, "mid_block.attentions.0", boc[nb - 1], c.mid_block_scale_factor);
+    make_res(m, m->mid_r1, "mid_block.resnets.1", boc[nb - 1], boc[nb - 1], c.mid_block_scale_factor);
+    // up (cond_unet_2d.py:199-228)
+    m->up.resize(nb);
+    out = boc[nb - 1];
+    for (int i = 0; i < nb; ++i) {
+        int prev = out;
+        out = boc[nb - 1 - i];
+        int cin = boc[nb - 1 - std::min(i + 1, nb - 1)];
+        UpB& u = m->up[i];
+        u.has_attn = c.up_attn[i] != 0;
+        u.has_up = i != nb - 1;
+        const int L = c.layers_per_block + 1;
+        u.res.resize(L);
+        if (u.has_attn) u.attn.resize(L);
+        std::string pfx = "up_blocks." + std::to_string(i);
+        for (int j = 0; j < L; ++j) {
+            int skip = (j == L - 1) ? cin : out;
+            int rin = (j == 0) ? prev : out;
+            make_res(m, u.res[j], pfx + ".resnets." + std::to_string(j), rin + skip, out, 1.f);
+            if (u.has_attn) make_attn(m, u.attn[j], pfx + ".attentions." + std::to_string(j), out, 1.f);
+        }
+        if (u.has_up) make_conv(m, u.up, pfx + ".upsamplers.0.conv", out, out, 3, 1, 1);
+    }
+    make_gn(m, m->norm_out, "conv_norm_out", boc[0]);
+    make_conv(m, m->conv_out, "conv_out", boc[0], c.out_channels, 3, 1, 1);
+    return 0;
+}
+
+template <typename T> static int dev_alloc(pd_unet* m, T** p, size_t n) {
+    PD_CHECK_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    m->owned.push_back((void*)*p);
+    return 0;
+}
+
+static int finalize_conv(pd_unet* m, ConvL& c, cudaStream_t s, bool tc) {
+    int rc;
+    if ((rc = dev_alloc(m, &c.w_simt, c.w->numel))) return rc;
+    if ((rc = launch_relayout_simt(c.w->dev, c.cout, c.cin, c.k, c.w_simt, s))) return rc;
+    if (tc && c.cin % 64 == 0 && c.cout % 64 == 0) {
+        const int ktot = c.k * c.k * c.cin;
+        if ((rc = dev_alloc(m, &c.w_tc, (size_t)c.cout * ktot))) return rc;
+        if ((rc = launch_relayout_tc(c.w->dev, c.cout, c.cin, c.k, c.w_tc, ktot, 0, s))) return rc;
+    }
+    return 0;
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+static int finalize_res(pd_unet* m, ResL& r, cudaStream_t s) {
+    int rc;
+    if ((rc = finalize_conv(m, r.c1, s, m->bf))) return rc;
+    if ((rc = finalize_conv(m, r.c2, s, m->bf))) return rc;
+    if (r.has_sc && (rc = finalize_conv(m, r.sc, s, m->bf))) return rc;
+    // time_emb_proj rows of the concatenated projection; conv1.bias folded into the projected vector
+    PD_CHECK_CUDA(cudaMemcpyAsync(m->wcat + (size_t)r.temb_off * m->D, r.tw->dev, r.tw->numel * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, s));
+    add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, s>>>(r.tb->dev, r.c1.b->dev, m->bcat + r.temb_off, r.cout);
+    if (r.has_sc) {
+        if ((rc = dev_alloc(m, &r.b2sc, (size_t)r.cout))) return rc;
+        add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, s>>>(r.c2.b->dev, r.sc.b->dev, r.b2sc, r.cout);
+        if (m->bf && r.cin % 64 == 0 && r.cout % 64 == 0) {
+            const int ktot = 9 * r.cout + r.cin;
+            if ((rc = dev_alloc(m, &r.w2sc_tc, (size_t)r.cout * ktot))) return rc;
+            if ((rc = launch_relayout_tc(r.c2.w->dev, r.cout, r.cout, 3, r.w2sc_tc, ktot, 0, s))) return rc;
+            if ((rc = launch_relayout_tc(r.sc.w->dev, r.cout, r.cin, 1, r.w2sc_tc, ktot, 9 * r.cout, s))) return rc;
+        }
+    }
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int finalize_attn(pd_unet* m, AttnL& a, cudaStream_t s) {
+    int rc;
+    const size_t CC = (size_t)a.C * a.C;
+    if ((rc = dev_alloc(m, &a.wqkv_raw, 3 * CC))) return rc;
+    if ((rc = dev_alloc(m, &a.bqkv, (size_t)3 * a.C))) return rc;
+    Param* ws[3] = {a.qw, a.kw, a.vw};
+    Param* bs[3] = {a.qb, a.kb, a.vb};
+    for (int i = 0; i < 3; ++i) {
+        PD_CHECK_CUDA(cudaMemcpyAsync(a.wqkv_raw + i * CC, ws[i]->dev, CC * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        PD_CHECK_CUDA(cudaMemcpyAsync(a.bqkv + (size_t)i * a.C, bs[i]->dev, a.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    if ((rc = dev_alloc(m, &a.wqkv_simt, 3 * CC))) return rc;
+    if ((rc = launch_relayout_simt(a.wqkv_raw, 3 * a.C, a.C, 1, a.wqkv_simt, s))) return rc;
+    if ((rc = dev_alloc(m, &a.wo_simt, CC))) return rc;
+    if ((rc = launch_relayout_simt(a.ow->dev, a.C, a.C, 1, a.wo_simt, s))) return rc;
+    if (m->bf && a.C % 64 == 0) {
+        if ((rc = dev_alloc(m, &a.wqkv_tc, 3 * CC))) return rc;
+        if ((rc = launch_cast_bf16(a.wqkv_raw, a.wqkv_tc, (int64_t)(3 * CC), s))) return rc;
+        if ((rc = dev_alloc(m, &a.wo_tc, CC))) return rc;
+        if ((rc = launch_cast_bf16(a.ow->dev, a.wo_tc, (int64_t)CC, s))) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// recording the forward program
+// ---------------------------------------------------------------------------------------------------------------------
+struct Rec {
+    pd_unet* m;
+    bool dry;
+    int mb;
+    size_t esz;   // bytes per activation element
+    int gn_idx = 0;
+    int rc = 0;
+
+    Tensor* alloc(int C, int H, int W) {
+        auto t = std::make_unique<Tensor>();
+        t->C = C; t->H = H; t->W = W; t->refs = 1;
+        t->bytes = (size_t)mb * H * W * C * esz;
+        t->off = m->arena.alloc(t->bytes);
+        Tensor* r = t.get();
+        m->tensors.push_back(std::move(t));
+        return r;
+    }
+    void retain(Tensor* t) { t->refs++; }
+    void release(Tensor* t) {
+        if (--t->refs == 0) m->arena.release(t->off, t->bytes);
+    }
+    void* ptr(const Tensor* t) const { return (void*)(m->arena.base + t->off); }
+    void* raw(size_t off) const { return (void*)(m->arena.base + off); }
+    void push(Op op, int nlaunch) {
+        if (dry) return;
+        pd_unet* mm = m;
+        m->ops.push_back([op, nlaunch, mm](const Ctx& c, cudaStream_t s) { mm->launches += nlaunch; return op(c, s); });
+    }
+
+    // GroupNorm(+SiLU) of concat(a, b) -> new tensor
+    Tensor* gn(const GNL& g, Tensor* a, Tensor* b, bool do_silu) {
+        const int C = a->C + (b ? b->C : 0);
+        Tensor* o = alloc(C, a->H, a->W);
+        GNArgs ga{};
+        ga.C1 = a->C; ga.C2 = b ? b->C : 0; ga.N = mb; ga.HW = a->H * a->W; ga.groups = m->cfg.norm_num_groups;
+        ga.eps = m->cfg.norm_eps; ga.gamma = g.g->dev; ga.beta = g.b->dev; ga.silu = do_silu;
+        const int idx = gn_idx++;
+        if (!dry) {
+            ga.x1 = ptr(a); ga.x2 = b ? ptr(b) : nullptr; ga.out = ptr(o);
+            ga.stats = (float*)raw(m->stats_off) + (size_t)idx * mb * ga.groups * 2;
+            const bool bf = m->bf, precise = !m->bf;
+            push([ga, bf, precise](const Ctx&, cudaStream_t s) {
+                int r = launch_gn_stats(bf, ga, s);
+                if (r) return r;
+                return launch_gn_apply(bf, precise, ga, s);
+            }, 2);
+        }
+        return o;
+    }
+
+    // generic conv: main input `x` (single tensor), optional fused 1x1 shortcut over (s1|s2) -> new tensor
+    // `bias` belongs to the main conv; `bias_fused` (main + shortcut bias) is used when the shortcut rides in the same GEMM
+    Tensor* conv(const ConvL& L, Tensor* x, const float* w_simt, const bf16* w_tc, const float* bias, const float* addvec,
+                 int addvec_stride, Tensor* residual, float out_scale, Tensor* s1 = nullptr, Tensor* s2 = nullptr,
+                 const ConvL* scL = nullptr, const float* bias_fused = nullptr) {
+        const int Ho = (L.stride == 2) ? x->H / 2 : x->H, Wo = (L.stride == 2) ? x->W / 2 : x->W;
+        Tensor* o = alloc(L.cout, Ho, Wo);
+        ConvTcDesc d{};
+        d.C = x->C; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = L.k; d.stride = L.stride; d.pad = L.pad;
+        d.Ho = Ho; d.Wo = Wo; d.Cout = L.cout;
+        d.Csc1 = s1 ? s1->C : 0; d.Csc2 = s2 ? s2->C : 0;
+        const bool want_tc = m->bf && m->cfg.conv_impl == 0 && w_tc != nullptr;
+        const bool use_tc = want_tc && conv_tc_supported(d, nullptr);
+        if (use_tc) {
+            m->tc_layers += dry ? 0 : 1;
+            if (!dry) {
+                d.x = (const bf16*)ptr(x); d.sc1 = s1 ? (const bf16*)ptr(s1) : nullptr; d.sc2 = s2 ? (const bf16*)ptr(s2) : nullptr;
+                d.wmat = w_tc; d.bias = s1 ? bias_fused : bias; d.addvec = addvec; d.addvec_stride = addvec_stride;
+                d.residual = residual ? (const bf16*)ptr(residual) : nullptr; d.out_scale = out_scale; d.out = (bf16*)ptr(o);
+                ConvTcPlan* pl = nullptr;
+                int r = conv_tc_plan_create(d, &pl);
+                if (r) { rc = r; return o; }
+                m->tc_plans.push_back(pl);
+                push([pl](const Ctx&, cudaStream_t s) { return conv_tc_launch(pl, s); }, 1);
+            }
+            return o;
+        }
+        // SIMT path; a fused shortcut request is split into (1x1 conv -> tmp) + (conv with residual = tmp)
+        m->simt_layers += dry ? 0 : 1;
+        Tensor* tmp = nullptr;
+        if (s1) {
+            tmp = alloc(L.cout, Ho, Wo);
+            ConvArgs ca{};
+            ca.C1 = s1->C; ca.C2 = s2 ? s2->C : 0; ca.N = mb; ca.H = Ho; ca.W = Wo; ca.Cout = L.cout; ca.ksize = 1; ca.stride = 1;
+            ca.pad = 0; ca.Ho = Ho; ca.Wo = Wo; ca.w = scL->w_simt; ca.bias = scL->b->dev; ca.out_scale = 1.f;
+            if (!dry) {
+                ca.x1 = ptr(s1); ca.x2 = s2 ? ptr(s2) : nullptr; ca.out = ptr(tmp);
+                const bool bf = m->bf;
+                push([ca, bf](const Ctx&, cudaStream_t s) { return launch_conv_simt(bf, ca, s); }, 1);
+            }
+        }
+        ConvArgs ca{};
+        ca.C1 = x->C; ca.C2 = 0; ca.N = mb; ca.H = x->H; ca.W = x->W; ca.Cout = L.cout; ca.ksize = L.k; ca.stride = L.stride;
+        ca.pad = L.pad; ca.Ho = Ho; ca.Wo = Wo; ca.w = w_simt; ca.bias = bias; ca.addvec = addvec; ca.addvec_stride = addvec_stride;
+        ca.out_scale = out_scale;
+        if (!dry) {
+            ca.x1 = ptr(x); ca.x2 = nullptr; ca.out = ptr(o);
+            ca.residual = tmp ? ptr(tmp) : (residual ? ptr(residual) : nullptr);
+            const bool bf = m->bf;
+            push([ca, bf](const Ctx&, cudaStream_t s) { return launch_conv_simt(bf, ca, s); }, 1);
+        }
+        if (tmp) release(tmp);
+        return o;
+    }
+
+    // ResnetBlock2D (A.1) on concat(a, b); returns the block output (refs = 1)
+    Tensor* resnet(ResL& R, Tensor* a, Tensor* b) {
+        Tensor* hn = gn(R.n1, a, b, true);
+        // conv1 (+ time embedding row; conv1.bias is folded into that row at finalize)
+        const float* temb = dry ? nullptr : (const float*)raw(m->temb_off) + R.temb_off;
+        Tensor* h1 = conv(R.c1, hn, R.c1.w_simt, R.c1.w_tc, nullptr, temb, m->J, nullptr, 1.f);
+        release(hn);
+        Tensor* h1n = gn(R.n2, h1, nullptr, true);
+        release(h1);
+        Tensor* o;
+        const float inv = 1.0f / R.scale;
+        if (R.has_sc) {
+            // out = (conv2(h) + conv_shortcut(x)) / scale: one K-concatenated GEMM on the tensor-core path
+            o = conv(R.c2, h1n, R.c2.w_simt, R.w2sc_tc, R.c2.b->dev, nullptr, 0, nullptr, inv, a, b, &R.sc, R.b2sc);
+        } else {
+            o = conv(R.c2, h1n, R.c2.w_simt, R.c2.w_tc, R.c2.b->dev, nullptr, 0, a, inv);
+        }
+        release(h1n);
+        return o;
+    }
+
+    // Attention (A.2): GN -> fused qkv projection -> softmax(qk^T/sqrt(d))v -> out projection + residual
+    Tensor* attention(AttnL& A, Tensor* x) {
+        Tensor* xn = gn(A.gn, x, nullptr, false);
+        ConvL lq; lq.cin = A.C; lq.cout = 3 * A.C; lq.k = 1; lq.stride = 1; lq.pad = 0;
+        Tensor* qkv = conv(lq, xn, A.wqkv_simt, A.wqkv_tc, A.bqkv, nullptr, 0, nullptr, 1.f);
+        release(xn);
+        Tensor* ao = alloc(A.C, x->H, x->W);
+        {
+            const int S = x->H * x->W, C = A.C, d = m->cfg.attention_head_dim > 0 ? m->cfg.attention_head_dim : A.C;
+            const bool use_mma = m->bf && m->cfg.attn_impl == 0 && (S % 64 == 0) && d == 8;
+            if (!dry) {
+                const void* qp = ptr(qkv);
+                void* op = ptr(ao);
+                const int N = mb;
+                const bool bf = m->bf;
+                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(qp, N, S, C, d, op, s); }, 1);
+                else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(bf, !bf, qp, N, S, C, d, op, s); }, 1);
+            }
+        }
+        release(qkv);
+        ConvL lo; lo.cin = A.C; lo.cout = A.C; lo.k = 1; lo.stride = 1; lo.pad = 0;
+        Tensor* o = conv(lo, ao, A.wo_simt, A.wo_tc, A.ob->dev, nullptr, 0, x, 1.0f / A.rescale);
+        release(ao);
+        return o;
+    }
+
+    int record() {
+        pd_unet* M = m;
+        const pd_unet_config_t& c = M->cfg;
+        const int H = M->H, W = M->W, C0 = c.block_out_channels[0];
+        // fixed small buffers
+        M->stats_bytes = (size_t)M->n_gn * mb * c.norm_num_groups * 2 * sizeof(float);
+        M->stats_off = M->arena.alloc(std::max<size_t>(M->stats_bytes, 1024));
+        M->emb_off = M->arena.alloc((size_t)mb * M->D * sizeof(float));
+        M->temb_off = M->arena.alloc((size_t)mb * M->J * sizeof(float));
+        if (!dry) {
+            float* stats = (float*)raw(M->stats_off);
+            const size_t sb = M->stats_bytes;
+            EmbedArgs ea{};
+            ea.w1 = M->te_w1->dev; ea.b1 = M->te_b1->dev; ea.w2 = M->te_w2->dev; ea.b2 = M->te_b2->dev;
+            ea.class_table = M->cls ? M->cls->dev : nullptr; ea.B = mb; ea.C0 = C0; ea.D = M->D; ea.ncls = c.num_class_embeds;
+            ea.flip = c.flip_sin_to_cos; ea.shift = c.freq_shift; ea.emb_act = (float*)raw(M->emb_off);
+            float* temb = (float*)raw(M->temb_off);
+            const float* wcat = M->wcat; const float* bcat = M->bcat;
+            const int D = M->D, J = M->J, MB = mb;
+            push([=](const Ctx& cx, cudaStream_t s) {
+                if (sb) { PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, sb, s)); }
+                EmbedArgs e = ea;
+                e.timesteps = cx.timesteps; e.t_scalar = cx.t_scalar; e.labels = cx.labels; e.class_emb = cx.class_emb;
+                int r = launch_embed(e, s);
+                if (r) return r;
+                return launch_temb_proj(e.emb_act, wcat, bcat, MB, D, J, temb, s);
+            }, 2);
+        }
+        // conv_in (cond_unet_2d.py:313)
+        Tensor* x = alloc(C0, H, W);
+        if (!dry) {
+            void* o = ptr(x);
+            const float* w = M->w_in; const float* b = M->conv_in.b->dev;
+            const int N = mb, Cin = c.in_channels; const bool bf = M->bf;
+            push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(bf, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1);
+        }
+        std::vector<Tensor*> skips;
+        retain(x); skips.push_back(x);
+        // down (cond_unet_2d.py:316-325)
+        for (auto& d : M->down) {
+            for (size_t j = 0; j < d.res.size(); ++j) {
+                Tensor* y = resnet(d.res[j], x, nullptr);
+                release(x); x = y;
+                if (d.has_attn) { Tensor* z = attention(d.attn[j], x); release(x); x = z; }
+                retain(x); skips.push_back(x);
+            }
+            if (d.has_down) {
+                Tensor* y = conv(d.down, x, d.down.w_simt, d.down.w_tc, d.down.b->dev, nullptr, 0, nullptr, 1.f);
+                release(x); x = y;
+                retain(x); skips.push_back(x);
+            }
+            if (rc) return rc;
+        }
+        // mid (cond_unet_2d.py:328)
+        { Tensor* y = resnet(M->mid_r0, x, nullptr); release(x); x = y; }
+        if (M->mid_has_attn) { Tensor* y = attention(M->mid_attn, x); release(x); x = y; }
+        { Tensor* y = resnet(M->mid_r1, x, nullptr); release(x); x = y; }
+        // up (cond_unet_2d.py:332-343)
+        for (auto& u : M->up) {
+            for (size_t j = 0; j < u.res.size(); ++j) {
+                Tensor* sk = skips.back(); skips.pop_back();
+                Tensor* y = resnet(u.res[j], x, sk);
+                release(sk); release(x); x = y;
+                if (u.has_attn) { Tensor* z = attention(u.attn[j], x); release(x); x = z; }
+            }
+            if (u.has_up) {
+                Tensor* big = alloc(x->C, x->H * 2, x->W * 2);
+                if (!dry) {
+                    const void* ip = ptr(x); void* op = ptr(big);
+                    const int N = mb, h = x->H, w = x->W, C = x->C; const bool bf = M->bf;
+                    push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(bf, ip, N, h, w, C, op, s); }, 1);
+                }
+                release(x);
+                Tensor* y = conv(u.up, big, u.up.w_simt, u.up.w_tc, u.up.b->dev, nullptr, 0, nullptr, 1.f);
+                release(big); x = y;
+            }
+            if (rc) return rc;
+        }
+        // out (cond_unet_2d.py:346-348) + optional fused scheduler update (A.5)
+        Tensor* xn = gn(M->norm_out, x, nullptr, true);
+        release(x);
+        if (!dry) {
+            ConvOutArgs oa{};
+            oa.act = ptr(xn); oa.w = M->w_out; oa.bias = M->conv_out.b->dev; oa.N = mb; oa.H = H; oa.W = W; oa.Cin = C0;
+            oa.Cout = c.out_channels;
+            const bool bf = M->bf;
+            push([=](const Ctx& cx, cudaStream_t s) {
+                ConvOutArgs a = oa;
+                a.model_out = cx.model_out; a.x = cx.x_update; a.step = cx.step;
+                return launch_conv_out(bf, a, s);
+            }, 1);
+        }
+        release(xn);
+        return rc;
+    }
+};
+
+static int count_gn(pd_unet* m) {
+    int n = 1;  // conv_norm_out
+    auto res = [&](const ResL&) { n += 2; };
+    for (auto& d : m->down) { for (auto& r : d.res) res(r); n += (int)d.attn.size(); }
+    res(m->mid_r0); res(m->mid_r1); if (m->mid_has_attn) n += 1;
+    for (auto& u : m->up) { for (auto& r : u.res) res(r); n += (int)u.attn.size(); }
+    return n;
+}
+
+static void clear_plan(pd_unet* m) {
+    for (auto* p : m->tc_plans) conv_tc_plan_destroy(p);
+    m->tc_plans.clear();
+    m->ops.clear();
+    m->tensors.clear();
+    m->bound = false;
+    m->tc_layers = m->simt_layers = 0;
+}
+
+static int run_program(pd_unet* m, const Ctx& c, cudaStream_t s) {
+    for (auto& op : m->ops) {
+        int r = op(c, s);
+        if (r) return r;
+    }
+    return 0;
+}
+
+}  // namespace pd
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+const char* pd_last_error(void) { return g_err.c_str(); }
+int pd_version(void) { return 100; }
+
+int pd_unet_create(const pd_unet_config_t* cfg, pd_unet_t** out) {
+    PD_REQUIRE(cfg && out, "null argument");
+    PD_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= PD_MAX_BLOCKS, "n_blocks out of range");
+    PD_REQUIRE(cfg->precision == PD_PREC_FP32 || cfg->precision == PD_PREC_BF16, "unknown precision");
+    PD_REQUIRE(cfg->layers_per_block >= 1, "layers_per_block must be >= 1");
+    PD_REQUIRE(cfg->norm_num_groups > 0, "norm_num_groups must be > 0");
+    for (int i = 0; i < cfg->n_blocks; ++i) {
+        PD_REQUIRE(cfg->block_out_channels[i] % cfg->norm_num_groups == 0, "block_out_channels must be divisible by norm_num_groups");
+        PD_REQUIRE(cfg->block_out_channels[i] % 16 == 0, "block_out_channels must be multiples of 16");
+    }
+    int ndev = 0;
+    PD_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    PD_REQUIRE(ndev > 0, "no CUDA device: phendiff_b200 has no CPU fallback");
+    pd_unet* m = new pd_unet();
+    m->cfg = *cfg;
+    m->bf = cfg->precision == PD_PREC_BF16;
+    PD_CHECK_CUDA(cudaGetDevice(&m->device));
+    cudaDeviceProp prop;
+    PD_CHECK_CUDA(cudaGetDeviceProperties(&prop, m->device));
+    if (prop.major != 10) {
+        delete m;
+        set_error("phendiff_b200 kernels are built for sm_100a only; found compute capability " +
+                  std::to_string(prop.major) + "." + std::to_string(prop.minor));
+        return 1;
+    }
+    build_graph(m);
+    m->n_gn = count_gn(m);
+    *out = m;
+    return 0;
+}
+
+int pd_unet_destroy(pd_unet_t* m) {
+    if (!m) return 0;
+    clear_plan(m);
+    for (auto& p : m->params) if (p->dev) cudaFree(p->dev);
+    for (void* p : m->owned) cudaFree(p);
+    delete m;
+    return 0;
+}
+
+int pd_unet_num_params(pd_unet_t* m, int32_t* n) {
+    PD_REQUIRE(m && n, "null argument");
+    *n = (int32_t)m->params.size();
+    return 0;
+}
+
+int pd_unet_param_info(pd_unet_t* m, int32_t idx, const char** name, int32_t* ndim, int64_t shape[4]) {
+    PD_REQUIRE(m && idx >= 0 && idx < (int)m->params.size(), "parameter index out of range");
+    Param* p = m->params[idx].get();
+    if (name) *name = p->name.c_str();
+    if (ndim) *ndim = (int32_t)p->shape.size();
+    if (shape) for (size_t i = 0; i < p->shape.size() && i < 4; ++i) shape[i] = p->shape[i];
+    return 0;
+}
+
+int pd_unet_load_weight(pd_unet_t* m, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+    PD_REQUIRE(m && name && data, "null argument");
+    std::string key(name);
+    auto al = m->alias.find(key);
+    if (al != m->alias.end()) key = al->second;
+    auto it = m->by_name.find(key);
+    PD_REQUIRE(it != m->by_name.end(), (std::string("unknown parameter name: ") + name).c_str());
+    Param* p = it->second;
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= (size_t)shape[i];
+    // 1x1 conv weights may arrive as (O,I) linear weights and vice versa (deprecated attention blocks): sizes must match
+    PD_REQUIRE(numel == p->numel, (std::string("shape mismatch for ") + name).c_str());
+    if (!p->dev) PD_CHECK_CUDA(cudaMalloc((void**)&p->dev, p->numel * sizeof(float)));
+    PD_CHECK_CUDA(cudaMemcpy(p->dev, data, p->numel * sizeof(float), cudaMemcpyDefault));
+    p->loaded = true;
+    m->finalized = false;
+    return 0;
+}
+
+int pd_unet_finalize(pd_unet_t* m, pd_stream_t stream) {
+    PD_REQUIRE(m, "null handle");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (auto& p : m->params) PD_REQUIRE(p->loaded, (std::string("parameter never loaded: ") + p->name).c_str());
+    clear_plan(m);
+    for (void* p : m->owned) cudaFree(p);
+    m->owned.clear();
+    int rc;
+    if ((rc = dev_alloc(m, &m->wcat, (size_t)m->J * m->D))) return rc;
+    if ((rc = dev_alloc(m, &m->bcat, (size_t)m->J))) return rc;
+    if ((rc = dev_alloc(m, &m->w_in, m->conv_in.w->numel))) return rc;
+    if ((rc = launch_relayout_simt(m->conv_in.w->dev, m->conv_in.cout, m->conv_in.cin, 3, m->w_in, s))) return rc;
+    if ((rc = dev_alloc(m, &m->w_out, (size_t)9 * m->conv_out.cin * 4))) return rc;
+    if ((rc = launch_relayout_convout(m->conv_out.w->dev, m->conv_out.cout, m->conv_out.cin, m->w_out, s))) return rc;
+    for (auto& d : m->down) {
+        for (auto& r : d.res) if ((rc = finalize_res(m, r, s))) return rc;
+        for (auto& a : d.attn) if ((rc = finalize_attn(m, a, s))) return rc;
+        if (d.has_down && (rc = finalize_conv(m, d.down, s, m->bf))) return rc;
+    }
+    if ((rc = finalize_res(m, m->mid_r0, s))) return rc;
+    if ((rc = finalize_res(m, m->mid_r1, s))) return rc;
+    if (m->mid_has_attn && (rc = finalize_attn(m, m->mid_attn, s))) return rc;
+    for (auto& u : m->up) {
+        for (auto& r : u.res) if ((rc = finalize_res(m, r, s))) return rc;
+        for (auto& a : u.attn) if ((rc = finalize_attn(m, a, s))) return rc;
+        if (u.has_up && (rc = finalize_conv(m, u.up, s, m->bf))) return rc;
+    }
+    PD_CHECK_CUDA(cudaStreamSynchronize(s));
+    m->finalized = true;
+    return 0;
+}
+
+int pd_unet_time_embed_dim(pd_unet_t* m, int32_t* dim) {
+    PD_REQUIRE(m && dim, "null argument");
+    *dim = m->D;
+    return 0;
+}
+
+int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes) {
+    PD_REQUIRE(m && workspace_bytes, "null argument");
+    PD_REQUIRE(m->finalized, "pd_unet_finalize must be called before planning");
+    PD_REQUIRE(batch > 0 && height > 0 && width > 0, "bad shape");
+    const int ds = 1 << (m->cfg.n_blocks - 1);
+    PD_REQUIRE(height % ds == 0 && width % ds == 0, "sample size must be a multiple of 2^(n_blocks-1)");
+    clear_plan(m);
+    m->B = batch; m->H = height; m->W = width;
+    int cap = m->cfg.max_microbatch > 0 ? m->cfg.max_microbatch : 32;
+    int mb = 1;
+    for (int d = 1; d <= std::min(cap, batch); ++d) if (batch % d == 0) mb = d;
+    m->mb = mb;
+    m->arena.reset(true, nullptr);
+    Rec r{m, true, mb, m->bf ? sizeof(bf16) : sizeof(float)};
+    int rc = r.record();
+    if (rc) return rc;
+    m->ws_bytes = m->arena.peak + 1024;
+    m->tensors.clear();
+    *workspace_bytes = m->ws_bytes;
+    return 0;
+}
+
+int pd_unet_bind_workspace(pd_unet_t* m, void* workspace, size_t bytes) {
+    PD_REQUIRE(m && workspace, "null argument");
+    PD_REQUIRE(m->B > 0, "pd_unet_plan must be called first");
+    PD_REQUIRE(bytes >= m->ws_bytes, "workspace too small");
+    PD_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+    for (auto* p : m->tc_plans) conv_tc_plan_destroy(p);
+    m->tc_plans.clear(); m->ops.clear(); m->tensors.clear();
+    m->tc_layers = m->simt_layers = 0;
+    m->arena.reset(false, (uint8_t*)workspace);
+    Rec r{m, false, m->mb, m->bf ? sizeof(bf16) : sizeof(float)};
+    int rc = r.record();
+    if (rc) return rc;
+    m->tensors.clear();
+    m->bound = true;
+    return 0;
+}
+
+int pd_unet_forward(pd_unet_t* m, const float* sample, const float* timesteps, const int64_t* class_labels,
+                    const float* class_emb, float* out, pd_stream_t stream) {
+    PD_REQUIRE(m && sample && timesteps && out, "null argument");
+    PD_REQUIRE(m->bound, "pd_unet_plan + pd_unet_bind_workspace must be called first");
+    PD_REQUIRE(!(class_labels && class_emb), "Cannot specify both class_labels and class_emb");
+    PD_REQUIRE(!(m->cls && !class_labels && !class_emb), "either class_labels or class_emb should be provided when doing class conditioning");
+    const size_t per_in = (size_t)m->cfg.in_channels * m->H * m->W, per_out = (size_t)m->cfg.out_channels * m->H * m->W;
+    for (int i = 0; i < m->B; i += m->mb) {
+        Ctx c;
+        c.x = sample + (size_t)i * per_in;
+        c.timesteps = timesteps + i;
+        c.labels = class_labels ? class_labels + i : nullptr;
+        c.class_emb = class_emb ? class_emb + (size_t)i * m->D : nullptr;
+        c.model_out = out + (size_t)i * per_out;
+        int rc = run_program(m, c, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int pd_ddim_step(const pd_step_coeffs_t* c, const float* x, const float* model_output, const float* noise, float* x_out,
+                 float* x0_out, int64_t n, pd_stream_t stream) {
+    PD_REQUIRE(c && x && model_output, "null argument");
+    PD_REQUIRE(c->sigma == 0.f || noise, "eta > 0 needs a noise tensor");
+    return launch_ddim_step(*c, x, model_output, noise, x_out, x0_out, n, (cudaStream_t)stream);
+}
+
+int pd_axpby_per_sample(const float* a, const float* b, const float* ca, const float* cb, float* out, int32_t batch,
+                        int64_t per_sample, pd_stream_t stream) {
+    PD_REQUIRE(a && b && ca && cb && out, "null argument");
+    return launch_axpby(a, b, ca, cb, out, batch, per_sample, (cudaStream_t)stream);
+}
+
+int pd_cfg_combine(const float* cond, const float* uncond, const float* w, int32_t eqn, float* out, int32_t batch,
+                   int64_t per_sample, pd_stream_t stream) {
+    PD_REQUIRE(cond && uncond && w && out, "null argument");
+    PD_REQUIRE(eqn == 0 || eqn == 1, "Unknown guidance equation; should be 'imagen' (0) or 'CFG' (1)");
+    return launch_cfg(cond, uncond, w, eqn, out, batch, per_sample, (cudaStream_t)stream);
+}
+
+int pd_denorm_nhwc(const float* x, float* out, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                   pd_stream_t stream) {
+    PD_REQUIRE(x && out, "null argument");
+    return launch_denorm(x, out, batch, channels, height, width, (cudaStream_t)stream);
+}
+
+int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const int64_t* tgt_labels,
+                     const pd_step_coeffs_t* steps_host, int32_t n_inv, int32_t n_gen, pd_stream_t stream) {
+    PD_REQUIRE(m && x && steps_host, "null argument");
+    PD_REQUIRE(m->bound, "pd_unet_plan + pd_unet_bind_workspace must be called first");
+    PD_REQUIRE(m->cfg.in_channels == m->cfg.out_channels, "in/out channels must match for sampling");
+    PD_REQUIRE(!m->cls || (src_labels && tgt_labels), "class-conditioned model needs source and target labels");
+    const size_t per = (size_t)m->cfg.in_channels * m->H * m->W;
+    for (int i = 0; i < m->B; i += m->mb) {
+        for (int sidx = 0; sidx < n_inv + n_gen; ++sidx) {
+            Ctx c;
+            c.x = x + (size_t)i * per;
+            c.timesteps = nullptr;
+            c.t_scalar = steps_host[sidx].timestep;
+            const int64_t* lab = sidx < n_inv ? src_labels : tgt_labels;
+            c.labels = lab ? lab + i : nullptr;
+            c.model_out = nullptr;
+            c.x_update = x + (size_t)i * per;
+            c.step = &steps_host[sidx];
+            int rc = run_program(m, c, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int pd_unet_launch_count(pd_unet_t* m, int64_t* n) {
+    PD_REQUIRE(m && n, "null argument");
+    *n = m->launches;
+    return 0;
+}
+
+// ---- kernel-level test entry points ----------------------------------------------------------------------------------
+int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout,
+                 int32_t ksize, int32_t stride, int32_t pad, const void* x1, const void* x2, const float* weight,
+                 const float* bias, const float* addvec, const void* residual, const void* sc1, const void* sc2,
+                 int32_t csc1, int32_t csc2, const float* sc_w, float out_scale, void* out, pd_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
+    const int ct = c1 + c2;
+    int rc = 0;
+    if (use_tc) {
+        PD_REQUIRE(bf, "tcgen05 path is bf16 only");
+        PD_REQUIRE(c2 == 0, "tcgen05 main segment takes one (already concatenated) source");
+        const int ktot = ksize * ksize * ct + csc1 + csc2;
+        bf16* wm = nullptr;
+        PD_CHECK_CUDA(cudaMalloc((void**)&wm, (size_t)cout * ktot * sizeof(bf16)));
+        rc = launch_relayout_tc(weight, cout, ct, ksize, wm, ktot, 0, s);
+        if (!rc && (csc1 + csc2)) rc = launch_relayout_tc(sc_w, cout, csc1 + csc2, 1, wm, ktot, ksize * ksize * ct, s);
+        ConvTcDesc d{};
+        d.x = (const bf16*)x1; d.C = ct; d.N = n; d.H = h; d.W = w; d.ksize = ksize; d.stride = stride; d.pad = pad;
+        d.Ho = ho; d.Wo = wo; d.Cout = cout; d.sc1 = (const bf16*)sc1; d.Csc1 = csc1; d.sc2 = (const bf16*)sc2; d.Csc2 = csc2;
+        d.wmat = wm; d.bias = bias; d.addvec = addvec; d.addvec_stride = cout; d.residual = (const bf16*)residual;
+        d.out_scale = out_scale; d.out = (bf16*)out;
+        ConvTcPlan* pl = nullptr;
+        if (!rc) rc = conv_tc_plan_create(d, &pl);
+        if (!rc) rc = conv_tc_launch(pl, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (pl) conv_tc_plan_destroy(pl);
+        cudaFree(wm);
+        if (!rc && e != cudaSuccess) { set_error(std::string("conv_tc kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
+        return rc;
+    }
+    float* wm = nullptr;
+    PD_CHECK_CUDA(cudaMalloc((void**)&wm, (size_t)cout * ct * ksize * ksize * sizeof(float)));
+    rc = launch_relayout_simt(weight, cout, ct, ksize, wm, s);
+    void* tmp = nullptr;
+    float* wsc = nullptr;
+    const size_t esz = bf ? 2 : 4;
+    if (!rc && (csc1 + csc2)) {
+        PD_CHECK_CUDA(cudaMalloc(&tmp, (size_t)n * ho * wo * cout * esz));
+        PD_CHECK_CUDA(cudaMalloc((void**)&wsc, (size_t)cout * (csc1 + csc2) * sizeof(float)));
+        rc = launch_relayout_simt(sc_w, cout, csc1 + csc2, 1, wsc, s);
+        ConvArgs ca{};
+        ca.x1 = sc1; ca.x2 = sc2; ca.C1 = csc1; ca.C2 = csc2; ca.N = n; ca.H = ho; ca.W = wo; ca.Cout = cout; ca.ksize = 1;
+        ca.stride = 1; ca.pad = 0; ca.Ho = ho; ca.Wo = wo; ca.w = wsc; ca.out_scale = 1.f; ca.out = tmp;
+        if (!rc) rc = launch_conv_simt(bf != 0, ca, s);
+    }
+    ConvArgs ca{};
+    ca.x1 = x1; ca.x2 = x2; ca.C1 = c1; ca.C2 = c2; ca.N = n; ca.H = h; ca.W = w; ca.Cout = cout; ca.ksize = ksize;
+    ca.stride = stride; ca.pad = pad; ca.Ho = ho; ca.Wo = wo; ca.w = wm; ca.bias = bias; ca.addvec = addvec;
+    ca.addvec_stride = cout; ca.residual = tmp ? tmp : residual; ca.out_scale = out_scale; ca.out = out;
+    if (!rc) rc = launch_conv_simt(bf != 0, ca, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(wm);
+    if (tmp) cudaFree(tmp);
+    if (wsc) cudaFree(wsc);
+    if (!rc && e != cudaSuccess) { set_error(std::string("conv_simt kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
+    return rc;
+}
+
+int pd_test_groupnorm(int32_t bf, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+                      int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta, void* out,
+                      pd_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    float* stats = nullptr;
+    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (size_t)n * groups * 2 * sizeof(float)));
+    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)n * groups * 2 * sizeof(float), s));
+    GNArgs ga{};
+    ga.x1 = x1; ga.x2 = x2; ga.C1 = c1; ga.C2 = c2; ga.N = n; ga.HW = hw; ga.groups = groups; ga.eps = eps; ga.gamma = gamma;
+    ga.beta = beta; ga.silu = do_silu; ga.stats = stats; ga.out = out;
+    int rc = launch_gn_stats(bf != 0, ga, s);
+    if (!rc) rc = launch_gn_apply(bf != 0, bf == 0, ga, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(stats);
+    if (!rc && e != cudaSuccess) { set_error(std::string("groupnorm kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
+    return rc;
+}
+
+int pd_test_attention(int32_t use_mma, int32_t bf, int32_t n, int32_t s_len, int32_t c, int32_t d, const void* qkv,
+                      void* out, pd_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (use_mma) {
+        PD_REQUIRE(bf, "attention_mma is bf16 only");
+        rc = launch_attention_mma(qkv, n, s_len, c, d, out, s);
+    } else {
+        rc = launch_attention_simt(bf != 0, bf == 0, qkv, n, s_len, c, d, out, s);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (!rc && e != cudaSuccess) { set_error(std::string("attention kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// phendiff_b200 — implicit-GEMM convolution / linear on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// GEMM view: M = N*Ho*Wo output pixels, Ncol = Cout, K = k*k*C (+ Csc of a fused 1x1 shortcut).
+//   A (activations, NHWC bf16): never materialised as im2col.  An M tile is a box of 128 output pixels
+//     (Wt x Ht x Nt); for filter tap (r,s) the A tile is the SAME box shifted by (r-pad, s-pad) in the input, i.e. one
+//     4-D tiled TMA load {64 ch, Wt, Ht, Nt} whose out-of-bounds rows/columns the TMA unit zero-fills (= conv padding).
+//     Each pixel is one 128-byte row (64 bf16), written with the 128B swizzle -> exactly the canonical K-major
+//     SWIZZLE_128B UMMA operand.  Stride-2 convs (Downsample2D) use a 5-D "phase" view of the input
+//     {(b,c), W/2, a, H/2, N} so that tap (r,s) is again a plain box.
+//   B (weights): (Cout, Ktot) bf16 K-major, Ktot ordered (tap, channel) then the shortcut channels; 2-D TMA boxes.
+//   D: fp32 accumulator in TMEM, 128 lanes x BLOCK_N columns, double buffered so the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias +time-embedding row +residual ->
+// bf16 -> global).
+#include "pd_kernels.h"
+#include <algorithm>
+#include <string>
+
+namespace pd {
+
+struct ConvTcParams {
+    CUtensorMap tmA;    // main activation view (4-D, or 5-D phase view when stride2)
+    CUtensorMap tmS1;   // shortcut source 1 (4-D, output resolution)
+    CUtensorMap tmS2;   // shortcut source 2
+    CUtensorMap tmB;    // weights (Ktot, Cout)
+    int ksize, pad, stride2, C;
+    int kb_main;        // 64-channel blocks per tap
+    int kb_s1, kb_s2;   // 64-channel blocks of the shortcut segments
+    int num_kb;
+    int Wt, Ht, Nt, tilesW, tilesH;
+    int Ho, Wo, Cout;
+    int m_tiles, n_tiles;
+    const float* bias;
+    const float* addvec;
+    int addvec_stride;
+    const bf16* residual;
+    float out_scale;
+    bf16* out;
+};
+
+struct ConvTcPlan {
+    ConvTcParams p;
+    int block_n;
+    int grid;
+    size_t smem;
+};
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB
+constexpr int TC_THREADS = 256;
+
+template <int BLOCK_N> struct TcCfg {
+    static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;   // power of two for 64/128/256
+    static constexpr size_t SMEM = (size_t)STAGES * (TC_A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// K-major SWIZZLE_128B operand descriptor (PTX "matrix descriptor"): start address >> 4, LBO unused for swizzled
+// K-major, SBO = 1024 B (8 rows x 128 B), version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    using Cfg = TcCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + (size_t)STAGES * TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * (TC_A_BYTES + Cfg::B_BYTES));
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmA);
+        prefetch_tmap(&p.tmB);
+        if (p.kb_s1) prefetch_tmap(&p.tmS1);
+        if (p.kb_s2) prefetch_tmap(&p.tmS2);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int tiles_per_group = p.tilesW * p.tilesH;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+                const int grp = m_tile / tiles_per_group, rem = m_tile - grp * tiles_per_group;
+                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+                const int n0 = grp * p.Nt, h0 = th * p.Ht, w0 = tw * p.Wt;
+                const int ntap = p.ksize * p.ksize;
+                const int kb_taps = ntap * p.kb_main;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], TC_A_BYTES + Cfg::B_BYTES);
+                    uint8_t* dstA = smA + (size_t)stage * TC_A_BYTES;
+                    uint8_t* dstB = smB + (size_t)stage * Cfg::B_BYTES;
+                    if (kb < kb_taps) {
+                        const int tap = kb / p.kb_main, c0 = (kb - tap * p.kb_main) * TC_BLOCK_K;
+                        const int r = tap / p.ksize, s = tap - r * p.ksize;
+                        if (!p.stride2) {
+                            tma_load_4d(&p.tmA, &full[stage], dstA, c0, w0 + s - p.pad, h0 + r - p.pad, n0);
+                        } else {
+                            // input row 2*ho + q, q = r - pad: phase a = q mod 2, half-resolution offset floor(q/2)
+                            const int qr = r - p.pad, qs = s - p.pad;
+                            const int ar = qr & 1, as = qs & 1;
+                            const int dr = (qr - ar) / 2, ds = (qs - as) / 2;
+                            tma_load_5d(&p.tmA, &full[stage], dstA, as * p.C + c0, w0 + ds, ar, h0 + dr, n0);
+                        }
+                    } else if (kb < kb_taps + p.kb_s1) {
+                        tma_load_4d(&p.tmS1, &full[stage], dstA, (kb - kb_taps) * TC_BLOCK_K, w0, h0, n0);
+                    } else {
+                        tma_load_4d(&p.tmS2, &full[stage], dstA, (kb - kb_taps - p.kb_s1) * TC_BLOCK_K, w0, h0, n0);
+                    }
+                    tma_load_2d(&p.tmB, &full[stage], dstB, kb * TC_BLOCK_K, n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ===================== MMA issuer (single thread) =====================
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = BLOCK_N, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                       ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smA + (size_t)stage * TC_A_BYTES);
+                    const uint32_t b_addr = smem_u32(smB + (size_t)stage * Cfg::B_BYTES);
+                    const uint64_t a_desc = make_sw128_desc(a_addr);
+                    const uint64_t b_desc = make_sw128_desc(b_addr);
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address
+                        umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);                       // smem slot free when these MMAs retire
+                    if (kb == p.num_kb - 1) umma_commit(&tfull[as]);  // accumulator ready for the epilogue
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+            const int grp = m_tile / tiles_per_group, rem = m_tile - grp * tiles_per_group;
+            const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+            const int per_img = p.Wt * p.Ht;
+            const int nn = row / per_img, rr = row - nn * per_img;
+            const int hh = rr / p.Wt, ww = rr - hh * p.Wt;
+            const int img = grp * p.Nt + nn;
+            const size_t pix = ((size_t)img * p.Ho + (th * p.Ht + hh)) * p.Wo + (tw * p.Wt + ww);
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            bf16* orow = p.out + pix * p.Cout;
+            const bf16* rrow = p.residual ? p.residual + pix * p.Cout : nullptr;
+            const float* avrow = p.addvec ? p.addvec + (size_t)img * p.addvec_stride : nullptr;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + chunk * 32), r);
+                tmem_ld_wait();
+                const int col0 = n_tile * BLOCK_N + chunk * 32;
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g8 * 8 + i]);
+                    const int c = col0 + g8 * 8;
+                    if (p.bias) {
+                        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                        float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+                    if (avrow) {
+                        float4 b0 = __ldg(reinterpret_cast<const float4*>(avrow + c));
+                        float4 b1 = __ldg(reinterpret_cast<const float4*>(avrow + c + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+                    if (rrow) {
+                        float rv[8];
+                        load8(rrow + c, rv);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += rv[i];
+                    }
+                    if (p.out_scale != 1.0f) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
+                    }
+                    store8(orow + c, v);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: tensor maps, plan, launch
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode();
+    PD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bd[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bd, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return 2;
+    }
+    return 0;
+}
+
+static bool tile_geometry(int N, int Ho, int Wo, int* Wt, int* Ht, int* Nt) {
+    int wt = std::min(Wo, TC_BLOCK_M);
+    if (wt <= 0 || TC_BLOCK_M % wt != 0 || Wo % wt != 0) return false;
+    int ht = std::min(Ho, TC_BLOCK_M / wt);
+    if (ht <= 0 || (TC_BLOCK_M / wt) % ht != 0 || Ho % ht != 0) return false;
+    int nt = TC_BLOCK_M / (wt * ht);
+    if (nt > 1 && (ht != Ho || wt != Wo)) return false;
+    if (N % nt != 0) return false;
+    *Wt = wt; *Ht = ht; *Nt = nt;
+    return true;
+}
+
+static int pick_block_n(int Cout) {
+    if (Cout % 256 == 0) return 256;
+    if (Cout % 128 == 0) return 128;
+    if (Cout % 64 == 0) return 64;
+    return 0;
+}
+
+bool conv_tc_supported(const ConvTcDesc& d, std::string* why) {
+    auto no = [&](const char* m) { if (why) *why = m; return false; };
+    if (d.C % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
+    if (pick_block_n(d.Cout) == 0) return no("Cout must be a multiple of 64");
+    if (!(d.ksize == 1 || d.ksize == 3)) return no("kernel size must be 1 or 3");
+    if (d.stride == 2) {
+        if (d.ksize != 3 || d.H % 2 || d.W % 2) return no("stride-2 needs a 3x3 kernel and even H, W");
+        if (d.Ho != d.H / 2 || d.Wo != d.W / 2) return no("stride-2 output shape");
+        if (d.pad != 0 && d.pad != 1) return no("stride-2 pad must be 0 or 1");
+        if (d.Csc1 || d.Csc2) return no("no shortcut segment on stride-2 convs");
+    } else if (d.stride == 1) {
+        if (d.Ho != d.H || d.Wo != d.W || d.pad != d.ksize / 2) return no("stride-1 convs must be 'same'");
+    } else return no("stride must be 1 or 2");
+    int Wt, Ht, Nt;
+    if (!tile_geometry(d.N, d.Ho, d.Wo, &Wt, &Ht, &Nt)) return no("output extent does not tile into 128-pixel boxes");
+    return true;
+}
+
+int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
+    std::string why;
+    PD_REQUIRE(conv_tc_supported(d, &why), ("conv_tc: unsupported shape: " + why).c_str());
+    ConvTcPlan* pl = new ConvTcPlan();
+    ConvTcParams& p = pl->p;
+    memset(&p, 0, sizeof(p));
+    p.ksize = d.ksize; p.pad = d.pad; p.stride2 = d.stride == 2; p.C = d.C;
+    p.kb_main = d.C / 64; p.kb_s1 = d.Csc1 / 64; p.kb_s2 = d.Csc2 / 64;
+    p.num_kb = d.ksize * d.ksize * p.kb_main + p.kb_s1 + p.kb_s2;
+    tile_geometry(d.N, d.Ho, d.Wo, &p.Wt, &p.Ht, &p.Nt);
+    p.tilesW = d.Wo / p.Wt; p.tilesH = d.Ho / p.Ht;
+    p.Ho = d.Ho; p.Wo = d.Wo; p.Cout = d.Cout;
+    p.m_tiles = (d.N / p.Nt) * p.tilesW * p.tilesH;
+    pl->block_n = pick_block_n(d.Cout);
+    p.n_tiles = d.Cout / pl->block_n;
+    p.bias = d.bias; p.addvec = d.addvec; p.addvec_stride = d.addvec_stride; p.residual = d.residual;
+    p.out_scale = d.out_scale; p.out = d.out;
+    const uint64_t C = d.C, H = d.H, W = d.W, N = d.N;
+    int rc = 0;
+    if (!p.stride2) {
+        uint64_t dims[4] = {C, W, H, N};
+        uint64_t st[3] = {C * 2, W * C * 2, H * W * C * 2};
+        uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Nt};
+        rc = encode_map(&p.tmA, d.x, 4, dims, st, box);
+    } else {
+        uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
+        uint64_t st[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+        uint32_t box[5] = {64, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Nt};
+        rc = encode_map(&p.tmA, d.x, 5, dims, st, box);
+    }
+    if (rc) { delete pl; return rc; }
+    const bf16* scs[2] = {d.sc1, d.sc2};
+    const int cscs[2] = {d.Csc1, d.Csc2};
+    CUtensorMap* tms[2] = {&p.tmS1, &p.tmS2};
+    for (int i = 0; i < 2; ++i) {
+        if (!cscs[i]) continue;
+        uint64_t Cs = cscs[i], Ho = d.Ho, Wo = d.Wo;
+        uint64_t dims[4] = {Cs, Wo, Ho, N};
+        uint64_t st[3] = {Cs * 2, Wo * Cs * 2, Ho * Wo * Cs * 2};
+        uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Nt};
+        rc = encode_map(tms[i], scs[i], 4, dims, st, box);
+        if (rc) { delete pl; return rc; }
+    }
+    {
+        const uint64_t Ktot = (uint64_t)p.num_kb * 64;
+        uint64_t dims[2] = {Ktot, (uint64_t)d.Cout};
+        uint64_t st[1] = {Ktot * 2};
+        uint32_t box[2] = {64, (uint32_t)pl->block_n};
+        rc = encode_map(&p.tmB, d.wmat, 2, dims, st, box);
+        if (rc) { delete pl; return rc; }
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    pl->grid = std::min(p.m_tiles * p.n_tiles, sms);
+    pl->smem = pl->block_n == 256 ? TcCfg<256>::SMEM : (pl->block_n == 128 ? TcCfg<128>::SMEM : TcCfg<64>::SMEM);
+    *out = pl;
+    return 0;
+}
+
+void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
+
+template <int BLOCK_N>
+static int launch_tc(const ConvTcPlan* pl, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TcCfg<BLOCK_N>::SMEM));
+        attr_set = true;
+    }
+    conv_tc_kernel<BLOCK_N><<<pl->grid, TC_THREADS, TcCfg<BLOCK_N>::SMEM, s>>>(pl->p);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
+    switch (pl->block_n) {
+        case 256: return launch_tc<256>(pl, s);
+        case 128: return launch_tc<128>(pl, s);
+        case 64: return launch_tc<64>(pl, s);
+    }
+    set_error("conv_tc: bad block_n");
+    return 1;
+}
+
+}  // namespace pd

@@ -1,0 +1,115 @@
+// phendiff_b200 — internal launch interface between the executor (pd_api.cu) and the kernel files.
+#pragma once
+#include "pd_common.cuh"
+#include "../../include/phendiff_b200.h"
+
+namespace pd {
+
+// ---- embeddings (cond_unet_2d.py:289-309; diffusers Timesteps/TimestepEmbedding) -------------------------------
+struct EmbedArgs {
+    const float* timesteps;       // (B), or null: every sample uses t_scalar
+    float t_scalar;
+    const int64_t* labels;        // (B) or null
+    const float* class_emb;       // (B,D) or null
+    const float *w1, *b1;         // (D,C0),(D)
+    const float *w2, *b2;         // (D,D),(D)
+    const float* class_table;     // (ncls,D) or null
+    int B, C0, D, ncls, flip;
+    float shift;
+    float* emb_act;               // (B,D) = SiLU(time_embedding + class embedding)
+};
+int launch_embed(const EmbedArgs& a, cudaStream_t s);
+// all ResnetBlock2D.time_emb_proj at once: out(B,J) = emb_act(B,D) @ wcat(J,D)^T + bcat(J)
+int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat, int B, int D, int J, float* out,
+                     cudaStream_t s);
+
+// ---- GroupNorm (+SiLU) over NHWC with two channel-concatenated sources ------------------------------------------
+struct GNArgs {
+    const void* x1; const void* x2;   // (N,HW,C1) , (N,HW,C2) or null
+    int C1, C2, N, HW, groups;
+    float eps;
+    const float *gamma, *beta;        // (C1+C2)
+    int silu;
+    float* stats;                     // (N,groups,2) sum / sumsq, zero on entry
+    void* out;                        // (N,HW,C1+C2)
+};
+int launch_gn_stats(bool bf, const GNArgs& a, cudaStream_t s);
+int launch_gn_apply(bool bf, bool precise, const GNArgs& a, cudaStream_t s);
+
+// ---- generic SIMT convolution (fp32 validation path; odd shapes of the bf16 path) -------------------------------
+struct ConvArgs {
+    const void* x1; const void* x2;   // NHWC sources, channel-concatenated
+    int C1, C2, N, H, W, Cout, ksize, stride, pad, Ho, Wo;
+    const float* w;                   // (k*k*(C1+C2), Cout) fp32, tap-major then input channel
+    const float* bias;                // (Cout) or null
+    const float* addvec;              // (N, addvec_stride) or null: per-image per-channel add (time embedding)
+    int addvec_stride;
+    const void* residual;             // (N,Ho,Wo,Cout) or null
+    float out_scale;                  // multiplies the final sum (1/output_scale_factor)
+    void* out;                        // (N,Ho,Wo,Cout)
+};
+int launch_conv_simt(bool bf, const ConvArgs& a, cudaStream_t s);
+
+// conv_in: NCHW fp32 sample -> NHWC activations (cond_unet_2d.py:313)
+int launch_conv_in(bool bf, const float* x, const float* w /*(9*Cin,Cout)*/, const float* bias, int N, int Cin, int H,
+                   int W, int Cout, void* out, cudaStream_t s);
+// conv_out (+ optional fused DDIM update): NHWC activations -> NCHW fp32 (cond_unet_2d.py:348, A.5)
+struct ConvOutArgs {
+    const void* act;                  // (N,H,W,Cin) = SiLU(GN(sample))
+    const float* w;                   // (9, Cin, 4) fp32 (out channel padded to 4)
+    const float* bias;                // (Cout)
+    int N, H, W, Cin, Cout;
+    float* model_out;                 // (N,Cout,H,W) or null
+    float* x;                         // (N,Cout,H,W) updated in place when `step` != null
+    const pd_step_coeffs_t* step;     // host pointer (copied by value into the launch) or null
+};
+int launch_conv_out(bool bf, const ConvOutArgs& a, cudaStream_t s);
+
+int launch_upsample2x(bool bf, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s);
+
+// ---- attention core: softmax(q k^T / sqrt(d)) v on packed qkv (N,S,3C) ------------------------------------------
+int launch_attention_simt(bool bf, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
+                          cudaStream_t s);
+int launch_attention_mma(const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s);  // bf16 only
+
+// ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
+int launch_ddim_step(const pd_step_coeffs_t& c, const float* x, const float* m, const float* noise, float* x_out,
+                     float* x0_out, int64_t n, cudaStream_t s);
+int launch_axpby(const float* a, const float* b, const float* ca, const float* cb, float* out, int B, int64_t per,
+                 cudaStream_t s);
+int launch_cfg(const float* cond, const float* uncond, const float* w, int eqn, float* out, int B, int64_t per,
+               cudaStream_t s);
+int launch_denorm(const float* x, float* out, int B, int C, int H, int W, cudaStream_t s);
+
+// ---- weight re-layout ---------------------------------------------------------------------------------------------
+// OIHW fp32 (O,I,k,k) -> (k*k*I, O) fp32
+int launch_relayout_simt(const float* w, int O, int I, int k, float* out, cudaStream_t s);
+// OIHW fp32 -> bf16 (O, ktot) at column offset koff, K index = tap*I + i
+int launch_relayout_tc(const float* w, int O, int I, int k, bf16* out, int ktot, int koff, cudaStream_t s);
+// conv_out OIHW (O,I,3,3) -> (9, I, 4) fp32
+int launch_relayout_convout(const float* w, int O, int I, float* out, cudaStream_t s);
+int launch_cast_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
+int launch_cast_f32(const bf16* x, float* out, int64_t n, cudaStream_t s);
+
+// ---- tcgen05 implicit-GEMM convolution (pd_conv_tc.cu) -----------------------------------------------------------
+struct ConvTcPlan;  // opaque: tensor maps + launch geometry for one layer at one (N,H,W)
+struct ConvTcDesc {
+    // main segment: ksize x ksize conv over `x` (N,H,W,C) bf16 NHWC (already normalised / concatenated)
+    const bf16* x; int C;
+    int N, H, W, ksize, stride, pad, Ho, Wo, Cout;
+    // optional 1x1 shortcut segment over up to two concatenated sources at the OUTPUT resolution
+    const bf16* sc1; int Csc1;
+    const bf16* sc2; int Csc2;
+    const bf16* wmat;                 // (Cout, Ktot) bf16, Ktot = k*k*C + Csc1 + Csc2
+    const float* bias;                // (Cout) or null
+    const float* addvec; int addvec_stride;
+    const bf16* residual;             // (N,Ho,Wo,Cout) or null
+    float out_scale;
+    bf16* out;                        // (N,Ho,Wo,Cout)
+};
+bool conv_tc_supported(const ConvTcDesc& d, std::string* why);
+int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out);
+void conv_tc_plan_destroy(ConvTcPlan* p);
+int conv_tc_launch(const ConvTcPlan* p, cudaStream_t s);
+
+}  // namespace pd

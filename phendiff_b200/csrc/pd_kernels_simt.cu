@@ -1,0 +1,803 @@
+// phendiff_b200 — CUDA-core kernels: embeddings, GroupNorm(+SiLU), SIMT convolution (fp32 validation mode and the
+// odd-shaped conv_in / conv_out of the bf16 path), fused conv_out + DDIM update, attention (SIMT), scheduler and
+// pipeline elementwise work, weight re-layout.  All of these are HBM- or latency-bound side work; the dense
+// contractions of the bf16 path live in pd_conv_tc.cu (tcgen05) and pd_attn_mma.cu.
+#include "pd_kernels.h"
+#include <algorithm>
+#include <vector>
+
+namespace pd {
+
+// =====================================================================================================================
+// time + class embedding  (reference: cond_unet_2d.py:289-309; diffusers get_timestep_embedding / TimestepEmbedding)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __restrict__ freqs) {
+    extern __shared__ float sm[];
+    float* e0 = sm;           // C0
+    float* h1 = sm + a.C0;    // D
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const float t = a.timesteps ? a.timesteps[b] : a.t_scalar;
+    const int half = a.C0 / 2;
+    for (int k = tid; k < half; k += blockDim.x) {
+        float arg = t * freqs[k];
+        float s = sinf(arg), c = cosf(arg);
+        if (a.flip) { e0[k] = c; e0[half + k] = s; } else { e0[k] = s; e0[half + k] = c; }
+    }
+    __syncthreads();
+    for (int j = warp; j < a.D; j += nwarp) {
+        const float* w = a.w1 + (size_t)j * a.C0;
+        float acc = 0.f;
+        for (int k = lane; k < a.C0; k += 32) acc += w[k] * e0[k];
+        acc = warp_sum(acc);
+        if (lane == 0) h1[j] = silu<true>(acc + a.b1[j]);
+    }
+    __syncthreads();
+    for (int j = warp; j < a.D; j += nwarp) {
+        const float* w = a.w2 + (size_t)j * a.D;
+        float acc = 0.f;
+        for (int k = lane; k < a.D; k += 32) acc += w[k] * h1[k];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float e = acc + a.b2[j];
+            if (a.class_emb) e += a.class_emb[(size_t)b * a.D + j];
+            else if (a.labels) e += a.class_table[(size_t)a.labels[b] * a.D + j];
+            a.emb_act[(size_t)b * a.D + j] = silu<true>(e);
+        }
+    }
+}
+
+static float* g_freqs = nullptr;   // per-process table, (<= 4096 entries); rebuilt when (C0, shift) change
+static int g_freqs_c0 = -1;
+static float g_freqs_shift = 0.f;
+
+int launch_embed(const EmbedArgs& a, cudaStream_t s) {
+    const int half = a.C0 / 2;
+    if (g_freqs == nullptr || g_freqs_c0 != a.C0 || g_freqs_shift != a.shift) {
+        PD_REQUIRE(half <= 4096, "time embedding too wide");
+        if (!g_freqs) PD_CHECK_CUDA(cudaMalloc(&g_freqs, 4096 * sizeof(float)));
+        std::vector<float> f(half);
+        for (int k = 0; k < half; ++k) {
+            // fp32 arithmetic in the order diffusers uses: (-ln(10000) * k) / (half - shift), then exp
+            float e = (-9.210340371976184f * (float)k) / ((float)half - a.shift);
+            f[k] = expf(e);
+        }
+        PD_CHECK_CUDA(cudaMemcpyAsync(g_freqs, f.data(), half * sizeof(float), cudaMemcpyHostToDevice, s));
+        PD_CHECK_CUDA(cudaStreamSynchronize(s));  // f is a local; one-time cost at first use
+        g_freqs_c0 = a.C0;
+        g_freqs_shift = a.shift;
+    }
+    size_t smem = (size_t)(a.C0 + a.D) * sizeof(float);
+    embed_kernel<<<a.B, 256, smem, s>>>(a, g_freqs);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict__ emb_act, const float* __restrict__ wcat,
+                                                         const float* __restrict__ bcat, int D, int J,
+                                                         float* __restrict__ out) {
+    extern __shared__ float e[];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < D; k += blockDim.x) e[k] = emb_act[(size_t)b * D + k];
+    __syncthreads();
+    const int j0 = blockIdx.x * 64;
+    for (int jj = warp; jj < 64; jj += 8) {
+        int j = j0 + jj;
+        if (j >= J) break;
+        const float* w = wcat + (size_t)j * D;
+        float acc = 0.f;
+        for (int k = lane; k < D; k += 32) acc += w[k] * e[k];
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)b * J + j] = acc + bcat[j];
+    }
+}
+
+int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat, int B, int D, int J, float* out,
+                     cudaStream_t s) {
+    dim3 grid((J + 63) / 64, B);
+    temb_proj_kernel<<<grid, 256, D * sizeof(float), s>>>(emb_act, wcat, bcat, D, J, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// GroupNorm (+SiLU), NHWC, two concatenated sources.  HBM-bound: stats = 1 read, apply = 1 read + 1 write.
+// Thread mapping: a thread owns one 8-channel vector column `cv` and walks pixel rows, so every global access is a
+// 16/32-byte vector and a warp covers contiguous memory.
+// =====================================================================================================================
+constexpr int GN_ROWS_PER_BLOCK = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(GNArgs a) {
+    extern __shared__ float sm[];  // [2][C]
+    const int C = a.C1 + a.C2, ncv = C / 8;
+    float* s_sum = sm;
+    float* s_sq = sm + C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
+    const int row_begin = blockIdx.x * GN_ROWS_PER_BLOCK;
+    const int row_end = min(row_begin + GN_ROWS_PER_BLOCK, a.HW);
+    const int c = cv * 8;
+    const T* src;
+    int pitch, coff;
+    if (c < a.C1) { src = (const T*)a.x1; pitch = a.C1; coff = c; } else { src = (const T*)a.x2; pitch = a.C2; coff = c - a.C1; }
+    src += (size_t)n * a.HW * pitch + coff;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    if (r0 < rstep) {
+        for (int r = row_begin + r0; r < row_end; r += rstep) {
+            float v[8];
+            load8(src + (size_t)r * pitch, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { atomicAdd(&s_sum[c + i], s[i]); atomicAdd(&s_sq[c + i], q[i]); }
+    }
+    __syncthreads();
+    const int cpg = C / a.groups;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        float ss = 0.f, qq = 0.f;
+        for (int i = 0; i < cpg; ++i) { ss += s_sum[g * cpg + i]; qq += s_sq[g * cpg + i]; }
+        atomicAdd(&a.stats[((size_t)n * a.groups + g) * 2 + 0], ss);
+        atomicAdd(&a.stats[((size_t)n * a.groups + g) * 2 + 1], qq);
+    }
+}
+
+template <typename T, bool kPrecise>
+__global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a) {
+    const int C = a.C1 + a.C2, ncv = C / 8;
+    const int n = blockIdx.y;
+    const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
+    if (r0 >= rstep) return;
+    const int row_begin = blockIdx.x * GN_ROWS_PER_BLOCK;
+    const int row_end = min(row_begin + GN_ROWS_PER_BLOCK, a.HW);
+    const int c = cv * 8;
+    const T* src;
+    int pitch, coff;
+    if (c < a.C1) { src = (const T*)a.x1; pitch = a.C1; coff = c; } else { src = (const T*)a.x2; pitch = a.C2; coff = c - a.C1; }
+    src += (size_t)n * a.HW * pitch + coff;
+    T* dst = (T*)a.out + (size_t)n * a.HW * C + c;
+    const int cpg = C / a.groups;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int g = (c + i) / cpg;
+        float sum = a.stats[((size_t)n * a.groups + g) * 2 + 0];
+        float sq = a.stats[((size_t)n * a.groups + g) * 2 + 1];
+        float mean = sum * inv_cnt;
+        float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        float rstd = rsqrtf(var + a.eps);
+        if (kPrecise) rstd = 1.0f / sqrtf(var + a.eps);
+        float gm = a.gamma[c + i], bt = a.beta[c + i];
+        sc[i] = rstd * gm;
+        sh[i] = bt - mean * rstd * gm;
+    }
+    for (int r = row_begin + r0; r < row_end; r += rstep) {
+        float v[8];
+        load8(src + (size_t)r * pitch, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y = v[i] * sc[i] + sh[i];
+            v[i] = a.silu ? silu<kPrecise>(y) : y;
+        }
+        store8(dst + (size_t)r * C, v);
+    }
+}
+
+static int gn_block(int C) {
+    int ncv = C / 8;
+    int rpp = 256 / ncv;
+    if (rpp < 1) rpp = 1;
+    return ncv * rpp;
+}
+
+int launch_gn_stats(bool bf, const GNArgs& a, cudaStream_t s) {
+    const int C = a.C1 + a.C2;
+    PD_REQUIRE(C % 8 == 0 && a.C1 % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
+    PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
+    dim3 grid((a.HW + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, a.N);
+    int block = gn_block(C);
+    size_t smem = 2 * C * sizeof(float);
+    if (bf) gn_stats_kernel<bf16><<<grid, block, smem, s>>>(a);
+    else gn_stats_kernel<float><<<grid, block, smem, s>>>(a);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gn_apply(bool bf, bool precise, const GNArgs& a, cudaStream_t s) {
+    const int C = a.C1 + a.C2;
+    dim3 grid((a.HW + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, a.N);
+    int block = gn_block(C);
+    if (bf) {
+        if (precise) gn_apply_kernel<bf16, true><<<grid, block, 0, s>>>(a);
+        else gn_apply_kernel<bf16, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (precise) gn_apply_kernel<float, true><<<grid, block, 0, s>>>(a);
+        else gn_apply_kernel<float, false><<<grid, block, 0, s>>>(a);
+    }
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// SIMT implicit-GEMM convolution, fp32 FMA.  M = N*Ho*Wo output pixels, Ncol = Cout, K = k*k*(C1+C2).
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile.  This is the fp32 validation path (<= 1e-4 vs the oracle)
+// and the in-CUDA fallback for shapes the tcgen05 kernel does not take.
+// =====================================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int M = a.N * a.Ho * a.Wo, Ct = a.C1 + a.C2;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // A-load role: pixel pi, 4 channels at chunk
+    const int pi = tid >> 2, chunk = (tid & 3) * 4;
+    const int m = m0 + pi;
+    int img = 0, ho = 0, wo = 0;
+    const bool mvalid = m < M;
+    if (mvalid) { img = m / (a.Ho * a.Wo); int rem = m - img * a.Ho * a.Wo; ho = rem / a.Wo; wo = rem - ho * a.Wo; }
+    // B-load role
+    const int brow = tid >> 4, bcol = (tid & 15) * 4;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int ntap = a.ksize * a.ksize;
+    for (int tap = 0; tap < ntap; ++tap) {
+        const int r = tap / a.ksize, sx = tap - r * a.ksize;
+        const int ih = ho * a.stride - a.pad + r, iw = wo * a.stride - a.pad + sx;
+        const bool pvalid = mvalid && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+        const size_t pix = ((size_t)img * a.H + ih) * a.W + iw;
+        for (int ci0 = 0; ci0 < Ct; ci0 += BK) {
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pvalid) {
+                int ci = ci0 + chunk;
+                const T* p = (ci < a.C1) ? (const T*)a.x1 + pix * a.C1 + ci : (const T*)a.x2 + pix * a.C2 + (ci - a.C1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = to_f(p[i]);
+            }
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + bcol < a.Cout)
+                bv = *reinterpret_cast<const float4*>(a.w + ((size_t)tap * Ct + ci0 + brow) * a.Cout + n0 + bcol);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[chunk + i][pi] = av[i];
+            *reinterpret_cast<float4*>(&Bs[brow][bcol]) = bv;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float4 af = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                float4 bf = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                float aa[4] = {af.x, af.y, af.z, af.w}, bb[4] = {bf.x, bf.y, bf.z, bf.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += aa[i] * bb[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int mm = m0 + ty * 4 + i;
+        if (mm >= M) continue;
+        const int im = mm / (a.Ho * a.Wo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c >= a.Cout) continue;
+            float v = acc[i][j];
+            if (a.bias) v += a.bias[c];
+            if (a.addvec) v += a.addvec[(size_t)im * a.addvec_stride + c];
+            if (a.residual) v += to_f(((const T*)a.residual)[(size_t)mm * a.Cout + c]);
+            v *= a.out_scale;
+            ((T*)a.out)[(size_t)mm * a.Cout + c] = from_f<T>(v);
+        }
+    }
+}
+
+int launch_conv_simt(bool bf, const ConvArgs& a, cudaStream_t s) {
+    const int Ct = a.C1 + a.C2;
+    PD_REQUIRE(Ct % 16 == 0 && a.C1 % 4 == 0 && a.Cout % 4 == 0, "conv_simt needs Cin % 16 == 0 and Cout % 4 == 0");
+    const int M = a.N * a.Ho * a.Wo;
+    dim3 grid((M + 63) / 64, (a.Cout + 63) / 64);
+    if (bf) conv_simt_kernel<bf16><<<grid, 256, 0, s>>>(a);
+    else conv_simt_kernel<float><<<grid, 256, 0, s>>>(a);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// conv_in: (N,Cin,H,W) fp32 NCHW -> (N,H,W,Cout) NHWC, 3x3 pad 1.  K = 9*Cin = 27: bandwidth-bound, weights in smem,
+// a warp covers 32 consecutive pixels of a row (coalesced NCHW reads, broadcast weight reads).
+// =====================================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, int N, int Cin, int H, int W,
+                                                       int Cout, T* __restrict__ out) {
+    extern __shared__ float sw[];  // (9*Cin, Cout) + bias
+    const int K = 9 * Cin;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
+    float* sb = sw + K * Cout;
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const size_t HW = (size_t)H * W, total = (size_t)N * HW;
+    const size_t p = (size_t)blockIdx.x * 32 + lane;
+    if (p >= total) return;
+    const int n = p / HW;
+    const int hw = p - (size_t)n * HW;
+    const int h = hw / W, ww = hw - h * W;
+    // gather the 9*Cin input values once (Cin <= 4 supported in registers)
+    float in[36];
+    for (int tap = 0; tap < 9; ++tap) {
+        int ih = h + tap / 3 - 1, iw = ww + tap % 3 - 1;
+        bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        for (int ci = 0; ci < Cin; ++ci)
+            in[tap * Cin + ci] = ok ? x[((size_t)n * Cin + ci) * HW + (size_t)ih * W + iw] : 0.f;
+    }
+    for (int cg = warp; cg * 16 < Cout; cg += nwarp) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = sb[cg * 16 + j];
+        for (int k = 0; k < K; ++k) {
+            const float v = in[k];
+            const float4* wr = reinterpret_cast<const float4*>(sw + (size_t)k * Cout + cg * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 w4 = wr[q];
+                acc[4 * q + 0] += v * w4.x; acc[4 * q + 1] += v * w4.y;
+                acc[4 * q + 2] += v * w4.z; acc[4 * q + 3] += v * w4.w;
+            }
+        }
+        T* o = out + p * Cout + cg * 16;
+        store8(o, acc);
+        store8(o + 8, acc + 8);
+    }
+}
+
+int launch_conv_in(bool bf, const float* x, const float* w, const float* bias, int N, int Cin, int H, int W, int Cout,
+                   void* out, cudaStream_t s) {
+    PD_REQUIRE(Cin <= 4 && Cout % 16 == 0, "conv_in supports in_channels <= 4 and block_out_channels[0] % 16 == 0");
+    size_t smem = ((size_t)9 * Cin * Cout + Cout) * sizeof(float);
+    PD_REQUIRE(smem <= 200 * 1024, "conv_in weights do not fit shared memory");
+    size_t total = (size_t)N * H * W;
+    int grid = (int)((total + 31) / 32);
+    if (bf) {
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_in_kernel<bf16><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (bf16*)out);
+    } else {
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_in_kernel<float><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (float*)out);
+    }
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// scheduler update, shared by the standalone step kernel and the conv_out epilogue
+// =====================================================================================================================
+__device__ __forceinline__ float ddim_update(const pd_step_coeffs_t& c, float x, float m, float noise, float* x0_out) {
+    float x0, e;
+    if (c.pred_type == PD_PRED_EPSILON) {
+        x0 = (x - c.sqrt_beta * m) / c.sqrt_alpha;   // IEEE: alpha = 0 gives +-inf / NaN exactly as the reference
+        e = m;
+    } else if (c.pred_type == PD_PRED_SAMPLE) {
+        x0 = m;
+        e = (x - c.sqrt_alpha * x0) / c.sqrt_beta;
+    } else {
+        x0 = c.sqrt_alpha * x - c.sqrt_beta * m;
+        e = c.sqrt_alpha * m + c.sqrt_beta * x;
+    }
+    if (c.clip) x0 = (x0 < -c.clip_range) ? -c.clip_range : ((x0 > c.clip_range) ? c.clip_range : x0);  // NaN stays NaN
+    if (c.use_clipped_model_output) e = (x - c.sqrt_alpha * x0) / c.sqrt_beta;
+    float out = c.sqrt_alpha_next * x0 + c.dir_coef * e;
+    if (c.sigma != 0.f) out += c.sigma * noise;
+    if (x0_out) *x0_out = x0;
+    return out;
+}
+
+__global__ void ddim_step_kernel(pd_step_coeffs_t c, const float* __restrict__ x, const float* __restrict__ m,
+                                 const float* __restrict__ noise, float* __restrict__ x_out, float* __restrict__ x0_out,
+                                 int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float x0;
+        float o = ddim_update(c, x[i], m[i], noise ? noise[i] : 0.f, &x0);
+        if (x_out) x_out[i] = o;
+        if (x0_out) x0_out[i] = x0;
+    }
+}
+
+int launch_ddim_step(const pd_step_coeffs_t& c, const float* x, const float* m, const float* noise, float* x_out,
+                     float* x0_out, int64_t n, cudaStream_t s) {
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    ddim_step_kernel<<<grid, 256, 0, s>>>(c, x, m, noise, x_out, x0_out, n);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// conv_out (+ fused DDIM update).  Cout <= 4, Cin = 32*CPL.  Each lane keeps its CPL input channels' 9*CPL*Cout
+// weights in registers; a warp reduces one pixel at a time and handles runs of 32 consecutive pixels so that the
+// NCHW fp32 writes (model output and x_t update) are coalesced.  x_t is read once and written once per step.
+// =====================================================================================================================
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_coeffs_t st, int has_step) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float wr[9][CPL][3];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            float4 w4 = *reinterpret_cast<const float4*>(a.w + ((size_t)tap * a.Cin + lane * CPL + j) * 4);
+            wr[tap][j][0] = w4.x; wr[tap][j][1] = w4.y; wr[tap][j][2] = w4.z;
+        }
+    const size_t HW = (size_t)a.H * a.W, total = (size_t)a.N * HW;
+    const size_t nruns = (total + 31) / 32;
+    for (size_t run = gwarp; run < nruns; run += nwarps) {
+        float keep[3] = {0.f, 0.f, 0.f};
+        for (int i = 0; i < 32; ++i) {
+            const size_t p = run * 32 + i;
+            if (p >= total) break;
+            const int n = p / HW;
+            const int hw = p - (size_t)n * HW;
+            const int h = hw / a.W, w = hw - h * a.W;
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+                if (ih < 0 || ih >= a.H || iw < 0 || iw >= a.W) continue;
+                const T* src = (const T*)a.act + (((size_t)n * a.H + ih) * a.W + iw) * a.Cin + lane * CPL;
+                float v[CPL];
+                if (CPL == 8) load8(src, v);
+                else if (CPL == 4 && sizeof(T) == 2) {
+                    uint2 r = *reinterpret_cast<const uint2*>(src);
+                    float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+                    float2 f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+                    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) v[j] = to_f(src[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    acc[0] += v[j] * wr[tap][j][0]; acc[1] += v[j] * wr[tap][j][1]; acc[2] += v[j] * wr[tap][j][2];
+                }
+            }
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                float v = warp_sum(acc[co]);
+                if (lane == i) keep[co] = v;
+            }
+        }
+        const size_t p = run * 32 + lane;
+        if (p < total) {
+            const int n = p / HW;
+            const size_t hw = p - (size_t)n * HW;
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                if (co >= a.Cout) break;
+                const float m = keep[co] + a.bias[co];
+                const size_t idx = ((size_t)n * a.Cout + co) * HW + hw;
+                if (a.model_out) a.model_out[idx] = m;
+                if (has_step) a.x[idx] = ddim_update(st, a.x[idx], m, 0.f, nullptr);
+            }
+        }
+    }
+}
+
+int launch_conv_out(bool bf, const ConvOutArgs& a, cudaStream_t s) {
+    PD_REQUIRE(a.Cout <= 3, "conv_out supports out_channels <= 3");
+    PD_REQUIRE(a.Cin % 32 == 0, "conv_out needs block_out_channels[0] % 32 == 0");
+    const int cpl = a.Cin / 32;
+    pd_step_coeffs_t st{};
+    int has = 0;
+    if (a.step) { st = *a.step; has = 1; PD_REQUIRE(st.sigma == 0.f, "fused conv_out update requires eta == 0"); }
+    size_t total = (size_t)a.N * a.H * a.W;
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 8);
+    if (grid < 1) grid = 1;
+#define PD_CO(TT, CPL) conv_out_kernel<TT, CPL><<<grid, 256, 0, s>>>(a, st, has)
+    if (bf) {
+        if (cpl == 2) PD_CO(bf16, 2); else if (cpl == 4) PD_CO(bf16, 4); else if (cpl == 8) PD_CO(bf16, 8);
+        else { set_error("conv_out: unsupported channel count"); return 1; }
+    } else {
+        if (cpl == 2) PD_CO(float, 2); else if (cpl == 4) PD_CO(float, 4); else if (cpl == 8) PD_CO(float, 8);
+        else { set_error("conv_out: unsupported channel count"); return 1; }
+    }
+#undef PD_CO
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// nearest-neighbour 2x upsample, NHWC (Upsample2D's F.interpolate; the conv that follows runs on the result)
+// =====================================================================================================================
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, int N, int H, int W, int C, T* __restrict__ out) {
+    const int cv = C / 8;
+    const size_t total = (size_t)N * 2 * H * 2 * W * cv;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int c = i % cv;
+        size_t p = i / cv;
+        int wo = p % (2 * W); p /= (2 * W);
+        int ho = p % (2 * H);
+        int n = p / (2 * H);
+        const T* src = x + (((size_t)n * H + ho / 2) * W + wo / 2) * C + c * 8;
+        T* dst = out + (((size_t)n * 2 * H + ho) * 2 * W + wo) * C + c * 8;
+        if (sizeof(T) == 2) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        else { float v[8]; load8(src, v); store8(dst, v); }
+    }
+}
+
+int launch_upsample2x(bool bf, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s) {
+    PD_REQUIRE(C % 8 == 0, "upsample needs C % 8 == 0");
+    size_t total = (size_t)N * 4 * H * W * (C / 8);
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+    if (bf) upsample2x_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, N, H, W, C, (bf16*)out);
+    else upsample2x_kernel<float><<<grid, 256, 0, s>>>((const float*)x, N, H, W, C, (float*)out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// attention core, SIMT (fp32 validation path).  One thread per query, K/V tiles of 128 keys in shared memory,
+// online softmax in chunks of 16 keys.  head_dim 8.
+// =====================================================================================================================
+template <typename T, bool kPrecise>
+__global__ void __launch_bounds__(128) attention_simt_kernel(const T* __restrict__ qkv, int S, int C, T* __restrict__ out) {
+    constexpr int D = 8, TK = 128;
+    __shared__ float Ks[TK][D];
+    __shared__ float Vs[TK][D];
+    const int n = blockIdx.z, head = blockIdx.y;
+    const int qi = blockIdx.x * 128 + threadIdx.x;
+    const size_t rowp = (size_t)3 * C;
+    const T* base = qkv + (size_t)n * S * rowp;
+    float q[D];
+    const float scale = 0.35355339059327373f;  // 1/sqrt(8)
+    if (qi < S) {
+        float v[8];
+        load8(base + (size_t)qi * rowp + head * D, v);
+#pragma unroll
+        for (int i = 0; i < D; ++i) q[i] = v[i] * scale;
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) q[i] = 0.f;
+    }
+    float mx = -INFINITY, l = 0.f, o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    for (int k0 = 0; k0 < S; k0 += TK) {
+        __syncthreads();
+        {
+            const int kj = k0 + threadIdx.x;
+            float kv[8], vv[8];
+            if (kj < S) {
+                load8(base + (size_t)kj * rowp + C + head * D, kv);
+                load8(base + (size_t)kj * rowp + 2 * C + head * D, vv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { kv[i] = 0.f; vv[i] = 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) { Ks[threadIdx.x][i] = kv[i]; Vs[threadIdx.x][i] = vv[i]; }
+        }
+        __syncthreads();
+        const int kmax = min(TK, S - k0);
+        for (int c0 = 0; c0 < kmax; c0 += 16) {
+            float sc[16];
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float s = -INFINITY;
+                if (c0 + j < kmax) {
+                    s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) s += q[i] * Ks[c0 + j][i];
+                }
+                sc[j] = s;
+                cm = fmaxf(cm, s);
+            }
+            const float nm = fmaxf(mx, cm);
+            const float corr = kPrecise ? expf(mx - nm) : __expf(mx - nm);
+            l *= corr;
+#pragma unroll
+            for (int i = 0; i < D; ++i) o[i] *= corr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (c0 + j < kmax) {
+                    const float p = kPrecise ? expf(sc[j] - nm) : __expf(sc[j] - nm);
+                    l += p;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) o[i] += p * Vs[c0 + j][i];
+                }
+            }
+            mx = nm;
+        }
+    }
+    if (qi < S) {
+        const float inv = 1.0f / l;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[i] = o[i] * inv;
+        store8(out + ((size_t)n * S + qi) * C + head * D, v);
+    }
+}
+
+int launch_attention_simt(bool bf, bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+    PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
+    PD_REQUIRE(C % 8 == 0, "attention channels must be a multiple of 8");
+    dim3 grid((S + 127) / 128, C / d, N);
+    if (bf) {
+        if (precise) attention_simt_kernel<bf16, true><<<grid, 128, 0, s>>>((const bf16*)qkv, S, C, (bf16*)out);
+        else attention_simt_kernel<bf16, false><<<grid, 128, 0, s>>>((const bf16*)qkv, S, C, (bf16*)out);
+    } else {
+        if (precise) attention_simt_kernel<float, true><<<grid, 128, 0, s>>>((const float*)qkv, S, C, (float*)out);
+        else attention_simt_kernel<float, false><<<grid, 128, 0, s>>>((const float*)qkv, S, C, (float*)out);
+    }
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// scheduler.add_noise / get_velocity, classifier-free guidance combine, pipeline de-normalisation
+// =====================================================================================================================
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ ca,
+                             const float* __restrict__ cb, float* __restrict__ out, int64_t per, int64_t total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int n = i / per;
+        out[i] = ca[n] * a[i] + cb[n] * b[i];
+    }
+}
+int launch_axpby(const float* a, const float* b, const float* ca, const float* cb, float* out, int B, int64_t per,
+                 cudaStream_t s) {
+    int64_t total = (int64_t)B * per;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    axpby_kernel<<<grid, 256, 0, s>>>(a, b, ca, cb, out, per, total);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void cfg_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, const float* __restrict__ w,
+                           int eqn, float* __restrict__ out, int64_t per, int64_t total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int n = i / per;
+        const float c = cond[i], u = uncond[i];
+        out[i] = (eqn == 0 ? u : c) + w[n] * (c - u);
+    }
+}
+int launch_cfg(const float* cond, const float* uncond, const float* w, int eqn, float* out, int B, int64_t per,
+               cudaStream_t s) {
+    int64_t total = (int64_t)B * per;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    cfg_kernel<<<grid, 256, 0, s>>>(cond, uncond, w, eqn, out, per, total);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void denorm_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int HW, int64_t total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into NHWC output
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int c = i % C;
+        const int64_t p = i / C;
+        const int64_t hw = p % HW, n = p / HW;
+        float v = x[(n * C + c) * HW + hw] / 2.f + 0.5f;
+        v = (v < 0.f) ? 0.f : ((v > 1.f) ? 1.f : v);   // NaN propagates like torch.clamp
+        out[i] = v;
+    }
+}
+int launch_denorm(const float* x, float* out, int B, int C, int H, int W, cudaStream_t s) {
+    int64_t total = (int64_t)B * C * H * W;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    denorm_kernel<<<grid, 256, 0, s>>>(x, out, C, H * W, total);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// weight re-layout (once, at pd_unet_finalize)
+// =====================================================================================================================
+__global__ void relayout_simt_kernel(const float* __restrict__ w, int O, int I, int k, float* __restrict__ out) {
+    const size_t total = (size_t)O * I * k * k;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {   // i indexes the output (tap, ci, o)
+        const int o = i % O;
+        size_t r = i / O;
+        const int ci = r % I;
+        const int tap = r / I;
+        out[i] = w[((size_t)o * I + ci) * k * k + tap];
+    }
+}
+int launch_relayout_simt(const float* w, int O, int I, int k, float* out, cudaStream_t s) {
+    size_t total = (size_t)O * I * k * k;
+    int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
+    relayout_simt_kernel<<<grid, 256, 0, s>>>(w, O, I, k, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void relayout_tc_kernel(const float* __restrict__ w, int O, int I, int k, bf16* __restrict__ out, int ktot,
+                                   int koff) {
+    const size_t total = (size_t)O * I * k * k;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {   // i indexes (o, tap, ci)
+        const int ci = i % I;
+        size_t r = i / I;
+        const int tap = r % (k * k);
+        const int o = r / (k * k);
+        out[(size_t)o * ktot + koff + (size_t)tap * I + ci] = __float2bfloat16_rn(w[((size_t)o * I + ci) * k * k + tap]);
+    }
+}
+int launch_relayout_tc(const float* w, int O, int I, int k, bf16* out, int ktot, int koff, cudaStream_t s) {
+    size_t total = (size_t)O * I * k * k;
+    int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
+    relayout_tc_kernel<<<grid, 256, 0, s>>>(w, O, I, k, out, ktot, koff);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void relayout_convout_kernel(const float* __restrict__ w, int O, int I, float* __restrict__ out) {
+    const int total = 9 * I * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int o = i % 4;
+        const int ci = (i / 4) % I;
+        const int tap = i / (4 * I);
+        out[i] = (o < O) ? w[((size_t)o * I + ci) * 9 + tap] : 0.f;
+    }
+}
+int launch_relayout_convout(const float* w, int O, int I, float* out, cudaStream_t s) {
+    relayout_convout_kernel<<<16, 256, 0, s>>>(w, O, I, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __float2bfloat16_rn(x[i]);
+}
+int launch_cast_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s) {
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    cast_bf16_kernel<<<grid, 256, 0, s>>>(x, out, n);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+__global__ void cast_f32_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __bfloat162float(x[i]);
+}
+int launch_cast_f32(const bf16* x, float* out, int64_t n, cudaStream_t s) {
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    cast_f32_kernel<<<grid, 256, 0, s>>>(x, out, n);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pd
