@@ -830,7 +830,7 @@ int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const in
     PD_REQUIRE(m && x && steps_host, "null argument");
     PD_REQUIRE(m->bound, "pd_unet_plan + pd_unet_bind_workspace must be called first");
     PD_REQUIRE(m->cfg.in_channels == m->cfg.out_channels, "in/out channels must match for sampling");
-    PD_REQUIRE(!m->cls || (src_labels && tgt_labels), "class-conditioned model needs source and target labels");
+    PD_REQUIRE(!m->cls || ((n_inv == 0 || src_labels) && (n_gen == 0 || tgt_labels)), "class-conditioned model needs source labels for inversion steps and target labels for generation steps");
     const size_t per = (size_t)m->cfg.in_channels * m->H * m->W;
     for (int i = 0; i < m->B; i += m->mb) {
         for (int sidx = 0; sidx < n_inv + n_gen; ++sidx) {
@@ -862,7 +862,9 @@ int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, in
                  const float* bias, const float* addvec, const void* residual, const void* sc1, const void* sc2,
                  int32_t csc1, int32_t csc2, const float* sc_w, float out_scale, void* out, pd_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
+    // stride-2 convs follow Downsample2D: output H/2 x W/2 (pad 1, or pad 0 with the implicit (0,1,0,1) zero pad)
+    const int ho = stride == 2 ? h / 2 : (h + 2 * pad - ksize) / stride + 1;
+    const int wo = stride == 2 ? w / 2 : (w + 2 * pad - ksize) / stride + 1;
     const int ct = c1 + c2;
     int rc = 0;
     if (use_tc) {

@@ -1,0 +1,77 @@
+"""DDIB drivers — drop-ins for the reference's `_inversion` and `_ddib`
+(reference: src/utils_Img2Img.py:763-800 and :566-612; called from perform_class_transfer_experiment :365-384).
+
+`_ddib` = invert the real images to noise with the SOURCE class, regenerate with the TARGET class.  Here both loops
+(2 x num_inference_steps UNet forwards + scheduler updates) run inside ONE C-ABI call on the current CUDA stream; x_t
+stays resident in HBM in fp32 and each scheduler update is fused into the UNet's conv_out epilogue.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .pipeline_conditional_ddim import ConditionalDDIMPipeline
+from .schedulers import DDIMInverseScheduler
+
+# which diffusers release's DDIMInverseScheduler semantics to reproduce; the reference pins 0.18.2
+INVERSE_SCHEDULER_VARIANT = "0.18.2"
+
+
+def _to_device(pipe, t: Optional[Tensor], dtype):
+    if t is None:
+        return None
+    return t.to(device=pipe.device, dtype=dtype, non_blocking=True)
+
+
+def _inversion_steps(pipe, num_inference_steps: int):
+    # the inverse scheduler is rebuilt from the pipeline's scheduler config on every call (utils_Img2Img.py:776-779)
+    inv = DDIMInverseScheduler.from_config(pipe.scheduler.config, variant=INVERSE_SCHEDULER_VARIANT)
+    inv.set_timesteps(num_inference_steps)
+    return inv, [inv.step_coeffs(t) for t in inv.timesteps]
+
+
+@torch.no_grad()
+def _inversion(pipe: ConditionalDDIMPipeline, input_images: Tensor, class_labels: Tensor, num_inference_steps: int,
+               proc_idx: Optional[int] = None) -> Tensor:
+    """Real images + source class -> Gaussian latents (the input is not modified: it is cloned, :773)."""
+    gauss = _to_device(pipe, input_images, torch.float32).contiguous().clone()
+    labels = _to_device(pipe, class_labels, torch.int64)
+    if pipe.fused and pipe.unet.class_embedding is not None:
+        _, steps = _inversion_steps(pipe, num_inference_steps)
+        return pipe._run_fused(gauss, labels, None, steps, len(steps), 0)
+    inv, _ = _inversion_steps(pipe, num_inference_steps)
+    for t in inv.timesteps:
+        model_output = pipe.unet(gauss, t, labels).sample
+        gauss = inv.step(model_output, t, gauss).prev_sample
+    return gauss
+
+
+@torch.no_grad()
+def ddib_transfer(pipe: ConditionalDDIMPipeline, clean_images: Tensor, orig_class_labels: Tensor,
+                  target_class_labels: Tensor, num_inference_steps: int) -> Tensor:
+    """The whole class transfer as one fused device pass; returns the regenerated x_0' (B,C,H,W) fp32 on the device."""
+    x = _to_device(pipe, clean_images, torch.float32).contiguous().clone()
+    src = _to_device(pipe, orig_class_labels, torch.int64)
+    tgt = _to_device(pipe, target_class_labels, torch.int64)
+    _, inv_steps = _inversion_steps(pipe, num_inference_steps)
+    pipe.scheduler.set_timesteps(num_inference_steps)
+    # frac_diffusion_skipped = 0 keeps every timestep (pipeline:250-258); w = 0 disables guidance (:272-284)
+    gen_steps = [pipe.scheduler.step_coeffs(t, 0.0, None) for t in pipe.scheduler.timesteps]
+    return pipe._run_fused(x, src, tgt, inv_steps + gen_steps, len(inv_steps), len(gen_steps))
+
+
+@torch.no_grad()
+def _ddib(pipe: ConditionalDDIMPipeline, clean_images: Tensor, orig_class_labels: Tensor, target_class_labels: Tensor,
+          num_inference_steps: int, process_idx: Optional[int] = None) -> List:
+    """Same contract as the reference: returns the list of PIL images `pipe(...).images` would return."""
+    if not isinstance(pipe, ConditionalDDIMPipeline):
+        raise NotImplementedError("only the pixel-space ConditionalDDIMPipeline path is implemented (SURVEY §8)")
+    if pipe.fused and pipe.unet.class_embedding is not None:
+        x = ddib_transfer(pipe, clean_images, orig_class_labels, target_class_labels, num_inference_steps)
+        return pipe.numpy_to_pil(pipe.postprocess(x))
+    inverted_gauss = _inversion(pipe, clean_images, orig_class_labels, num_inference_steps, process_idx)
+    return pipe(class_labels=target_class_labels, w=0, num_inference_steps=num_inference_steps,
+                start_image=inverted_gauss, add_forward_noise_to_image=False, frac_diffusion_skipped=0).images

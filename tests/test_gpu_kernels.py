@@ -1,0 +1,232 @@
+"""GPU parity tests, kernel level: each CUDA kernel behind the C ABI against the plain-PyTorch fp32 statement of the
+same op (the oracle's building blocks: F.conv2d, F.group_norm, softmax attention, the scheduler formulas).
+
+Tolerances: fp32 validation kernels <= 1e-4 max-abs; bf16 kernels are compared on bf16-rounded inputs with a
+relative bound that reflects one bf16 rounding of the output plus fp32 accumulation-order noise.
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import nchw, nhwc
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _conv_case(lib, use_tc, bf, n, h, w, c1, c2, cout, k, stride, pad, addvec, residual, sc, out_scale, seed=0):
+    """Run pd_test_conv and the torch fp32 reference; returns (got NCHW fp32, ref NCHW fp32)."""
+    L = lib.lib()
+    g = torch.Generator().manual_seed(seed)
+    dt = torch.bfloat16 if bf else torch.float32
+    dev = "cuda"
+    ct = c1 + c2
+    x = torch.randn(n, ct, h, w, generator=g)
+    wt = torch.randn(cout, ct, k, k, generator=g) / math.sqrt(ct * k * k)
+    b = torch.randn(cout, generator=g) * 0.1
+    ho = (h + 2 * pad - k) // stride + 1
+    wo = (w + 2 * pad - k) // stride + 1
+    av = torch.randn(n, cout, generator=g) * 0.5 if addvec else None
+    res = torch.randn(n, cout, ho, wo, generator=g) if residual else None
+    csc1 = csc2 = 0
+    scx = scw = None
+    if sc:
+        csc1, csc2 = sc
+        scx = torch.randn(n, csc1 + csc2, ho, wo, generator=g)
+        scw = torch.randn(cout, csc1 + csc2, 1, 1, generator=g) / math.sqrt(csc1 + csc2)
+
+    def q(t):  # what the kernel will actually see
+        return t.to(dt).float() if t is not None else None
+
+    xq, resq, scxq = q(x), q(res), q(scx)
+    wq = wt.to(dt).float() if (bf and use_tc) else wt
+    scwq = scw.to(dt).float() if (bf and use_tc and scw is not None) else scw
+    xin = xq
+    if pad == 0 and stride == 2:  # Downsample2D with padding 0 pads (0,1,0,1) first
+        xin = F.pad(xq, (0, 1, 0, 1))
+        ho, wo = (h + 1 - k) // 2 + 1, (w + 1 - k) // 2 + 1
+    ref = F.conv2d(xin.double(), wq.double(), b.double(), stride=stride, padding=pad)
+    if av is not None:
+        ref = ref + av.double()[:, :, None, None]
+    if res is not None:
+        ref = ref + resq.double()
+    if sc:
+        ref = ref + F.conv2d(scxq.double(), scwq.double())
+    ref = (ref * out_scale).float()
+
+    x1 = nhwc(x[:, :c1], dt).to(dev)
+    x2 = nhwc(x[:, c1:], dt).to(dev) if c2 else None
+    res_d = nhwc(res, dt).to(dev) if res is not None else None
+    s1 = nhwc(scx[:, :csc1], dt).to(dev) if sc else None
+    s2 = nhwc(scx[:, csc1:], dt).to(dev) if sc and csc2 else None
+    out = torch.zeros(n, ho, wo, cout, dtype=dt, device=dev)
+    wd, bd = wt.contiguous().to(dev), b.to(dev)
+    avd = av.contiguous().to(dev) if av is not None else None
+    scwd = scw.reshape(cout, -1).contiguous().to(dev) if sc else None
+    rc = L.pd_test_conv(int(use_tc), int(bf), n, h, w, c1, c2, cout, k, stride, pad, _p(x1), _p(x2), _p(wd), _p(bd),
+                        _p(avd), _p(res_d), _p(s1), _p(s2), csc1, csc2, _p(scwd), out_scale, _p(out), None)
+    lib.check(rc)
+    torch.cuda.synchronize()
+    return nchw(out.cpu()), ref
+
+
+SIMT_CASES = [
+    # n, h, w, c1, c2, cout, k, stride, pad, addvec, residual, sc
+    (2, 16, 16, 32, 0, 64, 3, 1, 1, True, False, None),
+    (1, 16, 16, 64, 32, 64, 3, 1, 1, False, True, None),
+    (2, 16, 16, 64, 0, 64, 3, 2, 1, False, False, None),
+    (2, 16, 16, 64, 0, 64, 3, 2, 0, False, False, None),
+    (2, 8, 8, 64, 64, 128, 1, 1, 0, False, False, None),
+    (1, 16, 16, 64, 0, 64, 3, 1, 1, False, False, (64, 32)),
+    (3, 10, 6, 16, 0, 20, 3, 1, 1, True, True, None),
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+def test_conv_simt_fp32(build_lib, case):
+    got, ref = _conv_case(build_lib, 0, 0, *case, out_scale=0.5)
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-4, f"conv_simt fp32 {case}: max abs err {err:.3e}"
+
+
+TC_CASES = [
+    # the GEMM shapes of SURVEY Appendix B at reduced extent, plus the tiling edge cases
+    (2, 16, 16, 64, 0, 64, 3, 1, 1, False, False, None),      # Nt = 1, Wt=16,Ht=8
+    (4, 8, 8, 64, 0, 64, 3, 1, 1, True, False, None),         # 2 images per 128-pixel tile
+    (1, 32, 32, 128, 0, 128, 3, 1, 1, True, False, None),     # BLOCK_N 128
+    (1, 32, 32, 128, 0, 256, 3, 1, 1, True, True, None),      # BLOCK_N 256 + residual
+    (1, 16, 16, 256, 0, 512, 3, 1, 1, False, False, None),    # two N tiles
+    (2, 128, 128, 64, 0, 64, 3, 1, 1, False, False, None),    # full-row tiles (Wt = 128)
+    (1, 32, 32, 64, 0, 128, 1, 1, 0, False, True, None),      # 1x1 / linear
+    (1, 32, 32, 128, 0, 384, 1, 1, 0, False, False, None),    # fused qkv-like (3 N tiles of 128)
+    (2, 32, 32, 64, 0, 64, 3, 2, 1, False, False, None),      # stride 2, pad 1 (Downsample2D)
+    (2, 32, 32, 64, 0, 64, 3, 2, 0, False, False, None),      # stride 2, pad 0 variant
+    (1, 32, 32, 128, 0, 128, 3, 1, 1, False, False, (128, 64)),  # conv2 + K-concatenated 1x1 shortcut over a concat
+    (1, 16, 16, 1024, 0, 512, 3, 1, 1, True, False, None),    # long K (up0.res0.conv1)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_bf16(build_lib, case):
+    got, ref = _conv_case(build_lib, 1, 1, *case, out_scale=1.0)
+    # output is rounded to bf16 once (rel 2^-9); accumulation is fp32
+    tol = 1e-2 * max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    assert err <= tol, f"conv_tcgen05 {case}: max abs err {err:.3e} (tol {tol:.3e}, ref max {ref.abs().max():.3f})"
+
+
+@pytest.mark.parametrize("case", TC_CASES[:4])
+def test_conv_tcgen05_matches_simt(build_lib, case):
+    """Same bf16 inputs through both CUDA conv kernels: separates 'kernel is wrong' from 'bf16 is bf16'."""
+    a, _ = _conv_case(build_lib, 1, 1, *case, out_scale=1.0)
+    b, _ = _conv_case(build_lib, 0, 1, *case, out_scale=1.0)
+    err = (a - b).abs().max().item()
+    assert err <= 3e-2 * max(1.0, b.abs().max().item()), f"tc vs simt {case}: {err:.3e}"
+
+
+@pytest.mark.parametrize("bf", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 0, 32, True), (2, 256, 512, 256, 32, True), (1, 1024, 256, 128, 32, False),
+                                   (3, 100, 64, 0, 32, True)])
+def test_groupnorm(build_lib, bf, shape):
+    n, hw, c1, c2, groups, silu = shape
+    L = build_lib.lib()
+    g = torch.Generator().manual_seed(3)
+    dt = torch.bfloat16 if bf else torch.float32
+    C_ = c1 + c2
+    x = torch.randn(n, hw, C_, generator=g) * 1.7 + 0.3
+    gamma, beta = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
+    xq = x.to(dt).float()
+    ref = F.group_norm(xq.permute(0, 2, 1).double(), groups, gamma.double(), beta.double(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).float()
+    x1 = x[..., :c1].contiguous().to(dt).cuda()
+    x2 = x[..., c1:].contiguous().to(dt).cuda() if c2 else None
+    out = torch.empty(n, hw, C_, dtype=dt, device="cuda")
+    build_lib.check(L.pd_test_groupnorm(bf, n, hw, c1, c2, groups, 1e-5, int(silu), _p(x1), _p(x2), _p(gamma.cuda()),
+                                        _p(beta.cuda()), _p(out), None))
+    err = (out.float().cpu() - ref).abs().max().item()
+    tol = 3e-2 if bf else 1e-4
+    assert err <= tol, f"groupnorm bf={bf} {shape}: {err:.3e}"
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "mma_bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (1, 1024, 64)])
+def test_attention(build_lib, mode, shape):
+    n, s, c = shape
+    L = build_lib.lib()
+    bf = mode.endswith("bf16")
+    dt = torch.bfloat16 if bf else torch.float32
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(n, s, 3 * c, generator=g) * 1.5
+    qq = qkv.to(dt).double()
+    h = c // 8
+    q, k, v = [t.reshape(n, s, h, 8).transpose(1, 2) for t in qq.split(c, dim=-1)]
+    ref = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(8), -1) @ v
+    ref = ref.transpose(1, 2).reshape(n, s, c).float()
+    out = torch.empty(n, s, c, dtype=dt, device="cuda")
+    build_lib.check(L.pd_test_attention(int(mode.startswith("mma")), int(bf), n, s, c, 8, _p(qkv.to(dt).cuda()), _p(out), None))
+    err = (out.float().cpu() - ref).abs().max().item()
+    tol = 1e-4 if not bf else 3e-2
+    assert err <= tol, f"attention {mode} {shape}: {err:.3e}"
+
+
+@pytest.mark.parametrize("sched", ["3k_steps_clipping_rescaling", "1k_epsilon_pred", "SD_orig_config", "better_SD_config"])
+def test_scheduler_steps_match_oracle(build_lib, sched):
+    """DDIMScheduler.step / DDIMInverseScheduler.step on the device vs the oracle, every step of a 10-step grid,
+    including the zero-terminal-SNR first step (alpha-bar = 0 -> +-inf -> clamp; NaN where x == m, kept)."""
+    from oracle import OracleDDIMInverseScheduler, OracleDDIMScheduler
+    from phendiff_b200 import DDIMInverseScheduler, DDIMScheduler
+    from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+
+    cfg = SCHEDULER_CONFIGS[sched]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 16, 16, generator=g)
+    m = torch.randn(2, 3, 16, 16, generator=g)
+    m[0, 0, 0, 0] = x[0, 0, 0, 0]  # the NaN case of eps-prediction at alpha-bar = 0
+    for O, P in ((OracleDDIMScheduler, DDIMScheduler), (OracleDDIMInverseScheduler, DDIMInverseScheduler)):
+        base = DDIMScheduler.from_config(cfg)
+        o = O.from_config(base.config)
+        p = P.from_config(base.config)
+        o.set_timesteps(10)
+        p.set_timesteps(10)
+        assert torch.equal(o.timesteps, p.timesteps)
+        for t in o.timesteps:
+            ro = o.step(m, t, x)
+            rp = p.step(m.cuda(), t, x.cuda())
+            for a, b in ((ro.prev_sample, rp.prev_sample), (ro.pred_original_sample, rp.pred_original_sample)):
+                b = b.cpu()
+                assert torch.equal(torch.isnan(a), torch.isnan(b)), f"{sched} t={int(t)}: NaN pattern differs"
+                err = (a - b)[~torch.isnan(a)].abs().max().item()
+                assert err <= 1e-5, f"{sched} {O.__name__} t={int(t)}: {err:.3e}"
+
+
+def test_add_noise_velocity_cfg_denorm(build_lib):
+    from oracle import OracleDDIMScheduler
+    from phendiff_b200 import DDIMScheduler
+    from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+
+    L = build_lib.lib()
+    cfg = SCHEDULER_CONFIGS["3k_steps_clipping_rescaling"]
+    o, p = OracleDDIMScheduler.from_config(cfg), DDIMScheduler.from_config(cfg)
+    g = torch.Generator().manual_seed(2)
+    x, nz = torch.randn(4, 3, 8, 8, generator=g), torch.randn(4, 3, 8, 8, generator=g)
+    t = torch.tensor([0, 17, 1500, 2999])
+    assert (o.add_noise(x, nz, t) - p.add_noise(x.cuda(), nz.cuda(), t).cpu()).abs().max() <= 1e-6
+    assert (o.get_velocity(x, nz, t) - p.get_velocity(x.cuda(), nz.cuda(), t).cpu()).abs().max() <= 1e-6
+    w = torch.tensor([0.5, 1.0, 2.0, 7.5])
+    for eqn in (0, 1):
+        out = torch.empty_like(x, device="cuda")
+        build_lib.check(L.pd_cfg_combine(_p(x.cuda()), _p(nz.cuda()), _p(w.cuda()), eqn, _p(out), 4, 3 * 64, None))
+        ref = (nz if eqn == 0 else x) + w.view(-1, 1, 1, 1) * (x - nz)
+        assert (out.cpu() - ref).abs().max() <= 1e-6
+    out = torch.empty(4, 8, 8, 3, device="cuda")
+    xx = x * 2
+    build_lib.check(L.pd_denorm_nhwc(_p(xx.cuda()), _p(out), 4, 3, 8, 8, None))
+    assert (out.cpu() - (xx / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)).abs().max() <= 1e-7

@@ -1,0 +1,177 @@
+"""GPU parity tests, model / path level: the C-ABI CUDA path against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): per-step eps max-abs error <= 1e-2 in bf16, <= 1e-4 in the fp32 validation mode;
+final translated images >= 40 dB PSNR against the oracle.
+"""
+import os
+
+import pytest
+import torch
+
+from tests.util import make_pair, psnr, synth_images
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _sched(name):
+    from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+
+    return SCHEDULER_CONFIGS[name]
+
+
+@pytest.mark.parametrize("denoiser,size,batch", [("super_small", 32, 2), ("small_denoiser_config", 64, 2)])
+def test_unet_forward_fp32_validation_mode(build_lib, denoiser, size, batch):
+    oracle, model = make_pair(denoiser, size, "fp32")
+    x, labels = synth_images(batch, size)
+    for t in (0, 9, 2999):
+        with torch.no_grad():
+            ref = oracle(x, torch.tensor(t), labels).sample
+        got = model(x.cuda(), torch.tensor(t), labels.cuda()).sample.cpu()
+        err = (got - ref).abs().max().item()
+        assert err <= 1e-4, f"{denoiser}@{size} t={t}: fp32 eps max-abs err {err:.3e} > 1e-4"
+
+
+@pytest.mark.parametrize("denoiser,size,batch", [("super_small", 64, 2), ("small_denoiser_config", 64, 4)])
+def test_unet_forward_bf16(build_lib, denoiser, size, batch):
+    oracle, model = make_pair(denoiser, size, "bf16")
+    x, labels = synth_images(batch, size)
+    for t in (0, 1500, 2999):
+        with torch.no_grad():
+            ref = oracle(x, torch.tensor(t), labels).sample
+        got = model(x.cuda(), torch.tensor(t), labels.cuda()).sample.cpu()
+        err = (got - ref).abs().max().item()
+        print(f"[bf16 fwd] {denoiser}@{size} t={t}: max abs err {err:.3e} (ref max {ref.abs().max():.3f})")
+        assert err <= 1e-2, f"{denoiser}@{size} t={t}: bf16 eps max-abs err {err:.3e} > 1e-2"
+
+
+def test_unet_forward_golden_fp32(build_lib):
+    """Committed fixture (tests/golden/make_golden.py): CUDA fp32 path vs the stored oracle output."""
+    g = torch.load(os.path.join(GOLDEN, "unet_super_small_32.pt"))
+    _, model = make_pair("super_small", 32, "fp32")
+    got = model(g["x"].cuda(), g["t"], g["labels"].cuda()).sample.cpu()
+    assert (got - g["eps"]).abs().max().item() <= 1e-4
+
+
+def test_forward_api_surface(build_lib):
+    import inspect
+
+    from phendiff_b200 import PhenDiffB200Error
+
+    _, model = make_pair("super_small", 32, "fp32")
+    assert "class_emb" in inspect.signature(model.forward).parameters  # pipeline:289-290
+    assert model.time_embed_dim == 256 and model.config.in_channels == 3
+    x, labels = synth_images(2, 32)
+    with pytest.raises(ValueError):
+        model(x.cuda(), 3, labels.cuda(), torch.zeros(2, 256).cuda())
+    with pytest.raises(ValueError):
+        model(x.cuda(), 3)
+    with pytest.raises(PhenDiffB200Error):
+        model(x, 3, labels)  # CPU tensor: no CPU fallback
+    out = model(x.cuda(), 3, labels.cuda(), return_dict=False)
+    assert isinstance(out, tuple) and out[0].shape == (2, 3, 32, 32)
+    # timestep forms: python int, 0-dim CPU tensor, 1-D tensor (cond_unet_2d.py:276-287)
+    a = model(x.cuda(), 7, labels.cuda()).sample
+    b = model(x.cuda(), torch.tensor(7), labels.cuda()).sample
+    c = model(x.cuda(), torch.tensor([7, 7]).cuda(), labels.cuda()).sample
+    assert torch.equal(a, b) and torch.equal(a, c)
+    # class_emb route == class_labels route when fed the table rows (zero embedding = unconditional, A.8)
+    emb = model.class_embedding.weight[labels.cuda()]
+    d = model(x.cuda(), 7, class_emb=emb).sample
+    assert (a - d).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("sched", ["3k_steps_clipping_rescaling", "1k_epsilon_pred"])
+def test_ddib_config0_fp32(build_lib, sched):
+    """BASELINE config[0] (64x64, batch 4, 10+10 steps) in the fp32 validation mode: trajectory must track the oracle."""
+    from oracle import OracleDDIMScheduler, OraclePipeline, oracle_ddib, oracle_inversion
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, _inversion, ddib_transfer
+
+    oracle, model = make_pair("super_small", 64, "fp32")
+    x, src = synth_images(4, 64)
+    tgt = 1 - src
+    o_pipe = OraclePipeline(oracle, OracleDDIMScheduler.from_config(_sched(sched)))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched(sched)))
+    ref_lat = oracle_inversion(o_pipe, x, src, 10)
+    got_lat = _inversion(pipe, x, src, 10).cpu()
+    mask = ~torch.isnan(ref_lat)
+    assert torch.equal(torch.isnan(ref_lat), torch.isnan(got_lat))
+    err = (ref_lat - got_lat)[mask].abs().max().item()
+    assert err <= 2e-3, f"{sched}: inverted latents differ by {err:.3e}"
+    ref = oracle_ddib(o_pipe, x, src, tgt, 10, return_raw=True)
+    got = ddib_transfer(pipe, x, src, tgt, 10).cpu()
+    ok = ~(torch.isnan(ref) | torch.isnan(got))
+    p = psnr(ref[ok], got[ok])
+    print(f"[ddib fp32] {sched}: PSNR {p:.1f} dB")
+    assert p >= 40.0, f"{sched}: fp32 DDIB PSNR {p:.1f} dB"
+
+
+def test_ddib_config0_bf16_psnr_and_teacher_forced_eps(build_lib):
+    """bf16 product path on BASELINE config[0] with the small_denoiser: per-step eps (teacher-forced on the oracle's x_t)
+    <= 1e-2 and final images >= 40 dB PSNR."""
+    from oracle import OracleDDIMScheduler, OraclePipeline, oracle_ddib, oracle_inversion
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, ddib_transfer
+
+    sched = "3k_steps_clipping_rescaling"
+    oracle, model = make_pair("small_denoiser_config", 64, "bf16")
+    x, src = synth_images(4, 64)
+    tgt = 1 - src
+    o_pipe = OraclePipeline(oracle, OracleDDIMScheduler.from_config(_sched(sched)))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched(sched)))
+    trace = []
+    oracle_inversion(o_pipe, x, src, 10, trace=trace)
+    worst = 0.0
+    for t, xt, eps in trace:
+        got = model(xt.cuda(), t, src.cuda()).sample.cpu()
+        worst = max(worst, (got - eps).abs().max().item())
+    print(f"[ddib bf16] teacher-forced per-step eps max-abs err {worst:.3e}")
+    assert worst <= 1e-2
+    ref = oracle_ddib(o_pipe, x, src, tgt, 10, return_raw=True)
+    got = ddib_transfer(pipe, x, src, tgt, 10).cpu()
+    p = psnr(ref, got)
+    print(f"[ddib bf16] PSNR {p:.1f} dB, max abs {float((ref - got).abs().max()):.3e}")
+    assert p >= 40.0
+
+
+def test_fused_and_stepwise_routes_agree(build_lib):
+    """pd_ddib_transfer (scheduler update fused in conv_out) vs UNet forward + pd_ddim_step per step."""
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, _ddib, _inversion
+
+    _, model = make_pair("super_small", 32, "fp32")
+    x, src = synth_images(2, 32)
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched("3k_steps_clipping_rescaling")))
+    a = _inversion(pipe, x, src, 6)
+    pipe.fused = False
+    b = _inversion(pipe, x, src, 6)
+    assert (a - b).abs().max().item() <= 1e-5
+    pipe.fused = True
+    imgs = _ddib(pipe, x, src, 1 - src, 4)
+    assert len(imgs) == 2 and imgs[0].size == (32, 32)
+
+
+def test_pipeline_call_matches_oracle_with_cfg(build_lib):
+    """The general __call__ route (forward noising, partial trajectory, classifier-free guidance) vs the oracle."""
+    from oracle import OracleDDIMScheduler, OraclePipeline
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler
+
+    oracle, model = make_pair("super_small", 32, "fp32")
+    x, labels = synth_images(2, 32)
+    o_pipe = OraclePipeline(oracle, OracleDDIMScheduler.from_config(_sched("3k_steps_clipping_rescaling")))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched("3k_steps_clipping_rescaling")))
+    for eqn, w in (("imagen", 2.0), ("CFG", 1.5), ("imagen", torch.tensor([1.5, 3.0]))):
+        ref = o_pipe(labels, w=w, num_inference_steps=5, start_image=x, add_forward_noise_to_image=False,
+                     frac_diffusion_skipped=0.4, guidance_eqn=eqn).images
+        got = pipe(labels, w=w, num_inference_steps=5, start_image=x.cuda(), add_forward_noise_to_image=False,
+                   frac_diffusion_skipped=0.4, guidance_eqn=eqn, output_type="numpy").images
+        assert got.shape == (2, 32, 32, 3)
+        err = float(abs(ref - got).max())
+        assert err <= 1e-3, f"{eqn} w={w}: {err:.3e}"
+    # no-CFG call as `_ddib` makes it, PIL output
+    out = pipe(class_labels=labels, w=0, num_inference_steps=4, start_image=x.cuda(), add_forward_noise_to_image=False,
+               frac_diffusion_skipped=0)
+    assert len(out.images) == 2
+    with pytest.raises(AssertionError):
+        pipe(labels, class_emb=torch.zeros(2, 256))
+    with pytest.raises(AssertionError):
+        pipe(labels, start_image=x.cuda())  # frac_diffusion_skipped missing
