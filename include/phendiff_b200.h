@@ -15,7 +15,8 @@
  *   - a handle is bound to the CUDA device that was current at pd_unet_create and is not thread-safe
  *     (one process per GPU, like the reference).
  *   - boundary tensors are NCHW fp32 contiguous (the reference's layout); inside, activations are NHWC
- *     bf16 (PD_PREC_BF16) or NHWC fp32 (PD_PREC_FP32 validation mode).
+ *     16-bit (PD_PREC_BF16, or PD_PREC_FP16 — the reference's own autocast type) feeding the tensor cores with fp32
+ *     accumulation, or NHWC fp32 on CUDA cores (PD_PREC_FP32 validation mode).
  */
 #ifndef PHENDIFF_B200_H
 #define PHENDIFF_B200_H
@@ -30,7 +31,7 @@ extern "C" {
 typedef struct pd_unet pd_unet_t;
 typedef void* pd_stream_t; /* cudaStream_t */
 
-enum { PD_PREC_FP32 = 0, PD_PREC_BF16 = 1 };
+enum { PD_PREC_FP32 = 0, PD_PREC_BF16 = 1, PD_PREC_FP16 = 2 };
 enum { PD_PRED_EPSILON = 0, PD_PRED_SAMPLE = 1, PD_PRED_V = 2 };
 #define PD_MAX_BLOCKS 8
 
@@ -56,8 +57,8 @@ typedef struct pd_unet_config {
     int32_t add_attention;
     int32_t precision;       /* PD_PREC_* */
     int32_t max_microbatch;  /* images processed per pass through the layer graph (0: library default) */
-    int32_t conv_impl;       /* 0: tcgen05 implicit GEMM where the shape allows (bf16 only), 1: force SIMT kernels */
-    int32_t attn_impl;       /* 0: tensor-core flash kernel (bf16 only), 1: force SIMT kernel */
+    int32_t conv_impl;       /* 0: tcgen05 implicit GEMM where the shape allows (16-bit modes), 1: force SIMT kernels */
+    int32_t attn_impl;       /* 0: tensor-core flash kernel (16-bit modes), 1: force SIMT kernel */
 } pd_unet_config_t;
 
 /* One scheduler update, host-computed scalars (reference: diffusers DDIMScheduler.step /
@@ -136,21 +137,21 @@ int pd_ddib_transfer(pd_unet_t* h, float* x, const int64_t* src_labels, const in
 int pd_unet_launch_count(pd_unet_t* h, int64_t* n);
 
 /* ---- unit-test entry points for individual kernels (used by tests/, not by the product path) ---- */
-/* generic NHWC convolution through the SIMT fp32 kernel or the tcgen05 kernel; activations bf16 when bf16 != 0.
+/* generic NHWC convolution through the SIMT fp32 kernel or the tcgen05 kernel; dtype: 0 fp32, 1 bf16, 2 fp16.
  * x1 (N,H,W,C1) and optional x2 (N,H,W,C2) are channel-concatenated; w is OIHW fp32 (O, C1+C2, k, k);
  * optional sc_w (O, Csc1+Csc2) 1x1 shortcut over (sc1|sc2) accumulated into the same output;
  * addvec (N,O) fp32, residual (N,Ho,Wo,O) optional.  out (N,Ho,Wo,O). */
-int pd_test_conv(int32_t use_tc, int32_t bf16, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2,
+int pd_test_conv(int32_t use_tc, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2,
                  int32_t cout, int32_t ksize, int32_t stride, int32_t pad, const void* x1, const void* x2,
                  const float* weight, const float* bias, const float* addvec, const void* residual,
                  const void* sc1, const void* sc2, int32_t csc1, int32_t csc2, const float* sc_w, float out_scale,
                  void* out, pd_stream_t stream);
 /* GroupNorm(+SiLU) over NHWC, two concatenated sources */
-int pd_test_groupnorm(int32_t bf16, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+int pd_test_groupnorm(int32_t dtype, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                       int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta,
                       void* out, pd_stream_t stream);
 /* self-attention core on packed qkv (N, S, 3C) -> (N, S, C), head_dim d */
-int pd_test_attention(int32_t use_mma, int32_t bf16, int32_t n, int32_t s, int32_t c, int32_t d, const void* qkv,
+int pd_test_attention(int32_t use_mma, int32_t dtype, int32_t n, int32_t s, int32_t c, int32_t d, const void* qkv,
                       void* out, pd_stream_t stream);
 
 #ifdef __cplusplus

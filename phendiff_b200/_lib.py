@@ -11,7 +11,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libphendiff_b200.so"
 
-PD_PREC_FP32, PD_PREC_BF16 = 0, 1
+PD_PREC_FP32, PD_PREC_BF16, PD_PREC_FP16 = 0, 1, 2
 PD_PRED = {"epsilon": 0, "sample": 1, "v_prediction": 2}
 PD_MAX_BLOCKS = 8
 

@@ -33,7 +33,7 @@ class _Holder(nn.Module):
         raise _lib.PhenDiffB200Error("sub-modules of CustomCondUNet2DModel only hold parameters; call the model itself")
 
 
-_PRECISIONS = {"bf16": _lib.PD_PREC_BF16, "fp32": _lib.PD_PREC_FP32}
+_PRECISIONS = {"bf16": _lib.PD_PREC_BF16, "fp16": _lib.PD_PREC_FP16, "fp32": _lib.PD_PREC_FP32}
 
 
 class CustomCondUNet2DModel(nn.Module, ConfigMixin):
@@ -233,7 +233,7 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
         return self._precision
 
     def set_precision(self, precision: str):
-        """'bf16' (product path) or 'fp32' (validation mode, SIMT fp32 kernels)."""
+        """'fp16' / 'bf16' (tensor-core product path, fp32 accumulation) or 'fp32' (validation mode, SIMT fp32 kernels)."""
         precision = precision.lower()
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {list(_PRECISIONS)}")

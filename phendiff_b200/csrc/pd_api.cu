@@ -34,7 +34,7 @@ struct ConvL {
     Param *w = nullptr, *b = nullptr;
     int cin = 0, cout = 0, k = 3, stride = 1, pad = 1;
     float* w_simt = nullptr;  // (k*k*cin, cout) fp32
-    bf16* w_tc = nullptr;     // (cout, k*k*cin) bf16
+    void* w_tc = nullptr;     // (cout, k*k*cin) bf16/fp16
 };
 struct GNL { Param *g = nullptr, *b = nullptr; int C = 0; };
 struct ResL {
@@ -44,7 +44,7 @@ struct ResL {
     Param *tw = nullptr, *tb = nullptr;
     int cin = 0, cout = 0, temb_off = 0;
     float scale = 1.f;
-    bf16* w2sc_tc = nullptr;   // (cout, 9*cout + cin): conv2 and the 1x1 shortcut as ONE K-concatenated GEMM
+    void* w2sc_tc = nullptr;   // (cout, 9*cout + cin): conv2 and the 1x1 shortcut as ONE K-concatenated GEMM
     float* b2sc = nullptr;     // conv2.bias + conv_shortcut.bias
 };
 struct AttnL {
@@ -55,9 +55,9 @@ struct AttnL {
     float* wqkv_raw = nullptr;   // (3C, C) fp32, rows q|k|v
     float* bqkv = nullptr;       // (3C)
     float* wqkv_simt = nullptr;  // (C, 3C)
-    bf16* wqkv_tc = nullptr;     // (3C, C)
+    void* wqkv_tc = nullptr;     // (3C, C)
     float* wo_simt = nullptr;    // (C, C) transposed
-    bf16* wo_tc = nullptr;       // (C, C)
+    void* wo_tc = nullptr;       // (C, C)
 };
 struct DownB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_down = false; ConvL down; };
 struct UpB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_up = false; ConvL up; };
@@ -122,7 +122,8 @@ using namespace pd;
 struct pd_unet {
     pd_unet_config_t cfg;
     int device = 0;
-    bool bf = false;
+    int dt = DT_F32;   // activation storage type
+    bool half = false; // bf16 / fp16: tensor-core path available
     int D = 0;  // time_embed_dim
     int J = 0;  // total time_emb_proj outputs
     std::vector<std::unique_ptr<Param>> params;
@@ -276,14 +277,20 @@ template <typename T> static int dev_alloc(pd_unet* m, T** p, size_t n) {
     return 0;
 }
 
+static int dev_alloc_bytes(pd_unet* m, void** p, size_t bytes) {
+    PD_CHECK_CUDA(cudaMalloc(p, bytes));
+    m->owned.push_back(*p);
+    return 0;
+}
+
 static int finalize_conv(pd_unet* m, ConvL& c, cudaStream_t s, bool tc) {
     int rc;
     if ((rc = dev_alloc(m, &c.w_simt, c.w->numel))) return rc;
     if ((rc = launch_relayout_simt(c.w->dev, c.cout, c.cin, c.k, c.w_simt, s))) return rc;
     if (tc && c.cin % 64 == 0 && c.cout % 64 == 0) {
         const int ktot = c.k * c.k * c.cin;
-        if ((rc = dev_alloc(m, &c.w_tc, (size_t)c.cout * ktot))) return rc;
-        if ((rc = launch_relayout_tc(c.w->dev, c.cout, c.cin, c.k, c.w_tc, ktot, 0, s))) return rc;
+        if ((rc = dev_alloc_bytes(m, &c.w_tc, (size_t)c.cout * ktot * 2))) return rc;
+        if ((rc = launch_relayout_tc(m->dt, c.w->dev, c.cout, c.cin, c.k, c.w_tc, ktot, 0, s))) return rc;
     }
     return 0;
 }
@@ -295,9 +302,9 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n
 
 static int finalize_res(pd_unet* m, ResL& r, cudaStream_t s) {
     int rc;
-    if ((rc = finalize_conv(m, r.c1, s, m->bf))) return rc;
-    if ((rc = finalize_conv(m, r.c2, s, m->bf))) return rc;
-    if (r.has_sc && (rc = finalize_conv(m, r.sc, s, m->bf))) return rc;
+    if ((rc = finalize_conv(m, r.c1, s, m->half))) return rc;
+    if ((rc = finalize_conv(m, r.c2, s, m->half))) return rc;
+    if (r.has_sc && (rc = finalize_conv(m, r.sc, s, m->half))) return rc;
     // time_emb_proj rows of the concatenated projection; conv1.bias folded into the projected vector
     PD_CHECK_CUDA(cudaMemcpyAsync(m->wcat + (size_t)r.temb_off * m->D, r.tw->dev, r.tw->numel * sizeof(float),
                                   cudaMemcpyDeviceToDevice, s));
@@ -305,11 +312,11 @@ static int finalize_res(pd_unet* m, ResL& r, cudaStream_t s) {
     if (r.has_sc) {
         if ((rc = dev_alloc(m, &r.b2sc, (size_t)r.cout))) return rc;
         add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, s>>>(r.c2.b->dev, r.sc.b->dev, r.b2sc, r.cout);
-        if (m->bf && r.cin % 64 == 0 && r.cout % 64 == 0) {
+        if (m->half && r.cin % 64 == 0 && r.cout % 64 == 0) {
             const int ktot = 9 * r.cout + r.cin;
-            if ((rc = dev_alloc(m, &r.w2sc_tc, (size_t)r.cout * ktot))) return rc;
-            if ((rc = launch_relayout_tc(r.c2.w->dev, r.cout, r.cout, 3, r.w2sc_tc, ktot, 0, s))) return rc;
-            if ((rc = launch_relayout_tc(r.sc.w->dev, r.cout, r.cin, 1, r.w2sc_tc, ktot, 9 * r.cout, s))) return rc;
+            if ((rc = dev_alloc_bytes(m, &r.w2sc_tc, (size_t)r.cout * ktot * 2))) return rc;
+            if ((rc = launch_relayout_tc(m->dt, r.c2.w->dev, r.cout, r.cout, 3, r.w2sc_tc, ktot, 0, s))) return rc;
+            if ((rc = launch_relayout_tc(m->dt, r.sc.w->dev, r.cout, r.cin, 1, r.w2sc_tc, ktot, 9 * r.cout, s))) return rc;
         }
     }
     PD_CHECK_CUDA(cudaGetLastError());
@@ -331,11 +338,11 @@ static int finalize_attn(pd_unet* m, AttnL& a, cudaStream_t s) {
     if ((rc = launch_relayout_simt(a.wqkv_raw, 3 * a.C, a.C, 1, a.wqkv_simt, s))) return rc;
     if ((rc = dev_alloc(m, &a.wo_simt, CC))) return rc;
     if ((rc = launch_relayout_simt(a.ow->dev, a.C, a.C, 1, a.wo_simt, s))) return rc;
-    if (m->bf && a.C % 64 == 0) {
-        if ((rc = dev_alloc(m, &a.wqkv_tc, 3 * CC))) return rc;
-        if ((rc = launch_cast_bf16(a.wqkv_raw, a.wqkv_tc, (int64_t)(3 * CC), s))) return rc;
-        if ((rc = dev_alloc(m, &a.wo_tc, CC))) return rc;
-        if ((rc = launch_cast_bf16(a.ow->dev, a.wo_tc, (int64_t)CC, s))) return rc;
+    if (m->half && a.C % 64 == 0) {
+        if ((rc = dev_alloc_bytes(m, &a.wqkv_tc, 3 * CC * 2))) return rc;
+        if ((rc = launch_cast_half(m->dt, a.wqkv_raw, a.wqkv_tc, (int64_t)(3 * CC), s))) return rc;
+        if ((rc = dev_alloc_bytes(m, &a.wo_tc, CC * 2))) return rc;
+        if ((rc = launch_cast_half(m->dt, a.ow->dev, a.wo_tc, (int64_t)CC, s))) return rc;
     }
     return 0;
 }
@@ -383,11 +390,12 @@ struct Rec {
         if (!dry) {
             ga.x1 = ptr(a); ga.x2 = b ? ptr(b) : nullptr; ga.out = ptr(o);
             ga.stats = (float*)raw(m->stats_off) + (size_t)idx * mb * ga.groups * 2;
-            const bool bf = m->bf, precise = !m->bf;
-            push([ga, bf, precise](const Ctx&, cudaStream_t s) {
-                int r = launch_gn_stats(bf, ga, s);
+            const int dt = m->dt;
+            const bool precise = !m->half;
+            push([ga, dt, precise](const Ctx&, cudaStream_t s) {
+                int r = launch_gn_stats(dt, ga, s);
                 if (r) return r;
-                return launch_gn_apply(bf, precise, ga, s);
+                return launch_gn_apply(dt, precise, ga, s);
             }, 2);
         }
         return o;
@@ -395,23 +403,23 @@ struct Rec {
 
     // generic conv: main input `x` (single tensor), optional fused 1x1 shortcut over (s1|s2) -> new tensor
     // `bias` belongs to the main conv; `bias_fused` (main + shortcut bias) is used when the shortcut rides in the same GEMM
-    Tensor* conv(const ConvL& L, Tensor* x, const float* w_simt, const bf16* w_tc, const float* bias, const float* addvec,
+    Tensor* conv(const ConvL& L, Tensor* x, const float* w_simt, const void* w_tc, const float* bias, const float* addvec,
                  int addvec_stride, Tensor* residual, float out_scale, Tensor* s1 = nullptr, Tensor* s2 = nullptr,
                  const ConvL* scL = nullptr, const float* bias_fused = nullptr) {
         const int Ho = (L.stride == 2) ? x->H / 2 : x->H, Wo = (L.stride == 2) ? x->W / 2 : x->W;
         Tensor* o = alloc(L.cout, Ho, Wo);
         ConvTcDesc d{};
-        d.C = x->C; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = L.k; d.stride = L.stride; d.pad = L.pad;
+        d.dt = m->dt; d.C = x->C; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = L.k; d.stride = L.stride; d.pad = L.pad;
         d.Ho = Ho; d.Wo = Wo; d.Cout = L.cout;
         d.Csc1 = s1 ? s1->C : 0; d.Csc2 = s2 ? s2->C : 0;
-        const bool want_tc = m->bf && m->cfg.conv_impl == 0 && w_tc != nullptr;
+        const bool want_tc = m->half && m->cfg.conv_impl == 0 && w_tc != nullptr;
         const bool use_tc = want_tc && conv_tc_supported(d, nullptr);
         if (use_tc) {
             m->tc_layers += dry ? 0 : 1;
             if (!dry) {
-                d.x = (const bf16*)ptr(x); d.sc1 = s1 ? (const bf16*)ptr(s1) : nullptr; d.sc2 = s2 ? (const bf16*)ptr(s2) : nullptr;
+                d.x = ptr(x); d.sc1 = s1 ? ptr(s1) : nullptr; d.sc2 = s2 ? ptr(s2) : nullptr;
                 d.wmat = w_tc; d.bias = s1 ? bias_fused : bias; d.addvec = addvec; d.addvec_stride = addvec_stride;
-                d.residual = residual ? (const bf16*)ptr(residual) : nullptr; d.out_scale = out_scale; d.out = (bf16*)ptr(o);
+                d.residual = residual ? ptr(residual) : nullptr; d.out_scale = out_scale; d.out = ptr(o);
                 ConvTcPlan* pl = nullptr;
                 int r = conv_tc_plan_create(d, &pl);
                 if (r) { rc = r; return o; }
@@ -430,8 +438,8 @@ struct Rec {
             ca.pad = 0; ca.Ho = Ho; ca.Wo = Wo; ca.w = scL->w_simt; ca.bias = scL->b->dev; ca.out_scale = 1.f;
             if (!dry) {
                 ca.x1 = ptr(s1); ca.x2 = s2 ? ptr(s2) : nullptr; ca.out = ptr(tmp);
-                const bool bf = m->bf;
-                push([ca, bf](const Ctx&, cudaStream_t s) { return launch_conv_simt(bf, ca, s); }, 1);
+                const int dt = m->dt;
+                push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1);
             }
         }
         ConvArgs ca{};
@@ -441,8 +449,8 @@ struct Rec {
         if (!dry) {
             ca.x1 = ptr(x); ca.x2 = nullptr; ca.out = ptr(o);
             ca.residual = tmp ? ptr(tmp) : (residual ? ptr(residual) : nullptr);
-            const bool bf = m->bf;
-            push([ca, bf](const Ctx&, cudaStream_t s) { return launch_conv_simt(bf, ca, s); }, 1);
+            const int dt = m->dt;
+            push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1);
         }
         if (tmp) release(tmp);
         return o;
@@ -478,14 +486,15 @@ struct Rec {
         Tensor* ao = alloc(A.C, x->H, x->W);
         {
             const int S = x->H * x->W, C = A.C, d = m->cfg.attention_head_dim > 0 ? m->cfg.attention_head_dim : A.C;
-            const bool use_mma = m->bf && m->cfg.attn_impl == 0 && (S % 64 == 0) && d == 8;
+            const bool use_mma = m->half && m->cfg.attn_impl == 0 && (S % 64 == 0) && d == 8;
             if (!dry) {
                 const void* qp = ptr(qkv);
                 void* op = ptr(ao);
                 const int N = mb;
-                const bool bf = m->bf;
-                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(qp, N, S, C, d, op, s); }, 1);
-                else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(bf, !bf, qp, N, S, C, d, op, s); }, 1);
+                const int dt = m->dt;
+                const bool precise = !m->half;
+                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, op, s); }, 1);
+                else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(dt, precise, qp, N, S, C, d, op, s); }, 1);
             }
         }
         release(qkv);
@@ -528,8 +537,8 @@ struct Rec {
         if (!dry) {
             void* o = ptr(x);
             const float* w = M->w_in; const float* b = M->conv_in.b->dev;
-            const int N = mb, Cin = c.in_channels; const bool bf = M->bf;
-            push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(bf, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1);
+            const int N = mb, Cin = c.in_channels, dt = M->dt;
+            push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1);
         }
         std::vector<Tensor*> skips;
         retain(x); skips.push_back(x);
@@ -564,8 +573,8 @@ struct Rec {
                 Tensor* big = alloc(x->C, x->H * 2, x->W * 2);
                 if (!dry) {
                     const void* ip = ptr(x); void* op = ptr(big);
-                    const int N = mb, h = x->H, w = x->W, C = x->C; const bool bf = M->bf;
-                    push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(bf, ip, N, h, w, C, op, s); }, 1);
+                    const int N = mb, h = x->H, w = x->W, C = x->C, dt = M->dt;
+                    push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(dt, ip, N, h, w, C, op, s); }, 1);
                 }
                 release(x);
                 Tensor* y = conv(u.up, big, u.up.w_simt, u.up.w_tc, u.up.b->dev, nullptr, 0, nullptr, 1.f);
@@ -580,11 +589,11 @@ struct Rec {
             ConvOutArgs oa{};
             oa.act = ptr(xn); oa.w = M->w_out; oa.bias = M->conv_out.b->dev; oa.N = mb; oa.H = H; oa.W = W; oa.Cin = C0;
             oa.Cout = c.out_channels;
-            const bool bf = M->bf;
+            const int dt = M->dt;
             push([=](const Ctx& cx, cudaStream_t s) {
                 ConvOutArgs a = oa;
                 a.model_out = cx.model_out; a.x = cx.x_update; a.step = cx.step;
-                return launch_conv_out(bf, a, s);
+                return launch_conv_out(dt, a, s);
             }, 1);
         }
         release(xn);
@@ -631,7 +640,7 @@ int pd_version(void) { return 100; }
 int pd_unet_create(const pd_unet_config_t* cfg, pd_unet_t** out) {
     PD_REQUIRE(cfg && out, "null argument");
     PD_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= PD_MAX_BLOCKS, "n_blocks out of range");
-    PD_REQUIRE(cfg->precision == PD_PREC_FP32 || cfg->precision == PD_PREC_BF16, "unknown precision");
+    PD_REQUIRE(cfg->precision == PD_PREC_FP32 || cfg->precision == PD_PREC_BF16 || cfg->precision == PD_PREC_FP16, "unknown precision");
     PD_REQUIRE(cfg->layers_per_block >= 1, "layers_per_block must be >= 1");
     PD_REQUIRE(cfg->norm_num_groups > 0, "norm_num_groups must be > 0");
     for (int i = 0; i < cfg->n_blocks; ++i) {
@@ -643,7 +652,8 @@ int pd_unet_create(const pd_unet_config_t* cfg, pd_unet_t** out) {
     PD_REQUIRE(ndev > 0, "no CUDA device: phendiff_b200 has no CPU fallback");
     pd_unet* m = new pd_unet();
     m->cfg = *cfg;
-    m->bf = cfg->precision == PD_PREC_BF16;
+    m->dt = cfg->precision;   // PD_PREC_* == DT_*
+    m->half = m->dt != DT_F32;
     PD_CHECK_CUDA(cudaGetDevice(&m->device));
     cudaDeviceProp prop;
     PD_CHECK_CUDA(cudaGetDeviceProperties(&prop, m->device));
@@ -719,7 +729,7 @@ int pd_unet_finalize(pd_unet_t* m, pd_stream_t stream) {
     for (auto& d : m->down) {
         for (auto& r : d.res) if ((rc = finalize_res(m, r, s))) return rc;
         for (auto& a : d.attn) if ((rc = finalize_attn(m, a, s))) return rc;
-        if (d.has_down && (rc = finalize_conv(m, d.down, s, m->bf))) return rc;
+        if (d.has_down && (rc = finalize_conv(m, d.down, s, m->half))) return rc;
     }
     if ((rc = finalize_res(m, m->mid_r0, s))) return rc;
     if ((rc = finalize_res(m, m->mid_r1, s))) return rc;
@@ -727,7 +737,7 @@ int pd_unet_finalize(pd_unet_t* m, pd_stream_t stream) {
     for (auto& u : m->up) {
         for (auto& r : u.res) if ((rc = finalize_res(m, r, s))) return rc;
         for (auto& a : u.attn) if ((rc = finalize_attn(m, a, s))) return rc;
-        if (u.has_up && (rc = finalize_conv(m, u.up, s, m->bf))) return rc;
+        if (u.has_up && (rc = finalize_conv(m, u.up, s, m->half))) return rc;
     }
     PD_CHECK_CUDA(cudaStreamSynchronize(s));
     m->finalized = true;
@@ -753,7 +763,7 @@ int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, siz
     for (int d = 1; d <= std::min(cap, batch); ++d) if (batch % d == 0) mb = d;
     m->mb = mb;
     m->arena.reset(true, nullptr);
-    Rec r{m, true, mb, m->bf ? sizeof(bf16) : sizeof(float)};
+    Rec r{m, true, mb, m->half ? (size_t)2 : sizeof(float)};
     int rc = r.record();
     if (rc) return rc;
     m->ws_bytes = m->arena.peak + 1024;
@@ -771,7 +781,7 @@ int pd_unet_bind_workspace(pd_unet_t* m, void* workspace, size_t bytes) {
     m->tc_plans.clear(); m->ops.clear(); m->tensors.clear();
     m->tc_layers = m->simt_layers = 0;
     m->arena.reset(false, (uint8_t*)workspace);
-    Rec r{m, false, m->mb, m->bf ? sizeof(bf16) : sizeof(float)};
+    Rec r{m, false, m->mb, m->half ? (size_t)2 : sizeof(float)};
     int rc = r.record();
     if (rc) return rc;
     m->tensors.clear();
@@ -857,7 +867,7 @@ int pd_unet_launch_count(pd_unet_t* m, int64_t* n) {
 }
 
 // ---- kernel-level test entry points ----------------------------------------------------------------------------------
-int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout,
+int pd_test_conv(int32_t use_tc, int32_t dt, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout,
                  int32_t ksize, int32_t stride, int32_t pad, const void* x1, const void* x2, const float* weight,
                  const float* bias, const float* addvec, const void* residual, const void* sc1, const void* sc2,
                  int32_t csc1, int32_t csc2, const float* sc_w, float out_scale, void* out, pd_stream_t stream) {
@@ -868,18 +878,18 @@ int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, in
     const int ct = c1 + c2;
     int rc = 0;
     if (use_tc) {
-        PD_REQUIRE(bf, "tcgen05 path is bf16 only");
+        PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "tcgen05 path takes bf16 / fp16 activations");
         PD_REQUIRE(c2 == 0, "tcgen05 main segment takes one (already concatenated) source");
         const int ktot = ksize * ksize * ct + csc1 + csc2;
-        bf16* wm = nullptr;
-        PD_CHECK_CUDA(cudaMalloc((void**)&wm, (size_t)cout * ktot * sizeof(bf16)));
-        rc = launch_relayout_tc(weight, cout, ct, ksize, wm, ktot, 0, s);
-        if (!rc && (csc1 + csc2)) rc = launch_relayout_tc(sc_w, cout, csc1 + csc2, 1, wm, ktot, ksize * ksize * ct, s);
+        void* wm = nullptr;
+        PD_CHECK_CUDA(cudaMalloc(&wm, (size_t)cout * ktot * 2));
+        rc = launch_relayout_tc(dt, weight, cout, ct, ksize, wm, ktot, 0, s);
+        if (!rc && (csc1 + csc2)) rc = launch_relayout_tc(dt, sc_w, cout, csc1 + csc2, 1, wm, ktot, ksize * ksize * ct, s);
         ConvTcDesc d{};
-        d.x = (const bf16*)x1; d.C = ct; d.N = n; d.H = h; d.W = w; d.ksize = ksize; d.stride = stride; d.pad = pad;
-        d.Ho = ho; d.Wo = wo; d.Cout = cout; d.sc1 = (const bf16*)sc1; d.Csc1 = csc1; d.sc2 = (const bf16*)sc2; d.Csc2 = csc2;
-        d.wmat = wm; d.bias = bias; d.addvec = addvec; d.addvec_stride = cout; d.residual = (const bf16*)residual;
-        d.out_scale = out_scale; d.out = (bf16*)out;
+        d.dt = dt; d.x = x1; d.C = ct; d.N = n; d.H = h; d.W = w; d.ksize = ksize; d.stride = stride; d.pad = pad;
+        d.Ho = ho; d.Wo = wo; d.Cout = cout; d.sc1 = sc1; d.Csc1 = csc1; d.sc2 = sc2; d.Csc2 = csc2;
+        d.wmat = wm; d.bias = bias; d.addvec = addvec; d.addvec_stride = cout; d.residual = residual;
+        d.out_scale = out_scale; d.out = out;
         ConvTcPlan* pl = nullptr;
         if (!rc) rc = conv_tc_plan_create(d, &pl);
         if (!rc) rc = conv_tc_launch(pl, s);
@@ -894,7 +904,7 @@ int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, in
     rc = launch_relayout_simt(weight, cout, ct, ksize, wm, s);
     void* tmp = nullptr;
     float* wsc = nullptr;
-    const size_t esz = bf ? 2 : 4;
+    const size_t esz = dt ? 2 : 4;
     if (!rc && (csc1 + csc2)) {
         PD_CHECK_CUDA(cudaMalloc(&tmp, (size_t)n * ho * wo * cout * esz));
         PD_CHECK_CUDA(cudaMalloc((void**)&wsc, (size_t)cout * (csc1 + csc2) * sizeof(float)));
@@ -902,13 +912,13 @@ int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, in
         ConvArgs ca{};
         ca.x1 = sc1; ca.x2 = sc2; ca.C1 = csc1; ca.C2 = csc2; ca.N = n; ca.H = ho; ca.W = wo; ca.Cout = cout; ca.ksize = 1;
         ca.stride = 1; ca.pad = 0; ca.Ho = ho; ca.Wo = wo; ca.w = wsc; ca.out_scale = 1.f; ca.out = tmp;
-        if (!rc) rc = launch_conv_simt(bf != 0, ca, s);
+        if (!rc) rc = launch_conv_simt(dt, ca, s);
     }
     ConvArgs ca{};
     ca.x1 = x1; ca.x2 = x2; ca.C1 = c1; ca.C2 = c2; ca.N = n; ca.H = h; ca.W = w; ca.Cout = cout; ca.ksize = ksize;
     ca.stride = stride; ca.pad = pad; ca.Ho = ho; ca.Wo = wo; ca.w = wm; ca.bias = bias; ca.addvec = addvec;
     ca.addvec_stride = cout; ca.residual = tmp ? tmp : residual; ca.out_scale = out_scale; ca.out = out;
-    if (!rc) rc = launch_conv_simt(bf != 0, ca, s);
+    if (!rc) rc = launch_conv_simt(dt, ca, s);
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(wm);
     if (tmp) cudaFree(tmp);
@@ -917,7 +927,7 @@ int pd_test_conv(int32_t use_tc, int32_t bf, int32_t n, int32_t h, int32_t w, in
     return rc;
 }
 
-int pd_test_groupnorm(int32_t bf, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+int pd_test_groupnorm(int32_t dt, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                       int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta, void* out,
                       pd_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -927,23 +937,22 @@ int pd_test_groupnorm(int32_t bf, int32_t n, int32_t hw, int32_t c1, int32_t c2,
     GNArgs ga{};
     ga.x1 = x1; ga.x2 = x2; ga.C1 = c1; ga.C2 = c2; ga.N = n; ga.HW = hw; ga.groups = groups; ga.eps = eps; ga.gamma = gamma;
     ga.beta = beta; ga.silu = do_silu; ga.stats = stats; ga.out = out;
-    int rc = launch_gn_stats(bf != 0, ga, s);
-    if (!rc) rc = launch_gn_apply(bf != 0, bf == 0, ga, s);
+    int rc = launch_gn_stats(dt, ga, s);
+    if (!rc) rc = launch_gn_apply(dt, dt == 0, ga, s);
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(stats);
     if (!rc && e != cudaSuccess) { set_error(std::string("groupnorm kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
     return rc;
 }
 
-int pd_test_attention(int32_t use_mma, int32_t bf, int32_t n, int32_t s_len, int32_t c, int32_t d, const void* qkv,
+int pd_test_attention(int32_t use_mma, int32_t dt, int32_t n, int32_t s_len, int32_t c, int32_t d, const void* qkv,
                       void* out, pd_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     if (use_mma) {
-        PD_REQUIRE(bf, "attention_mma is bf16 only");
-        rc = launch_attention_mma(qkv, n, s_len, c, d, out, s);
+        rc = launch_attention_mma(dt, qkv, n, s_len, c, d, out, s);
     } else {
-        rc = launch_attention_simt(bf != 0, bf == 0, qkv, n, s_len, c, d, out, s);
+        rc = launch_attention_simt(dt, dt == 0, qkv, n, s_len, c, d, out, s);
     }
     cudaError_t e = cudaStreamSynchronize(s);
     if (!rc && e != cudaSuccess) { set_error(std::string("attention kernel failed: ") + cudaGetErrorString(e)); rc = 2; }

@@ -6,6 +6,7 @@
 // shapes fit d = 8 exactly (QK^T: m16n8k8, P.V: m16n8k16 with the S accumulator fragment reused as the A operand),
 // so this round's kernel is a register-resident flash kernel on those; K and V^T of one head live in shared memory.
 #include "pd_kernels.h"
+#include <type_traits>
 
 namespace pd {
 
@@ -18,28 +19,42 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+template <typename T>
 __device__ __forceinline__ void mma_16x8x8(float c[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(b0));
+    if (std::is_same<T, bf16>::value)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(b0));
+    else
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(b0));
 }
+template <typename T>
 __device__ __forceinline__ void mma_16x8x16(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                             uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    if (std::is_same<T, bf16>::value)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    else
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const bf16* __restrict__ qkv, int S, int C,
-                                                                      bf16* __restrict__ out) {
-    __shared__ __align__(16) bf16 Ks[AT_TK * 8];
-    __shared__ __align__(16) bf16 Vt[8 * AT_VPITCH];
+template <typename T>
+__global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* __restrict__ qkv, int S, int C,
+                                                                      T* __restrict__ out) {
+    __shared__ __align__(16) T Ks[AT_TK * 8];
+    __shared__ __align__(16) T Vt[8 * AT_VPITCH];
     const int n = blockIdx.z, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const size_t rowp = (size_t)3 * C;
-    const bf16* base = qkv + (size_t)n * S * rowp + head * 8;
+    const T* base = qkv + (size_t)n * S * rowp + head * 8;
     const int q0 = blockIdx.x * (AT_WARPS * 16) + warp * 16;
     const bool active = q0 < S;   // S % 16 == 0 is required, so a warp is fully in or fully out
 
@@ -57,11 +72,11 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const bf16
         const int tk = min(AT_TK, S - k0);
         __syncthreads();
         for (int j = threadIdx.x; j < tk; j += blockDim.x) {
-            const bf16* kp = base + (size_t)(k0 + j) * rowp + C;
+            const T* kp = base + (size_t)(k0 + j) * rowp + C;
             uint4 kv = *reinterpret_cast<const uint4*>(kp);
             uint4 vv = *reinterpret_cast<const uint4*>(kp + C);
             *reinterpret_cast<uint4*>(&Ks[j * 8]) = kv;
-            const bf16* ve = reinterpret_cast<const bf16*>(&vv);
+            const T* ve = reinterpret_cast<const T*>(&vv);
 #pragma unroll
             for (int d = 0; d < 8; ++d) Vt[d * AT_VPITCH + j] = ve[d];
         }
@@ -73,7 +88,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const bf16
             for (int kb = 0; kb < 8; ++kb) {
                 s[kb][0] = s[kb][1] = s[kb][2] = s[kb][3] = 0.f;
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[(c0 + kb * 8 + g) * 8 + 2 * t]);
-                mma_16x8x8(s[kb], qa0, qa1, b0);
+                mma_16x8x8<T>(s[kb], qa0, qa1, b0);
             }
             float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
@@ -100,14 +115,14 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const bf16
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t a0 = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-                const uint32_t a1 = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-                const uint32_t a2 = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-                const uint32_t a3 = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-                const bf16* vp = &Vt[g * AT_VPITCH + c0 + 16 * j + 2 * t];
+                const uint32_t a0 = pack2<T>(s[2 * j][0], s[2 * j][1]);
+                const uint32_t a1 = pack2<T>(s[2 * j][2], s[2 * j][3]);
+                const uint32_t a2 = pack2<T>(s[2 * j + 1][0], s[2 * j + 1][1]);
+                const uint32_t a3 = pack2<T>(s[2 * j + 1][2], s[2 * j + 1][3]);
+                const T* vp = &Vt[g * AT_VPITCH + c0 + 16 * j + 2 * t];
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
-                mma_16x8x16(o, a0, a1, a2, a3, b0, b1);
+                mma_16x8x16<T>(o, a0, a1, a2, a3, b0, b1);
             }
         }
     }
@@ -117,16 +132,17 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const bf16
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    bf16* ob = out + (size_t)n * S * C + head * 8 + 2 * t;
-    *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g) * C) = pack_bf16x2(o[0] * i0, o[1] * i0);
-    *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g + 8) * C) = pack_bf16x2(o[2] * i1, o[3] * i1);
+    T* ob = out + (size_t)n * S * C + head * 8 + 2 * t;
+    *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g) * C) = pack2<T>(o[0] * i0, o[1] * i0);
+    *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g + 8) * C) = pack2<T>(o[2] * i1, o[3] * i1);
 }
 
-int launch_attention_mma(const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+    PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "attention_mma takes bf16 or fp16 activations");
     PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
     PD_REQUIRE(S % 64 == 0 && C % 8 == 0, "attention_mma needs S % 64 == 0");
     dim3 grid((S + AT_WARPS * 16 - 1) / (AT_WARPS * 16), C / 8, N);
-    attention_mma_kernel<<<grid, AT_WARPS * 32, 0, s>>>((const bf16*)qkv, S, C, (bf16*)out);
+    PD_DISPATCH_HALF(dt, T, (attention_mma_kernel<T><<<grid, AT_WARPS * 32, 0, s>>>((const T*)qkv, S, C, (T*)out)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

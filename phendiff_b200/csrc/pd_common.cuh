@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <string>
@@ -35,6 +36,9 @@ void set_error(const std::string& msg);
     } while (0)
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
+// activation storage types: 0 = fp32 (validation mode), 1 = bf16, 2 = fp16 (both on the tensor-core path)
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // 8-wide vector load/store of activations held as fp32 or bf16 (math is always fp32)
@@ -53,6 +57,15 @@ __device__ __forceinline__ void load8(const bf16* p, float v[8]) {
         v[2 * i] = f.x; v[2 * i + 1] = f.y;
     }
 }
+__device__ __forceinline__ void load8(const f16* p, float v[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
 __device__ __forceinline__ void store8(float* p, const float v[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -67,11 +80,38 @@ __device__ __forceinline__ void store8(bf16* p, const float v[8]) {
     r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(p) = r;
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store8(f16* p, const float v[8]) {
+    uint4 r;
+    r.x = pack_f16x2(v[0], v[1]); r.y = pack_f16x2(v[2], v[3]);
+    r.z = pack_f16x2(v[4], v[5]); r.w = pack_f16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float lo, float hi) { return pack_f16x2(lo, hi); }
+__device__ __forceinline__ float to_f(f16 x) { return __half2float(x); }
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);
 template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ f16 from_f<f16>(float x) { return __float2half_rn(x); }
+// host-side dispatch on the activation storage type
+#define PD_DISPATCH_DT(dt, T, ...)                         \
+    do {                                                   \
+        if ((dt) == ::pd::DT_BF16) { typedef ::pd::bf16 T; __VA_ARGS__; }      \
+        else if ((dt) == ::pd::DT_F16) { typedef ::pd::f16 T; __VA_ARGS__; }   \
+        else { typedef float T; __VA_ARGS__; }             \
+    } while (0)
+#define PD_DISPATCH_HALF(dt, T, ...)                       \
+    do {                                                   \
+        if ((dt) == ::pd::DT_F16) { typedef ::pd::f16 T; __VA_ARGS__; }        \
+        else { typedef ::pd::bf16 T; __VA_ARGS__; }        \
+    } while (0)
 
 template <bool kPrecise> __device__ __forceinline__ float silu(float x) {
     if (kPrecise) return x / (1.0f + expf(-x));
@@ -173,7 +213,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16kind(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"

@@ -16,6 +16,7 @@
 #include "pd_kernels.h"
 #include <algorithm>
 #include <string>
+#include <type_traits>
 
 namespace pd {
 
@@ -34,13 +35,14 @@ struct ConvTcParams {
     const float* bias;
     const float* addvec;
     int addvec_stride;
-    const bf16* residual;
+    const void* residual;
     float out_scale;
-    bf16* out;
+    void* out;
 };
 
 struct ConvTcPlan {
     ConvTcParams p;
+    int dt;
     int block_n;
     int grid;
     size_t smem;
@@ -69,7 +71,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     using Cfg = TcCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
@@ -151,8 +153,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     } else if (warp == 1) {
         if (elect_one()) {
             // ===================== MMA issuer (single thread) =====================
-            // instruction descriptor: D fp32, A/B bf16, both K-major, N = BLOCK_N, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+            // instruction descriptor: D fp32 (bit 4), A/B format at bits 7/10 (0 = fp16, 1 = bf16), both K-major,
+            // N = BLOCK_N at bits 17.., M = 128 at bits 24..
+            constexpr uint32_t fmt = sizeof(T) == 2 && std::is_same<T, bf16>::value ? 1u : 0u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                        ((uint32_t)(TC_BLOCK_M >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address
-                        umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        umma_f16kind(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                                   (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);                       // smem slot free when these MMAs retire
@@ -200,8 +204,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            bf16* orow = p.out + pix * p.Cout;
-            const bf16* rrow = p.residual ? p.residual + pix * p.Cout : nullptr;
+            T* orow = reinterpret_cast<T*>(p.out) + pix * p.Cout;
+            const T* rrow = p.residual ? reinterpret_cast<const T*>(p.residual) + pix * p.Cout : nullptr;
             const float* avrow = p.addvec ? p.addvec + (size_t)img * p.addvec_stride : nullptr;
 #pragma unroll 1
             for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
@@ -271,15 +275,15 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+static int encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
     PFN_encodeTiled enc = get_encode();
     PD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t gd[5], gs[4];
     cuuint32_t bd[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = 1; }
     for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bd, es,
+    CUresult r = enc(tm, dt == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bd, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -310,6 +314,7 @@ static int pick_block_n(int Cout) {
 
 bool conv_tc_supported(const ConvTcDesc& d, std::string* why) {
     auto no = [&](const char* m) { if (why) *why = m; return false; };
+    if (d.dt != DT_BF16 && d.dt != DT_F16) return no("tcgen05 path takes bf16 or fp16 activations");
     if (d.C % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
     if (pick_block_n(d.Cout) == 0) return no("Cout must be a multiple of 64");
     if (!(d.ksize == 1 || d.ksize == 3)) return no("kernel size must be 1 or 3");
@@ -339,6 +344,7 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
     p.tilesW = d.Wo / p.Wt; p.tilesH = d.Ho / p.Ht;
     p.Ho = d.Ho; p.Wo = d.Wo; p.Cout = d.Cout;
     p.m_tiles = (d.N / p.Nt) * p.tilesW * p.tilesH;
+    pl->dt = d.dt;
     pl->block_n = pick_block_n(d.Cout);
     p.n_tiles = d.Cout / pl->block_n;
     p.bias = d.bias; p.addvec = d.addvec; p.addvec_stride = d.addvec_stride; p.residual = d.residual;
@@ -349,15 +355,15 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
         uint64_t dims[4] = {C, W, H, N};
         uint64_t st[3] = {C * 2, W * C * 2, H * W * C * 2};
         uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Nt};
-        rc = encode_map(&p.tmA, d.x, 4, dims, st, box);
+        rc = encode_map(&p.tmA, d.dt, d.x, 4, dims, st, box);
     } else {
         uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
         uint64_t st[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
         uint32_t box[5] = {64, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Nt};
-        rc = encode_map(&p.tmA, d.x, 5, dims, st, box);
+        rc = encode_map(&p.tmA, d.dt, d.x, 5, dims, st, box);
     }
     if (rc) { delete pl; return rc; }
-    const bf16* scs[2] = {d.sc1, d.sc2};
+    const void* scs[2] = {d.sc1, d.sc2};
     const int cscs[2] = {d.Csc1, d.Csc2};
     CUtensorMap* tms[2] = {&p.tmS1, &p.tmS2};
     for (int i = 0; i < 2; ++i) {
@@ -366,7 +372,7 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
         uint64_t dims[4] = {Cs, Wo, Ho, N};
         uint64_t st[3] = {Cs * 2, Wo * Cs * 2, Ho * Wo * Cs * 2};
         uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Nt};
-        rc = encode_map(tms[i], scs[i], 4, dims, st, box);
+        rc = encode_map(tms[i], d.dt, scs[i], 4, dims, st, box);
         if (rc) { delete pl; return rc; }
     }
     {
@@ -374,7 +380,7 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
         uint64_t dims[2] = {Ktot, (uint64_t)d.Cout};
         uint64_t st[1] = {Ktot * 2};
         uint32_t box[2] = {64, (uint32_t)pl->block_n};
-        rc = encode_map(&p.tmB, d.wmat, 2, dims, st, box);
+        rc = encode_map(&p.tmB, d.dt, d.wmat, 2, dims, st, box);
         if (rc) { delete pl; return rc; }
     }
     int dev = 0, sms = 148;
@@ -388,25 +394,27 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
 
 void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 
-template <int BLOCK_N>
+template <int BLOCK_N, typename T>
 static int launch_tc(const ConvTcPlan* pl, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)TcCfg<BLOCK_N>::SMEM));
         attr_set = true;
     }
-    conv_tc_kernel<BLOCK_N><<<pl->grid, TC_THREADS, TcCfg<BLOCK_N>::SMEM, s>>>(pl->p);
+    conv_tc_kernel<BLOCK_N, T><<<pl->grid, TC_THREADS, TcCfg<BLOCK_N>::SMEM, s>>>(pl->p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
-    switch (pl->block_n) {
-        case 256: return launch_tc<256>(pl, s);
-        case 128: return launch_tc<128>(pl, s);
-        case 64: return launch_tc<64>(pl, s);
-    }
+    PD_DISPATCH_HALF(pl->dt, T, {
+        switch (pl->block_n) {
+            case 256: return launch_tc<256, T>(pl, s);
+            case 128: return launch_tc<128, T>(pl, s);
+            case 64: return launch_tc<64, T>(pl, s);
+        }
+    });
     set_error("conv_tc: bad block_n");
     return 1;
 }

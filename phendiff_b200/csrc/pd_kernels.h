@@ -33,8 +33,8 @@ struct GNArgs {
     float* stats;                     // (N,groups,2) sum / sumsq, zero on entry
     void* out;                        // (N,HW,C1+C2)
 };
-int launch_gn_stats(bool bf, const GNArgs& a, cudaStream_t s);
-int launch_gn_apply(bool bf, bool precise, const GNArgs& a, cudaStream_t s);
+int launch_gn_stats(int dt, const GNArgs& a, cudaStream_t s);
+int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s);
 
 // ---- generic SIMT convolution (fp32 validation path; odd shapes of the bf16 path) -------------------------------
 struct ConvArgs {
@@ -48,10 +48,10 @@ struct ConvArgs {
     float out_scale;                  // multiplies the final sum (1/output_scale_factor)
     void* out;                        // (N,Ho,Wo,Cout)
 };
-int launch_conv_simt(bool bf, const ConvArgs& a, cudaStream_t s);
+int launch_conv_simt(int dt, const ConvArgs& a, cudaStream_t s);
 
 // conv_in: NCHW fp32 sample -> NHWC activations (cond_unet_2d.py:313)
-int launch_conv_in(bool bf, const float* x, const float* w /*(9*Cin,Cout)*/, const float* bias, int N, int Cin, int H,
+int launch_conv_in(int dt, const float* x, const float* w /*(9*Cin,Cout)*/, const float* bias, int N, int Cin, int H,
                    int W, int Cout, void* out, cudaStream_t s);
 // conv_out (+ optional fused DDIM update): NHWC activations -> NCHW fp32 (cond_unet_2d.py:348, A.5)
 struct ConvOutArgs {
@@ -63,14 +63,14 @@ struct ConvOutArgs {
     float* x;                         // (N,Cout,H,W) updated in place when `step` != null
     const pd_step_coeffs_t* step;     // host pointer (copied by value into the launch) or null
 };
-int launch_conv_out(bool bf, const ConvOutArgs& a, cudaStream_t s);
+int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s);
 
-int launch_upsample2x(bool bf, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s);
+int launch_upsample2x(int dt, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s);
 
 // ---- attention core: softmax(q k^T / sqrt(d)) v on packed qkv (N,S,3C) ------------------------------------------
-int launch_attention_simt(bool bf, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
+int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
                           cudaStream_t s);
-int launch_attention_mma(const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s);  // bf16 only
+int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s);  // bf16 / fp16
 
 // ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
 int launch_ddim_step(const pd_step_coeffs_t& c, const float* x, const float* m, const float* noise, float* x_out,
@@ -84,28 +84,28 @@ int launch_denorm(const float* x, float* out, int B, int C, int H, int W, cudaSt
 // ---- weight re-layout ---------------------------------------------------------------------------------------------
 // OIHW fp32 (O,I,k,k) -> (k*k*I, O) fp32
 int launch_relayout_simt(const float* w, int O, int I, int k, float* out, cudaStream_t s);
-// OIHW fp32 -> bf16 (O, ktot) at column offset koff, K index = tap*I + i
-int launch_relayout_tc(const float* w, int O, int I, int k, bf16* out, int ktot, int koff, cudaStream_t s);
+// OIHW fp32 -> bf16/fp16 (O, ktot) at column offset koff, K index = tap*I + i
+int launch_relayout_tc(int dt, const float* w, int O, int I, int k, void* out, int ktot, int koff, cudaStream_t s);
 // conv_out OIHW (O,I,3,3) -> (9, I, 4) fp32
 int launch_relayout_convout(const float* w, int O, int I, float* out, cudaStream_t s);
-int launch_cast_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
-int launch_cast_f32(const bf16* x, float* out, int64_t n, cudaStream_t s);
+int launch_cast_half(int dt, const float* x, void* out, int64_t n, cudaStream_t s);
 
 // ---- tcgen05 implicit-GEMM convolution (pd_conv_tc.cu) -----------------------------------------------------------
 struct ConvTcPlan;  // opaque: tensor maps + launch geometry for one layer at one (N,H,W)
 struct ConvTcDesc {
-    // main segment: ksize x ksize conv over `x` (N,H,W,C) bf16 NHWC (already normalised / concatenated)
-    const bf16* x; int C;
+    // main segment: ksize x ksize conv over `x` (N,H,W,C) bf16/fp16 NHWC (already normalised / concatenated)
+    int dt;                           // DT_BF16 or DT_F16
+    const void* x; int C;
     int N, H, W, ksize, stride, pad, Ho, Wo, Cout;
     // optional 1x1 shortcut segment over up to two concatenated sources at the OUTPUT resolution
-    const bf16* sc1; int Csc1;
-    const bf16* sc2; int Csc2;
-    const bf16* wmat;                 // (Cout, Ktot) bf16, Ktot = k*k*C + Csc1 + Csc2
+    const void* sc1; int Csc1;
+    const void* sc2; int Csc2;
+    const void* wmat;                 // (Cout, Ktot) bf16/fp16, Ktot = k*k*C + Csc1 + Csc2
     const float* bias;                // (Cout) or null
     const float* addvec; int addvec_stride;
-    const bf16* residual;             // (N,Ho,Wo,Cout) or null
+    const void* residual;             // (N,Ho,Wo,Cout) or null
     float out_scale;
-    bf16* out;                        // (N,Ho,Wo,Cout)
+    void* out;                        // (N,Ho,Wo,Cout)
 };
 bool conv_tc_supported(const ConvTcDesc& d, std::string* why);
 int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out);

@@ -195,30 +195,24 @@ static int gn_block(int C) {
     return ncv * rpp;
 }
 
-int launch_gn_stats(bool bf, const GNArgs& a, cudaStream_t s) {
+int launch_gn_stats(int dt, const GNArgs& a, cudaStream_t s) {
     const int C = a.C1 + a.C2;
     PD_REQUIRE(C % 8 == 0 && a.C1 % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
     PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
     dim3 grid((a.HW + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, a.N);
     int block = gn_block(C);
     size_t smem = 2 * C * sizeof(float);
-    if (bf) gn_stats_kernel<bf16><<<grid, block, smem, s>>>(a);
-    else gn_stats_kernel<float><<<grid, block, smem, s>>>(a);
+    PD_DISPATCH_DT(dt, T, (gn_stats_kernel<T><<<grid, block, smem, s>>>(a)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_gn_apply(bool bf, bool precise, const GNArgs& a, cudaStream_t s) {
+int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s) {
     const int C = a.C1 + a.C2;
     dim3 grid((a.HW + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, a.N);
     int block = gn_block(C);
-    if (bf) {
-        if (precise) gn_apply_kernel<bf16, true><<<grid, block, 0, s>>>(a);
-        else gn_apply_kernel<bf16, false><<<grid, block, 0, s>>>(a);
-    } else {
-        if (precise) gn_apply_kernel<float, true><<<grid, block, 0, s>>>(a);
-        else gn_apply_kernel<float, false><<<grid, block, 0, s>>>(a);
-    }
+    if (precise) PD_DISPATCH_DT(dt, T, (gn_apply_kernel<T, true><<<grid, block, 0, s>>>(a)));
+    else PD_DISPATCH_DT(dt, T, (gn_apply_kernel<T, false><<<grid, block, 0, s>>>(a)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -304,13 +298,12 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
     }
 }
 
-int launch_conv_simt(bool bf, const ConvArgs& a, cudaStream_t s) {
+int launch_conv_simt(int dt, const ConvArgs& a, cudaStream_t s) {
     const int Ct = a.C1 + a.C2;
     PD_REQUIRE(Ct % 16 == 0 && a.C1 % 4 == 0 && a.Cout % 4 == 0, "conv_simt needs Cin % 16 == 0 and Cout % 4 == 0");
     const int M = a.N * a.Ho * a.Wo;
     dim3 grid((M + 63) / 64, (a.Cout + 63) / 64);
-    if (bf) conv_simt_kernel<bf16><<<grid, 256, 0, s>>>(a);
-    else conv_simt_kernel<float><<<grid, 256, 0, s>>>(a);
+    PD_DISPATCH_DT(dt, T, (conv_simt_kernel<T><<<grid, 256, 0, s>>>(a)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -364,20 +357,17 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     }
 }
 
-int launch_conv_in(bool bf, const float* x, const float* w, const float* bias, int N, int Cin, int H, int W, int Cout,
+int launch_conv_in(int dt, const float* x, const float* w, const float* bias, int N, int Cin, int H, int W, int Cout,
                    void* out, cudaStream_t s) {
     PD_REQUIRE(Cin <= 4 && Cout % 16 == 0, "conv_in supports in_channels <= 4 and block_out_channels[0] % 16 == 0");
     size_t smem = ((size_t)9 * Cin * Cout + Cout) * sizeof(float);
     PD_REQUIRE(smem <= 200 * 1024, "conv_in weights do not fit shared memory");
     size_t total = (size_t)N * H * W;
     int grid = (int)((total + 31) / 32);
-    if (bf) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_in_kernel<bf16><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (bf16*)out);
-    } else {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_in_kernel<float><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (float*)out);
-    }
+    PD_DISPATCH_DT(dt, T, {
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_in_kernel<T><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (T*)out);
+    });
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -432,6 +422,23 @@ int launch_ddim_step(const pd_step_coeffs_t& c, const float* x, const float* m, 
 // weights in registers; a warp reduces one pixel at a time and handles runs of 32 consecutive pixels so that the
 // NCHW fp32 writes (model output and x_t update) are coalesced.  x_t is read once and written once per step.
 // =====================================================================================================================
+__device__ __forceinline__ void load4(const float* p, float v[]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float v[]) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+    float2 f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+}
+__device__ __forceinline__ void load4(const f16* p, float v[]) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&r.x));
+    float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+}
+
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_coeffs_t st, int has_step) {
     const int lane = threadIdx.x & 31;
@@ -463,12 +470,8 @@ __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_co
                 const T* src = (const T*)a.act + (((size_t)n * a.H + ih) * a.W + iw) * a.Cin + lane * CPL;
                 float v[CPL];
                 if (CPL == 8) load8(src, v);
-                else if (CPL == 4 && sizeof(T) == 2) {
-                    uint2 r = *reinterpret_cast<const uint2*>(src);
-                    float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
-                    float2 f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
-                    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
-                } else {
+                else if (CPL == 4) load4(src, v);
+                else {
 #pragma unroll
                     for (int j = 0; j < CPL; ++j) v[j] = to_f(src[j]);
                 }
@@ -499,25 +502,22 @@ __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_co
     }
 }
 
-int launch_conv_out(bool bf, const ConvOutArgs& a, cudaStream_t s) {
+int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s) {
     PD_REQUIRE(a.Cout <= 3, "conv_out supports out_channels <= 3");
     PD_REQUIRE(a.Cin % 32 == 0, "conv_out needs block_out_channels[0] % 32 == 0");
     const int cpl = a.Cin / 32;
+    PD_REQUIRE(cpl == 2 || cpl == 4 || cpl == 8, "conv_out: block_out_channels[0] must be 64, 128 or 256");
     pd_step_coeffs_t st{};
     int has = 0;
     if (a.step) { st = *a.step; has = 1; PD_REQUIRE(st.sigma == 0.f, "fused conv_out update requires eta == 0"); }
     size_t total = (size_t)a.N * a.H * a.W;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 8);
     if (grid < 1) grid = 1;
-#define PD_CO(TT, CPL) conv_out_kernel<TT, CPL><<<grid, 256, 0, s>>>(a, st, has)
-    if (bf) {
-        if (cpl == 2) PD_CO(bf16, 2); else if (cpl == 4) PD_CO(bf16, 4); else if (cpl == 8) PD_CO(bf16, 8);
-        else { set_error("conv_out: unsupported channel count"); return 1; }
-    } else {
-        if (cpl == 2) PD_CO(float, 2); else if (cpl == 4) PD_CO(float, 4); else if (cpl == 8) PD_CO(float, 8);
-        else { set_error("conv_out: unsupported channel count"); return 1; }
-    }
-#undef PD_CO
+    PD_DISPATCH_DT(dt, T, {
+        if (cpl == 2) conv_out_kernel<T, 2><<<grid, 256, 0, s>>>(a, st, has);
+        else if (cpl == 4) conv_out_kernel<T, 4><<<grid, 256, 0, s>>>(a, st, has);
+        else conv_out_kernel<T, 8><<<grid, 256, 0, s>>>(a, st, has);
+    });
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -544,12 +544,11 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, int N, int H, int W, 
     }
 }
 
-int launch_upsample2x(bool bf, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s) {
+int launch_upsample2x(int dt, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s) {
     PD_REQUIRE(C % 8 == 0, "upsample needs C % 8 == 0");
     size_t total = (size_t)N * 4 * H * W * (C / 8);
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
-    if (bf) upsample2x_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, N, H, W, C, (bf16*)out);
-    else upsample2x_kernel<float><<<grid, 256, 0, s>>>((const float*)x, N, H, W, C, (float*)out);
+    PD_DISPATCH_DT(dt, T, (upsample2x_kernel<T><<<grid, 256, 0, s>>>((const T*)x, N, H, W, C, (T*)out)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -638,17 +637,12 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const T* __restrict
     }
 }
 
-int launch_attention_simt(bool bf, bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
     PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
     PD_REQUIRE(C % 8 == 0, "attention channels must be a multiple of 8");
     dim3 grid((S + 127) / 128, C / d, N);
-    if (bf) {
-        if (precise) attention_simt_kernel<bf16, true><<<grid, 128, 0, s>>>((const bf16*)qkv, S, C, (bf16*)out);
-        else attention_simt_kernel<bf16, false><<<grid, 128, 0, s>>>((const bf16*)qkv, S, C, (bf16*)out);
-    } else {
-        if (precise) attention_simt_kernel<float, true><<<grid, 128, 0, s>>>((const float*)qkv, S, C, (float*)out);
-        else attention_simt_kernel<float, false><<<grid, 128, 0, s>>>((const float*)qkv, S, C, (float*)out);
-    }
+    if (precise) PD_DISPATCH_DT(dt, T, (attention_simt_kernel<T, true><<<grid, 128, 0, s>>>((const T*)qkv, S, C, (T*)out)));
+    else PD_DISPATCH_DT(dt, T, (attention_simt_kernel<T, false><<<grid, 128, 0, s>>>((const T*)qkv, S, C, (T*)out)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -739,7 +733,8 @@ int launch_relayout_simt(const float* w, int O, int I, int k, float* out, cudaSt
     return 0;
 }
 
-__global__ void relayout_tc_kernel(const float* __restrict__ w, int O, int I, int k, bf16* __restrict__ out, int ktot,
+template <typename T>
+__global__ void relayout_tc_kernel(const float* __restrict__ w, int O, int I, int k, T* __restrict__ out, int ktot,
                                    int koff) {
     const size_t total = (size_t)O * I * k * k;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -749,13 +744,13 @@ __global__ void relayout_tc_kernel(const float* __restrict__ w, int O, int I, in
         size_t r = i / I;
         const int tap = r % (k * k);
         const int o = r / (k * k);
-        out[(size_t)o * ktot + koff + (size_t)tap * I + ci] = __float2bfloat16_rn(w[((size_t)o * I + ci) * k * k + tap]);
+        out[(size_t)o * ktot + koff + (size_t)tap * I + ci] = from_f<T>(w[((size_t)o * I + ci) * k * k + tap]);
     }
 }
-int launch_relayout_tc(const float* w, int O, int I, int k, bf16* out, int ktot, int koff, cudaStream_t s) {
+int launch_relayout_tc(int dt, const float* w, int O, int I, int k, void* out, int ktot, int koff, cudaStream_t s) {
     size_t total = (size_t)O * I * k * k;
     int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
-    relayout_tc_kernel<<<grid, 256, 0, s>>>(w, O, I, k, out, ktot, koff);
+    PD_DISPATCH_HALF(dt, T, (relayout_tc_kernel<T><<<grid, 256, 0, s>>>(w, O, I, k, (T*)out, ktot, koff)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -775,27 +770,16 @@ int launch_relayout_convout(const float* w, int O, int I, float* out, cudaStream
     return 0;
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int64_t n) {
+template <typename T>
+__global__ void cast_half_kernel(const float* __restrict__ x, T* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = __float2bfloat16_rn(x[i]);
+    for (; i < n; i += stride) out[i] = from_f<T>(x[i]);
 }
-int launch_cast_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s) {
+int launch_cast_half(int dt, const float* x, void* out, int64_t n, cudaStream_t s) {
     int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
     if (grid < 1) grid = 1;
-    cast_bf16_kernel<<<grid, 256, 0, s>>>(x, out, n);
-    PD_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-__global__ void cast_f32_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = __bfloat162float(x[i]);
-}
-int launch_cast_f32(const bf16* x, float* out, int64_t n, cudaStream_t s) {
-    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-    if (grid < 1) grid = 1;
-    cast_f32_kernel<<<grid, 256, 0, s>>>(x, out, n);
+    PD_DISPATCH_HALF(dt, T, (cast_half_kernel<T><<<grid, 256, 0, s>>>(x, (T*)out, n)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

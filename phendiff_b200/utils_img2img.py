@@ -21,6 +21,9 @@ INVERSE_SCHEDULER_VARIANT = "0.18.2"
 
 
 def _to_device(pipe, t: Optional[Tensor], dtype):
+    if pipe.device.type != "cuda":
+        raise _lib.PhenDiffB200Error(
+            f"the pipeline lives on {pipe.device}: move it to a CUDA device (pipe.to('cuda')); there is no CPU fallback")
     if t is None:
         return None
     return t.to(device=pipe.device, dtype=dtype, non_blocking=True)

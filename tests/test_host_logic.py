@@ -1,0 +1,208 @@
+"""CPU tests of the product's host side: config parsing, scheduler tables / step scalars (bit-compared with the oracle),
+the drop-in API surface and its error behaviour, and that the C-ABI library loads and exports every declared symbol.
+No compute call is made without a GPU."""
+import inspect
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from phendiff_b200 import (ConditionalDDIMPipeline, CustomCondUNet2DModel, CustomEmbedding, DDIMInverseScheduler,
+                           DDIMScheduler, PhenDiffB200Error, _ddib, _inversion)
+from phendiff_b200.reference_configs import DENOISER_CONFIGS, SCHEDULER_CONFIGS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol(build_lib):
+    hdr = open(os.path.join(ROOT, "include", "phendiff_b200.h")).read()
+    declared = set(re.findall(r"\b(pd_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pd_unet_t"}
+    assert len(declared) >= 20
+    l = build_lib.lib()
+    for name in sorted(declared):
+        assert hasattr(l, name), f"{name} declared in include/phendiff_b200.h but not exported"
+    assert set(build_lib.EXPORTED_SYMBOLS) == declared
+    assert l.pd_version() >= 100
+    assert isinstance(l.pd_last_error(), bytes)
+
+
+def test_struct_layouts_match_header(build_lib):
+    import ctypes as C
+
+    assert C.sizeof(build_lib.StepCoeffs) == 40
+    assert C.sizeof(build_lib.UnetConfig) == 4 * (3 + 3 * 8 + 14)
+
+
+@pytest.mark.parametrize("name", list(SCHEDULER_CONFIGS))
+def test_scheduler_tables_bit_equal_oracle(name):
+    from oracle import OracleDDIMInverseScheduler, OracleDDIMScheduler
+
+    cfg = SCHEDULER_CONFIGS[name]
+    a, b = DDIMScheduler.from_config(cfg), OracleDDIMScheduler.from_config(cfg)
+    assert torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+    assert float(a.final_alpha_cumprod) == float(b.final_alpha_cumprod)
+    for n in (10, 50, 100):
+        a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps)
+    for variant in ("0.18.2", ">=0.19"):
+        ai = DDIMInverseScheduler.from_config(a.config, variant=variant)
+        bi = OracleDDIMInverseScheduler.from_config(b.config, variant=variant)
+        assert torch.equal(ai.alphas_cumprod, bi.alphas_cumprod)
+        ai.set_timesteps(100)
+        bi.set_timesteps(100)
+        assert torch.equal(ai.timesteps, bi.timesteps)
+
+
+def test_step_coeffs_reproduce_oracle_step_on_cpu():
+    """The host scalars handed to the CUDA kernel, applied with the documented formula in numpy, equal the oracle step."""
+    from oracle import OracleDDIMInverseScheduler, OracleDDIMScheduler
+
+    g = torch.Generator().manual_seed(0)
+    x, m = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    for name in ("3k_steps_clipping_rescaling", "SD_orig_config", "1k_epsilon_pred"):
+        cfg = SCHEDULER_CONFIGS[name]
+        for P, O in ((DDIMScheduler, OracleDDIMScheduler), (DDIMInverseScheduler, OracleDDIMInverseScheduler)):
+            base = DDIMScheduler.from_config(cfg)
+            p, o = P.from_config(base.config), O.from_config(base.config)
+            p.set_timesteps(10)
+            o.set_timesteps(10)
+            for t in p.timesteps[1:]:   # skip the alpha-bar = 0 step (inf arithmetic; covered on the GPU)
+                c = p.step_coeffs(t)
+                xs, ms = x.numpy(), m.numpy()
+                f = np.float32
+                if c.pred_type == 0:
+                    x0 = (xs - f(c.sqrt_beta) * ms) / f(c.sqrt_alpha); e = ms
+                elif c.pred_type == 1:
+                    x0 = ms; e = (xs - f(c.sqrt_alpha) * x0) / f(c.sqrt_beta)
+                else:
+                    x0 = f(c.sqrt_alpha) * xs - f(c.sqrt_beta) * ms; e = f(c.sqrt_alpha) * ms + f(c.sqrt_beta) * xs
+                if c.clip:
+                    x0 = np.clip(x0, -c.clip_range, c.clip_range)
+                out = f(c.sqrt_alpha_next) * x0 + f(c.dir_coef) * e
+                ref = o.step(m, t, x).prev_sample.numpy()
+                assert np.abs(out - ref).max() <= 2e-6, (name, P.__name__, int(t))
+                assert c.timestep == float(t)
+
+
+def test_config_parsing_from_json_file(tmp_path):
+    cfg = dict(DENOISER_CONFIGS["small_denoiser_config"])
+    cfg["some_future_key"] = 1  # unknown keys are ignored (A.7)
+    p = tmp_path / "denoiser.json"
+    p.write_text(json.dumps(cfg))
+    loaded = CustomCondUNet2DModel.load_config(str(p))
+    assert loaded["_class_name"] == "CondUNet2DModel"
+    loaded["sample_size"] = 64  # utils_models.py:167 overrides sample_size like this
+    m = CustomCondUNet2DModel.from_config(loaded)
+    assert m.config.sample_size == 64 and m.config.block_out_channels == (128, 256, 512)
+    assert m.time_embed_dim == 512 and m.config.class_embed_type is None and not m.config.center_input_sample
+    assert sum(p.numel() for p in m.parameters()) == 62826243
+    with pytest.raises(AttributeError):
+        m.config.sample_size = 3
+    s = DDIMScheduler.from_config(SCHEDULER_CONFIGS["3k_steps_clipping_rescaling"])
+    assert s.config.prediction_type == "v_prediction" and s.config.set_alpha_to_one is True
+    i = DDIMInverseScheduler.from_config(s.config)
+    assert "rescale_betas_zero_snr" not in i.config and i.config.set_alpha_to_zero is True
+
+
+def test_param_table_matches_oracle_state_dict():
+    from oracle import OracleCondUNet2D
+
+    for name in ("small_denoiser_config", "super_small"):
+        cfg = DENOISER_CONFIGS[name]
+        o = OracleCondUNet2D(**cfg)
+        m = CustomCondUNet2DModel.from_config(cfg)
+        so, sm = o.state_dict(), m.state_dict()
+        assert set(so) == set(sm)
+        assert all(so[k].shape == sm[k].shape for k in so)
+        m.load_state_dict(so)
+        # deprecated attention spellings are accepted on load (A.7)
+        ren = {"to_q": "query", "to_k": "key", "to_v": "value", "to_out.0": "proj_attn"}
+        old = {}
+        for k, v in so.items():
+            for new_, old_ in ren.items():
+                if ".attentions." in k and f".{new_}." in k:
+                    k = k.replace(f".{new_}.", f".{old_}.")
+            old[k] = v
+        m.load_state_dict(old)
+
+
+def test_unsupported_options_raise():
+    base = dict(DENOISER_CONFIGS["super_small"])
+    with pytest.raises(NotImplementedError):
+        CustomCondUNet2DModel.from_config(dict(base, time_embedding_type="fourier"))
+    with pytest.raises(NotImplementedError):
+        CustomCondUNet2DModel.from_config(dict(base, class_embed_type="timestep"))
+    with pytest.raises(ValueError):
+        CustomCondUNet2DModel.from_config(dict(base, block_out_channels=[64, 128]))
+    with pytest.raises(NotImplementedError):
+        DDIMScheduler(thresholding=True)
+
+
+def test_api_surface_and_cpu_tensors_fail_loudly():
+    m = CustomCondUNet2DModel.from_config(dict(DENOISER_CONFIGS["super_small"], sample_size=32))
+    sig = inspect.signature(m.forward)
+    assert list(sig.parameters) == ["sample", "timestep", "class_labels", "class_emb", "return_dict"]
+    pipe = ConditionalDDIMPipeline(m, DDIMInverseScheduler.from_config(SCHEDULER_CONFIGS["1k_epsilon_pred"]))
+    assert isinstance(pipe.scheduler, DDIMScheduler)  # pipeline:44-45 always converts to DDIM
+    call = inspect.signature(pipe.__call__)
+    assert list(call.parameters) == ["class_labels", "class_emb", "w", "generator", "eta", "num_inference_steps",
+                                     "use_clipped_model_output", "output_type", "return_dict", "start_image",
+                                     "add_forward_noise_to_image", "frac_diffusion_skipped", "guidance_eqn"]
+    assert set(pipe.components) == {"unet", "scheduler"}
+    x, lab = torch.zeros(2, 3, 32, 32), torch.tensor([0, 1])
+    with pytest.raises(ValueError):
+        m(x, 1, lab, torch.zeros(2, 256))
+    with pytest.raises(ValueError):
+        m(x, 1)
+    with pytest.raises(PhenDiffB200Error):
+        m(x, 1, lab)
+    with pytest.raises(PhenDiffB200Error):
+        _inversion(pipe, x, lab, 2)
+    with pytest.raises(PhenDiffB200Error):
+        _ddib(pipe, x, lab, 1 - lab, 2)
+    with pytest.raises(PhenDiffB200Error):
+        pipe.scheduler.set_timesteps(4) or pipe.scheduler.step(x, 999, x)
+    # check_inputs keeps the reference's assertions (pipeline:91-137)
+    with pytest.raises(AssertionError):
+        pipe.check_inputs(class_labels=torch.zeros(2, 2))
+    with pytest.raises(AssertionError):
+        pipe.check_inputs(class_labels=lab, class_emb=torch.zeros(2, 256))
+    with pytest.raises(AssertionError):
+        pipe.check_inputs(class_labels=lab, w=torch.zeros(3))
+    with pytest.raises(ValueError):
+        pipe.check_inputs(class_labels=lab, generator=[torch.Generator()])
+    with pytest.raises(AssertionError):
+        pipe.check_inputs(class_labels=lab, start_image=x)
+    with pytest.raises(AssertionError):
+        pipe.check_inputs(class_labels=lab, start_image=x, frac_diffusion_skipped=1.5)
+    pipe.check_inputs(class_labels=lab, w=0, start_image=x, frac_diffusion_skipped=0)
+    e = CustomEmbedding(2, 1024)
+    assert e(torch.tensor([1, 0])).shape == (2, 1024) and e.config.num_classes == 2
+
+
+def test_save_and_load_pretrained_roundtrip(tmp_path):
+    m = CustomCondUNet2DModel.from_config(dict(DENOISER_CONFIGS["super_small"], sample_size=32))
+    pipe = ConditionalDDIMPipeline(m, DDIMScheduler.from_config(SCHEDULER_CONFIGS["3k_steps_clipping_rescaling"]))
+    pipe.save_pretrained(str(tmp_path / "p"))
+    p2 = ConditionalDDIMPipeline.from_pretrained(str(tmp_path / "p"))
+    assert p2.scheduler.config.num_train_timesteps == 3000 and p2.unet.config.sample_size == 32
+    for (k, a), (_, b) in zip(m.state_dict().items(), p2.unet.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_shard_ranges():
+    from phendiff_b200.sharding import shard_range, shard_sizes
+
+    for total in (0, 1, 7, 256, 257):
+        for world in (1, 2, 3, 8):
+            rs = [shard_range(total, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == total
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            assert max(shard_sizes(total, world)) - min(shard_sizes(total, world)) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)

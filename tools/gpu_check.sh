@@ -17,5 +17,5 @@ run tests/test_gpu_kernels.py -m gpu -k "groupnorm or scheduler or add_noise"
 run tests/test_gpu_kernels.py -m gpu -k "attention"
 run tests/test_gpu_kernels.py -m gpu -k "tcgen05"
 run tests/test_gpu_unet.py -m gpu -k "fp32 or api or fused or pipeline or golden"
-run tests/test_gpu_unet.py -m gpu -k "bf16"
-grep -E "^(=== |exit=|FAILED|ERROR|[0-9]+ (passed|failed))|passed|failed|\[ddib|\[bf16" "$log" | tail -80
+run tests/test_gpu_unet.py -m gpu -k "half"
+grep -E "^(=== |exit=|FAILED|ERROR|[0-9]+ (passed|failed))|passed|failed|\[ddib|\[bf16|\[fp16" "$log" | tail -80
