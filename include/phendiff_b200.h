@@ -135,6 +135,18 @@ int pd_ddib_transfer(pd_unet_t* h, float* x, const int64_t* src_labels, const in
 
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int pd_unet_launch_count(pd_unet_t* h, int64_t* n);
+/* current plan: images per pass, layers on the tcgen05 kernel / on the SIMT kernel, recorded ops per forward */
+int pd_unet_plan_info(pd_unet_t* h, int32_t* microbatch, int32_t* tc_layers, int32_t* simt_layers, int32_t* ops);
+
+/* ---- measurement support (bench.py roofline): sampled per-op device timing with CUDA events on the launch stream.
+ *      Every `every_n`-th forward is bracketed op by op (at most max_samples forwards); _end synchronises those events
+ *      (call it after the timed region) and accumulates per kernel class:
+ *      0 conv_tcgen05, 1 conv_simt, 2 groupnorm, 3 attention, 4 embedding, 5 conv_in, 6 conv_out(+DDIM), 7 upsample. */
+enum { PD_CLS_CONV_TC = 0, PD_CLS_CONV_SIMT, PD_CLS_GN, PD_CLS_ATTN, PD_CLS_EMBED, PD_CLS_CONV_IN, PD_CLS_CONV_OUT,
+       PD_CLS_UPSAMPLE, PD_CLS_COUNT };
+int pd_unet_profile_begin(pd_unet_t* h, int32_t every_n, int32_t max_samples);
+int pd_unet_profile_end(pd_unet_t* h, int32_t* samples);
+int pd_unet_profile_query(pd_unet_t* h, int32_t cls, double* ms, int64_t* launches, double* flops);
 
 /* ---- unit-test entry points for individual kernels (used by tests/, not by the product path) ---- */
 /* generic NHWC convolution through the SIMT fp32 kernel or the tcgen05 kernel; dtype: 0 fp32, 1 bf16, 2 fp16.

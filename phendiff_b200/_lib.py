@@ -57,6 +57,10 @@ _SIGNATURES = {
     "pd_denorm_nhwc": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "pd_ddib_transfer": (C.c_int, [_P, _P, _P, _P, C.POINTER(StepCoeffs), C.c_int32, C.c_int32, _P]),
     "pd_unet_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "pd_unet_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pd_unet_profile_begin": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "pd_unet_profile_end": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "pd_unet_profile_query": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "pd_test_conv": (C.c_int, [C.c_int32] * 11 + [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_float, _P, _P]),
     "pd_test_groupnorm": (C.c_int, [C.c_int32] * 6 + [C.c_float, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "pd_test_attention": (C.c_int, [C.c_int32] * 6 + [_P, _P, _P]),

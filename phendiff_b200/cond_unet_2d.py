@@ -344,6 +344,28 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
         _lib.check(_lib.lib().pd_unet_launch_count(self._handle, C.byref(n)))
         return n.value
 
+    KERNEL_CLASSES = ("conv_tcgen05", "conv_simt", "groupnorm", "attention", "embedding", "conv_in", "conv_out_ddim", "upsample")
+
+    def plan_info(self) -> dict:
+        mb, tc, simt, ops = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().pd_unet_plan_info(self._handle, C.byref(mb), C.byref(tc), C.byref(simt), C.byref(ops)))
+        return {"microbatch": mb.value, "tcgen05_layers": tc.value, "simt_layers": simt.value, "ops_per_forward": ops.value,
+                "workspace_bytes": int(self._workspace.numel()) if self._workspace is not None else 0}
+
+    def profile_begin(self, every_n: int = 50, max_samples: int = 64):
+        _lib.check(_lib.lib().pd_unet_profile_begin(self._handle, every_n, max_samples))
+
+    def profile_end(self) -> dict:
+        """Per kernel class: summed device ms, launches and algorithmic FLOPs over the sampled forwards."""
+        n = C.c_int32()
+        _lib.check(_lib.lib().pd_unet_profile_end(self._handle, C.byref(n)))
+        out = {"samples": n.value}
+        for i, name in enumerate(self.KERNEL_CLASSES):
+            ms, la, fl = C.c_double(), C.c_int64(), C.c_double()
+            _lib.check(_lib.lib().pd_unet_profile_query(self._handle, i, C.byref(ms), C.byref(la), C.byref(fl)))
+            out[name] = {"ms": ms.value, "launches": la.value, "flops": fl.value}
+        return out
+
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         # A.7: diffusers 0.17-0.19 wrote attention weights under deprecated names; accept both spellings
         ren = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}

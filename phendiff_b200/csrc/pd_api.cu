@@ -113,7 +113,9 @@ struct Ctx {   // per-call inputs of the recorded program
     const pd_step_coeffs_t* step = nullptr;
 };
 
-typedef std::function<int(const Ctx&, cudaStream_t)> Op;
+typedef std::function<int(const Ctx&, cudaStream_t)> OpFn;
+enum { CLS_CONV_TC = 0, CLS_CONV_SIMT, CLS_GN, CLS_ATTN, CLS_EMBED, CLS_CONV_IN, CLS_CONV_OUT, CLS_UPSAMPLE, CLS_COUNT };
+struct Op { OpFn fn; int cls; double flops; int nlaunch; };
 
 }  // namespace pd
 
@@ -156,6 +158,13 @@ struct pd_unet {
     size_t stats_off = 0, stats_bytes = 0, emb_off = 0, temb_off = 0;
     int64_t launches = 0;
     int tc_layers = 0, simt_layers = 0;
+    // sampled per-op device timing (bench.py's roofline): every `prof_every`-th program run is bracketed with events
+    int prof_every = 0, prof_max = 0;
+    int64_t prof_runs = 0;
+    std::vector<std::vector<cudaEvent_t>> prof_events;   // one chain of (ops + 1) events per sampled run
+    double prof_ms[CLS_COUNT] = {0};
+    double prof_flops[CLS_COUNT] = {0};
+    int64_t prof_launches[CLS_COUNT] = {0};
 };
 
 namespace pd {
@@ -373,10 +382,9 @@ struct Rec {
     }
     void* ptr(const Tensor* t) const { return (void*)(m->arena.base + t->off); }
     void* raw(size_t off) const { return (void*)(m->arena.base + off); }
-    void push(Op op, int nlaunch) {
+    void push(OpFn op, int nlaunch, int cls, double flops = 0.0) {
         if (dry) return;
-        pd_unet* mm = m;
-        m->ops.push_back([op, nlaunch, mm](const Ctx& c, cudaStream_t s) { mm->launches += nlaunch; return op(c, s); });
+        m->ops.push_back(Op{op, cls, flops, nlaunch});
     }
 
     // GroupNorm(+SiLU) of concat(a, b) -> new tensor
@@ -396,7 +404,7 @@ struct Rec {
                 int r = launch_gn_stats(dt, ga, s);
                 if (r) return r;
                 return launch_gn_apply(dt, precise, ga, s);
-            }, 2);
+            }, 2, CLS_GN);
         }
         return o;
     }
@@ -424,7 +432,8 @@ struct Rec {
                 int r = conv_tc_plan_create(d, &pl);
                 if (r) { rc = r; return o; }
                 m->tc_plans.push_back(pl);
-                push([pl](const Ctx&, cudaStream_t s) { return conv_tc_launch(pl, s); }, 1);
+                push([pl](const Ctx&, cudaStream_t s) { return conv_tc_launch(pl, s); }, 1, CLS_CONV_TC,
+                     2.0 * mb * Ho * Wo * (double)L.cout * (double)(L.k * L.k * x->C + d.Csc1 + d.Csc2));
             }
             return o;
         }
@@ -439,7 +448,8 @@ struct Rec {
             if (!dry) {
                 ca.x1 = ptr(s1); ca.x2 = s2 ? ptr(s2) : nullptr; ca.out = ptr(tmp);
                 const int dt = m->dt;
-                push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1);
+                push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1, CLS_CONV_SIMT,
+                     2.0 * ca.N * ca.Ho * ca.Wo * (double)ca.Cout * (double)(ca.ksize * ca.ksize * (ca.C1 + ca.C2)));
             }
         }
         ConvArgs ca{};
@@ -450,7 +460,8 @@ struct Rec {
             ca.x1 = ptr(x); ca.x2 = nullptr; ca.out = ptr(o);
             ca.residual = tmp ? ptr(tmp) : (residual ? ptr(residual) : nullptr);
             const int dt = m->dt;
-            push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1);
+            push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1, CLS_CONV_SIMT,
+                     2.0 * ca.N * ca.Ho * ca.Wo * (double)ca.Cout * (double)(ca.ksize * ca.ksize * (ca.C1 + ca.C2)));
         }
         if (tmp) release(tmp);
         return o;
@@ -493,8 +504,8 @@ struct Rec {
                 const int N = mb;
                 const int dt = m->dt;
                 const bool precise = !m->half;
-                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, op, s); }, 1);
-                else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(dt, precise, qp, N, S, C, d, op, s); }, 1);
+                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C);
+                else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(dt, precise, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C);
             }
         }
         release(qkv);
@@ -530,7 +541,7 @@ struct Rec {
                 int r = launch_embed(e, s);
                 if (r) return r;
                 return launch_temb_proj(e.emb_act, wcat, bcat, MB, D, J, temb, s);
-            }, 2);
+            }, 2, CLS_EMBED);
         }
         // conv_in (cond_unet_2d.py:313)
         Tensor* x = alloc(C0, H, W);
@@ -538,7 +549,8 @@ struct Rec {
             void* o = ptr(x);
             const float* w = M->w_in; const float* b = M->conv_in.b->dev;
             const int N = mb, Cin = c.in_channels, dt = M->dt;
-            push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1);
+            push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1, CLS_CONV_IN,
+                 2.0 * N * H * W * 9.0 * Cin * C0);
         }
         std::vector<Tensor*> skips;
         retain(x); skips.push_back(x);
@@ -574,7 +586,7 @@ struct Rec {
                 if (!dry) {
                     const void* ip = ptr(x); void* op = ptr(big);
                     const int N = mb, h = x->H, w = x->W, C = x->C, dt = M->dt;
-                    push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(dt, ip, N, h, w, C, op, s); }, 1);
+                    push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(dt, ip, N, h, w, C, op, s); }, 1, CLS_UPSAMPLE);
                 }
                 release(x);
                 Tensor* y = conv(u.up, big, u.up.w_simt, u.up.w_tc, u.up.b->dev, nullptr, 0, nullptr, 1.f);
@@ -594,7 +606,7 @@ struct Rec {
                 ConvOutArgs a = oa;
                 a.model_out = cx.model_out; a.x = cx.x_update; a.step = cx.step;
                 return launch_conv_out(dt, a, s);
-            }, 1);
+            }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels);
         }
         release(xn);
         return rc;
@@ -615,14 +627,30 @@ static void clear_plan(pd_unet* m) {
     m->tc_plans.clear();
     m->ops.clear();
     m->tensors.clear();
+    for (auto& chain : m->prof_events) for (auto& e : chain) cudaEventDestroy(e);
+    m->prof_events.clear();
+    m->prof_every = 0;
     m->bound = false;
     m->tc_layers = m->simt_layers = 0;
 }
 
 static int run_program(pd_unet* m, const Ctx& c, cudaStream_t s) {
-    for (auto& op : m->ops) {
-        int r = op(c, s);
+    std::vector<cudaEvent_t>* ev = nullptr;
+    if (m->prof_every > 0) {
+        if (m->prof_runs % m->prof_every == 0 && (int)m->prof_events.size() < m->prof_max) {
+            m->prof_events.emplace_back(m->ops.size() + 1);
+            ev = &m->prof_events.back();
+            for (auto& e : *ev) PD_CHECK_CUDA(cudaEventCreate(&e));
+            PD_CHECK_CUDA(cudaEventRecord((*ev)[0], s));
+        }
+        m->prof_runs++;
+    }
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+        Op& op = m->ops[i];
+        m->launches += op.nlaunch;
+        int r = op.fn(c, s);
         if (r) return r;
+        if (ev) PD_CHECK_CUDA(cudaEventRecord((*ev)[i + 1], s));
     }
     return 0;
 }
@@ -857,6 +885,52 @@ int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const in
             if (rc) return rc;
         }
     }
+    return 0;
+}
+
+int pd_unet_profile_begin(pd_unet_t* m, int32_t every_n, int32_t max_samples) {
+    PD_REQUIRE(m && every_n > 0 && max_samples > 0, "bad argument");
+    PD_REQUIRE(m->prof_events.empty(), "profile already running: call pd_unet_profile_end first");
+    m->prof_every = every_n; m->prof_max = max_samples; m->prof_runs = 0;
+    for (int i = 0; i < CLS_COUNT; ++i) { m->prof_ms[i] = 0; m->prof_flops[i] = 0; m->prof_launches[i] = 0; }
+    return 0;
+}
+
+int pd_unet_profile_end(pd_unet_t* m, int32_t* samples) {
+    PD_REQUIRE(m, "null handle");
+    m->prof_every = 0;
+    int rc = 0;
+    for (auto& chain : m->prof_events) {
+        if (chain.size() != m->ops.size() + 1) continue;
+        cudaError_t e = cudaEventSynchronize(chain.back());
+        if (e != cudaSuccess) { set_error(std::string("profile: ") + cudaGetErrorString(e)); rc = 2; break; }
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, chain[i], chain[i + 1]);
+            const Op& op = m->ops[i];
+            m->prof_ms[op.cls] += ms; m->prof_flops[op.cls] += op.flops; m->prof_launches[op.cls] += op.nlaunch;
+        }
+    }
+    if (samples) *samples = (int32_t)m->prof_events.size();
+    for (auto& chain : m->prof_events) for (auto& e : chain) cudaEventDestroy(e);
+    m->prof_events.clear();
+    return rc;
+}
+
+int pd_unet_profile_query(pd_unet_t* m, int32_t cls, double* ms, int64_t* launches, double* flops) {
+    PD_REQUIRE(m && cls >= 0 && cls < CLS_COUNT, "bad class id");
+    if (ms) *ms = m->prof_ms[cls];
+    if (launches) *launches = m->prof_launches[cls];
+    if (flops) *flops = m->prof_flops[cls];
+    return 0;
+}
+
+int pd_unet_plan_info(pd_unet_t* m, int32_t* microbatch, int32_t* tc_layers, int32_t* simt_layers, int32_t* ops) {
+    PD_REQUIRE(m && m->bound, "no bound plan");
+    if (microbatch) *microbatch = m->mb;
+    if (tc_layers) *tc_layers = m->tc_layers;
+    if (simt_layers) *simt_layers = m->simt_layers;
+    if (ops) *ops = (int32_t)m->ops.size();
     return 0;
 }
 
