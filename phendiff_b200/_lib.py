@@ -37,6 +37,15 @@ class StepCoeffs(C.Structure):
     ]
 
 
+class TestConvArgs(C.Structure):
+    """pd_test_conv_args_t (kernel-level test entry point)."""
+    _fields_ = ([(n, C.c_int32) for n in ("impl", "dtype", "n", "h", "w", "c1", "c2", "cout", "ksize", "stride", "pad", "upsample",
+                                            "mode", "stats_cw", "csc1", "csc2")]
+                + [(n, C.c_void_p) for n in ("x1", "x2", "weight", "bias", "addvec", "addvec_row", "residual", "sc1", "sc2", "sc_w")]
+                + [("out_scale", C.c_float)]
+                + [(n, C.c_void_p) for n in ("out", "stats_out", "model_out", "x_t", "step")])
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "pd_last_error": (C.c_char_p, []),
@@ -62,6 +71,7 @@ _SIGNATURES = {
     "pd_unet_profile_end": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "pd_unet_profile_query": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "pd_test_conv": (C.c_int, [C.c_int32] * 11 + [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_float, _P, _P]),
+    "pd_test_conv_ex": (C.c_int, [C.POINTER(TestConvArgs), _P]),
     "pd_test_groupnorm": (C.c_int, [C.c_int32] * 6 + [C.c_float, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "pd_test_attention": (C.c_int, [C.c_int32] * 6 + [_P, _P, _P]),
 }

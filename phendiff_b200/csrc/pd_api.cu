@@ -5,6 +5,7 @@
 // checkpoint keys (Appendix A.7).  The executor records the whole forward once per (micro-batch, H, W) as a flat list of
 // kernel launches over a statically planned workspace (no allocation, no host sync on the step path).
 #include "pd_kernels.h"
+#include "pd_tc_common.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -60,7 +61,7 @@ struct AttnL {
     void* wo_tc = nullptr;       // (C, C)
 };
 struct DownB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_down = false; ConvL down; };
-struct UpB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_up = false; ConvL up; };
+struct UpB { std::vector<ResL> res; std::vector<AttnL> attn; bool has_attn = false, has_up = false; ConvL up; void* w_up_tc = nullptr; };
 
 struct Arena {
     bool dry = true;
@@ -100,6 +101,7 @@ struct Arena {
 struct Tensor {   // NHWC activation of the current micro-batch
     size_t off = 0, bytes = 0;
     int C = 0, H = 0, W = 0, refs = 0;
+    size_t stats_off = (size_t)-1;   // chunk statistics slot (bytes into the statistics region), or -1: none
 };
 
 struct Ctx {   // per-call inputs of the recorded program
@@ -144,6 +146,10 @@ struct pd_unet {
     float* bcat = nullptr;      // (J)  time_emb_proj.bias + conv1.bias
     float* w_in = nullptr;      // (9*Cin, C0)
     float* w_out = nullptr;     // (9, C0, 4)
+    void* w_in_tc = nullptr;    // (C0, 64) 16-bit: conv_in as a K = 64 GEMM over im2col rows (k = tap*Cin + ci)
+    void* w_out_tc = nullptr;   // (16, 9*C0) 16-bit: conv_out rows zero-padded to 16
+    int stats_cw = 4;           // channels per GroupNorm statistics chunk (divides every group width)
+    size_t stats_needed = 0, rowidx_off = 0;
     bool finalized = false;
     std::vector<void*> owned;   // derived device buffers
     // plan
@@ -154,7 +160,6 @@ struct pd_unet {
     std::vector<ConvTcPlan*> tc_plans;
     std::vector<std::unique_ptr<Tensor>> tensors;
     bool bound = false;
-    int n_gn = 0;
     size_t stats_off = 0, stats_bytes = 0, emb_off = 0, temb_off = 0;
     int64_t launches = 0;
     int tc_layers = 0, simt_layers = 0;
@@ -359,13 +364,27 @@ static int finalize_attn(pd_unet* m, AttnL& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------------------
 // recording the forward program
 // ---------------------------------------------------------------------------------------------------------------------
+struct ConvOpt {
+    const float* w_simt = nullptr;   // (k*k*Cin, Cout) fp32
+    const void* w_tc = nullptr;      // (Cout, Ktot) 16-bit, or null: no tensor-core weights for this layer
+    const float* bias = nullptr;     // bias of the main conv
+    const float* bias_fused = nullptr;   // main + shortcut bias (used when the shortcut rides in the same GEMM)
+    const float* addvec = nullptr;   // projected time-embedding table (rows, J) at this layer's column offset
+    int addvec_stride = 0;
+    Tensor* residual = nullptr;
+    float out_scale = 1.f;
+    Tensor *s1 = nullptr, *s2 = nullptr;   // fused 1x1 shortcut sources
+    const ConvL* scL = nullptr;
+    bool want_stats = true;          // the output feeds a GroupNorm
+};
+
 struct Rec {
     pd_unet* m;
     bool dry;
     int mb;
     size_t esz;   // bytes per activation element
-    int gn_idx = 0;
     int rc = 0;
+    size_t stats_bump = 0;
 
     Tensor* alloc(int C, int H, int W) {
         auto t = std::make_unique<Tensor>();
@@ -386,67 +405,85 @@ struct Rec {
         if (dry) return;
         m->ops.push_back(Op{op, cls, flops, nlaunch});
     }
+    // chunk-statistics slot of a tensor: (mb, C/cw, 2) fp32 inside the per-forward zeroed statistics region
+    void stats_alloc(Tensor* t) {
+        t->stats_off = stats_bump;
+        stats_bump += (((size_t)mb * (t->C / m->stats_cw) * 2 * sizeof(float)) + 255) & ~(size_t)255;
+    }
+    float* stats_ptr(const Tensor* t) const { return (float*)((uint8_t*)raw(m->stats_off) + t->stats_off); }
+    // standalone producer of chunk statistics (SIMT-produced tensors, shapes whose epilogue cannot emit them)
+    void stats_kernel(Tensor* t) {
+        stats_alloc(t);
+        if (dry) return;
+        const void* x = ptr(t); float* st = stats_ptr(t);
+        const int N = mb, HW = t->H * t->W, C = t->C, cw = m->stats_cw, dt = m->dt;
+        push([=](const Ctx&, cudaStream_t s) { return launch_gn_chunk_stats(dt, x, N, HW, C, cw, st, s); }, 1, CLS_GN);
+    }
 
-    // GroupNorm(+SiLU) of concat(a, b) -> new tensor
+    // GroupNorm(+SiLU) of concat(a, b) -> new tensor; group statistics come from the sources' chunk statistics
     Tensor* gn(const GNL& g, Tensor* a, Tensor* b, bool do_silu) {
         const int C = a->C + (b ? b->C : 0);
         Tensor* o = alloc(C, a->H, a->W);
+        if (a->stats_off == (size_t)-1 || (b && b->stats_off == (size_t)-1)) { rc = 1; set_error("internal: GroupNorm source without statistics"); return o; }
         GNArgs ga{};
         ga.C1 = a->C; ga.C2 = b ? b->C : 0; ga.N = mb; ga.HW = a->H * a->W; ga.groups = m->cfg.norm_num_groups;
-        ga.eps = m->cfg.norm_eps; ga.gamma = g.g->dev; ga.beta = g.b->dev; ga.silu = do_silu;
-        const int idx = gn_idx++;
+        ga.eps = m->cfg.norm_eps; ga.gamma = g.g->dev; ga.beta = g.b->dev; ga.silu = do_silu; ga.stats_cw = m->stats_cw;
         if (!dry) {
             ga.x1 = ptr(a); ga.x2 = b ? ptr(b) : nullptr; ga.out = ptr(o);
-            ga.stats = (float*)raw(m->stats_off) + (size_t)idx * mb * ga.groups * 2;
+            ga.stats1 = stats_ptr(a); ga.stats2 = b ? stats_ptr(b) : nullptr;
             const int dt = m->dt;
             const bool precise = !m->half;
-            push([ga, dt, precise](const Ctx&, cudaStream_t s) {
-                int r = launch_gn_stats(dt, ga, s);
-                if (r) return r;
-                return launch_gn_apply(dt, precise, ga, s);
-            }, 2, CLS_GN);
+            push([ga, dt, precise](const Ctx&, cudaStream_t s) { return launch_gn_apply(dt, precise, ga, s); }, 1, CLS_GN);
         }
         return o;
     }
 
-    // generic conv: main input `x` (single tensor), optional fused 1x1 shortcut over (s1|s2) -> new tensor
-    // `bias` belongs to the main conv; `bias_fused` (main + shortcut bias) is used when the shortcut rides in the same GEMM
-    Tensor* conv(const ConvL& L, Tensor* x, const float* w_simt, const void* w_tc, const float* bias, const float* addvec,
-                 int addvec_stride, Tensor* residual, float out_scale, Tensor* s1 = nullptr, Tensor* s2 = nullptr,
-                 const ConvL* scL = nullptr, const float* bias_fused = nullptr) {
-        const int Ho = (L.stride == 2) ? x->H / 2 : x->H, Wo = (L.stride == 2) ? x->W / 2 : x->W;
+    // generic conv of `x` (+ optional fused 1x1 shortcut over (s1|s2)) -> new tensor
+    Tensor* conv(const ConvL& L, Tensor* x, const ConvOpt& o_, bool upsample = false) {
+        const ConvOpt& c = o_;
+        const int Ho = upsample ? 2 * x->H : ((L.stride == 2) ? x->H / 2 : x->H);
+        const int Wo = upsample ? 2 * x->W : ((L.stride == 2) ? x->W / 2 : x->W);
         Tensor* o = alloc(L.cout, Ho, Wo);
         ConvTcDesc d{};
         d.dt = m->dt; d.C = x->C; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = L.k; d.stride = L.stride; d.pad = L.pad;
-        d.Ho = Ho; d.Wo = Wo; d.Cout = L.cout;
-        d.Csc1 = s1 ? s1->C : 0; d.Csc2 = s2 ? s2->C : 0;
-        const bool want_tc = m->half && m->cfg.conv_impl == 0 && w_tc != nullptr;
-        const bool use_tc = want_tc && conv_tc_supported(d, nullptr);
+        d.Ho = Ho; d.Wo = Wo; d.Cout = L.cout; d.upsample = upsample ? 1 : 0; d.mode = TC_MODE_STD;
+        d.Csc1 = c.s1 ? c.s1->C : 0; d.Csc2 = c.s2 ? c.s2->C : 0;
+        d.stats_cw = m->stats_cw;
+        const bool want_tc = m->half && m->cfg.conv_impl == 0 && c.w_tc != nullptr;
+        bool use_tc = want_tc && (conv_halo_supported(d, nullptr) || conv_tc_supported(d, nullptr));
+        if (upsample && !use_tc) { rc = 1; set_error("internal: fused upsample conv requested for an unsupported shape"); return o; }
         if (use_tc) {
+            const bool fused_stats = c.want_stats && m->stats_cw >= 2 && (conv_halo_supported(d, nullptr) || conv_tc_can_emit_stats(d));
+            if (fused_stats) stats_alloc(o);
             m->tc_layers += dry ? 0 : 1;
             if (!dry) {
-                d.x = ptr(x); d.sc1 = s1 ? ptr(s1) : nullptr; d.sc2 = s2 ? ptr(s2) : nullptr;
-                d.wmat = w_tc; d.bias = s1 ? bias_fused : bias; d.addvec = addvec; d.addvec_stride = addvec_stride;
-                d.residual = residual ? ptr(residual) : nullptr; d.out_scale = out_scale; d.out = ptr(o);
+                d.x = ptr(x); d.sc1 = c.s1 ? ptr(c.s1) : nullptr; d.sc2 = c.s2 ? ptr(c.s2) : nullptr;
+                d.wmat = c.w_tc; d.bias = c.s1 ? c.bias_fused : c.bias; d.addvec = c.addvec; d.addvec_stride = c.addvec_stride;
+                d.addvec_row = c.addvec ? (const int32_t*)raw(m->rowidx_off) : nullptr;
+                d.residual = c.residual ? ptr(c.residual) : nullptr; d.out_scale = c.out_scale; d.out = ptr(o);
+                d.stats_out = fused_stats ? stats_ptr(o) : nullptr;
                 ConvTcPlan* pl = nullptr;
                 int r = conv_tc_plan_create(d, &pl);
                 if (r) { rc = r; return o; }
                 m->tc_plans.push_back(pl);
+                const double ktot = upsample ? 4.0 * x->C : (double)(L.k * L.k * x->C + d.Csc1 + d.Csc2);
                 push([pl](const Ctx&, cudaStream_t s) { return conv_tc_launch(pl, s); }, 1, CLS_CONV_TC,
-                     2.0 * mb * Ho * Wo * (double)L.cout * (double)(L.k * L.k * x->C + d.Csc1 + d.Csc2));
+                     2.0 * mb * Ho * Wo * (double)L.cout * ktot);
             }
+            if (c.want_stats && !fused_stats) stats_kernel(o);
             return o;
         }
         // SIMT path; a fused shortcut request is split into (1x1 conv -> tmp) + (conv with residual = tmp)
         m->simt_layers += dry ? 0 : 1;
+        const int32_t* rowidx = (!dry && c.addvec) ? (const int32_t*)raw(m->rowidx_off) : nullptr;
         Tensor* tmp = nullptr;
-        if (s1) {
+        if (c.s1) {
             tmp = alloc(L.cout, Ho, Wo);
             ConvArgs ca{};
-            ca.C1 = s1->C; ca.C2 = s2 ? s2->C : 0; ca.N = mb; ca.H = Ho; ca.W = Wo; ca.Cout = L.cout; ca.ksize = 1; ca.stride = 1;
-            ca.pad = 0; ca.Ho = Ho; ca.Wo = Wo; ca.w = scL->w_simt; ca.bias = scL->b->dev; ca.out_scale = 1.f;
+            ca.C1 = c.s1->C; ca.C2 = c.s2 ? c.s2->C : 0; ca.N = mb; ca.H = Ho; ca.W = Wo; ca.Cout = L.cout; ca.ksize = 1; ca.stride = 1;
+            ca.pad = 0; ca.Ho = Ho; ca.Wo = Wo; ca.w = c.scL->w_simt; ca.bias = c.scL->b->dev; ca.out_scale = 1.f;
             if (!dry) {
-                ca.x1 = ptr(s1); ca.x2 = s2 ? ptr(s2) : nullptr; ca.out = ptr(tmp);
+                ca.x1 = ptr(c.s1); ca.x2 = c.s2 ? ptr(c.s2) : nullptr; ca.out = ptr(tmp);
                 const int dt = m->dt;
                 push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1, CLS_CONV_SIMT,
                      2.0 * ca.N * ca.Ho * ca.Wo * (double)ca.Cout * (double)(ca.ksize * ca.ksize * (ca.C1 + ca.C2)));
@@ -454,16 +491,17 @@ struct Rec {
         }
         ConvArgs ca{};
         ca.C1 = x->C; ca.C2 = 0; ca.N = mb; ca.H = x->H; ca.W = x->W; ca.Cout = L.cout; ca.ksize = L.k; ca.stride = L.stride;
-        ca.pad = L.pad; ca.Ho = Ho; ca.Wo = Wo; ca.w = w_simt; ca.bias = bias; ca.addvec = addvec; ca.addvec_stride = addvec_stride;
-        ca.out_scale = out_scale;
+        ca.pad = L.pad; ca.Ho = Ho; ca.Wo = Wo; ca.w = c.w_simt; ca.bias = c.bias; ca.addvec = c.addvec; ca.addvec_stride = c.addvec_stride;
+        ca.addvec_row = rowidx; ca.out_scale = c.out_scale;
         if (!dry) {
             ca.x1 = ptr(x); ca.x2 = nullptr; ca.out = ptr(o);
-            ca.residual = tmp ? ptr(tmp) : (residual ? ptr(residual) : nullptr);
+            ca.residual = tmp ? ptr(tmp) : (c.residual ? ptr(c.residual) : nullptr);
             const int dt = m->dt;
             push([ca, dt](const Ctx&, cudaStream_t s) { return launch_conv_simt(dt, ca, s); }, 1, CLS_CONV_SIMT,
                      2.0 * ca.N * ca.Ho * ca.Wo * (double)ca.Cout * (double)(ca.ksize * ca.ksize * (ca.C1 + ca.C2)));
         }
         if (tmp) release(tmp);
+        if (c.want_stats) stats_kernel(o);
         return o;
     }
 
@@ -471,19 +509,22 @@ struct Rec {
     Tensor* resnet(ResL& R, Tensor* a, Tensor* b) {
         Tensor* hn = gn(R.n1, a, b, true);
         // conv1 (+ time embedding row; conv1.bias is folded into that row at finalize)
-        const float* temb = dry ? nullptr : (const float*)raw(m->temb_off) + R.temb_off;
-        Tensor* h1 = conv(R.c1, hn, R.c1.w_simt, R.c1.w_tc, nullptr, temb, m->J, nullptr, 1.f);
+        ConvOpt o1;
+        o1.w_simt = R.c1.w_simt; o1.w_tc = R.c1.w_tc;
+        o1.addvec = dry ? nullptr : (const float*)raw(m->temb_off) + R.temb_off; o1.addvec_stride = m->J;
+        Tensor* h1 = conv(R.c1, hn, o1);
         release(hn);
         Tensor* h1n = gn(R.n2, h1, nullptr, true);
         release(h1);
-        Tensor* o;
-        const float inv = 1.0f / R.scale;
+        ConvOpt o2;
+        o2.w_simt = R.c2.w_simt; o2.bias = R.c2.b->dev; o2.out_scale = 1.0f / R.scale;
         if (R.has_sc) {
             // out = (conv2(h) + conv_shortcut(x)) / scale: one K-concatenated GEMM on the tensor-core path
-            o = conv(R.c2, h1n, R.c2.w_simt, R.w2sc_tc, R.c2.b->dev, nullptr, 0, nullptr, inv, a, b, &R.sc, R.b2sc);
+            o2.w_tc = R.w2sc_tc; o2.s1 = a; o2.s2 = b; o2.scL = &R.sc; o2.bias_fused = R.b2sc;
         } else {
-            o = conv(R.c2, h1n, R.c2.w_simt, R.c2.w_tc, R.c2.b->dev, nullptr, 0, a, inv);
+            o2.w_tc = R.c2.w_tc; o2.residual = a;
         }
+        Tensor* o = conv(R.c2, h1n, o2);
         release(h1n);
         return o;
     }
@@ -492,7 +533,9 @@ struct Rec {
     Tensor* attention(AttnL& A, Tensor* x) {
         Tensor* xn = gn(A.gn, x, nullptr, false);
         ConvL lq; lq.cin = A.C; lq.cout = 3 * A.C; lq.k = 1; lq.stride = 1; lq.pad = 0;
-        Tensor* qkv = conv(lq, xn, A.wqkv_simt, A.wqkv_tc, A.bqkv, nullptr, 0, nullptr, 1.f);
+        ConvOpt oq;
+        oq.w_simt = A.wqkv_simt; oq.w_tc = A.wqkv_tc; oq.bias = A.bqkv; oq.want_stats = false;
+        Tensor* qkv = conv(lq, xn, oq);
         release(xn);
         Tensor* ao = alloc(A.C, x->H, x->W);
         {
@@ -510,7 +553,9 @@ struct Rec {
         }
         release(qkv);
         ConvL lo; lo.cin = A.C; lo.cout = A.C; lo.k = 1; lo.stride = 1; lo.pad = 0;
-        Tensor* o = conv(lo, ao, A.wo_simt, A.wo_tc, A.ob->dev, nullptr, 0, x, 1.0f / A.rescale);
+        ConvOpt oo;
+        oo.w_simt = A.wo_simt; oo.w_tc = A.wo_tc; oo.bias = A.ob->dev; oo.residual = x; oo.out_scale = 1.0f / A.rescale;
+        Tensor* o = conv(lo, ao, oo);
         release(ao);
         return o;
     }
@@ -519,11 +564,12 @@ struct Rec {
         pd_unet* M = m;
         const pd_unet_config_t& c = M->cfg;
         const int H = M->H, W = M->W, C0 = c.block_out_channels[0];
-        // fixed small buffers
-        M->stats_bytes = (size_t)M->n_gn * mb * c.norm_num_groups * 2 * sizeof(float);
+        const int rows_max = std::max(mb, c.num_class_embeds);
+        // fixed small buffers: statistics region (zeroed once per forward), embedding rows, projected table, row index
         M->stats_off = M->arena.alloc(std::max<size_t>(M->stats_bytes, 1024));
-        M->emb_off = M->arena.alloc((size_t)mb * M->D * sizeof(float));
-        M->temb_off = M->arena.alloc((size_t)mb * M->J * sizeof(float));
+        M->emb_off = M->arena.alloc((size_t)rows_max * M->D * sizeof(float));
+        M->temb_off = M->arena.alloc((size_t)rows_max * M->J * sizeof(float));
+        M->rowidx_off = M->arena.alloc((size_t)mb * sizeof(int32_t));
         if (!dry) {
             float* stats = (float*)raw(M->stats_off);
             const size_t sb = M->stats_bytes;
@@ -531,27 +577,55 @@ struct Rec {
             ea.w1 = M->te_w1->dev; ea.b1 = M->te_b1->dev; ea.w2 = M->te_w2->dev; ea.b2 = M->te_b2->dev;
             ea.class_table = M->cls ? M->cls->dev : nullptr; ea.B = mb; ea.C0 = C0; ea.D = M->D; ea.ncls = c.num_class_embeds;
             ea.flip = c.flip_sin_to_cos; ea.shift = c.freq_shift; ea.emb_act = (float*)raw(M->emb_off);
+            ea.row_idx = (int32_t*)raw(M->rowidx_off);
             float* temb = (float*)raw(M->temb_off);
             const float* wcat = M->wcat; const float* bcat = M->bcat;
-            const int D = M->D, J = M->J, MB = mb;
+            const int D = M->D, J = M->J;
             push([=](const Ctx& cx, cudaStream_t s) {
                 if (sb) { PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, sb, s)); }
                 EmbedArgs e = ea;
                 e.timesteps = cx.timesteps; e.t_scalar = cx.t_scalar; e.labels = cx.labels; e.class_emb = cx.class_emb;
+                // one scalar timestep + integer labels (the DDIB path): only ncls distinct embedding rows exist
+                e.dedupe = (!cx.timesteps && cx.labels && !cx.class_emb && e.class_table && e.ncls > 0 && e.ncls <= e.B) ? 1 : 0;
                 int r = launch_embed(e, s);
                 if (r) return r;
-                return launch_temb_proj(e.emb_act, wcat, bcat, MB, D, J, temb, s);
-            }, 2, CLS_EMBED);
+                return launch_temb_proj(e.emb_act, wcat, bcat, embed_rows(e), D, J, temb, s);
+            }, 3, CLS_EMBED);
         }
         // conv_in (cond_unet_2d.py:313)
-        Tensor* x = alloc(C0, H, W);
-        if (!dry) {
-            void* o = ptr(x);
-            const float* w = M->w_in; const float* b = M->conv_in.b->dev;
-            const int N = mb, Cin = c.in_channels, dt = M->dt;
-            push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1, CLS_CONV_IN,
-                 2.0 * N * H * W * 9.0 * Cin * C0);
+        Tensor* x = nullptr;
+        bool in_tc = false;
+        if (M->half && c.conv_impl == 0 && M->w_in_tc && c.in_channels <= 4) {
+            ConvTcDesc d{};
+            d.dt = M->dt; d.C = 64; d.N = mb; d.H = H; d.W = W; d.ksize = 1; d.stride = 1; d.pad = 0; d.Ho = H; d.Wo = W; d.Cout = C0;
+            d.stats_cw = M->stats_cw;
+            in_tc = conv_halo_supported(d, nullptr) || conv_tc_supported(d, nullptr);
         }
+        if (in_tc) {
+            // im2col (NCHW fp32 -> (N,H,W,64) 16-bit, k = tap*Cin + ci) + one 1x1 tcgen05 GEMM with K = 64
+            Tensor* col = alloc(64, H, W);
+            if (!dry) {
+                void* o = ptr(col);
+                const int N = mb, Cin = c.in_channels, dt = M->dt;
+                push([=](const Ctx& cx, cudaStream_t s) { return launch_im2col_in(dt, cx.x, N, Cin, H, W, o, s); }, 1, CLS_CONV_IN);
+            }
+            ConvL l1; l1.cin = 64; l1.cout = C0; l1.k = 1; l1.stride = 1; l1.pad = 0;
+            ConvOpt oi;
+            oi.w_tc = M->w_in_tc; oi.bias = M->conv_in.b->dev;
+            x = conv(l1, col, oi);
+            release(col);
+        } else {
+            x = alloc(C0, H, W);
+            if (!dry) {
+                void* o = ptr(x);
+                const float* w = M->w_in; const float* b = M->conv_in.b->dev;
+                const int N = mb, Cin = c.in_channels, dt = M->dt;
+                push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1, CLS_CONV_IN,
+                     2.0 * N * H * W * 9.0 * Cin * C0);
+            }
+            stats_kernel(x);
+        }
+        if (rc) return rc;
         std::vector<Tensor*> skips;
         retain(x); skips.push_back(x);
         // down (cond_unet_2d.py:316-325)
@@ -563,7 +637,9 @@ struct Rec {
                 retain(x); skips.push_back(x);
             }
             if (d.has_down) {
-                Tensor* y = conv(d.down, x, d.down.w_simt, d.down.w_tc, d.down.b->dev, nullptr, 0, nullptr, 1.f);
+                ConvOpt od;
+                od.w_simt = d.down.w_simt; od.w_tc = d.down.w_tc; od.bias = d.down.b->dev;
+                Tensor* y = conv(d.down, x, od);
                 release(x); x = y;
                 retain(x); skips.push_back(x);
             }
@@ -582,22 +658,53 @@ struct Rec {
                 if (u.has_attn) { Tensor* z = attention(u.attn[j], x); release(x); x = z; }
             }
             if (u.has_up) {
-                Tensor* big = alloc(x->C, x->H * 2, x->W * 2);
-                if (!dry) {
-                    const void* ip = ptr(x); void* op = ptr(big);
-                    const int N = mb, h = x->H, w = x->W, C = x->C, dt = M->dt;
-                    push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(dt, ip, N, h, w, C, op, s); }, 1, CLS_UPSAMPLE);
+                ConvOpt ou;
+                ou.w_simt = u.up.w_simt; ou.bias = u.up.b->dev;
+                ConvTcDesc d{};
+                d.dt = M->dt; d.C = x->C; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = 3; d.stride = 1; d.pad = 1;
+                d.Ho = 2 * x->H; d.Wo = 2 * x->W; d.Cout = u.up.cout; d.upsample = 1; d.stats_cw = M->stats_cw;
+                if (M->half && c.conv_impl == 0 && u.w_up_tc && conv_halo_supported(d, nullptr)) {
+                    // Upsample2D as four sub-pixel phase convs on the low-res tensor (no 4x intermediate)
+                    ou.w_tc = u.w_up_tc;
+                    Tensor* y = conv(u.up, x, ou, true);
+                    release(x); x = y;
+                } else {
+                    Tensor* big = alloc(x->C, x->H * 2, x->W * 2);
+                    if (!dry) {
+                        const void* ip = ptr(x); void* op = ptr(big);
+                        const int N = mb, h = x->H, w = x->W, C = x->C, dt = M->dt;
+                        push([=](const Ctx&, cudaStream_t s) { return launch_upsample2x(dt, ip, N, h, w, C, op, s); }, 1, CLS_UPSAMPLE);
+                    }
+                    release(x);
+                    ou.w_tc = u.up.w_tc;
+                    Tensor* y = conv(u.up, big, ou);
+                    release(big); x = y;
                 }
-                release(x);
-                Tensor* y = conv(u.up, big, u.up.w_simt, u.up.w_tc, u.up.b->dev, nullptr, 0, nullptr, 1.f);
-                release(big); x = y;
             }
             if (rc) return rc;
         }
         // out (cond_unet_2d.py:346-348) + optional fused scheduler update (A.5)
         Tensor* xn = gn(M->norm_out, x, nullptr, true);
         release(x);
-        if (!dry) {
+        bool out_tc = false;
+        ConvTcDesc od{};
+        od.dt = M->dt; od.C = C0; od.N = mb; od.H = H; od.W = W; od.ksize = 3; od.stride = 1; od.pad = 1; od.Ho = H; od.Wo = W;
+        od.Cout = c.out_channels; od.mode = TC_MODE_DDIM;
+        if (M->half && c.conv_impl == 0 && M->w_out_tc) out_tc = conv_halo_supported(od, nullptr);
+        if (out_tc) {
+            if (!dry) {
+                od.x = ptr(xn); od.wmat = M->w_out_tc; od.bias = M->conv_out.b->dev; od.out_scale = 1.f;
+                ConvTcPlan* pl = nullptr;
+                int r = conv_tc_plan_create(od, &pl);
+                if (r) return r;
+                M->tc_plans.push_back(pl);
+                M->tc_layers += 1;
+                push([pl](const Ctx& cx, cudaStream_t s) {
+                    ConvTcLaunch ex{cx.model_out, cx.x_update, cx.step};
+                    return conv_tc_launch(pl, s, &ex);
+                }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels);
+            }
+        } else if (!dry) {
             ConvOutArgs oa{};
             oa.act = ptr(xn); oa.w = M->w_out; oa.bias = M->conv_out.b->dev; oa.N = mb; oa.H = H; oa.W = W; oa.Cin = C0;
             oa.Cout = c.out_channels;
@@ -609,17 +716,23 @@ struct Rec {
             }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels);
         }
         release(xn);
+        M->stats_needed = stats_bump;
+        if (!dry && stats_bump > M->stats_bytes) { set_error("internal: statistics region too small"); return 1; }
         return rc;
     }
 };
 
-static int count_gn(pd_unet* m) {
-    int n = 1;  // conv_norm_out
-    auto res = [&](const ResL&) { n += 2; };
-    for (auto& d : m->down) { for (auto& r : d.res) res(r); n += (int)d.attn.size(); }
-    res(m->mid_r0); res(m->mid_r1); if (m->mid_has_attn) n += 1;
-    for (auto& u : m->up) { for (auto& r : u.res) res(r); n += (int)u.attn.size(); }
-    return n;
+// widest statistics chunk (4, 2 or 1 channels) that divides every GroupNorm group width of the graph, concats included
+static int pick_stats_cw(pd_unet* m) {
+    const int G = m->cfg.norm_num_groups;
+    int cw = 4;
+    auto see = [&](int C) { while (cw > 1 && ((C / G) % cw != 0)) cw >>= 1; };
+    auto res = [&](const ResL& r) { see(r.cin); see(r.cout); };
+    for (auto& d : m->down) { for (auto& r : d.res) res(r); for (auto& a : d.attn) see(a.C); }
+    res(m->mid_r0); res(m->mid_r1); if (m->mid_has_attn) see(m->mid_attn.C);
+    for (auto& u : m->up) { for (auto& r : u.res) res(r); for (auto& a : u.attn) see(a.C); }
+    see(m->norm_out.C);
+    return cw;
 }
 
 static void clear_plan(pd_unet* m) {
@@ -692,7 +805,7 @@ int pd_unet_create(const pd_unet_config_t* cfg, pd_unet_t** out) {
         return 1;
     }
     build_graph(m);
-    m->n_gn = count_gn(m);
+    m->stats_cw = pick_stats_cw(m);
     *out = m;
     return 0;
 }
@@ -754,6 +867,19 @@ int pd_unet_finalize(pd_unet_t* m, pd_stream_t stream) {
     if ((rc = launch_relayout_simt(m->conv_in.w->dev, m->conv_in.cout, m->conv_in.cin, 3, m->w_in, s))) return rc;
     if ((rc = dev_alloc(m, &m->w_out, (size_t)9 * m->conv_out.cin * 4))) return rc;
     if ((rc = launch_relayout_convout(m->conv_out.w->dev, m->conv_out.cout, m->conv_out.cin, m->w_out, s))) return rc;
+    m->w_in_tc = m->w_out_tc = nullptr;
+    if (m->half && m->conv_in.cin <= 4 && m->conv_in.cout % 64 == 0) {
+        // conv_in as one K = 64 GEMM: (C0, 64) rows, k = tap*Cin + ci, zero beyond 9*Cin
+        if ((rc = dev_alloc_bytes(m, &m->w_in_tc, (size_t)m->conv_in.cout * 64 * 2))) return rc;
+        PD_CHECK_CUDA(cudaMemsetAsync(m->w_in_tc, 0, (size_t)m->conv_in.cout * 64 * 2, s));
+        if ((rc = launch_relayout_tc(m->dt, m->conv_in.w->dev, m->conv_in.cout, m->conv_in.cin, 3, m->w_in_tc, 64, 0, s))) return rc;
+    }
+    if (m->half && m->conv_out.cout <= 16 && m->conv_out.cin % 64 == 0) {
+        const int ktot = 9 * m->conv_out.cin;
+        if ((rc = dev_alloc_bytes(m, &m->w_out_tc, (size_t)16 * ktot * 2))) return rc;
+        PD_CHECK_CUDA(cudaMemsetAsync(m->w_out_tc, 0, (size_t)16 * ktot * 2, s));
+        if ((rc = launch_relayout_tc(m->dt, m->conv_out.w->dev, m->conv_out.cout, m->conv_out.cin, 3, m->w_out_tc, ktot, 0, s))) return rc;
+    }
     for (auto& d : m->down) {
         for (auto& r : d.res) if ((rc = finalize_res(m, r, s))) return rc;
         for (auto& a : d.attn) if ((rc = finalize_attn(m, a, s))) return rc;
@@ -766,6 +892,11 @@ int pd_unet_finalize(pd_unet_t* m, pd_stream_t stream) {
         for (auto& r : u.res) if ((rc = finalize_res(m, r, s))) return rc;
         for (auto& a : u.attn) if ((rc = finalize_attn(m, a, s))) return rc;
         if (u.has_up && (rc = finalize_conv(m, u.up, s, m->half))) return rc;
+        u.w_up_tc = nullptr;
+        if (u.has_up && m->half && u.up.cin % 64 == 0 && u.up.cout % 64 == 0) {
+            if ((rc = dev_alloc_bytes(m, &u.w_up_tc, (size_t)16 * u.up.cout * u.up.cin * 2))) return rc;
+            if ((rc = launch_relayout_upsample(m->dt, u.up.w->dev, u.up.cout, u.up.cin, u.w_up_tc, s))) return rc;
+        }
     }
     PD_CHECK_CUDA(cudaStreamSynchronize(s));
     m->finalized = true;
@@ -790,9 +921,16 @@ int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, siz
     int mb = 1;
     for (int d = 1; d <= std::min(cap, batch); ++d) if (batch % d == 0) mb = d;
     m->mb = mb;
-    m->arena.reset(true, nullptr);
-    Rec r{m, true, mb, m->half ? (size_t)2 : sizeof(float)};
-    int rc = r.record();
+    // dry pass 1 sizes the statistics region, dry pass 2 gives the arena peak with that region in place
+    m->stats_bytes = 0;
+    int rc = 0;
+    for (int pass = 0; pass < 2 && !rc; ++pass) {
+        m->arena.reset(true, nullptr);
+        m->tensors.clear();
+        Rec r{m, true, mb, m->half ? (size_t)2 : sizeof(float)};
+        rc = r.record();
+        m->stats_bytes = m->stats_needed;
+    }
     if (rc) return rc;
     m->ws_bytes = m->arena.peak + 1024;
     m->tensors.clear();
@@ -941,58 +1079,70 @@ int pd_unet_launch_count(pd_unet_t* m, int64_t* n) {
 }
 
 // ---- kernel-level test entry points ----------------------------------------------------------------------------------
-int pd_test_conv(int32_t use_tc, int32_t dt, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout,
-                 int32_t ksize, int32_t stride, int32_t pad, const void* x1, const void* x2, const float* weight,
-                 const float* bias, const float* addvec, const void* residual, const void* sc1, const void* sc2,
-                 int32_t csc1, int32_t csc2, const float* sc_w, float out_scale, void* out, pd_stream_t stream) {
+int pd_test_conv_ex(const pd_test_conv_args_t* a, pd_stream_t stream) {
+    PD_REQUIRE(a, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
+    const int dt = a->dtype, n = a->n, h = a->h, w = a->w, c1 = a->c1, c2 = a->c2, cout = a->cout, ksize = a->ksize;
+    const int stride = a->stride, pad = a->pad, csc1 = a->csc1, csc2 = a->csc2;
     // stride-2 convs follow Downsample2D: output H/2 x W/2 (pad 1, or pad 0 with the implicit (0,1,0,1) zero pad)
-    const int ho = stride == 2 ? h / 2 : (h + 2 * pad - ksize) / stride + 1;
-    const int wo = stride == 2 ? w / 2 : (w + 2 * pad - ksize) / stride + 1;
+    int ho = stride == 2 ? h / 2 : (h + 2 * pad - ksize) / stride + 1;
+    int wo = stride == 2 ? w / 2 : (w + 2 * pad - ksize) / stride + 1;
+    if (a->upsample) { ho = 2 * h; wo = 2 * w; }
     const int ct = c1 + c2;
+    const int cw = a->stats_cw ? a->stats_cw : 4;
     int rc = 0;
-    if (use_tc) {
+    if (a->impl == 1 || a->impl == 2) {
         PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "tcgen05 path takes bf16 / fp16 activations");
         PD_REQUIRE(c2 == 0, "tcgen05 main segment takes one (already concatenated) source");
-        const int ktot = ksize * ksize * ct + csc1 + csc2;
+        const bool ddim = a->mode == TC_MODE_DDIM;
+        const int rows = ddim ? 16 : (a->upsample ? 4 * cout : cout);
+        const int ktot = a->upsample ? 4 * ct : ksize * ksize * ct + csc1 + csc2;
         void* wm = nullptr;
-        PD_CHECK_CUDA(cudaMalloc(&wm, (size_t)cout * ktot * 2));
-        rc = launch_relayout_tc(dt, weight, cout, ct, ksize, wm, ktot, 0, s);
-        if (!rc && (csc1 + csc2)) rc = launch_relayout_tc(dt, sc_w, cout, csc1 + csc2, 1, wm, ktot, ksize * ksize * ct, s);
+        PD_CHECK_CUDA(cudaMalloc(&wm, (size_t)rows * ktot * 2));
+        PD_CHECK_CUDA(cudaMemsetAsync(wm, 0, (size_t)rows * ktot * 2, s));
+        if (a->upsample) rc = launch_relayout_upsample(dt, a->weight, cout, ct, wm, s);
+        else rc = launch_relayout_tc(dt, a->weight, cout, ct, ksize, wm, ktot, 0, s);
+        if (!rc && (csc1 + csc2)) rc = launch_relayout_tc(dt, a->sc_w, cout, csc1 + csc2, 1, wm, ktot, ksize * ksize * ct, s);
         ConvTcDesc d{};
-        d.dt = dt; d.x = x1; d.C = ct; d.N = n; d.H = h; d.W = w; d.ksize = ksize; d.stride = stride; d.pad = pad;
-        d.Ho = ho; d.Wo = wo; d.Cout = cout; d.sc1 = sc1; d.Csc1 = csc1; d.sc2 = sc2; d.Csc2 = csc2;
-        d.wmat = wm; d.bias = bias; d.addvec = addvec; d.addvec_stride = cout; d.residual = residual;
-        d.out_scale = out_scale; d.out = out;
-        ConvTcPlan* pl = nullptr;
-        if (!rc) rc = conv_tc_plan_create(d, &pl);
-        if (!rc) rc = conv_tc_launch(pl, s);
+        d.dt = dt; d.x = a->x1; d.C = ct; d.N = n; d.H = h; d.W = w; d.ksize = ksize; d.stride = stride; d.pad = pad;
+        d.Ho = ho; d.Wo = wo; d.Cout = cout; d.upsample = a->upsample; d.sc1 = a->sc1; d.Csc1 = csc1; d.sc2 = a->sc2; d.Csc2 = csc2;
+        d.wmat = wm; d.bias = a->bias; d.addvec = a->addvec; d.addvec_stride = cout; d.addvec_row = a->addvec_row;
+        d.residual = a->residual; d.out_scale = a->out_scale; d.out = a->out; d.stats_out = a->stats_out; d.stats_cw = cw;
+        d.mode = a->mode;
+        ConvTapPlan* tp = nullptr;
+        ConvHaloPlan* hp = nullptr;
+        if (!rc) rc = a->impl == 2 ? conv_halo_plan_create(d, &hp) : conv_tap_plan_create(d, &tp);
+        ConvTcLaunch ex{a->model_out, a->x_t, a->step};
+        if (!rc) rc = a->impl == 2 ? conv_halo_launch(hp, s, ddim ? &ex : nullptr) : conv_tap_launch(tp, s);
         cudaError_t e = cudaStreamSynchronize(s);
-        if (pl) conv_tc_plan_destroy(pl);
+        if (tp) conv_tap_plan_destroy(tp);
+        if (hp) conv_halo_plan_destroy(hp);
         cudaFree(wm);
         if (!rc && e != cudaSuccess) { set_error(std::string("conv_tc kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
         return rc;
     }
+    PD_REQUIRE(!a->upsample && a->mode == TC_MODE_STD, "the SIMT test path has no upsample / conv_out mode");
     float* wm = nullptr;
     PD_CHECK_CUDA(cudaMalloc((void**)&wm, (size_t)cout * ct * ksize * ksize * sizeof(float)));
-    rc = launch_relayout_simt(weight, cout, ct, ksize, wm, s);
+    rc = launch_relayout_simt(a->weight, cout, ct, ksize, wm, s);
     void* tmp = nullptr;
     float* wsc = nullptr;
     const size_t esz = dt ? 2 : 4;
     if (!rc && (csc1 + csc2)) {
         PD_CHECK_CUDA(cudaMalloc(&tmp, (size_t)n * ho * wo * cout * esz));
         PD_CHECK_CUDA(cudaMalloc((void**)&wsc, (size_t)cout * (csc1 + csc2) * sizeof(float)));
-        rc = launch_relayout_simt(sc_w, cout, csc1 + csc2, 1, wsc, s);
+        rc = launch_relayout_simt(a->sc_w, cout, csc1 + csc2, 1, wsc, s);
         ConvArgs ca{};
-        ca.x1 = sc1; ca.x2 = sc2; ca.C1 = csc1; ca.C2 = csc2; ca.N = n; ca.H = ho; ca.W = wo; ca.Cout = cout; ca.ksize = 1;
+        ca.x1 = a->sc1; ca.x2 = a->sc2; ca.C1 = csc1; ca.C2 = csc2; ca.N = n; ca.H = ho; ca.W = wo; ca.Cout = cout; ca.ksize = 1;
         ca.stride = 1; ca.pad = 0; ca.Ho = ho; ca.Wo = wo; ca.w = wsc; ca.out_scale = 1.f; ca.out = tmp;
         if (!rc) rc = launch_conv_simt(dt, ca, s);
     }
     ConvArgs ca{};
-    ca.x1 = x1; ca.x2 = x2; ca.C1 = c1; ca.C2 = c2; ca.N = n; ca.H = h; ca.W = w; ca.Cout = cout; ca.ksize = ksize;
-    ca.stride = stride; ca.pad = pad; ca.Ho = ho; ca.Wo = wo; ca.w = wm; ca.bias = bias; ca.addvec = addvec;
-    ca.addvec_stride = cout; ca.residual = tmp ? tmp : residual; ca.out_scale = out_scale; ca.out = out;
+    ca.x1 = a->x1; ca.x2 = a->x2; ca.C1 = c1; ca.C2 = c2; ca.N = n; ca.H = h; ca.W = w; ca.Cout = cout; ca.ksize = ksize;
+    ca.stride = stride; ca.pad = pad; ca.Ho = ho; ca.Wo = wo; ca.w = wm; ca.bias = a->bias; ca.addvec = a->addvec;
+    ca.addvec_row = a->addvec_row; ca.addvec_stride = cout; ca.residual = tmp ? tmp : a->residual; ca.out_scale = a->out_scale; ca.out = a->out;
     if (!rc) rc = launch_conv_simt(dt, ca, s);
+    if (!rc && a->stats_out) rc = launch_gn_chunk_stats(dt, a->out, n, ho * wo, cout, cw, a->stats_out, s);
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(wm);
     if (tmp) cudaFree(tmp);
@@ -1001,17 +1151,35 @@ int pd_test_conv(int32_t use_tc, int32_t dt, int32_t n, int32_t h, int32_t w, in
     return rc;
 }
 
+int pd_test_conv(int32_t use_tc, int32_t dt, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout,
+                 int32_t ksize, int32_t stride, int32_t pad, const void* x1, const void* x2, const float* weight,
+                 const float* bias, const float* addvec, const void* residual, const void* sc1, const void* sc2,
+                 int32_t csc1, int32_t csc2, const float* sc_w, float out_scale, void* out, pd_stream_t stream) {
+    pd_test_conv_args_t a;
+    memset(&a, 0, sizeof(a));
+    a.impl = use_tc; a.dtype = dt; a.n = n; a.h = h; a.w = w; a.c1 = c1; a.c2 = c2; a.cout = cout; a.ksize = ksize;
+    a.stride = stride; a.pad = pad; a.x1 = x1; a.x2 = x2; a.weight = weight; a.bias = bias; a.addvec = addvec;
+    a.residual = residual; a.sc1 = sc1; a.sc2 = sc2; a.csc1 = csc1; a.csc2 = csc2; a.sc_w = sc_w; a.out_scale = out_scale;
+    a.out = out;
+    return pd_test_conv_ex(&a, stream);
+}
+
 int pd_test_groupnorm(int32_t dt, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                       int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta, void* out,
                       pd_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    PD_REQUIRE(groups > 0 && (c1 + c2) % groups == 0, "channels not divisible by groups");
+    int cw = 4;
+    while (cw > 1 && (((c1 + c2) / groups) % cw != 0 || c1 % cw != 0)) cw >>= 1;
     float* stats = nullptr;
-    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (size_t)n * groups * 2 * sizeof(float)));
-    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)n * groups * 2 * sizeof(float), s));
+    const size_t n1 = (size_t)n * (c1 / cw) * 2, n2 = (size_t)n * (c2 / cw) * 2;
+    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (n1 + n2 + 2) * sizeof(float)));
+    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (n1 + n2 + 2) * sizeof(float), s));
     GNArgs ga{};
     ga.x1 = x1; ga.x2 = x2; ga.C1 = c1; ga.C2 = c2; ga.N = n; ga.HW = hw; ga.groups = groups; ga.eps = eps; ga.gamma = gamma;
-    ga.beta = beta; ga.silu = do_silu; ga.stats = stats; ga.out = out;
-    int rc = launch_gn_stats(dt, ga, s);
+    ga.beta = beta; ga.silu = do_silu; ga.stats1 = stats; ga.stats2 = c2 ? stats + n1 : nullptr; ga.stats_cw = cw; ga.out = out;
+    int rc = launch_gn_chunk_stats(dt, x1, n, hw, c1, cw, stats, s);
+    if (!rc && c2) rc = launch_gn_chunk_stats(dt, x2, n, hw, c2, cw, stats + n1, s);
     if (!rc) rc = launch_gn_apply(dt, dt == 0, ga, s);
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(stats);

@@ -1,0 +1,372 @@
+// phendiff_b200 — implicit-GEMM convolution on tcgen05 + TMEM with HALO tiles: the activation tile is loaded from L2
+// ONCE per 64-channel block and reused by all filter taps.
+//
+// Why: the per-tap kernel (pd_conv_tc.cu) re-loads a shifted copy of the same activation box for each of the 9 taps, so
+// every CTA pulls (128 + BLOCK_N) x 128 B from L2 per 64-deep K block: 32..43 MAC/B.  ncu (profiles/r1a_ncu_conv_tc.md)
+// shows both of its variants pinned at ~12 TB/s of L2->SM traffic with the tensor pipe 40 % active: the path is bounded
+// by L2 delivery, not by the MMA rate.  Here one TMA box {64 ch, Wt+2, Ht+2} (a 16x8-pixel output tile plus its halo,
+// 23 KB) lands in shared memory with the 128-byte swizzle, and tap (r,s) is the SAME buffer addressed from a start that
+// is shifted by (r*(Wt+2)+s) pixel rows: 8 consecutive pixels of one image row form one 8x128 B swizzle atom, and output
+// row h+1 is exactly (Wt+2)*128 B further, i.e. a uniform stride-between-8-row-groups (SBO = 1280 B) in the UMMA descriptor.
+// Measured on B200 (tools/gpu_halo_probe.sh, profiles/r1b_halo_probe.md): the tensor core applies the 128-byte swizzle to
+// the ABSOLUTE shared-memory address bits (like TMA does when writing), so a start shifted by whole 128-byte rows and an
+// SBO that is not a multiple of 1024 both address the right data with the descriptor's base-offset field left at 0
+// (setting base offset = row phase breaks it).  A-traffic drops 6.2x.
+//
+// GEMM view: M = N*Ho*Wo pixels (tiles of Ht=16 x Wt=8), Ncol = Cout, K = taps*C (+ shortcut C).
+//   segments of K: [main: taps x C] [1x1 shortcut over source 1] [1x1 shortcut over source 2]   (conv2 + conv_shortcut
+//   of a ResnetBlock2D run as ONE GEMM; the concat of the up blocks is never materialised for the shortcut)
+//   upsample mode: nearest-2x + 3x3 conv (Upsample2D) = four 2x2 sub-pixel phase convs on the low-res input (2.25x
+//   fewer MACs, no 4x tensor): phase (a,b) reads rows {i-1+a, i+a}, cols {j-1+b, j+b} and writes pixel (2i+a, 2j+b).
+//   TC_MODE_DDIM: conv_out (Cout = 3 padded to 16); the epilogue applies the scheduler update to x_t in place.
+// Warp roles (256 threads, 1 CTA/SM, persistent): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM
+// allocator, warps 4-7 epilogue.  Rings: A (halo tiles, SA stages) and B (weight tiles, SB stages) are decoupled: one A
+// stage lives through `taps` B stages.  The fp32 accumulator is double buffered in TMEM.
+#include "pd_tc_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace pd {
+
+struct HaloParams {
+    CUtensorMap tmA, tmS1, tmS2, tmB;
+    int ntaps, kw, pitch_px;
+    int a_bytes_main, a_bytes_sc, a_stage_bytes, SA, SB;
+    int kb_main, kb_s1, kb_s2, C;
+    int tilesW, tilesH;
+    int off_h, off_w;              // box origin relative to the tile origin (-pad); upsample adds the phase
+    int m_tiles, n_tiles, phases, b_rows_per_phase;
+    int Ho, Wo;                    // output extent (2x the tile-space extent in upsample mode)
+    int upsample, use_base_offset;
+    TcEpi epi;
+};
+
+struct ConvHaloPlan {
+    HaloParams p;
+    int dt, block_n, grid, mode;
+    size_t smem;
+};
+
+constexpr int HL_WT = 8, HL_HT = 16;
+
+template <int BLOCK_N, typename T, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+    constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+    constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int SA = p.SA, SB = p.SB;
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + (size_t)SA * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)SB * B_BYTES);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + SA;
+    uint64_t* fullB = emptyA + SA;
+    uint64_t* emptyB = fullB + SB;
+    uint64_t* tfull = emptyB + SB;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmA);
+        prefetch_tmap(&p.tmB);
+        if (p.kb_s1) prefetch_tmap(&p.tmS1);
+        if (p.kb_s2) prefetch_tmap(&p.tmS2);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.phases * p.n_tiles;
+    const int tiles_per_img = p.tilesW * p.tilesH;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===================== TMA producer =====================
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const int t2 = tile / p.n_tiles;
+                const int phase = t2 % p.phases, m_tile = t2 / p.phases;
+                const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+                const int h0 = th * HL_HT, w0 = tw * HL_WT;
+                const int oh = p.off_h + (p.upsample ? (phase >> 1) : 0), ow = p.off_w + (p.upsample ? (phase & 1) : 0);
+                const int brow = phase * p.b_rows_per_phase + n_tile * BLOCK_N;
+                int kcol = 0;
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
+                    const int ntap = seg == 0 ? p.ntaps : 1;
+                    const int segC = nkb * TC_BLOCK_K;
+                    for (int cb = 0; cb < nkb; ++cb) {
+                        mbar_wait(&emptyA[sa], pha ^ 1);
+                        uint8_t* dstA = smA + (size_t)sa * p.a_stage_bytes;
+                        if (seg == 0) {
+                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_main);
+                            tma_load_4d(&p.tmA, &fullA[sa], dstA, cb * TC_BLOCK_K, w0 + ow, h0 + oh, img);
+                        } else {
+                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_sc);
+                            tma_load_4d(seg == 1 ? &p.tmS1 : &p.tmS2, &fullA[sa], dstA, cb * TC_BLOCK_K, w0, h0, img);
+                        }
+                        if (++sa == SA) { sa = 0; pha ^= 1; }
+                        for (int tap = 0; tap < ntap; ++tap) {
+                            mbar_wait(&emptyB[sb], phb ^ 1);
+                            mbar_arrive_expect_tx(&fullB[sb], B_BYTES);
+                            tma_load_2d(&p.tmB, &fullB[sb], smB + (size_t)sb * B_BYTES, kcol + tap * segC + cb * TC_BLOCK_K, brow);
+                            if (++sb == SB) { sb = 0; phb ^= 1; }
+                        }
+                    }
+                    kcol += ntap * segC;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ===================== MMA issuer (single thread) =====================
+            constexpr uint32_t idesc = make_idesc<T, BLOCK_N>();
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                uint32_t accum = 0;
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
+                    const int ntap = seg == 0 ? p.ntaps : 1;
+                    const int pitch = seg == 0 ? p.pitch_px : HL_WT;
+                    const uint32_t sbo = (uint32_t)pitch * 128u;
+                    for (int cb = 0; cb < nkb; ++cb) {
+                        mbar_wait(&fullA[sa], pha);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(smA + (size_t)sa * p.a_stage_bytes);
+                        for (int tap = 0; tap < ntap; ++tap) {
+                            mbar_wait(&fullB[sb], phb);
+                            tc_fence_after();
+                            const int r = tap / p.kw, s = tap - r * p.kw;
+                            const uint32_t row_off = (uint32_t)(r * pitch + s);
+                            const uint64_t a_desc = make_sw128_desc(a_base + row_off * 128u, sbo, p.use_base_offset ? row_off : 0u);
+                            const uint64_t b_desc = make_sw128_desc(smem_u32(smB + (size_t)sb * B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                                umma_f16kind(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+                                accum = 1;
+                            }
+                            umma_commit(&emptyB[sb]);
+                            if (++sb == SB) { sb = 0; phb ^= 1; }
+                        }
+                        umma_commit(&emptyA[sa]);
+                        if (++sa == SA) { sa = 0; pha ^= 1; }
+                    }
+                }
+                umma_commit(&tfull[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        const int hh = row >> 3, ww = row & 7;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int n_tile = tile % p.n_tiles;
+            const int t2 = tile / p.n_tiles;
+            const int phase = t2 % p.phases, m_tile = t2 / p.phases;
+            const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+            const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+            int oh = th * HL_HT + hh, ow = tw * HL_WT + ww;
+            if (p.upsample) { oh = 2 * oh + (phase >> 1); ow = 2 * ow + (phase & 1); }
+            const int hw = oh * p.Wo + ow;
+            const size_t pix = (size_t)img * p.Ho * p.Wo + hw;
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+            if (MODE == TC_MODE_DDIM) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(t_addr, r);
+                tmem_ld_wait();
+                tc_epilogue_ddim(p.epi, r, img, hw);
+            } else {
+#pragma unroll 1
+                for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(chunk * 32), r);
+                    tmem_ld_wait();
+                    tc_epilogue_chunk32<T>(p.epi, r, n_tile * BLOCK_N + chunk * 32, pix, img, lane);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+static int halo_block_n(const ConvTcDesc& d) {
+    if (d.mode == TC_MODE_DDIM) return d.Cout <= 16 ? 16 : 0;
+    if (d.Cout % 256 == 0) return 256;
+    if (d.Cout % 128 == 0) return 128;
+    if (d.Cout % 64 == 0) return 64;
+    return 0;
+}
+
+bool conv_halo_supported(const ConvTcDesc& d, std::string* why) {
+    auto no = [&](const char* m) { if (why) *why = m; return false; };
+    if (const char* off = getenv("PHENDIFF_B200_HALO")) if (off[0] == '0') return no("halo kernel disabled by PHENDIFF_B200_HALO=0");
+    if (d.dt != DT_BF16 && d.dt != DT_F16) return no("tcgen05 path takes bf16 or fp16 activations");
+    if (d.C % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
+    if (halo_block_n(d) == 0) return no("Cout must be a multiple of 64 (or <= 16 for the conv_out mode)");
+    if (d.stride != 1) return no("halo kernel takes stride-1 convolutions");
+    if (!(d.ksize == 1 || d.ksize == 3)) return no("kernel size must be 1 or 3");
+    if (d.pad != d.ksize / 2) return no("convolution must be 'same'");
+    if (d.upsample) {
+        if (d.ksize != 3 || d.Ho != 2 * d.H || d.Wo != 2 * d.W || d.Csc1 || d.Csc2) return no("upsample mode: 3x3, 2x output, no shortcut");
+    } else if (d.Ho != d.H || d.Wo != d.W) return no("output extent must equal the input extent");
+    if (d.W % HL_WT != 0 || d.H % HL_HT != 0) return no("extent must tile into 16x8-pixel boxes");
+    if (d.mode == TC_MODE_DDIM && (d.upsample || d.Csc1 || d.residual || d.addvec || d.stats_out)) return no("conv_out mode takes a plain 3x3 conv");
+    if (d.stats_out && d.stats_cw != 4 && d.stats_cw != 2) return no("fused statistics need a chunk width of 4 or 2");
+    return true;
+}
+
+int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
+    std::string why;
+    PD_REQUIRE(conv_halo_supported(d, &why), ("conv_halo: unsupported shape: " + why).c_str());
+    ConvHaloPlan* pl = new ConvHaloPlan();
+    HaloParams& p = pl->p;
+    memset(&p, 0, sizeof(p));
+    pl->dt = d.dt; pl->mode = d.mode; pl->block_n = halo_block_n(d);
+    const int kh = d.upsample ? 2 : d.ksize, kw = kh;
+    p.ntaps = kh * kw; p.kw = kw;
+    // probe knobs for the descriptor semantics (see file header; defaults = the measured-correct variant):
+    // PHENDIFF_B200_HALO_PITCH=pow2 pads the halo row to 16 pixels (SBO 2048); PHENDIFF_B200_HALO_BASEOFF=1 sets the
+    // descriptor base offset to the row phase of the shifted start
+    const char* pk = getenv("PHENDIFF_B200_HALO_PITCH");
+    const bool pow2 = pk && std::string(pk) == "pow2";
+    p.pitch_px = (kw == 1) ? HL_WT : (pow2 ? 16 : HL_WT + kw - 1);
+    const char* bo = getenv("PHENDIFF_B200_HALO_BASEOFF");
+    p.use_base_offset = bo ? (bo[0] != '0') : 0;
+    const int rows = HL_HT + kh - 1;
+    p.a_bytes_main = 128 * p.pitch_px * rows;
+    p.a_bytes_sc = 128 * HL_WT * HL_HT;
+    p.a_stage_bytes = ((std::max(p.a_bytes_main, p.a_bytes_sc) + 1023) / 1024) * 1024;
+    p.C = d.C; p.kb_main = d.C / 64; p.kb_s1 = d.Csc1 / 64; p.kb_s2 = d.Csc2 / 64;
+    p.tilesW = d.W / HL_WT; p.tilesH = d.H / HL_HT;
+    p.off_h = p.off_w = d.upsample ? -1 : -d.pad;
+    p.m_tiles = d.N * p.tilesW * p.tilesH;
+    p.phases = d.upsample ? 4 : 1;
+    const int cout_rows = d.mode == TC_MODE_DDIM ? 16 : d.Cout;
+    p.b_rows_per_phase = cout_rows;
+    p.n_tiles = cout_rows / pl->block_n;
+    p.Ho = d.Ho; p.Wo = d.Wo; p.upsample = d.upsample;
+    TcEpi& e = p.epi;
+    e.bias = d.bias; e.addvec = d.addvec; e.addvec_row = d.addvec_row; e.addvec_stride = d.addvec_stride;
+    e.residual = d.residual; e.out_scale = d.out_scale; e.out = d.out; e.stats = d.stats_out; e.stats_cw = d.stats_cw;
+    e.Cout = d.Cout; e.c_valid = d.Cout; e.plane = d.Ho * d.Wo;
+    // shared memory budget: B ring as deep as fits beside SA halo stages
+    const int b_bytes = pl->block_n * 128;
+    const int budget = 227 * 1024 - 1024 - 512;
+    p.SA = pl->block_n >= 256 ? 2 : 3;
+    if (pl->block_n == 16) p.SA = 4;
+    p.SB = std::min(16, (budget - p.SA * p.a_stage_bytes) / b_bytes);
+    if (p.SB < 2) { delete pl; set_error("conv_halo: shared memory budget too small"); return 1; }
+    pl->smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * b_bytes + 1024 + 512;
+    const uint64_t C = d.C, H = d.H, W = d.W, N = d.N;
+    int rc;
+    {
+        uint64_t dims[4] = {C, W, H, N};
+        uint64_t st[3] = {C * 2, W * C * 2, H * W * C * 2};
+        uint32_t box[4] = {64, (uint32_t)p.pitch_px, (uint32_t)rows, 1};
+        if ((rc = tc_encode_map(&p.tmA, d.dt, d.x, 4, dims, st, box))) { delete pl; return rc; }
+    }
+    const void* scs[2] = {d.sc1, d.sc2};
+    const int cscs[2] = {d.Csc1, d.Csc2};
+    CUtensorMap* tms[2] = {&p.tmS1, &p.tmS2};
+    for (int i = 0; i < 2; ++i) {
+        if (!cscs[i]) continue;
+        uint64_t Cs = cscs[i];
+        uint64_t dims[4] = {Cs, W, H, N};
+        uint64_t st[3] = {Cs * 2, W * Cs * 2, H * W * Cs * 2};
+        uint32_t box[4] = {64, HL_WT, HL_HT, 1};
+        if ((rc = tc_encode_map(tms[i], d.dt, scs[i], 4, dims, st, box))) { delete pl; return rc; }
+    }
+    {
+        const uint64_t Ktot = (uint64_t)(p.ntaps * p.kb_main + p.kb_s1 + p.kb_s2) * 64;
+        uint64_t dims[2] = {Ktot, (uint64_t)cout_rows * p.phases};
+        uint64_t st[1] = {Ktot * 2};
+        uint32_t box[2] = {64, (uint32_t)pl->block_n};
+        if ((rc = tc_encode_map(&p.tmB, d.dt, d.wmat, 2, dims, st, box))) { delete pl; return rc; }
+    }
+    pl->grid = std::min(p.m_tiles * p.phases * p.n_tiles, tc_num_sms());
+    *out = pl;
+    return 0;
+}
+
+void conv_halo_plan_destroy(ConvHaloPlan* p) { delete p; }
+
+template <int BLOCK_N, typename T, int MODE>
+static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t s) {
+    static size_t attr_smem = 0;
+    if (pl->smem > attr_smem) {
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)pl->smem));
+        attr_smem = pl->smem;
+    }
+    conv_halo_kernel<BLOCK_N, T, MODE><<<pl->grid, TC_THREADS, pl->smem, s>>>(p);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch* extra) {
+    if (pl->mode == TC_MODE_DDIM) {
+        PD_REQUIRE(extra != nullptr, "conv_out plan needs per-launch outputs");
+        HaloParams p = pl->p;
+        p.epi.model_out = extra->model_out;
+        p.epi.x_t = extra->x_t;
+        if (extra->x_t) {
+            PD_REQUIRE(extra->step != nullptr, "x_t update needs step coefficients");
+            PD_REQUIRE(extra->step->sigma == 0.f, "fused conv_out update requires eta == 0");
+            p.epi.step = *extra->step;
+        }
+        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM>(pl, p, s); });
+    }
+    PD_DISPATCH_HALF(pl->dt, T, {
+        switch (pl->block_n) {
+            case 256: return launch_halo<256, T, TC_MODE_STD>(pl, pl->p, s);
+            case 128: return launch_halo<128, T, TC_MODE_STD>(pl, pl->p, s);
+            case 64: return launch_halo<64, T, TC_MODE_STD>(pl, pl->p, s);
+        }
+    });
+    set_error("conv_halo: bad block_n");
+    return 1;
+}
+
+}  // namespace pd

@@ -13,10 +13,13 @@
 // Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
 // thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias +time-embedding row +residual ->
 // bf16 -> global).
-#include "pd_kernels.h"
+//
+// This is the per-tap kernel: it serves the stride-2 convolutions (Downsample2D) and shapes the halo kernel
+// (pd_conv_halo.cu, which re-uses one activation tile for all taps) does not tile; conv_tc_plan_create picks.
+#include "pd_tc_common.cuh"
 #include <algorithm>
+#include <cstring>
 #include <string>
-#include <type_traits>
 
 namespace pd {
 
@@ -32,15 +35,10 @@ struct ConvTcParams {
     int Wt, Ht, Nt, tilesW, tilesH;
     int Ho, Wo, Cout;
     int m_tiles, n_tiles;
-    const float* bias;
-    const float* addvec;
-    int addvec_stride;
-    const void* residual;
-    float out_scale;
-    void* out;
+    TcEpi epi;
 };
 
-struct ConvTcPlan {
+struct ConvTapPlan {
     ConvTcParams p;
     int dt;
     int block_n;
@@ -48,10 +46,7 @@ struct ConvTcPlan {
     size_t smem;
 };
 
-constexpr int TC_BLOCK_M = 128;
-constexpr int TC_BLOCK_K = 64;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB
-constexpr int TC_THREADS = 256;
 
 template <int BLOCK_N> struct TcCfg {
     static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
@@ -59,17 +54,6 @@ template <int BLOCK_N> struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;   // power of two for 64/128/256
     static constexpr size_t SMEM = (size_t)STAGES * (TC_A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-// K-major SWIZZLE_128B operand descriptor (PTX "matrix descriptor"): start address >> 4, LBO unused for swizzled
-// K-major, SBO = 1024 B (8 rows x 128 B), version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 template <int BLOCK_N, typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
@@ -153,11 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     } else if (warp == 1) {
         if (elect_one()) {
             // ===================== MMA issuer (single thread) =====================
-            // instruction descriptor: D fp32 (bit 4), A/B format at bits 7/10 (0 = fp16, 1 = bf16), both K-major,
-            // N = BLOCK_N at bits 17.., M = 128 at bits 24..
-            constexpr uint32_t fmt = sizeof(T) == 2 && std::is_same<T, bf16>::value ? 1u : 0u;
-            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                                       ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+            constexpr uint32_t idesc = make_idesc<T, BLOCK_N>();
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
@@ -204,45 +184,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            T* orow = reinterpret_cast<T*>(p.out) + pix * p.Cout;
-            const T* rrow = p.residual ? reinterpret_cast<const T*>(p.residual) + pix * p.Cout : nullptr;
-            const float* avrow = p.addvec ? p.addvec + (size_t)img * p.addvec_stride : nullptr;
 #pragma unroll 1
             for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + chunk * 32), r);
                 tmem_ld_wait();
-                const int col0 = n_tile * BLOCK_N + chunk * 32;
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g8 * 8 + i]);
-                    const int c = col0 + g8 * 8;
-                    if (p.bias) {
-                        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                        float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-                    if (avrow) {
-                        float4 b0 = __ldg(reinterpret_cast<const float4*>(avrow + c));
-                        float4 b1 = __ldg(reinterpret_cast<const float4*>(avrow + c + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-                    if (rrow) {
-                        float rv[8];
-                        load8(rrow + c, rv);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] += rv[i];
-                    }
-                    if (p.out_scale != 1.0f) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
-                    }
-                    store8(orow + c, v);
-                }
+                tc_epilogue_chunk32<T>(p.epi, r, n_tile * BLOCK_N + chunk * 32, pix, img, lane);
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);
@@ -275,8 +222,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box) {
+int tc_encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box) {
     PFN_encodeTiled enc = get_encode();
     PD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t gd[5], gs[4];
@@ -315,6 +262,8 @@ static int pick_block_n(int Cout) {
 bool conv_tc_supported(const ConvTcDesc& d, std::string* why) {
     auto no = [&](const char* m) { if (why) *why = m; return false; };
     if (d.dt != DT_BF16 && d.dt != DT_F16) return no("tcgen05 path takes bf16 or fp16 activations");
+    if (d.upsample || d.mode != TC_MODE_STD) return no("the per-tap kernel has no upsample / conv_out mode");
+    if (d.stats_out && d.stats_cw != 4 && d.stats_cw != 2) return no("fused statistics need a chunk width of 4 or 2");
     if (d.C % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
     if (pick_block_n(d.Cout) == 0) return no("Cout must be a multiple of 64");
     if (!(d.ksize == 1 || d.ksize == 3)) return no("kernel size must be 1 or 3");
@@ -331,10 +280,10 @@ bool conv_tc_supported(const ConvTcDesc& d, std::string* why) {
     return true;
 }
 
-int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
+int conv_tap_plan_create(const ConvTcDesc& d, ConvTapPlan** out) {
     std::string why;
     PD_REQUIRE(conv_tc_supported(d, &why), ("conv_tc: unsupported shape: " + why).c_str());
-    ConvTcPlan* pl = new ConvTcPlan();
+    ConvTapPlan* pl = new ConvTapPlan();
     ConvTcParams& p = pl->p;
     memset(&p, 0, sizeof(p));
     p.ksize = d.ksize; p.pad = d.pad; p.stride2 = d.stride == 2; p.C = d.C;
@@ -347,20 +296,23 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
     pl->dt = d.dt;
     pl->block_n = pick_block_n(d.Cout);
     p.n_tiles = d.Cout / pl->block_n;
-    p.bias = d.bias; p.addvec = d.addvec; p.addvec_stride = d.addvec_stride; p.residual = d.residual;
-    p.out_scale = d.out_scale; p.out = d.out;
+    TcEpi& e = p.epi;
+    e.bias = d.bias; e.addvec = d.addvec; e.addvec_row = d.addvec_row; e.addvec_stride = d.addvec_stride;
+    e.residual = d.residual; e.out_scale = d.out_scale; e.out = d.out; e.Cout = d.Cout;
+    e.stats = d.stats_out; e.stats_cw = d.stats_cw;
+    PD_REQUIRE(!d.stats_out || conv_tc_can_emit_stats(d), "conv_tc: fused statistics need 32-row groups inside one image");
     const uint64_t C = d.C, H = d.H, W = d.W, N = d.N;
     int rc = 0;
     if (!p.stride2) {
         uint64_t dims[4] = {C, W, H, N};
         uint64_t st[3] = {C * 2, W * C * 2, H * W * C * 2};
         uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Nt};
-        rc = encode_map(&p.tmA, d.dt, d.x, 4, dims, st, box);
+        rc = tc_encode_map(&p.tmA, d.dt, d.x, 4, dims, st, box);
     } else {
         uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
         uint64_t st[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
         uint32_t box[5] = {64, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Nt};
-        rc = encode_map(&p.tmA, d.dt, d.x, 5, dims, st, box);
+        rc = tc_encode_map(&p.tmA, d.dt, d.x, 5, dims, st, box);
     }
     if (rc) { delete pl; return rc; }
     const void* scs[2] = {d.sc1, d.sc2};
@@ -372,7 +324,7 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
         uint64_t dims[4] = {Cs, Wo, Ho, N};
         uint64_t st[3] = {Cs * 2, Wo * Cs * 2, Ho * Wo * Cs * 2};
         uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Nt};
-        rc = encode_map(tms[i], d.dt, scs[i], 4, dims, st, box);
+        rc = tc_encode_map(tms[i], d.dt, scs[i], 4, dims, st, box);
         if (rc) { delete pl; return rc; }
     }
     {
@@ -380,22 +332,19 @@ int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
         uint64_t dims[2] = {Ktot, (uint64_t)d.Cout};
         uint64_t st[1] = {Ktot * 2};
         uint32_t box[2] = {64, (uint32_t)pl->block_n};
-        rc = encode_map(&p.tmB, d.dt, d.wmat, 2, dims, st, box);
+        rc = tc_encode_map(&p.tmB, d.dt, d.wmat, 2, dims, st, box);
         if (rc) { delete pl; return rc; }
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->grid = std::min(p.m_tiles * p.n_tiles, sms);
+    pl->grid = std::min(p.m_tiles * p.n_tiles, tc_num_sms());
     pl->smem = pl->block_n == 256 ? TcCfg<256>::SMEM : (pl->block_n == 128 ? TcCfg<128>::SMEM : TcCfg<64>::SMEM);
     *out = pl;
     return 0;
 }
 
-void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
+void conv_tap_plan_destroy(ConvTapPlan* p) { delete p; }
 
 template <int BLOCK_N, typename T>
-static int launch_tc(const ConvTcPlan* pl, cudaStream_t s) {
+static int launch_tc(const ConvTapPlan* pl, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -407,7 +356,7 @@ static int launch_tc(const ConvTcPlan* pl, cudaStream_t s) {
     return 0;
 }
 
-int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
+int conv_tap_launch(const ConvTapPlan* pl, cudaStream_t s) {
     PD_DISPATCH_HALF(pl->dt, T, {
         switch (pl->block_n) {
             case 256: return launch_tc<256, T>(pl, s);
@@ -417,6 +366,47 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
     });
     set_error("conv_tc: bad block_n");
     return 1;
+}
+
+bool conv_tc_can_emit_stats(const ConvTcDesc& d) {
+    int Wt, Ht, Nt;
+    if (!tile_geometry(d.N, d.Ho, d.Wo, &Wt, &Ht, &Nt)) return false;
+    return (Wt * Ht) % 32 == 0;   // a warp's 32 accumulator rows stay inside one image
+}
+
+int tc_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ---- dispatch between the two kernels ----------------------------------------------------------------------------------
+int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out) {
+    ConvTcPlan* pl = new ConvTcPlan();
+    int rc;
+    if (conv_halo_supported(d, nullptr)) {
+        pl->kind = TC_KIND_HALO;
+        rc = conv_halo_plan_create(d, &pl->halo);
+    } else {
+        pl->kind = TC_KIND_TAP;
+        rc = conv_tap_plan_create(d, &pl->tap);
+    }
+    if (rc) { delete pl; return rc; }
+    *out = pl;
+    return 0;
+}
+void conv_tc_plan_destroy(ConvTcPlan* p) {
+    if (!p) return;
+    if (p->tap) conv_tap_plan_destroy(p->tap);
+    if (p->halo) conv_halo_plan_destroy(p->halo);
+    delete p;
+}
+int conv_tc_launch(const ConvTcPlan* p, cudaStream_t s, const ConvTcLaunch* extra) {
+    return p->kind == TC_KIND_HALO ? conv_halo_launch(p->halo, s, extra) : conv_tap_launch(p->tap, s);
 }
 
 }  // namespace pd

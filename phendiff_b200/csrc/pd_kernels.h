@@ -16,8 +16,13 @@ struct EmbedArgs {
     const float* class_table;     // (ncls,D) or null
     int B, C0, D, ncls, flip;
     float shift;
-    float* emb_act;               // (B,D) = SiLU(time_embedding + class embedding)
+    float* emb_act;               // (rows,D) = SiLU(time_embedding + class embedding)
+    // The embedding depends only on (t, class): with one scalar t and integer labels (the DDIB path) only `ncls`
+    // distinct rows exist.  dedupe != 0: rows = ncls, row_idx[b] = labels[b]; else rows = B, row_idx[b] = b.
+    int dedupe;
+    int32_t* row_idx;             // (B) out: row of emb_act / of the projected table used by image b
 };
+inline int embed_rows(const EmbedArgs& a) { return a.dedupe ? a.ncls : a.B; }
 int launch_embed(const EmbedArgs& a, cudaStream_t s);
 // all ResnetBlock2D.time_emb_proj at once: out(B,J) = emb_act(B,D) @ wcat(J,D)^T + bcat(J)
 int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat, int B, int D, int J, float* out,
@@ -30,10 +35,15 @@ struct GNArgs {
     float eps;
     const float *gamma, *beta;        // (C1+C2)
     int silu;
-    float* stats;                     // (N,groups,2) sum / sumsq, zero on entry
+    // per-tensor "chunk statistics": (N, C/4, 2) fp32 = sum and sum of squares over H*W of every 4-channel chunk.
+    // Written by the producing conv's epilogue (tensor-core path) or by launch_gn_chunk_stats; the chunk
+    // width cw (4, 2 or 1; model-wide) divides every group width, so any GroupNorm over any concat is finalised from them.
+    int stats_cw;
+    const float* stats1; const float* stats2;
     void* out;                        // (N,HW,C1+C2)
 };
-int launch_gn_stats(int dt, const GNArgs& a, cudaStream_t s);
+// standalone producer of chunk statistics for one NHWC tensor (stats zero on entry)
+int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, float* stats, cudaStream_t s);
 int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s);
 
 // ---- generic SIMT convolution (fp32 validation path; odd shapes of the bf16 path) -------------------------------
@@ -42,7 +52,8 @@ struct ConvArgs {
     int C1, C2, N, H, W, Cout, ksize, stride, pad, Ho, Wo;
     const float* w;                   // (k*k*(C1+C2), Cout) fp32, tap-major then input channel
     const float* bias;                // (Cout) or null
-    const float* addvec;              // (N, addvec_stride) or null: per-image per-channel add (time embedding)
+    const float* addvec;              // (rows, addvec_stride) or null: per-image per-channel add (time embedding)
+    const int32_t* addvec_row;        // (N) row of addvec used by image n, or null (row = n)
     int addvec_stride;
     const void* residual;             // (N,Ho,Wo,Cout) or null
     float out_scale;                  // multiplies the final sum (1/output_scale_factor)
@@ -66,6 +77,9 @@ struct ConvOutArgs {
 int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s);
 
 int launch_upsample2x(int dt, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s);
+// conv_in on the tensor cores: gather the 3x3 neighbourhood of the NCHW fp32 sample into (N,H,W,64) 16-bit rows
+// (k = tap*Cin + ci, zero padded), which a 1x1 tcgen05 GEMM with the (Cout, 64) re-laid-out weights consumes
+int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void* out, cudaStream_t s);
 
 // ---- attention core: softmax(q k^T / sqrt(d)) v on packed qkv (N,S,3C) ------------------------------------------
 int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
@@ -73,6 +87,28 @@ int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, i
 int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s);  // bf16 / fp16
 
 // ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+// one scheduler update, shared by the standalone step kernel and the conv_out epilogues
+__device__ __forceinline__ float ddim_update(const pd_step_coeffs_t& c, float x, float m, float noise, float* x0_out) {
+    float x0, e;
+    if (c.pred_type == PD_PRED_EPSILON) {
+        x0 = (x - c.sqrt_beta * m) / c.sqrt_alpha;   // IEEE: alpha = 0 gives +-inf / NaN exactly as the reference
+        e = m;
+    } else if (c.pred_type == PD_PRED_SAMPLE) {
+        x0 = m;
+        e = (x - c.sqrt_alpha * x0) / c.sqrt_beta;
+    } else {
+        x0 = c.sqrt_alpha * x - c.sqrt_beta * m;
+        e = c.sqrt_alpha * m + c.sqrt_beta * x;
+    }
+    if (c.clip) x0 = (x0 < -c.clip_range) ? -c.clip_range : ((x0 > c.clip_range) ? c.clip_range : x0);  // NaN stays NaN
+    if (c.use_clipped_model_output) e = (x - c.sqrt_alpha * x0) / c.sqrt_beta;
+    float out = c.sqrt_alpha_next * x0 + c.dir_coef * e;
+    if (c.sigma != 0.f) out += c.sigma * noise;
+    if (x0_out) *x0_out = x0;
+    return out;
+}
+#endif
 int launch_ddim_step(const pd_step_coeffs_t& c, const float* x, const float* m, const float* noise, float* x_out,
                      float* x0_out, int64_t n, cudaStream_t s);
 int launch_axpby(const float* a, const float* b, const float* ca, const float* cb, float* out, int B, int64_t per,
@@ -90,26 +126,44 @@ int launch_relayout_tc(int dt, const float* w, int O, int I, int k, void* out, i
 int launch_relayout_convout(const float* w, int O, int I, float* out, cudaStream_t s);
 int launch_cast_half(int dt, const float* x, void* out, int64_t n, cudaStream_t s);
 
-// ---- tcgen05 implicit-GEMM convolution (pd_conv_tc.cu) -----------------------------------------------------------
+// ---- tcgen05 implicit-GEMM convolution (pd_conv_tc.cu: per-tap TMA tiles; pd_conv_halo.cu: halo tiles) -------------
 struct ConvTcPlan;  // opaque: tensor maps + launch geometry for one layer at one (N,H,W)
+enum { TC_MODE_STD = 0, TC_MODE_DDIM = 1 };
 struct ConvTcDesc {
     // main segment: ksize x ksize conv over `x` (N,H,W,C) bf16/fp16 NHWC (already normalised / concatenated)
     int dt;                           // DT_BF16 or DT_F16
     const void* x; int C;
     int N, H, W, ksize, stride, pad, Ho, Wo, Cout;
+    // upsample != 0: nearest-2x upsample followed by the 3x3 conv (Upsample2D), executed as four 2x2 sub-pixel phase
+    // convolutions on the LOW-resolution input (H,W); Ho = 2H, Wo = 2W; wmat = (4*Cout, 4*C) phase weights
+    int upsample;
     // optional 1x1 shortcut segment over up to two concatenated sources at the OUTPUT resolution
     const void* sc1; int Csc1;
     const void* sc2; int Csc2;
     const void* wmat;                 // (Cout, Ktot) bf16/fp16, Ktot = k*k*C + Csc1 + Csc2
     const float* bias;                // (Cout) or null
     const float* addvec; int addvec_stride;
+    const int32_t* addvec_row;        // (N) or null
     const void* residual;             // (N,Ho,Wo,Cout) or null
     float out_scale;
     void* out;                        // (N,Ho,Wo,Cout)
+    float* stats_out;                 // (N, Cout/stats_cw, 2) chunk statistics of the stored output (atomic adds); or null
+    int stats_cw;                     // 4 or 2
+    int mode;                         // TC_MODE_STD, or TC_MODE_DDIM: conv_out (Cout <= 16, wmat rows padded to 16) whose
+                                      // epilogue writes NCHW fp32 model output and/or updates x_t in place
 };
-bool conv_tc_supported(const ConvTcDesc& d, std::string* why);
-int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out);
+struct ConvTcLaunch {                 // per-launch values of a TC_MODE_DDIM plan
+    float* model_out;                 // (N,Cout,Ho,Wo) fp32 or null
+    float* x_t;                       // (N,Cout,Ho,Wo) fp32 updated in place, or null
+    const pd_step_coeffs_t* step;     // host pointer, copied by value; required when x_t != null
+};
+bool conv_tc_supported(const ConvTcDesc& d, std::string* why);      // per-tap kernel (v1)
+bool conv_halo_supported(const ConvTcDesc& d, std::string* why);    // halo kernel (v2)
+bool conv_tc_can_emit_stats(const ConvTcDesc& d);                   // v1 only: false when a warp's 32 rows span images
+int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out);     // picks the halo kernel when it supports the shape
 void conv_tc_plan_destroy(ConvTcPlan* p);
-int conv_tc_launch(const ConvTcPlan* p, cudaStream_t s);
+int conv_tc_launch(const ConvTcPlan* p, cudaStream_t s, const ConvTcLaunch* extra = nullptr);
+// OIHW fp32 (O,I,3,3) -> (4*O, 4*I) 16-bit sub-pixel phase weights (row = phase*O + o, k = (dr*2+dc)*I + i)
+int launch_relayout_upsample(int dt, const float* w, int O, int I, void* out, cudaStream_t s);
 
 }  // namespace pd

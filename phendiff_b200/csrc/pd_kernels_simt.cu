@@ -16,7 +16,11 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
     float* e0 = sm;           // C0
     float* h1 = sm + a.C0;    // D
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const float t = a.timesteps ? a.timesteps[b] : a.t_scalar;
+    // dedupe: block b computes the row of class b at the (single) timestep; else the row of image b
+    const float t = a.timesteps ? a.timesteps[a.dedupe ? 0 : b] : a.t_scalar;
+    if (b == 0) {
+        for (int i = tid; i < a.B; i += blockDim.x) a.row_idx[i] = a.dedupe ? (int32_t)a.labels[i] : i;
+    }
     const int half = a.C0 / 2;
     for (int k = tid; k < half; k += blockDim.x) {
         float arg = t * freqs[k];
@@ -39,7 +43,8 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
         acc = warp_sum(acc);
         if (lane == 0) {
             float e = acc + a.b2[j];
-            if (a.class_emb) e += a.class_emb[(size_t)b * a.D + j];
+            if (a.dedupe) e += a.class_table[(size_t)b * a.D + j];
+            else if (a.class_emb) e += a.class_emb[(size_t)b * a.D + j];
             else if (a.labels) e += a.class_table[(size_t)a.labels[b] * a.D + j];
             a.emb_act[(size_t)b * a.D + j] = silu<true>(e);
         }
@@ -66,8 +71,10 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
         g_freqs_c0 = a.C0;
         g_freqs_shift = a.shift;
     }
+    PD_REQUIRE(a.row_idx != nullptr, "embed: row index buffer missing");
+    PD_REQUIRE(!a.dedupe || (a.labels && a.class_table && !a.class_emb && !a.timesteps && a.ncls > 0), "embed: dedupe needs labels and one scalar timestep");
     size_t smem = (size_t)(a.C0 + a.D) * sizeof(float);
-    embed_kernel<<<a.B, 256, smem, s>>>(a, g_freqs);
+    embed_kernel<<<embed_rows(a), 256, smem, s>>>(a, g_freqs);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -104,87 +111,35 @@ int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat,
 // Thread mapping: a thread owns one 8-channel vector column `cv` and walks pixel rows, so every global access is a
 // 16/32-byte vector and a warp covers contiguous memory.
 // =====================================================================================================================
-constexpr int GN_ROWS_PER_BLOCK = 64;
-
+// chunk statistics (N, C/cw, 2): sum and sum of squares over H*W of every cw-channel chunk (cw = 4, 2 or 1)
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(GNArgs a) {
-    extern __shared__ float sm[];  // [2][C]
-    const int C = a.C1 + a.C2, ncv = C / 8;
-    float* s_sum = sm;
-    float* s_sq = sm + C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
+__global__ void __launch_bounds__(256) gn_chunk_stats_kernel(const T* __restrict__ x, int HW, int C, int cw, int rows_per_block,
+                                                              float* __restrict__ stats) {
+    const int ncv = C / 8;
     const int n = blockIdx.y;
     const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
-    const int row_begin = blockIdx.x * GN_ROWS_PER_BLOCK;
-    const int row_end = min(row_begin + GN_ROWS_PER_BLOCK, a.HW);
-    const int c = cv * 8;
-    const T* src;
-    int pitch, coff;
-    if (c < a.C1) { src = (const T*)a.x1; pitch = a.C1; coff = c; } else { src = (const T*)a.x2; pitch = a.C2; coff = c - a.C1; }
-    src += (size_t)n * a.HW * pitch + coff;
+    const int row_begin = blockIdx.x * rows_per_block;
+    const int row_end = min(row_begin + rows_per_block, HW);
+    const T* src = x + (size_t)n * HW * C + cv * 8;
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    if (r0 < rstep) {
-        for (int r = row_begin + r0; r < row_end; r += rstep) {
-            float v[8];
-            load8(src + (size_t)r * pitch, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { atomicAdd(&s_sum[c + i], s[i]); atomicAdd(&s_sq[c + i], q[i]); }
-    }
-    __syncthreads();
-    const int cpg = C / a.groups;
-    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-        float ss = 0.f, qq = 0.f;
-        for (int i = 0; i < cpg; ++i) { ss += s_sum[g * cpg + i]; qq += s_sq[g * cpg + i]; }
-        atomicAdd(&a.stats[((size_t)n * a.groups + g) * 2 + 0], ss);
-        atomicAdd(&a.stats[((size_t)n * a.groups + g) * 2 + 1], qq);
-    }
-}
-
-template <typename T, bool kPrecise>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a) {
-    const int C = a.C1 + a.C2, ncv = C / 8;
-    const int n = blockIdx.y;
-    const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
-    if (r0 >= rstep) return;
-    const int row_begin = blockIdx.x * GN_ROWS_PER_BLOCK;
-    const int row_end = min(row_begin + GN_ROWS_PER_BLOCK, a.HW);
-    const int c = cv * 8;
-    const T* src;
-    int pitch, coff;
-    if (c < a.C1) { src = (const T*)a.x1; pitch = a.C1; coff = c; } else { src = (const T*)a.x2; pitch = a.C2; coff = c - a.C1; }
-    src += (size_t)n * a.HW * pitch + coff;
-    T* dst = (T*)a.out + (size_t)n * a.HW * C + c;
-    const int cpg = C / a.groups;
-    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
-    float sc[8], sh[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int g = (c + i) / cpg;
-        float sum = a.stats[((size_t)n * a.groups + g) * 2 + 0];
-        float sq = a.stats[((size_t)n * a.groups + g) * 2 + 1];
-        float mean = sum * inv_cnt;
-        float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        float rstd = rsqrtf(var + a.eps);
-        if (kPrecise) rstd = 1.0f / sqrtf(var + a.eps);
-        float gm = a.gamma[c + i], bt = a.beta[c + i];
-        sc[i] = rstd * gm;
-        sh[i] = bt - mean * rstd * gm;
-    }
     for (int r = row_begin + r0; r < row_end; r += rstep) {
         float v[8];
-        load8(src + (size_t)r * pitch, v);
+        load8(src + (size_t)r * C, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float y = v[i] * sc[i] + sh[i];
-            v[i] = a.silu ? silu<kPrecise>(y) : y;
-        }
-        store8(dst + (size_t)r * C, v);
+        for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+    }
+    float* dst = stats + ((size_t)n * (C / cw) + (cv * 8) / cw) * 2;
+    if (cw == 4) {
+        atomicAdd(dst + 0, (s[0] + s[1]) + (s[2] + s[3])); atomicAdd(dst + 1, (q[0] + q[1]) + (q[2] + q[3]));
+        atomicAdd(dst + 2, (s[4] + s[5]) + (s[6] + s[7])); atomicAdd(dst + 3, (q[4] + q[5]) + (q[6] + q[7]));
+    } else if (cw == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, s[2 * j] + s[2 * j + 1]); atomicAdd(dst + 2 * j + 1, q[2 * j] + q[2 * j + 1]); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, s[j]); atomicAdd(dst + 2 * j + 1, q[j]); }
     }
 }
 
@@ -195,24 +150,107 @@ static int gn_block(int C) {
     return ncv * rpp;
 }
 
-int launch_gn_stats(int dt, const GNArgs& a, cudaStream_t s) {
-    const int C = a.C1 + a.C2;
-    PD_REQUIRE(C % 8 == 0 && a.C1 % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
-    PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
-    dim3 grid((a.HW + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, a.N);
-    int block = gn_block(C);
-    size_t smem = 2 * C * sizeof(float);
-    PD_DISPATCH_DT(dt, T, (gn_stats_kernel<T><<<grid, block, smem, s>>>(a)));
+int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, float* stats, cudaStream_t s) {
+    PD_REQUIRE(C % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
+    PD_REQUIRE(cw == 4 || cw == 2 || cw == 1, "statistics chunk width must be 4, 2 or 1");
+    const int block = gn_block(C);
+    const int rstep = block / (C / 8);
+    int rows = rstep * 16;   // 16 vector loads per thread, then a handful of atomics
+    if (rows > HW) rows = HW;
+    dim3 grid((HW + rows - 1) / rows, N);
+    PD_DISPATCH_DT(dt, T, (gn_chunk_stats_kernel<T><<<grid, block, 0, s>>>((const T*)x, HW, C, cw, rows, stats)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
+// normalise + affine (+SiLU) of concat(x1, x2): group statistics are finalised from the sources' chunk statistics in the
+// block prologue (per-channel scale / shift in shared memory), then every thread streams 8-channel vectors.
+template <typename T, bool kPrecise>
+__global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_block) {
+    extern __shared__ float sm[];   // scale[C], shift[C], mean[groups], rstd[groups]
+    const int C = a.C1 + a.C2, ncv = C / 8;
+    float* s_sc = sm;
+    float* s_sh = sm + C;
+    float* s_mean = sm + 2 * C;
+    float* s_rstd = s_mean + a.groups;
+    const int n = blockIdx.y;
+    const int cpg = C / a.groups, cw = a.stats_cw;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        float sum = 0.f, sq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; c += cw) {
+            const float* st = (c < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + c / cw) * 2
+                                         : a.stats2 + ((size_t)n * (a.C2 / cw) + (c - a.C1) / cw) * 2;
+            sum += st[0]; sq += st[1];
+        }
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        s_mean[g] = mean;
+        s_rstd[g] = kPrecise ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = s_rstd[g] * a.gamma[c];
+        s_sc[c] = sc;
+        s_sh[c] = a.beta[c] - s_mean[g] * sc;
+    }
+    __syncthreads();
+    const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
+    if (r0 >= rstep) return;
+    const int row_begin = blockIdx.x * rows_per_block;
+    const int row_end = min(row_begin + rows_per_block, a.HW);
+    const int c = cv * 8;
+    const T* src;
+    int pitch, coff;
+    if (c < a.C1) { src = (const T*)a.x1; pitch = a.C1; coff = c; } else { src = (const T*)a.x2; pitch = a.C2; coff = c - a.C1; }
+    src += (size_t)n * a.HW * pitch + coff;
+    T* dst = (T*)a.out + (size_t)n * a.HW * C + c;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = s_sc[c + i]; sh[i] = s_sh[c + i]; }
+    int r = row_begin + r0;
+    for (; r + 3 * rstep < row_end; r += 4 * rstep) {   // 4 independent 16-byte loads in flight per thread
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(src + (size_t)(r + u * rstep) * pitch, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float y = v[u][i] * sc[i] + sh[i];
+                v[u][i] = a.silu ? silu<kPrecise>(y) : y;
+            }
+            store8(dst + (size_t)(r + u * rstep) * C, v[u]);
+        }
+    }
+    for (; r < row_end; r += rstep) {
+        float v[8];
+        load8(src + (size_t)r * pitch, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float y = v[i] * sc[i] + sh[i];
+            v[i] = a.silu ? silu<kPrecise>(y) : y;
+        }
+        store8(dst + (size_t)r * C, v);
+    }
+}
+
 int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s) {
     const int C = a.C1 + a.C2;
-    dim3 grid((a.HW + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK, a.N);
-    int block = gn_block(C);
-    if (precise) PD_DISPATCH_DT(dt, T, (gn_apply_kernel<T, true><<<grid, block, 0, s>>>(a)));
-    else PD_DISPATCH_DT(dt, T, (gn_apply_kernel<T, false><<<grid, block, 0, s>>>(a)));
+    PD_REQUIRE(C % 8 == 0 && a.C1 % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
+    PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
+    const int cw = a.stats_cw;
+    PD_REQUIRE((cw == 4 || cw == 2 || cw == 1) && (C / a.groups) % cw == 0 && a.C1 % cw == 0, "statistics chunk width must divide the group width");
+    PD_REQUIRE(a.stats1 && (a.C2 == 0 || a.stats2), "GroupNorm sources need chunk statistics");
+    const int block = gn_block(C);
+    const int rstep = block / (C / 8);
+    int rows = rstep * 16;
+    if (rows > a.HW) rows = a.HW;
+    dim3 grid((a.HW + rows - 1) / rows, a.N);
+    const size_t smem = (size_t)(2 * C + 2 * a.groups) * sizeof(float);
+    if (precise) PD_DISPATCH_DT(dt, T, (gn_apply_kernel<T, true><<<grid, block, smem, s>>>(a, rows)));
+    else PD_DISPATCH_DT(dt, T, (gn_apply_kernel<T, false><<<grid, block, smem, s>>>(a, rows)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -290,7 +328,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
             if (c >= a.Cout) continue;
             float v = acc[i][j];
             if (a.bias) v += a.bias[c];
-            if (a.addvec) v += a.addvec[(size_t)im * a.addvec_stride + c];
+            if (a.addvec) v += a.addvec[(size_t)(a.addvec_row ? a.addvec_row[im] : im) * a.addvec_stride + c];
             if (a.residual) v += to_f(((const T*)a.residual)[(size_t)mm * a.Cout + c]);
             v *= a.out_scale;
             ((T*)a.out)[(size_t)mm * a.Cout + c] = from_f<T>(v);
@@ -375,26 +413,6 @@ int launch_conv_in(int dt, const float* x, const float* w, const float* bias, in
 // =====================================================================================================================
 // scheduler update, shared by the standalone step kernel and the conv_out epilogue
 // =====================================================================================================================
-__device__ __forceinline__ float ddim_update(const pd_step_coeffs_t& c, float x, float m, float noise, float* x0_out) {
-    float x0, e;
-    if (c.pred_type == PD_PRED_EPSILON) {
-        x0 = (x - c.sqrt_beta * m) / c.sqrt_alpha;   // IEEE: alpha = 0 gives +-inf / NaN exactly as the reference
-        e = m;
-    } else if (c.pred_type == PD_PRED_SAMPLE) {
-        x0 = m;
-        e = (x - c.sqrt_alpha * x0) / c.sqrt_beta;
-    } else {
-        x0 = c.sqrt_alpha * x - c.sqrt_beta * m;
-        e = c.sqrt_alpha * m + c.sqrt_beta * x;
-    }
-    if (c.clip) x0 = (x0 < -c.clip_range) ? -c.clip_range : ((x0 > c.clip_range) ? c.clip_range : x0);  // NaN stays NaN
-    if (c.use_clipped_model_output) e = (x - c.sqrt_alpha * x0) / c.sqrt_beta;
-    float out = c.sqrt_alpha_next * x0 + c.dir_coef * e;
-    if (c.sigma != 0.f) out += c.sigma * noise;
-    if (x0_out) *x0_out = x0;
-    return out;
-}
-
 __global__ void ddim_step_kernel(pd_step_coeffs_t c, const float* __restrict__ x, const float* __restrict__ m,
                                  const float* __restrict__ noise, float* __restrict__ x_out, float* __restrict__ x0_out,
                                  int64_t n) {
@@ -549,6 +567,49 @@ int launch_upsample2x(int dt, const void* x, int N, int H, int W, int C, void* o
     size_t total = (size_t)N * 4 * H * W * (C / 8);
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
     PD_DISPATCH_DT(dt, T, (upsample2x_kernel<T><<<grid, 256, 0, s>>>((const T*)x, N, H, W, C, (T*)out)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================================
+// conv_in on the tensor cores: im2col of the NCHW fp32 sample into (N,H,W,64) 16-bit rows, k = tap*Cin + ci (zero padded)
+// =====================================================================================================================
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict__ x, int N, int H, int W, T* __restrict__ out) {
+    const size_t HW = (size_t)H * W, total = (size_t)N * HW;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int n = p / HW;
+    const int hw = p - (size_t)n * HW;
+    const int h = hw / W, w = hw - h * W;
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+            v[tap * CIN + ci] = ok ? __ldg(x + ((size_t)n * CIN + ci) * HW + (size_t)ih * W + iw) : 0.f;
+    }
+    T* o = out + p * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) store8(o + j * 8, v + j * 8);
+}
+
+int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void* out, cudaStream_t s) {
+    PD_REQUIRE(Cin >= 1 && Cin <= 4, "im2col conv_in supports 1..4 input channels");
+    const size_t total = (size_t)N * H * W;
+    const int grid = (int)((total + 255) / 256);
+    PD_DISPATCH_HALF(dt, T, {
+        switch (Cin) {
+            case 1: im2col_in_kernel<T, 1><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
+            case 2: im2col_in_kernel<T, 2><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
+            case 3: im2col_in_kernel<T, 3><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
+            default: im2col_in_kernel<T, 4><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
+        }
+    });
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -766,6 +827,37 @@ __global__ void relayout_convout_kernel(const float* __restrict__ w, int O, int 
 }
 int launch_relayout_convout(const float* w, int O, int I, float* out, cudaStream_t s) {
     relayout_convout_kernel<<<16, 256, 0, s>>>(w, O, I, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Upsample2D (nearest 2x, then 3x3 conv) as four 2x2 sub-pixel phase convolutions: phase (a,b) tap (dr,dc) sums the 3x3
+// weights whose upsampled source pixel falls on low-res pixel (i-1+a+dr, j-1+b+dc):  a=0: dr0<-{r0} dr1<-{r1,r2};
+// a=1: dr0<-{r0,r1} dr1<-{r2}; same for columns.  out (4*O, 4*I): row = (a*2+b)*O + o, k = (dr*2+dc)*I + i.
+template <typename T>
+__global__ void relayout_upsample_kernel(const float* __restrict__ w, int O, int I, T* __restrict__ out) {
+    const size_t total = (size_t)16 * O * I;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < total; idx += stride) {
+        const int i = idx % I;
+        size_t r = idx / I;
+        const int tap = r % 4; r /= 4;
+        const int o = r % O;
+        const int ph = r / O;
+        const int a = ph >> 1, b = ph & 1, dr = tap >> 1, dc = tap & 1;
+        const int r_lo = (a == 0) ? (dr == 0 ? 0 : 1) : (dr == 0 ? 0 : 2), r_hi = (a == 0) ? (dr == 0 ? 0 : 2) : (dr == 0 ? 1 : 2);
+        const int s_lo = (b == 0) ? (dc == 0 ? 0 : 1) : (dc == 0 ? 0 : 2), s_hi = (b == 0) ? (dc == 0 ? 0 : 2) : (dc == 0 ? 1 : 2);
+        float acc = 0.f;
+        for (int rr = r_lo; rr <= r_hi; ++rr)
+            for (int ss = s_lo; ss <= s_hi; ++ss) acc += w[((size_t)o * I + i) * 9 + rr * 3 + ss];
+        out[((size_t)ph * O + o) * (4 * (size_t)I) + (size_t)tap * I + i] = from_f<T>(acc);
+    }
+}
+int launch_relayout_upsample(int dt, const float* w, int O, int I, void* out, cudaStream_t s) {
+    size_t total = (size_t)16 * O * I;
+    int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
+    PD_DISPATCH_HALF(dt, T, (relayout_upsample_kernel<T><<<grid, 256, 0, s>>>(w, O, I, (T*)out)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

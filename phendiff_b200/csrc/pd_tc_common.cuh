@@ -1,0 +1,185 @@
+// phendiff_b200 — pieces shared by the two tcgen05 convolution kernels (pd_conv_tc.cu, pd_conv_halo.cu):
+// UMMA shared-memory / instruction descriptors, the fused epilogue (bias + time-embedding row + residual + scale ->
+// 16-bit NHWC store + GroupNorm chunk statistics of the stored values), and the conv_out epilogue that applies the
+// DDIM / inverse-DDIM update to x_t in place.
+#pragma once
+#include "pd_kernels.h"
+#include <type_traits>
+
+namespace pd {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;
+constexpr int TC_THREADS = 256;
+
+struct TcEpi {
+    const float* bias;          // (Cout) or null
+    const float* addvec;        // (rows, addvec_stride) or null
+    const int32_t* addvec_row;  // (N) or null
+    int addvec_stride;
+    const void* residual;       // NHWC, same geometry as out, or null
+    float out_scale;
+    void* out;                  // NHWC 16-bit
+    float* stats;               // (N, Cout/stats_cw, 2) or null
+    int stats_cw;               // channels per statistics chunk: 4 or 2
+    int Cout;
+    // TC_MODE_DDIM
+    float* model_out;           // NCHW fp32 or null
+    float* x_t;                 // NCHW fp32, updated in place, or null
+    pd_step_coeffs_t step;
+    int c_valid;                // real output channels (<= 16)
+    int plane;                  // Ho*Wo
+};
+
+// K-major SWIZZLE_128B operand descriptor (PTX "matrix descriptor"): start address >> 4, LBO unused for swizzled
+// K-major, SBO = byte stride between 8-row groups, version 1 (sm_100), base offset = phase of the first row inside the
+// 1024-byte swizzle pattern when the start address is not 1024-aligned, layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024, uint32_t base_off = 0) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor, kind::f16: D fp32 (bit 4), A/B format at bits 7/10 (0 = fp16, 1 = bf16), both K-major,
+// N >> 3 at bits 17.., M >> 4 at bits 24..
+template <typename T, int BLOCK_N> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+    constexpr uint32_t fmt = std::is_same<T, bf16>::value ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// Sum NV per-lane values across the 32 lanes of a warp with a transpose-reduce butterfly (NV-1 shuffles + 1 instead of
+// 5*NV): on return v[0] of lane L holds the full sum of value index (L >> (5 - log2(NV))) ... see callers.
+template <int NV> __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane) {
+    static_assert(NV == 16 || NV == 32, "NV must be 16 or 32");
+    int m = 16;
+#pragma unroll
+    for (int k = NV / 2; k >= 1; k >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            const float keep = up ? v[i + k] : v[i];
+            const float send = up ? v[i] : v[i + k];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+        m >>= 1;
+    }
+    if (NV == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+// Epilogue of one accumulator row (= one output pixel) x 32 consecutive output channels starting at col0.
+// All 32 lanes of the calling warp must belong to the same image `img` when e.stats != null.
+template <typename T>
+__device__ __forceinline__ void tc_epilogue_chunk32(const TcEpi& e, const uint32_t (&r)[32], int col0, size_t pix, int img,
+                                                    int lane) {
+    T* orow = reinterpret_cast<T*>(e.out) + pix * e.Cout + col0;
+    const T* rrow = e.residual ? reinterpret_cast<const T*>(e.residual) + pix * e.Cout + col0 : nullptr;
+    const float* av = nullptr;
+    if (e.addvec) av = e.addvec + (size_t)(e.addvec_row ? e.addvec_row[img] : img) * e.addvec_stride + col0;
+    const float* bs = e.bias ? e.bias + col0 : nullptr;
+    float s4[16];   // cw == 4: [0..7] sums of the eight 4-channel chunks, [8..15] sums of squares
+    float s2[32];   // cw == 2: [0..15] sums, [16..31] sums of squares
+    const bool st4 = e.stats != nullptr && e.stats_cw == 4, st2 = e.stats != nullptr && e.stats_cw == 2;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g8 * 8 + i]);
+        if (bs) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs + g8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bs + g8 * 8 + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (av) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(av + g8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(av + g8 * 8 + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (rrow) {
+            float rv[8];
+            load8(rrow + g8 * 8, rv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += rv[i];
+        }
+        if (e.out_scale != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= e.out_scale;
+        }
+        store8(orow + g8 * 8, v);
+        if (st4 || st2) {
+            // statistics of the values as stored (rounded to the 16-bit type), like GroupNorm reading them back
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = to_f(from_f<T>(v[i]));
+            if (st4) {
+                s4[g8 * 2 + 0] = (v[0] + v[1]) + (v[2] + v[3]);
+                s4[g8 * 2 + 1] = (v[4] + v[5]) + (v[6] + v[7]);
+                s4[8 + g8 * 2 + 0] = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+                s4[8 + g8 * 2 + 1] = (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s2[g8 * 4 + j] = v[2 * j] + v[2 * j + 1];
+                    s2[16 + g8 * 4 + j] = v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+                }
+            }
+        }
+    }
+    if (st4) {
+        const float tot = warp_transpose_reduce<16>(s4, lane);
+        if ((lane & 1) == 0) {
+            const int idx = lane >> 1;   // 0..7: sum of chunk idx, 8..15: sum of squares of chunk idx-8
+            atomicAdd(e.stats + ((size_t)img * (e.Cout >> 2) + (col0 >> 2) + (idx & 7)) * 2 + (idx >> 3), tot);
+        }
+    } else if (st2) {
+        const float tot = warp_transpose_reduce<32>(s2, lane);
+        atomicAdd(e.stats + ((size_t)img * (e.Cout >> 1) + (col0 >> 1) + (lane & 15)) * 2 + (lane >> 4), tot);
+    }
+}
+
+// conv_out epilogue: one pixel x (up to 16) output channels -> NCHW fp32 model output and / or in-place x_t update
+__device__ __forceinline__ void tc_epilogue_ddim(const TcEpi& e, const uint32_t (&r)[16], int img, int hw) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        if (c < e.c_valid) {
+            const float m = __uint_as_float(r[c]) + (e.bias ? __ldg(e.bias + c) : 0.f);
+            const size_t idx = ((size_t)img * e.c_valid + c) * e.plane + hw;
+            if (e.model_out) e.model_out[idx] = m;
+            if (e.x_t) e.x_t[idx] = ddim_update(e.step, e.x_t[idx], m, 0.f, nullptr);
+        }
+    }
+}
+
+// ---- host-side helpers shared by both kernels ---------------------------------------------------------------------
+int tc_encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+int tc_num_sms();
+
+enum { TC_KIND_TAP = 0, TC_KIND_HALO = 1 };
+struct ConvTapPlan;
+struct ConvHaloPlan;
+struct ConvTcPlan {
+    int kind;
+    ConvTapPlan* tap = nullptr;
+    ConvHaloPlan* halo = nullptr;
+};
+int conv_tap_plan_create(const ConvTcDesc& d, ConvTapPlan** out);
+void conv_tap_plan_destroy(ConvTapPlan* p);
+int conv_tap_launch(const ConvTapPlan* p, cudaStream_t s);
+int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out);
+void conv_halo_plan_destroy(ConvHaloPlan* p);
+int conv_halo_launch(const ConvHaloPlan* p, cudaStream_t s, const ConvTcLaunch* extra);
+
+}  // namespace pd

@@ -135,6 +135,162 @@ def test_conv_tcgen05_matches_simt(build_lib, case):
     assert err <= 3e-2 * max(1.0, b.abs().max().item()), f"tc vs simt {case}: {err:.3e}"
 
 
+# ---- halo kernel (pd_conv_halo.cu): one activation tile re-used by all taps ------------------------------------------
+def _conv_ex(lib, impl, bf, n, h, w, cin, cout, k, pad, *, upsample=False, addvec=False, addvec_rows=None, residual=False, sc=None,
+             stats_cw=0, out_scale=1.0, seed=0):
+    """pd_test_conv_ex against torch; returns dict(got, ref, stats, stats_ref)."""
+    L = lib.lib()
+    g = torch.Generator().manual_seed(seed)
+    dt = DT[bf]
+    dev = "cuda"
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g) * 0.1
+    ho, wo = (2 * h, 2 * w) if upsample else (h, w)
+    rows = addvec_rows or n
+    av = torch.randn(rows, cout, generator=g) * 0.5 if addvec else None
+    ridx = (torch.arange(n) % rows).to(torch.int32) if addvec_rows else None
+    res = torch.randn(n, cout, ho, wo, generator=g) if residual else None
+    csc1 = csc2 = 0
+    scx = scw = None
+    if sc:
+        csc1, csc2 = sc
+        scx = torch.randn(n, csc1 + csc2, ho, wo, generator=g)
+        scw = torch.randn(cout, csc1 + csc2, 1, 1, generator=g) / math.sqrt(csc1 + csc2)
+    q = lambda t: t.to(dt).float() if t is not None else None
+    xin = q(x)
+    if upsample:
+        xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+    # the fused upsample path pre-sums 3x3 taps in fp32 and rounds once; compare against unrounded weights there
+    wq = wt if upsample else q(wt)
+    ref = F.conv2d(xin.double(), wq.double(), b.double(), padding=pad)
+    if av is not None:
+        ref = ref + (av[ridx.long()] if ridx is not None else av).double()[:, :, None, None]
+    if res is not None:
+        ref = ref + q(res).double()
+    if sc:
+        ref = ref + F.conv2d(q(scx).double(), q(scw).double())
+    ref = (ref * out_scale).float()
+    a = lib.TestConvArgs()
+    a.impl, a.dtype, a.n, a.h, a.w, a.c1, a.c2, a.cout, a.ksize, a.stride, a.pad = impl, bf, n, h, w, cin, 0, cout, k, 1, pad
+    a.upsample, a.mode, a.stats_cw, a.csc1, a.csc2, a.out_scale = int(upsample), 0, stats_cw, csc1, csc2, out_scale
+    keep = []
+
+    def dp(t):
+        if t is None:
+            return None
+        t = t.contiguous().to(dev)
+        keep.append(t)
+        return t.data_ptr()
+
+    a.x1 = dp(nhwc(x, dt)); a.weight = dp(wt); a.bias = dp(b); a.addvec = dp(av); a.addvec_row = dp(ridx)
+    a.residual = dp(nhwc(res, dt)) if res is not None else None
+    if sc:
+        a.sc1 = dp(nhwc(scx[:, :csc1], dt)); a.sc2 = dp(nhwc(scx[:, csc1:], dt)) if csc2 else None
+        a.sc_w = dp(scw.reshape(cout, -1))
+    out = torch.zeros(n, ho, wo, cout, dtype=dt, device=dev)
+    a.out = out.data_ptr()
+    stats = None
+    if stats_cw:
+        stats = torch.zeros(n, cout // stats_cw, 2, dtype=torch.float32, device=dev)
+        a.stats_out = stats.data_ptr()
+    lib.check(L.pd_test_conv_ex(C.byref(a), None))
+    torch.cuda.synchronize()
+    r = {"got": nchw(out.cpu()), "ref": ref}
+    if stats_cw:
+        o = out.float().cpu().reshape(n, ho * wo, cout // stats_cw, stats_cw).double()   # statistics of the STORED values
+        r["stats"] = stats.cpu()
+        r["stats_ref"] = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).float()
+    return r
+
+
+HALO_CASES = [
+    # n, h, w, cin, cout, k, pad, kwargs
+    (2, 16, 16, 64, 64, 3, 1, {}),                                          # one tile per image (Ht=16 x Wt=8 x 2)
+    (1, 32, 32, 128, 128, 3, 1, dict(addvec=True)),                         # BLOCK_N 128, several tiles, halo crosses tiles
+    (1, 32, 32, 128, 256, 3, 1, dict(addvec=True, residual=True)),          # BLOCK_N 256 + residual
+    (1, 16, 16, 256, 512, 3, 1, {}),                                        # two N tiles, 4 channel blocks
+    (2, 128, 128, 64, 64, 3, 1, {}),                                        # the 128x128 extent of the bench
+    (1, 32, 32, 64, 128, 1, 0, dict(residual=True)),                        # 1x1 / linear (no halo)
+    (1, 32, 32, 128, 384, 1, 0, {}),                                        # qkv-like
+    (1, 32, 32, 128, 128, 3, 1, dict(sc=(128, 64))),                        # conv2 + K-concatenated 1x1 shortcut over a concat
+    (1, 16, 16, 1024, 512, 3, 1, dict(addvec=True)),                        # long K (up0.res0.conv1)
+    (4, 16, 16, 64, 64, 3, 1, dict(addvec=True, addvec_rows=2)),            # time-embedding rows indexed by class label
+]
+
+
+@pytest.mark.parametrize("dtype", [1, 2])
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo(build_lib, case, dtype):
+    n, h, w, cin, cout, k, pad, kw = case
+    r = _conv_ex(build_lib, 2, dtype, n, h, w, cin, cout, k, pad, **kw)
+    rel = 1e-2 if dtype == 1 else 2e-3
+    tol = rel * max(1.0, r["ref"].abs().max().item())
+    err = (r["got"] - r["ref"]).abs().max().item()
+    assert err <= tol, f"conv_halo dt={dtype} {case}: max abs err {err:.3e} (tol {tol:.3e})"
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 32, 32, 128, 256), (1, 64, 64, 256, 256)])
+def test_conv_halo_fused_upsample(build_lib, case):
+    """Upsample2D = nearest 2x + conv3x3 run as four sub-pixel phase convs on the low-res input."""
+    n, h, w, cin, cout = case
+    for dtype in (1, 2):
+        r = _conv_ex(build_lib, 2, dtype, n, h, w, cin, cout, 3, 1, upsample=True)
+        rel = 1.5e-2 if dtype == 1 else 3e-3   # weights are summed in fp32 then rounded once: not the same rounding as the reference
+        tol = rel * max(1.0, r["ref"].abs().max().item())
+        err = (r["got"] - r["ref"]).abs().max().item()
+        assert err <= tol, f"fused upsample conv dt={dtype} {case}: max abs err {err:.3e} (tol {tol:.3e})"
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("cw", [4, 2])
+def test_conv_epilogue_chunk_statistics(build_lib, impl, cw):
+    """GroupNorm chunk statistics emitted by the conv epilogue == sums over the stored 16-bit output."""
+    for dtype in (1, 2):
+        r = _conv_ex(build_lib, impl, dtype, 2, 32, 32, 64, 128, 3, 1, addvec=True, stats_cw=cw)
+        s, sr = r["stats"], r["stats_ref"]
+        err = ((s - sr).abs() / (sr.abs() + 1.0)).max().item()
+        assert err <= 2e-4, f"impl={impl} cw={cw} dt={dtype}: statistics rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("sched", ["3k_steps_clipping_rescaling", "1k_epsilon_pred"])
+def test_conv_out_ddim_epilogue(build_lib, sched):
+    """conv_out on the tensor cores (Cout 3 padded to 16) with the scheduler update applied to x_t in the epilogue."""
+    from oracle import OracleDDIMScheduler
+    from phendiff_b200 import DDIMScheduler
+    from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+
+    lib = build_lib
+    L = lib.lib()
+    g = torch.Generator().manual_seed(3)
+    n, h, w, cin, cout = 2, 32, 32, 128, 3
+    for dtype in (1, 2):
+        dt = DT[dtype]
+        act = torch.randn(n, cin, h, w, generator=g) * 0.5
+        wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+        b = torch.randn(cout, generator=g) * 0.1
+        x_t = torch.randn(n, cout, h, w, generator=g)
+        m_ref = F.conv2d(act.to(dt).double(), wt.to(dt).double(), b.double(), padding=1).float()
+        osch = OracleDDIMScheduler.from_config(SCHEDULER_CONFIGS[sched]); osch.set_timesteps(10)
+        sch = DDIMScheduler.from_config(SCHEDULER_CONFIGS[sched]); sch.set_timesteps(10)
+        t = osch.timesteps[3]
+        x_ref = osch.step(m_ref, t, x_t).prev_sample
+        coeffs = sch.step_coeffs(sch.timesteps[3], 0.0, None)
+        a = lib.TestConvArgs()
+        a.impl, a.dtype, a.n, a.h, a.w, a.c1, a.c2, a.cout, a.ksize, a.stride, a.pad = 2, dtype, n, h, w, cin, 0, cout, 3, 1, 1
+        a.mode, a.out_scale = 1, 1.0
+        xd = nhwc(act, dt).cuda(); wd = wt.cuda(); bd = b.cuda()
+        mo = torch.zeros(n, cout, h, w, device="cuda"); xt = x_t.clone().cuda()
+        a.x1, a.weight, a.bias, a.model_out, a.x_t = xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), mo.data_ptr(), xt.data_ptr()
+        a.step = C.cast(C.pointer(coeffs), C.c_void_p)
+        lib.check(L.pd_test_conv_ex(C.byref(a), None))
+        torch.cuda.synchronize()
+        tol = (1e-2 if dtype == 1 else 2e-3) * max(1.0, m_ref.abs().max().item())
+        e1 = (mo.cpu() - m_ref).abs().max().item()
+        e2 = (xt.cpu() - x_ref).abs().max().item()
+        assert e1 <= tol and e2 <= 2 * tol, f"conv_out+ddim {sched} dt={dtype}: model_out err {e1:.3e}, x_t err {e2:.3e} (tol {tol:.3e})"
+
+
 @pytest.mark.parametrize("bf", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(2, 64, 64, 0, 32, True), (2, 256, 512, 256, 32, True), (1, 1024, 256, 128, 32, False),
                                    (3, 100, 64, 0, 32, True)])
