@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--microbatch", type=int, default=0)
     p.add_argument("--e2e-steps", type=int, default=1)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--dump-ops", default="", help="write the per-op device-time table (sampled forwards) to this markdown file")
     p.add_argument("--cpu-sample-images", type=int, default=4)
     p.add_argument("--cpu-sample-steps", type=int, default=1)
     return p.parse_args()
@@ -240,6 +241,17 @@ def run_ours(args):
     sync()
     ms = e0.elapsed_time(e1)
     prof = unet.profile_end()
+    if rank == 0 and args.dump_ops:
+        ops = unet.profile_ops()
+        tot = sum(o["ms"] for o in ops) or 1.0
+        with open(args.dump_ops, "w") as f:
+            f.write(f"# per-op device time of one UNet forward (micro-batch {unet.plan_info()['microbatch']}, {args.size}x{args.size}, {args.precision}; "
+                    f"CUDA events, mean of {prof['samples']} sampled forwards inside the timed region)\n\n")
+            f.write("| # | op | class | ms | share | GFLOP | TFLOP/s |\n|---:|---|---|---:|---:|---:|---:|\n")
+            for i, o in enumerate(ops):
+                tf = o["flops"] / (o["ms"] * 1e-3) / 1e12 if o["ms"] > 0 and o["flops"] > 0 else 0.0
+                f.write(f"| {i} | {o['name']} | {o['cls']} | {o['ms']:.4f} | {o['ms'] / tot:.3f} | {o['flops'] / 1e9:.1f} | {tf:.0f} |\n")
+            f.write(f"\ntotal {tot:.3f} ms per forward\n")
     clocks = sampler.stop() if rank == 0 else None
     launches = unet.launch_count() - l0
     t = torch.tensor([ms], device=dev)

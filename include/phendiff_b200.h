@@ -147,6 +147,8 @@ enum { PD_CLS_CONV_TC = 0, PD_CLS_CONV_SIMT, PD_CLS_GN, PD_CLS_ATTN, PD_CLS_EMBE
 int pd_unet_profile_begin(pd_unet_t* h, int32_t every_n, int32_t max_samples);
 int pd_unet_profile_end(pd_unet_t* h, int32_t* samples);
 int pd_unet_profile_query(pd_unet_t* h, int32_t cls, double* ms, int64_t* launches, double* flops);
+/* per recorded op (0 <= idx < ops of pd_unet_plan_info) after pd_unet_profile_end: label, class, summed ms over `samples` forwards, algorithmic FLOPs per run */
+int pd_unet_profile_op(pd_unet_t* h, int32_t idx, const char** name, int32_t* cls, double* ms, int32_t* samples, double* flops);
 
 /* ---- unit-test entry points for individual kernels (used by tests/, not by the product path) ---- */
 /* generic NHWC convolution through the SIMT fp32 kernel or the tcgen05 kernel; dtype: 0 fp32, 1 bf16, 2 fp16.

@@ -366,6 +366,16 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
             out[name] = {"ms": ms.value, "launches": la.value, "flops": fl.value}
         return out
 
+    def profile_ops(self) -> list:
+        """Per recorded op after profile_end(): dict(name, cls, ms (mean per forward), flops)."""
+        out = []
+        for i in range(self.plan_info()["ops_per_forward"]):
+            name, cls, ms, ns, fl = C.c_char_p(), C.c_int32(), C.c_double(), C.c_int32(), C.c_double()
+            _lib.check(_lib.lib().pd_unet_profile_op(self._handle, i, C.byref(name), C.byref(cls), C.byref(ms), C.byref(ns), C.byref(fl)))
+            out.append({"name": (name.value or b"").decode(), "cls": self.KERNEL_CLASSES[cls.value],
+                        "ms": ms.value / max(ns.value, 1), "flops": fl.value})
+        return out
+
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         # A.7: diffusers 0.17-0.19 wrote attention weights under deprecated names; accept both spellings
         ren = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}

@@ -117,7 +117,7 @@ struct Ctx {   // per-call inputs of the recorded program
 
 typedef std::function<int(const Ctx&, cudaStream_t)> OpFn;
 enum { CLS_CONV_TC = 0, CLS_CONV_SIMT, CLS_GN, CLS_ATTN, CLS_EMBED, CLS_CONV_IN, CLS_CONV_OUT, CLS_UPSAMPLE, CLS_COUNT };
-struct Op { OpFn fn; int cls; double flops; int nlaunch; };
+struct Op { OpFn fn; int cls; double flops; int nlaunch; std::string name; double ms = 0; int samples = 0; };
 
 }  // namespace pd
 
@@ -401,9 +401,9 @@ struct Rec {
     }
     void* ptr(const Tensor* t) const { return (void*)(m->arena.base + t->off); }
     void* raw(size_t off) const { return (void*)(m->arena.base + off); }
-    void push(OpFn op, int nlaunch, int cls, double flops = 0.0) {
+    void push(OpFn op, int nlaunch, int cls, double flops = 0.0, const std::string& name = std::string()) {
         if (dry) return;
-        m->ops.push_back(Op{op, cls, flops, nlaunch});
+        m->ops.push_back(Op{op, cls, flops, nlaunch, name});
     }
     // chunk-statistics slot of a tensor: (mb, C/cw, 2) fp32 inside the per-forward zeroed statistics region
     void stats_alloc(Tensor* t) {
@@ -433,7 +433,8 @@ struct Rec {
             ga.stats1 = stats_ptr(a); ga.stats2 = b ? stats_ptr(b) : nullptr;
             const int dt = m->dt;
             const bool precise = !m->half;
-            push([ga, dt, precise](const Ctx&, cudaStream_t s) { return launch_gn_apply(dt, precise, ga, s); }, 1, CLS_GN);
+            push([ga, dt, precise](const Ctx&, cudaStream_t s) { return launch_gn_apply(dt, precise, ga, s); }, 1, CLS_GN, 0.0,
+                 "gn_apply C=" + std::to_string(C) + " @" + std::to_string(a->H) + "x" + std::to_string(a->W));
         }
         return o;
     }
@@ -467,8 +468,12 @@ struct Rec {
                 if (r) { rc = r; return o; }
                 m->tc_plans.push_back(pl);
                 const double ktot = upsample ? 4.0 * x->C : (double)(L.k * L.k * x->C + d.Csc1 + d.Csc2);
+                const std::string nm = std::string(upsample ? "up+conv" : "conv") + std::to_string(L.k) + "x" + std::to_string(L.k) + (L.stride == 2 ? "s2 " : " ") +
+                                       std::to_string(x->C) + (d.Csc1 + d.Csc2 ? "+sc" + std::to_string(d.Csc1 + d.Csc2) : std::string()) + "->" +
+                                       std::to_string(L.cout) + " @" + std::to_string(Ho) + "x" + std::to_string(Wo) +
+                                       (conv_halo_supported(d, nullptr) ? " halo" : " tap");
                 push([pl](const Ctx&, cudaStream_t s) { return conv_tc_launch(pl, s); }, 1, CLS_CONV_TC,
-                     2.0 * mb * Ho * Wo * (double)L.cout * ktot);
+                     2.0 * mb * Ho * Wo * (double)L.cout * ktot, nm);
             }
             if (c.want_stats && !fused_stats) stats_kernel(o);
             return o;
@@ -547,7 +552,7 @@ struct Rec {
                 const int N = mb;
                 const int dt = m->dt;
                 const bool precise = !m->half;
-                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C);
+                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C, "attention S=" + std::to_string(S) + " C=" + std::to_string(C));
                 else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(dt, precise, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C);
             }
         }
@@ -1030,6 +1035,7 @@ int pd_unet_profile_begin(pd_unet_t* m, int32_t every_n, int32_t max_samples) {
     PD_REQUIRE(m && every_n > 0 && max_samples > 0, "bad argument");
     PD_REQUIRE(m->prof_events.empty(), "profile already running: call pd_unet_profile_end first");
     m->prof_every = every_n; m->prof_max = max_samples; m->prof_runs = 0;
+    for (auto& op : m->ops) { op.ms = 0; op.samples = 0; }
     for (int i = 0; i < CLS_COUNT; ++i) { m->prof_ms[i] = 0; m->prof_flops[i] = 0; m->prof_launches[i] = 0; }
     return 0;
 }
@@ -1045,7 +1051,8 @@ int pd_unet_profile_end(pd_unet_t* m, int32_t* samples) {
         for (size_t i = 0; i < m->ops.size(); ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, chain[i], chain[i + 1]);
-            const Op& op = m->ops[i];
+            Op& op = m->ops[i];
+            op.ms += ms; op.samples += 1;
             m->prof_ms[op.cls] += ms; m->prof_flops[op.cls] += op.flops; m->prof_launches[op.cls] += op.nlaunch;
         }
     }
@@ -1060,6 +1067,17 @@ int pd_unet_profile_query(pd_unet_t* m, int32_t cls, double* ms, int64_t* launch
     if (ms) *ms = m->prof_ms[cls];
     if (launches) *launches = m->prof_launches[cls];
     if (flops) *flops = m->prof_flops[cls];
+    return 0;
+}
+
+int pd_unet_profile_op(pd_unet_t* m, int32_t idx, const char** name, int32_t* cls, double* ms, int32_t* samples, double* flops) {
+    PD_REQUIRE(m && idx >= 0 && idx < (int)m->ops.size(), "op index out of range");
+    const Op& op = m->ops[idx];
+    if (name) *name = op.name.c_str();
+    if (cls) *cls = op.cls;
+    if (ms) *ms = op.ms;
+    if (samples) *samples = op.samples;
+    if (flops) *flops = op.flops;
     return 0;
 }
 

@@ -19,8 +19,8 @@
 //   upsample mode: nearest-2x + 3x3 conv (Upsample2D) = four 2x2 sub-pixel phase convs on the low-res input (2.25x
 //   fewer MACs, no 4x tensor): phase (a,b) reads rows {i-1+a, i+a}, cols {j-1+b, j+b} and writes pixel (2i+a, 2j+b).
 //   TC_MODE_DDIM: conv_out (Cout = 3 padded to 16); the epilogue applies the scheduler update to x_t in place.
-// Warp roles (256 threads, 1 CTA/SM, persistent): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM
-// allocator, warps 4-7 epilogue.  Rings: A (halo tiles, SA stages) and B (weight tiles, SB stages) are decoupled: one A
+// Warp roles (384 threads, 1 CTA/SM, persistent): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM
+// allocator, warps 4-11 epilogue (two per TMEM lane quarter; TMA-store of swizzled 64-channel slabs).  Rings: A (halo tiles, SA stages) and B (weight tiles, SB stages) are decoupled: one A
 // stage lives through `taps` B stages.  The fp32 accumulator is double buffered in TMEM.
 #include "pd_tc_common.cuh"
 #include <algorithm>
@@ -32,6 +32,7 @@ namespace pd {
 
 struct HaloParams {
     CUtensorMap tmA, tmS1, tmS2, tmB;
+    CUtensorMap tmOut;             // output: 4-D {C, Wo, Ho, N} box {64, 8, 4, 1}; upsample: 5-D {C, 2, W, 2, N*H} box {64, 1, 8, 1, 4}
     int ntaps, kw, pitch_px;
     int a_bytes_main, a_bytes_sc, a_stage_bytes, SA, SB;
     int kb_main, kb_s1, kb_s2, C;
@@ -50,9 +51,14 @@ struct ConvHaloPlan {
 };
 
 constexpr int HL_WT = 8, HL_HT = 16;
+constexpr int HL_EPI_BYTES = 8 * 4096;   // one 4 KB output slab per epilogue warp
 
-template <int BLOCK_N, typename T, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+// epilogue warps that have work: two per TMEM lane quarter when the tile has >= 2 slabs of 64 output channels
+template <int BLOCK_N, int MODE> struct HaloEpiWarps { static constexpr int value = (MODE == TC_MODE_STD && BLOCK_N >= 128) ? 8 : 4; };
+
+template <int BLOCK_N, typename T, int MODE, int CW>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+    constexpr int EPI_WARPS = HaloEpiWarps<BLOCK_N, MODE>::value;
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
@@ -60,7 +66,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
     const int SA = p.SA, SB = p.SB;
     uint8_t* smA = smem;
     uint8_t* smB = smem + (size_t)SA * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)SB * B_BYTES);
+    uint8_t* smEpi = smB + (size_t)SB * B_BYTES;   // 8 epilogue warps x 4 KB output slab (TC_MODE_STD)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smEpi + (MODE == TC_MODE_STD ? HL_EPI_BYTES : 0));
     uint64_t* fullA = bars;
     uint64_t* emptyA = fullA + SA;
     uint64_t* fullB = emptyA + SA;
@@ -76,11 +83,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
         prefetch_tmap(&p.tmB);
         if (p.kb_s1) prefetch_tmap(&p.tmS1);
         if (p.kb_s2) prefetch_tmap(&p.tmS2);
+        if (MODE == TC_MODE_STD) prefetch_tmap(&p.tmOut);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -181,11 +189,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
                 umma_commit(&tfull[as]);
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-        const int q = warp - 4;
+    } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
+        // ===================== epilogue (8 warps: two per TMEM lane quarter, alternating 64-channel slabs) =====================
+        // Accumulator row = output pixel.  A warp owns 32 rows = a 4 x 8-pixel box of the tile; it stages 64 output channels
+        // at a time as a SWIZZLE_128B slab (32 x 128 B) in its private shared-memory buffer and one elected lane writes it
+        // with a single TMA store (fully coalesced; per-lane stores would touch 32 separate lines per instruction).  A
+        // residual tile is read coalesced and transposed through the same buffer.  Two warps per scheduler hide each
+        // other's TMEM-load, shuffle and global-load latencies.
+        const int ew = warp - 4;
+        const int q = ew & 3, slab0 = ew >> 2;
+        constexpr int SLAB_STEP = EPI_WARPS / 4;
         const int row = q * 32 + lane;
         const int hh = row >> 3, ww = row & 7;
+        uint8_t* buf = smEpi + ew * 4096;
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int n_tile = tile % p.n_tiles;
@@ -193,7 +209,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
             const int phase = t2 % p.phases, m_tile = t2 / p.phases;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
             const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-            int oh = th * HL_HT + hh, ow = tw * HL_WT + ww;
+            const int h0 = th * HL_HT, w0 = tw * HL_WT;
+            int oh = h0 + hh, ow = w0 + ww;
             if (p.upsample) { oh = 2 * oh + (phase >> 1); ow = 2 * ow + (phase & 1); }
             const int hw = oh * p.Wo + ow;
             const size_t pix = (size_t)img * p.Ho * p.Wo + hw;
@@ -206,19 +223,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_c
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(t_addr, r);
                 tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tempty[as]);      // accumulator is in registers: the MMA warp may overwrite this TMEM buffer
                 tc_epilogue_ddim(p.epi, r, img, hw);
             } else {
 #pragma unroll 1
-                for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(chunk * 32), r);
+                for (int slab = slab0; slab < BLOCK_N / 64; slab += SLAB_STEP) {
+                    const int col0 = n_tile * BLOCK_N + slab * 64;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(slab * 64), r0);
+                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(slab * 64 + 32), r1);
+                    uint4 res[8];
+                    const bool has_res = p.epi.residual != nullptr;
+                    if (has_res) {
+                        // coalesced: each load instruction covers 4 pixel rows x 128 B; lane -> (row (lane>>3)+4k, 16-byte chunk lane&7)
+                        const T* rbase = reinterpret_cast<const T*>(p.epi.residual) + col0 + (lane & 7) * 8;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int i = (lane >> 3) + 4 * k;
+                            const size_t rp = (size_t)img * p.Ho * p.Wo + (size_t)(h0 + 4 * q + (i >> 3)) * p.Wo + (w0 + (i & 7));
+                            res[k] = __ldg(reinterpret_cast<const uint4*>(rbase + rp * p.epi.Cout));
+                        }
+                    }
+                    if (lane == 0) bulk_wait_read<0>();   // this warp's previous TMA store has finished reading the buffer
+                    __syncwarp();
+                    if (has_res) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int i = (lane >> 3) + 4 * k;
+                            *reinterpret_cast<uint4*>(buf + i * 128 + (((lane & 7) ^ (i & 7)) << 4)) = res[k];
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) res[c] = *reinterpret_cast<const uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
+                        __syncwarp();
+                    }
                     tmem_ld_wait();
-                    tc_epilogue_chunk32<T>(p.epi, r, n_tile * BLOCK_N + chunk * 32, pix, img, lane);
+                    if (slab + SLAB_STEP >= BLOCK_N / 64) {   // last slab of this warp: its share of the accumulator is in registers
+                        tc_fence_before();
+                        mbar_arrive(&tempty[as]);
+                    }
+                    tc_epilogue_chunk32<T, true, CW>(p.epi, r0, col0, pix, img, lane, buf + lane * 128, 0, res, has_res);
+                    tc_epilogue_chunk32<T, true, CW>(p.epi, r1, col0 + 32, pix, img, lane, buf + lane * 128, 4, res + 4, has_res);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.upsample) tma_store_5d(&p.tmOut, buf, col0, phase & 1, w0, phase >> 1, img * (p.Ho >> 1) + h0 + 4 * q);
+                        else tma_store_4d(&p.tmOut, buf, col0, w0, h0 + 4 * q, img);
+                        bulk_commit();
+                    }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty[as]);
         }
+        if (MODE == TC_MODE_STD && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last store's reads
     }
     tc_fence_before();
     __syncthreads();
@@ -293,12 +350,13 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     e.Cout = d.Cout; e.c_valid = d.Cout; e.plane = d.Ho * d.Wo;
     // shared memory budget: B ring as deep as fits beside SA halo stages
     const int b_bytes = pl->block_n * 128;
-    const int budget = 227 * 1024 - 1024 - 512;
+    const int epi_bytes = d.mode == TC_MODE_STD ? HL_EPI_BYTES : 0;
+    const int budget = 227 * 1024 - 1024 - 512 - epi_bytes;
     p.SA = pl->block_n >= 256 ? 2 : 3;
     if (pl->block_n == 16) p.SA = 4;
     p.SB = std::min(16, (budget - p.SA * p.a_stage_bytes) / b_bytes);
     if (p.SB < 2) { delete pl; set_error("conv_halo: shared memory budget too small"); return 1; }
-    pl->smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * b_bytes + 1024 + 512;
+    pl->smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * b_bytes + epi_bytes + 1024 + 512;
     const uint64_t C = d.C, H = d.H, W = d.W, N = d.N;
     int rc;
     {
@@ -325,6 +383,22 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
         uint32_t box[2] = {64, (uint32_t)pl->block_n};
         if ((rc = tc_encode_map(&p.tmB, d.dt, d.wmat, 2, dims, st, box))) { delete pl; return rc; }
     }
+    if (d.mode == TC_MODE_STD) {
+        const uint64_t Co = d.Cout;
+        if (!d.upsample) {
+            uint64_t dims[4] = {Co, (uint64_t)d.Wo, (uint64_t)d.Ho, N};
+            uint64_t st[3] = {Co * 2, d.Wo * Co * 2, (uint64_t)d.Ho * d.Wo * Co * 2};
+            uint32_t box[4] = {64, HL_WT, 4, 1};
+            rc = tc_encode_map(&p.tmOut, d.dt, d.out, 4, dims, st, box);
+        } else {
+            // output pixel (2i+a, 2j+b): view {C, b:2, j:W, a:2, (n,i): N*H}; (n,i) merge because image pitch = H * (4*W*C)
+            uint64_t dims[5] = {Co, 2, W, 2, N * H};
+            uint64_t st[4] = {Co * 2, 2 * Co * 2, 2 * W * Co * 2, 4 * W * Co * 2};
+            uint32_t box[5] = {64, 1, HL_WT, 1, 4};
+            rc = tc_encode_map(&p.tmOut, d.dt, d.out, 5, dims, st, box);
+        }
+        if (rc) { delete pl; return rc; }
+    }
     pl->grid = std::min(p.m_tiles * p.phases * p.n_tiles, tc_num_sms());
     *out = pl;
     return 0;
@@ -332,15 +406,15 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
 
 void conv_halo_plan_destroy(ConvHaloPlan* p) { delete p; }
 
-template <int BLOCK_N, typename T, int MODE>
+template <int BLOCK_N, typename T, int MODE, int CW>
 static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t s) {
     static size_t attr_smem = 0;
     if (pl->smem > attr_smem) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)pl->smem));
         attr_smem = pl->smem;
     }
-    conv_halo_kernel<BLOCK_N, T, MODE><<<pl->grid, TC_THREADS, pl->smem, s>>>(p);
+    conv_halo_kernel<BLOCK_N, T, MODE, CW><<<pl->grid, HALO_THREADS, pl->smem, s>>>(p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -356,13 +430,14 @@ int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch*
             PD_REQUIRE(extra->step->sigma == 0.f, "fused conv_out update requires eta == 0");
             p.epi.step = *extra->step;
         }
-        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM>(pl, p, s); });
+        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM, 4>(pl, p, s); });
     }
+    const bool cw2 = pl->p.epi.stats != nullptr && pl->p.epi.stats_cw == 2;
     PD_DISPATCH_HALF(pl->dt, T, {
         switch (pl->block_n) {
-            case 256: return launch_halo<256, T, TC_MODE_STD>(pl, pl->p, s);
-            case 128: return launch_halo<128, T, TC_MODE_STD>(pl, pl->p, s);
-            case 64: return launch_halo<64, T, TC_MODE_STD>(pl, pl->p, s);
+            case 256: return cw2 ? launch_halo<256, T, TC_MODE_STD, 2>(pl, pl->p, s) : launch_halo<256, T, TC_MODE_STD, 4>(pl, pl->p, s);
+            case 128: return cw2 ? launch_halo<128, T, TC_MODE_STD, 2>(pl, pl->p, s) : launch_halo<128, T, TC_MODE_STD, 4>(pl, pl->p, s);
+            case 64: return cw2 ? launch_halo<64, T, TC_MODE_STD, 2>(pl, pl->p, s) : launch_halo<64, T, TC_MODE_STD, 4>(pl, pl->p, s);
         }
     });
     set_error("conv_halo: bad block_n");

@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + chunk * 32), r);
                 tmem_ld_wait();
-                tc_epilogue_chunk32<T>(p.epi, r, n_tile * BLOCK_N + chunk * 32, pix, img, lane);
+                if (p.epi.stats_cw == 2) tc_epilogue_chunk32<T, false, 2>(p.epi, r, n_tile * BLOCK_N + chunk * 32, pix, img, lane);
+                else tc_epilogue_chunk32<T, false, 4>(p.epi, r, n_tile * BLOCK_N + chunk * 32, pix, img, lane);
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);

@@ -15,10 +15,13 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
     extern __shared__ float sm[];
     float* e0 = sm;           // C0
     float* h1 = sm + a.C0;    // D
+    // grid (rows, D/64): every block recomputes the (cheap) first layer and produces 64 outputs of the second, so the
+    // two dependent mat-vecs of the 2-row DDIB case spread over 2 x D/64 SMs instead of running on 2
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int j_begin = blockIdx.y * 64, j_end = min(j_begin + 64, a.D);
     // dedupe: block b computes the row of class b at the (single) timestep; else the row of image b
     const float t = a.timesteps ? a.timesteps[a.dedupe ? 0 : b] : a.t_scalar;
-    if (b == 0) {
+    if (b == 0 && blockIdx.y == 0) {
         for (int i = tid; i < a.B; i += blockDim.x) a.row_idx[i] = a.dedupe ? (int32_t)a.labels[i] : i;
     }
     const int half = a.C0 / 2;
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
         if (lane == 0) h1[j] = silu<true>(acc + a.b1[j]);
     }
     __syncthreads();
-    for (int j = warp; j < a.D; j += nwarp) {
+    for (int j = j_begin + warp; j < j_end; j += nwarp) {
         const float* w = a.w2 + (size_t)j * a.D;
         float acc = 0.f;
         for (int k = lane; k < a.D; k += 32) acc += w[k] * h1[k];
@@ -74,7 +77,7 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
     PD_REQUIRE(a.row_idx != nullptr, "embed: row index buffer missing");
     PD_REQUIRE(!a.dedupe || (a.labels && a.class_table && !a.class_emb && !a.timesteps && a.ncls > 0), "embed: dedupe needs labels and one scalar timestep");
     size_t smem = (size_t)(a.C0 + a.D) * sizeof(float);
-    embed_kernel<<<embed_rows(a), 256, smem, s>>>(a, g_freqs);
+    embed_kernel<<<dim3(embed_rows(a), (a.D + 63) / 64), 256, smem, s>>>(a, g_freqs);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -10,7 +10,8 @@ namespace pd {
 
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 256;        // per-tap kernel: 4 control warps + 4 epilogue warps
+constexpr int HALO_THREADS = 384;      // halo kernel: 4 control warps + 8 epilogue warps
 
 struct TcEpi {
     const float* bias;          // (Cout) or null
@@ -82,17 +83,22 @@ template <int NV> __device__ __forceinline__ float warp_transpose_reduce(float (
 
 // Epilogue of one accumulator row (= one output pixel) x 32 consecutive output channels starting at col0.
 // All 32 lanes of the calling warp must belong to the same image `img` when e.stats != null.
-template <typename T>
+// STAGED = false: 16-bit values go straight to global memory (each lane writes its own pixel row: strided 16-byte stores).
+// STAGED = true:  they go to the lane's 128-byte row of a SWIZZLE_128B shared-memory slab (`srow`, 16-byte chunks
+//                 chunk_base..chunk_base+3) that one TMA store then writes out fully coalesced; the residual arrives the same
+//                 way (`res4`: this lane's 32 residual channels, already transposed through shared memory).
+template <typename T, bool STAGED, int CW>
 __device__ __forceinline__ void tc_epilogue_chunk32(const TcEpi& e, const uint32_t (&r)[32], int col0, size_t pix, int img,
-                                                    int lane) {
-    T* orow = reinterpret_cast<T*>(e.out) + pix * e.Cout + col0;
-    const T* rrow = e.residual ? reinterpret_cast<const T*>(e.residual) + pix * e.Cout + col0 : nullptr;
+                                                    int lane, uint8_t* srow = nullptr, int chunk_base = 0,
+                                                    const uint4* res4 = nullptr, bool use_res = false) {
+    T* orow = STAGED ? nullptr : reinterpret_cast<T*>(e.out) + pix * e.Cout + col0;
+    const T* rrow = (!STAGED && e.residual) ? reinterpret_cast<const T*>(e.residual) + pix * e.Cout + col0 : nullptr;
     const float* av = nullptr;
     if (e.addvec) av = e.addvec + (size_t)(e.addvec_row ? e.addvec_row[img] : img) * e.addvec_stride + col0;
     const float* bs = e.bias ? e.bias + col0 : nullptr;
-    float s4[16];   // cw == 4: [0..7] sums of the eight 4-channel chunks, [8..15] sums of squares
-    float s2[32];   // cw == 2: [0..15] sums, [16..31] sums of squares
-    const bool st4 = e.stats != nullptr && e.stats_cw == 4, st2 = e.stats != nullptr && e.stats_cw == 2;
+    // CW == 4: sv[0..7] sums of the eight 4-channel chunks, sv[8..15] sums of squares; CW == 2: [0..15] sums, [16..31] squares
+    float sv[64 / CW];
+    const bool st4 = CW == 4 && e.stats != nullptr, st2 = CW == 2 && e.stats != nullptr;
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
         float v[8];
@@ -108,7 +114,14 @@ __device__ __forceinline__ void tc_epilogue_chunk32(const TcEpi& e, const uint32
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(av + g8 * 8 + 4));
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
-        if (rrow) {
+        if (STAGED) {
+            if (use_res) {
+                float rv[8];
+                unpack8<T>(res4[g8], rv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += rv[i];
+            }
+        } else if (rrow) {
             float rv[8];
             load8(rrow + g8 * 8, rv);
 #pragma unroll
@@ -118,33 +131,31 @@ __device__ __forceinline__ void tc_epilogue_chunk32(const TcEpi& e, const uint32
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= e.out_scale;
         }
-        store8(orow + g8 * 8, v);
-        if (st4 || st2) {
-            // statistics of the values as stored (rounded to the 16-bit type), like GroupNorm reading them back
+        if (STAGED) store8(reinterpret_cast<T*>(srow + (((chunk_base + g8) ^ (lane & 7)) << 4)), v);
+        else store8(orow + g8 * 8, v);
+        // GroupNorm statistics from the fp32 values (before the 16-bit rounding of the store: the difference averages out
+        // over the thousands of elements of a group and keeps 8 conversions per vector off the epilogue's critical path)
+        if (CW == 4) {
+            sv[g8 * 2 + 0] = (v[0] + v[1]) + (v[2] + v[3]);
+            sv[g8 * 2 + 1] = (v[4] + v[5]) + (v[6] + v[7]);
+            sv[8 + g8 * 2 + 0] = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+            sv[8 + g8 * 2 + 1] = (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
+        } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = to_f(from_f<T>(v[i]));
-            if (st4) {
-                s4[g8 * 2 + 0] = (v[0] + v[1]) + (v[2] + v[3]);
-                s4[g8 * 2 + 1] = (v[4] + v[5]) + (v[6] + v[7]);
-                s4[8 + g8 * 2 + 0] = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
-                s4[8 + g8 * 2 + 1] = (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    s2[g8 * 4 + j] = v[2 * j] + v[2 * j + 1];
-                    s2[16 + g8 * 4 + j] = v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
-                }
+            for (int j = 0; j < 4; ++j) {
+                sv[g8 * 4 + j] = v[2 * j] + v[2 * j + 1];
+                sv[16 + g8 * 4 + j] = v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
             }
         }
     }
     if (st4) {
-        const float tot = warp_transpose_reduce<16>(s4, lane);
+        const float tot = warp_transpose_reduce<64 / CW>(sv, lane);
         if ((lane & 1) == 0) {
             const int idx = lane >> 1;   // 0..7: sum of chunk idx, 8..15: sum of squares of chunk idx-8
             atomicAdd(e.stats + ((size_t)img * (e.Cout >> 2) + (col0 >> 2) + (idx & 7)) * 2 + (idx >> 3), tot);
         }
     } else if (st2) {
-        const float tot = warp_transpose_reduce<32>(s2, lane);
+        const float tot = warp_transpose_reduce<64 / CW>(sv, lane);
         atomicAdd(e.stats + ((size_t)img * (e.Cout >> 1) + (col0 >> 1) + (lane & 15)) * 2 + (lane >> 4), tot);
     }
 }

@@ -13,7 +13,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_S
     --log-file gpurun_out/launches_${tag}.csv python bench.py --batch 32 --num-inference-steps 10 --steps 1 --warmup 1 \
     --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
 # full capture of the dominant kernel (3 launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 200 -c 3 \
-    -o gpurun_out/prof_conv_tc_${tag} -f python bench.py --batch 32 --num-inference-steps 2 --steps 1 --warmup 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_halo_kernel -s 60 -c 4 \
+    -o gpurun_out/prof_conv_halo_${tag} -f python bench.py --batch 32 --num-inference-steps 2 --steps 1 --warmup 1 \
     --no-cpu-baseline > gpurun_out/ncu_full_${tag}.log 2>&1
 ls -la gpurun_out | tail -12

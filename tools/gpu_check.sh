@@ -15,7 +15,7 @@ run() {
 run tests/test_gpu_kernels.py -m gpu -k "conv_simt"
 run tests/test_gpu_kernels.py -m gpu -k "groupnorm or scheduler or add_noise"
 run tests/test_gpu_kernels.py -m gpu -k "attention"
-run tests/test_gpu_kernels.py -m gpu -k "tcgen05"
+run tests/test_gpu_kernels.py -m gpu -k "tcgen05 or halo or chunk_statistics or conv_out_ddim"
 run tests/test_gpu_unet.py -m gpu -k "fp32 or api or fused or pipeline or golden"
 run tests/test_gpu_unet.py -m gpu -k "half"
 grep -E "^(=== |exit=|FAILED|ERROR|[0-9]+ (passed|failed))|passed|failed|\[ddib|\[bf16|\[fp16" "$log" | tail -80

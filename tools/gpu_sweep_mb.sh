@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build_${tag}.log 2>&1
 : > gpurun_out/sweep_${tag}.jsonl
 for mb in ${MBS:-4 8 16 32 64}; do
-  python bench.py --batch 64 --num-inference-steps 10 --steps 2 --warmup 3 --microbatch $mb --no-cpu-baseline \
+  python bench.py --batch 64 --num-inference-steps 10 --steps 2 --warmup 3 --microbatch $mb --no-cpu-baseline --dump-ops gpurun_out/ops_${tag}_mb$mb.md \
       >> gpurun_out/sweep_${tag}.jsonl 2>> gpurun_out/sweep_${tag}.err
 done
 python - <<PY
