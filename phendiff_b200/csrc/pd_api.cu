@@ -922,7 +922,7 @@ int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, siz
     PD_REQUIRE(height % ds == 0 && width % ds == 0, "sample size must be a multiple of 2^(n_blocks-1)");
     clear_plan(m);
     m->B = batch; m->H = height; m->W = width;
-    int cap = m->cfg.max_microbatch > 0 ? m->cfg.max_microbatch : 32;
+    int cap = m->cfg.max_microbatch > 0 ? m->cfg.max_microbatch : 64;   // 64 images: >= 6.9 waves of 148 CTAs at every UNet level
     int mb = 1;
     for (int d = 1; d <= std::min(cap, batch); ++d) if (batch % d == 0) mb = d;
     m->mb = mb;
