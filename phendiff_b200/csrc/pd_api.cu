@@ -57,6 +57,8 @@ struct AttnL {
     float* bqkv = nullptr;       // (3C)
     float* wqkv_simt = nullptr;  // (C, 3C)
     void* wqkv_tc = nullptr;     // (3C, C)
+    void* wqkv_tc_fold = nullptr;   // (3C, C) with the q rows pre-multiplied by PD_ATTN_QFOLD (head_dim-8 tensor-core attention)
+    float* bqkv_fold = nullptr;  // (3C) bias matching wqkv_tc_fold
     float* wo_simt = nullptr;    // (C, C) transposed
     void* wo_tc = nullptr;       // (C, C)
 };
@@ -309,6 +311,10 @@ static int finalize_conv(pd_unet* m, ConvL& c, cudaStream_t s, bool tc) {
     return 0;
 }
 
+__global__ void scale_vec_kernel(float* a, float f, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] *= f;
+}
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
@@ -355,6 +361,18 @@ static int finalize_attn(pd_unet* m, AttnL& a, cudaStream_t s) {
     if (m->half && a.C % 64 == 0) {
         if ((rc = dev_alloc_bytes(m, &a.wqkv_tc, 3 * CC * 2))) return rc;
         if ((rc = launch_cast_half(m->dt, a.wqkv_raw, a.wqkv_tc, (int64_t)(3 * CC), s))) return rc;
+        // head_dim-8 tensor-core attention takes q in log2 units: a second copy of the fused qkv projection has
+        // log2(e)/sqrt(d) folded into its q rows (weight and bias, in fp32, before the one rounding to 16 bits), so the
+        // softmax needs no scale multiply.  wqkv_simt was taken from wqkv_raw above and stays unscaled.
+        const int hd = m->cfg.attention_head_dim > 0 ? m->cfg.attention_head_dim : a.C;
+        if (hd == 8) {
+            if ((rc = dev_alloc(m, &a.bqkv_fold, (size_t)3 * a.C))) return rc;
+            PD_CHECK_CUDA(cudaMemcpyAsync(a.bqkv_fold, a.bqkv, (size_t)3 * a.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            scale_vec_kernel<<<(a.C + 255) / 256, 256, 0, s>>>(a.bqkv_fold, PD_ATTN_QFOLD, (int64_t)a.C);
+            scale_vec_kernel<<<(int)((CC + 255) / 256), 256, 0, s>>>(a.wqkv_raw, PD_ATTN_QFOLD, (int64_t)CC);
+            if ((rc = dev_alloc_bytes(m, &a.wqkv_tc_fold, 3 * CC * 2))) return rc;
+            if ((rc = launch_cast_half(m->dt, a.wqkv_raw, a.wqkv_tc_fold, (int64_t)(3 * CC), s))) return rc;
+        }
         if ((rc = dev_alloc_bytes(m, &a.wo_tc, CC * 2))) return rc;
         if ((rc = launch_cast_half(m->dt, a.ow->dev, a.wo_tc, (int64_t)CC, s))) return rc;
     }
@@ -369,6 +387,7 @@ struct ConvOpt {
     const void* w_tc = nullptr;      // (Cout, Ktot) 16-bit, or null: no tensor-core weights for this layer
     const float* bias = nullptr;     // bias of the main conv
     const float* bias_fused = nullptr;   // main + shortcut bias (used when the shortcut rides in the same GEMM)
+    const float* bias_tc = nullptr;      // bias to use instead of `bias` when the tensor-core path runs (pre-scaled q rows)
     const float* addvec = nullptr;   // projected time-embedding table (rows, J) at this layer's column offset
     int addvec_stride = 0;
     Tensor* residual = nullptr;
@@ -385,6 +404,7 @@ struct Rec {
     size_t esz;   // bytes per activation element
     int rc = 0;
     size_t stats_bump = 0;
+    bool last_used_tc = false;   // whether the most recent conv() took the tensor-core path
 
     Tensor* alloc(int C, int H, int W) {
         auto t = std::make_unique<Tensor>();
@@ -452,6 +472,7 @@ struct Rec {
         d.stats_cw = m->stats_cw;
         const bool want_tc = m->half && m->cfg.conv_impl == 0 && c.w_tc != nullptr;
         bool use_tc = want_tc && (conv_halo_supported(d, nullptr) || conv_tc_supported(d, nullptr));
+        last_used_tc = use_tc;
         if (upsample && !use_tc) { rc = 1; set_error("internal: fused upsample conv requested for an unsupported shape"); return o; }
         if (use_tc) {
             const bool fused_stats = c.want_stats && m->stats_cw >= 2 && (conv_halo_supported(d, nullptr) || conv_tc_can_emit_stats(d));
@@ -459,7 +480,7 @@ struct Rec {
             m->tc_layers += dry ? 0 : 1;
             if (!dry) {
                 d.x = ptr(x); d.sc1 = c.s1 ? ptr(c.s1) : nullptr; d.sc2 = c.s2 ? ptr(c.s2) : nullptr;
-                d.wmat = c.w_tc; d.bias = c.s1 ? c.bias_fused : c.bias; d.addvec = c.addvec; d.addvec_stride = c.addvec_stride;
+                d.wmat = c.w_tc; d.bias = c.s1 ? c.bias_fused : (c.bias_tc ? c.bias_tc : c.bias); d.addvec = c.addvec; d.addvec_stride = c.addvec_stride;
                 d.addvec_row = c.addvec ? (const int32_t*)raw(m->rowidx_off) : nullptr;
                 d.residual = c.residual ? ptr(c.residual) : nullptr; d.out_scale = c.out_scale; d.out = ptr(o);
                 d.stats_out = fused_stats ? stats_ptr(o) : nullptr;
@@ -539,20 +560,23 @@ struct Rec {
         Tensor* xn = gn(A.gn, x, nullptr, false);
         ConvL lq; lq.cin = A.C; lq.cout = 3 * A.C; lq.k = 1; lq.stride = 1; lq.pad = 0;
         ConvOpt oq;
-        oq.w_simt = A.wqkv_simt; oq.w_tc = A.wqkv_tc; oq.bias = A.bqkv; oq.want_stats = false;
+        const int S = x->H * x->W, C = A.C, d = m->cfg.attention_head_dim > 0 ? m->cfg.attention_head_dim : A.C;
+        const bool use_mma = m->half && m->cfg.attn_impl == 0 && (S % 64 == 0) && d == 8;
+        const bool fold = use_mma && A.wqkv_tc_fold != nullptr;
+        oq.w_simt = A.wqkv_simt; oq.w_tc = fold ? A.wqkv_tc_fold : A.wqkv_tc; oq.bias = A.bqkv; oq.want_stats = false;
+        if (fold) oq.bias_tc = A.bqkv_fold;
         Tensor* qkv = conv(lq, xn, oq);
+        const float qfold = (fold && last_used_tc) ? PD_ATTN_QFOLD : 1.0f;   // the SIMT projection uses the raw weights
         release(xn);
         Tensor* ao = alloc(A.C, x->H, x->W);
         {
-            const int S = x->H * x->W, C = A.C, d = m->cfg.attention_head_dim > 0 ? m->cfg.attention_head_dim : A.C;
-            const bool use_mma = m->half && m->cfg.attn_impl == 0 && (S % 64 == 0) && d == 8;
             if (!dry) {
                 const void* qp = ptr(qkv);
                 void* op = ptr(ao);
                 const int N = mb;
                 const int dt = m->dt;
                 const bool precise = !m->half;
-                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C, "attention S=" + std::to_string(S) + " C=" + std::to_string(C));
+                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, qfold, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C, "attention S=" + std::to_string(S) + " C=" + std::to_string(C));
                 else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(dt, precise, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C);
             }
         }
@@ -1210,7 +1234,7 @@ int pd_test_attention(int32_t use_mma, int32_t dt, int32_t n, int32_t s_len, int
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     if (use_mma) {
-        rc = launch_attention_mma(dt, qkv, n, s_len, c, d, out, s);
+        rc = launch_attention_mma(dt, qkv, n, s_len, c, d, use_mma == 2 ? PD_ATTN_QFOLD : 1.0f, out, s);
     } else {
         rc = launch_attention_simt(dt, dt == 0, qkv, n, s_len, c, d, out, s);
     }

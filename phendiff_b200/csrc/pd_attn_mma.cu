@@ -28,7 +28,7 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^x for x <= 0 on the FMA / ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial,
 // scaled by 2^n through the exponent field
 __device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -100.0f);
+    x = fminf(fmaxf(x, -100.0f), 128.0f);   // 128 -> exponent field 255 = +inf (overflow of a stale row max stays visible)
     const float t = x + 12582912.0f;
     const float f = x - (t - 12582912.0f);
     float p = 0.05508868396282196f;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void mma_16x8x16(float c[4], uint32_t a0, uint32_t a1
 // lane (g = lane >> 2, t = lane & 3) reads its 8 words of either with two 16-byte loads at word offset lane * 8.
 template <typename T, int kPolyEvery>
 __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* __restrict__ qkv, int S, int C,
-                                                                      T* __restrict__ out) {
+                                                                      float sl, T* __restrict__ out) {
     __shared__ __align__(16) uint32_t Kf[AT_MAXS * 4];
     __shared__ __align__(16) uint32_t Vf[AT_MAXS * 4];
     const int n = blockIdx.z, head = blockIdx.y;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* _
         qa0 = *reinterpret_cast<const uint32_t*>(base + (size_t)(q0 + g) * rowp + 2 * t);
         qa1 = *reinterpret_cast<const uint32_t*>(base + (size_t)(q0 + g + 8) * rowp + 2 * t);
     }
-    const float sl = 0.35355339059327373f * 1.4426950408889634f;  // 1/sqrt(8) * log2(e)
+    // sl = log2(e) / sqrt(8) divided by whatever factor the caller already folded into q
     const uint32_t ones = std::is_same<T, bf16>::value ? 0x3F803F80u : 0x3C003C00u;
     float m0 = -INFINITY, m1 = -INFINITY;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* _
     *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g + 8) * C) = pack2<T>(o[2] * i1, o[3] * i1);
 }
 
-int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+static int launch_attention_chunked(int dt, const void* qkv, int N, int S, int C, int d, float sl, void* out, cudaStream_t s) {
     PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "attention_mma takes bf16 or fp16 activations");
     PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
     PD_REQUIRE(S % 64 == 0 && C % 8 == 0, "attention_mma needs S % 64 == 0");
@@ -182,7 +182,7 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, vo
         if (poly_every != 0 && poly_every != 2 && poly_every != 3 && poly_every != 4 && poly_every != 8) poly_every = 4;
     }
     dim3 grid((S + AT_WARPS * 16 - 1) / (AT_WARPS * 16), C / 8, N);
-#define PD_ATT(PE) PD_DISPATCH_HALF(dt, T, (attention_mma_kernel<T, PE><<<grid, AT_WARPS * 32, 0, s>>>((const T*)qkv, S, C, (T*)out)))
+#define PD_ATT(PE) PD_DISPATCH_HALF(dt, T, (attention_mma_kernel<T, PE><<<grid, AT_WARPS * 32, 0, s>>>((const T*)qkv, S, C, sl, (T*)out)))
     switch (poly_every) {
         case 0: PD_ATT(0); break;
         case 2: PD_ATT(2); break;
@@ -191,6 +191,289 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, vo
         default: PD_ATT(4); break;
     }
 #undef PD_ATT
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// =====================================================================================================================
+// v3: one CTA per (image, head) — K / V^T of the head are staged into shared memory ONCE (fragment order, conflict-free
+// 128-bit fragment loads) and every warp walks its 16-query blocks over them.  ncu on v2 (profiles/r1h_ncu_attention.md):
+// MUFU 63 %, legacy HMMA pipe 38 % (a m16n8k8 costs as much pipe time as a m16n8k16), ALU 39 %, FMA 32 %, issue-bound at
+// ~10.8 cycles per (lane, score).  What v3 removes from the per-score instruction stream:
+//   * the scale FFMA: log2(e)/sqrt(d) is folded into the q rows of the fused qkv weight at finalize (pd_api.cu), so
+//     scores leave the tensor core in log2 units;
+//   * the max subtraction and the zero-initialisation of the S accumulators: -m rides in as the C operand of the QK^T MMA;
+//   * the per-step running max, its shuffles and the rescale of (o, l): m is the exact row max of key block 0 and stays
+//     fixed; fp32 accumulators absorb a stale (low) m, and P only overflows 16-bit storage if a later score exceeds m
+//     by 2^16 — detected as a non-finite row sum, upon which the warp redoes that query block with the exact online
+//     softmax (same code as block 0);
+//   * half of the MUFU work: every other (row, key-octet) pair of scores is exponentiated on the FMA/ALU pipes, for
+//     fp16 in PACKED half2 arithmetic (range reduction by the 1039 magic add, degree-3 minimax polynomial, exponent
+//     field built from the magic sum: 12 instructions per 2 scores, 2.4e-4 rms relative error ~ the fp16 rounding of P).
+// Expected balance per 64-key step and warp (issue ~146, MUFU 128, HMMA 128 cycles) vs ~346 measured for v2.
+// =====================================================================================================================
+constexpr int AH_WARPS = 8;
+#ifndef AH_MIN_CTAS
+#define AH_MIN_CTAS 4
+#endif
+constexpr float AH_SL = PD_ATTN_QFOLD;   // log2(e) / sqrt(8)
+
+template <typename T>
+__device__ __forceinline__ void mma_16x8x8_c(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, const float (&c)[4]) {
+    if (std::is_same<T, bf16>::value)
+        asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+            : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+            : "r"(a0), "r"(a1), "r"(b0), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+    else
+        asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+            : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+            : "r"(a0), "r"(a1), "r"(b0), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+
+__device__ __forceinline__ uint32_t h2op_add(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2op_sub(uint32_t a, uint32_t b) { uint32_t d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2op_mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2op_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t h2op_min(uint32_t a, uint32_t b) { uint32_t d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2op_max(uint32_t a, uint32_t b) { uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+
+// (2^xa, 2^xb) as packed fp16 (low half = xa), on the FMA / ALU pipes.  x is clamped to [-15, 16]: n = round(x) rides in
+// the low mantissa bits of w = x + 1039 (ulp 1 in [1024, 2048)) as 15 + n = the fp16 exponent field of 2^n, so
+// x <= -14.5 gives exactly 0 and x >= 15.5 gives +inf (which is what flags the overflow of a stale row max).
+__device__ __forceinline__ uint32_t ex2_pair_h2(float xa, float xb) {
+    uint32_t x = pack_f16x2(xa, xb);
+    x = h2op_min(h2op_max(x, 0xCB80CB80u /* -15 */), 0x4C004C00u /* 16 */);
+    const uint32_t w = h2op_add(x, 0x640F640Fu /* 1039 */);
+    const uint32_t f = h2op_sub(x, h2op_sub(w, 0x640F640Fu));          // x - n in [-0.5, 0.5], exact
+    uint32_t p = h2op_fma(0x2B0D2B0Du /* 0.05508868 */, f, 0x33C333C3u /* 0.24260405 */);
+    p = h2op_fma(p, f, 0x398C398Cu /* 0.69327623 */);
+    p = h2op_fma(p, f, 0x3C003C00u /* 0.99992895 -> 1 */);
+    // exponent fields (15 + n) << 10 of both halves in one IMAD: (w - 0x64006400) * 1024, the subtraction folded into the addend
+    return h2op_mul(p, w * 1024u + (0u - 0x64006400u * 1024u));
+}
+
+template <typename T> __device__ __forceinline__ uint32_t ex2_pair_poly(float xa, float xb);
+template <> __device__ __forceinline__ uint32_t ex2_pair_poly<f16>(float xa, float xb) { return ex2_pair_h2(xa, xb); }
+template <> __device__ __forceinline__ uint32_t ex2_pair_poly<bf16>(float xa, float xb) { return pack_bf16x2(ex2_poly(xa), ex2_poly(xb)); }
+
+// One exact online-softmax step over a 64-key block (scores in log2 units): block 0 of every query block, and every block
+// of a query block whose fast pass overflowed.
+template <typename T>
+__device__ __forceinline__ void attn_exact_step(const uint32_t* Kblk, const uint32_t* Vblk, int lane, uint32_t qa0, uint32_t qa1,
+                                                uint32_t ones, float& m0, float& m1, float (&o)[4], float (&l)[4]) {
+    const uint4* kf = reinterpret_cast<const uint4*>(Kblk) + lane;
+    const uint4 kA = kf[0], kB = kf[32];
+    const uint32_t kb_[8] = {kA.x, kA.y, kA.z, kA.w, kB.x, kB.y, kB.z, kB.w};
+    float s[8][4];
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) mma_16x8x8_c<T>(s[kb], qa0, qa1, kb_[kb], zero4);
+    float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        cm0 = fmaxf(cm0, fmaxf(s[kb][0], s[kb][1]));
+        cm1 = fmaxf(cm1, fmaxf(s[kb][2], s[kb][3]));
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
+    const float corr0 = ex2(m0 - nm0), corr1 = ex2(m1 - nm1);
+    m0 = nm0; m1 = nm1;
+    o[0] *= corr0; o[1] *= corr0; o[2] *= corr1; o[3] *= corr1;
+    l[0] *= corr0; l[1] *= corr0; l[2] *= corr1; l[3] *= corr1;
+    uint32_t pa[8][2];
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        pa[kb][0] = pack2<T>(ex2(s[kb][0] - m0), ex2(s[kb][1] - m0));
+        pa[kb][1] = pack2<T>(ex2(s[kb][2] - m1), ex2(s[kb][3] - m1));
+    }
+    const uint4* vf = reinterpret_cast<const uint4*>(Vblk) + lane;
+    const uint4 vA = vf[0], vB = vf[32];
+    const uint32_t vb_[8] = {vA.x, vA.y, vA.z, vA.w, vB.x, vB.y, vB.z, vB.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        mma_16x8x16<T>(o, pa[2 * j][0], pa[2 * j][1], pa[2 * j + 1][0], pa[2 * j + 1][1], vb_[2 * j], vb_[2 * j + 1]);
+        mma_16x8x16<T>(l, pa[2 * j][0], pa[2 * j][1], pa[2 * j + 1][0], pa[2 * j + 1][1], ones, ones);
+    }
+}
+
+// POLY_MASK: bit 2*kb (2*kb+1) set = the score pair of accumulator rows g (g+8) of key octet kb goes to the polynomial
+template <typename T, uint32_t POLY_MASK>
+__global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_kernel(const T* __restrict__ qkv, int S, int C, float qmul,
+                                                                          T* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t ah_smem[];
+    uint32_t* Kf = ah_smem;             // [S/64][2][32 lanes][4]: plane h, lane (g,t), word i = K[key 64 blk + 8 (4h+i) + g][dims 2t, 2t+1]
+    uint32_t* Vf = ah_smem + S * 4;     // [S/64][2][32 lanes][4]: plane p, lane (g,t), word i = V[keys 64 blk + 16 (2p + (i>>1)) + 8 (i&1) + 2t, +1][dim g]
+    const int n = blockIdx.z, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const size_t rowp = (size_t)3 * C;
+    const T* base = qkv + (size_t)n * S * rowp + head * 8;
+
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const T* kp = base + (size_t)j * rowp + C;
+        const uint4 kv = *reinterpret_cast<const uint4*>(kp);
+        const uint4 vv = *reinterpret_cast<const uint4*>(kp + C);
+        const int blk = j >> 6, r = j & 63;
+        {
+            const int kb = r >> 3, gg = r & 7;
+            uint32_t* dst = Kf + blk * 256 + (kb >> 2) * 128 + gg * 16 + (kb & 3);
+            dst[0] = kv.x; dst[4] = kv.y; dst[8] = kv.z; dst[12] = kv.w;      // lane (gg, tt) at word (gg*4 + tt)*4
+        }
+        {
+            const int jj = r >> 4, h = (r >> 3) & 1, tt = (r >> 1) & 3, e = r & 1;
+            T* dst = reinterpret_cast<T*>(Vf + blk * 256 + (jj >> 1) * 128 + tt * 4 + (jj & 1) * 2 + h) + e;
+            const T* ve = reinterpret_cast<const T*>(&vv);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) dst[d * 32] = ve[d];                    // lane (d, tt): 16 words = 32 halves per dim
+        }
+    }
+    __syncthreads();
+
+    const uint32_t ones = std::is_same<T, bf16>::value ? 0x3F803F80u : 0x3C003C00u;
+    constexpr bool kRecentre = std::is_same<T, f16>::value && (POLY_MASK & 0xFFFFu) != 0u && (POLY_MASK & 0xFFFFu) != 0xFFFFu;
+    const int nblk = S >> 6, nqb = S >> 4;
+    for (int qb = blockIdx.x * AH_WARPS + warp; qb < nqb; qb += gridDim.x * AH_WARPS) {
+        const int q0 = qb * 16;
+        uint32_t qa0 = *reinterpret_cast<const uint32_t*>(base + (size_t)(q0 + g) * rowp + 2 * t);
+        uint32_t qa1 = *reinterpret_cast<const uint32_t*>(base + (size_t)(q0 + g + 8) * rowp + 2 * t);
+        if (qmul != 1.0f) {   // q not pre-scaled by the caller (test entry, SIMT qkv projection)
+            const T* h0 = reinterpret_cast<const T*>(&qa0);
+            const T* h1 = reinterpret_cast<const T*>(&qa1);
+            qa0 = pack2<T>(to_f(h0[0]) * qmul, to_f(h0[1]) * qmul);
+            qa1 = pack2<T>(to_f(h1[0]) * qmul, to_f(h1[1]) * qmul);
+        }
+        float o[4] = {0.f, 0.f, 0.f, 0.f}, l[4] = {0.f, 0.f, 0.f, 0.f};
+        float m0 = -INFINITY, m1 = -INFINITY;
+        // key block 0: exact step, fixes the row maxima for the fast steps
+        attn_exact_step<T>(Kf, Vf, lane, qa0, qa1, ones, m0, m1, o, l);
+        {
+            // C operand of the QK^T MMAs: scores arrive as s - m.  The quad is produced BY an MMA (0 * 0 + c) so that ptxas keeps
+            // it in four consecutive registers for the whole loop instead of re-assembling it with moves before every HMMA.
+            const float cinit[4] = {-m0, -m0, -m1, -m1};
+            float cq[4];
+            mma_16x8x8_c<T>(cq, 0u, 0u, 0u, cinit);
+            // 32 keys per half step (one 128-bit K fragment load, one V fragment load): short live ranges keep the kernel at
+            // 64 registers = 8 warps per scheduler, which is what lets the MUFU / HMMA / FMA pipes overlap
+            // (tools/microbench/pipes.cu: the same instruction mix runs 1.34x faster at 8 than at 6 warps per scheduler)
+            const uint4* kf = reinterpret_cast<const uint4*>(Kf + 256) + lane;
+            const uint4* vf = reinterpret_cast<const uint4*>(Vf + 256) + lane;
+            // largest P seen on the MUFU path since the last re-centring (fp16 only): a stale row max costs the packed-half
+            // polynomial input precision (x is rounded to fp16 before the range reduction), so when the sampled P exceeds
+            // 2^2 the row is re-centred on it — o and l are scaled by 1/P, m grows by log2(P).  Sampling the MUFU half of the
+            // scores is enough for precision; overflow proper is still caught by the non-finite check below.
+            float pm0 = 0.f, pm1 = 0.f;
+#pragma unroll 2
+            for (int hb = 2; hb < 2 * nblk; ++hb, kf += 32, vf += 32) {
+                const uint4 kA = *kf;
+                const uint32_t kb_[4] = {kA.x, kA.y, kA.z, kA.w};
+                uint32_t pa[4][2];
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    float s[4];
+                    mma_16x8x8_c<T>(s, qa0, qa1, kb_[kb], cq);
+                    if ((POLY_MASK >> (2 * kb)) & 1u) pa[kb][0] = ex2_pair_poly<T>(s[0], s[1]);
+                    else {
+                        const float p0 = ex2(s[0]), p1 = ex2(s[1]);
+                        if (kRecentre) pm0 = fmaxf(pm0, fmaxf(p0, p1));
+                        pa[kb][0] = pack2<T>(p0, p1);
+                    }
+                    if ((POLY_MASK >> (2 * kb + 1)) & 1u) pa[kb][1] = ex2_pair_poly<T>(s[2], s[3]);
+                    else {
+                        const float p2 = ex2(s[2]), p3 = ex2(s[3]);
+                        if (kRecentre) pm1 = fmaxf(pm1, fmaxf(p2, p3));
+                        pa[kb][1] = pack2<T>(p2, p3);
+                    }
+                }
+                const uint4 vA = *vf;
+                const uint32_t vb_[4] = {vA.x, vA.y, vA.z, vA.w};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mma_16x8x16<T>(o, pa[2 * j][0], pa[2 * j][1], pa[2 * j + 1][0], pa[2 * j + 1][1], vb_[2 * j], vb_[2 * j + 1]);
+                    mma_16x8x16<T>(l, pa[2 * j][0], pa[2 * j][1], pa[2 * j + 1][0], pa[2 * j + 1][1], ones, ones);
+                }
+                if (kRecentre && (hb & 1) && __any_sync(0xffffffffu, fmaxf(pm0, pm1) > 4.0f)) {
+                    pm0 = fmaxf(pm0, __shfl_xor_sync(0xffffffffu, pm0, 1));
+                    pm0 = fmaxf(pm0, __shfl_xor_sync(0xffffffffu, pm0, 2));
+                    pm1 = fmaxf(pm1, __shfl_xor_sync(0xffffffffu, pm1, 1));
+                    pm1 = fmaxf(pm1, __shfl_xor_sync(0xffffffffu, pm1, 2));
+                    // shift by the power of two below the sampled maximum (exact scaling; never re-centre downwards)
+                    const int d0 = (__float_as_int(fminf(fmaxf(pm0, 1.0f), 1.0e30f)) >> 23) - 127;
+                    const int d1 = (__float_as_int(fminf(fmaxf(pm1, 1.0f), 1.0e30f)) >> 23) - 127;
+                    const float r0 = __int_as_float((127 - d0) << 23), r1 = __int_as_float((127 - d1) << 23);
+                    o[0] *= r0; o[1] *= r0; o[2] *= r1; o[3] *= r1;
+                    l[0] *= r0; l[1] *= r0; l[2] *= r1; l[3] *= r1;
+                    m0 += (float)d0; m1 += (float)d1;
+                    const float cnew[4] = {-m0, -m0, -m1, -m1};
+                    mma_16x8x8_c<T>(cq, 0u, 0u, 0u, cnew);
+                    pm0 = pm1 = 0.f;
+                }
+            }
+        }
+        const bool bad = !(fabsf(l[0]) <= 3.0e38f) || !(fabsf(l[2]) <= 3.0e38f) || !(fabsf(o[0]) <= 3.0e38f) ||
+                         !(fabsf(o[1]) <= 3.0e38f) || !(fabsf(o[2]) <= 3.0e38f) || !(fabsf(o[3]) <= 3.0e38f);
+        if (__any_sync(0xffffffffu, bad)) {
+            // a score beyond the block-0 maximum by 2^16 overflowed the 16-bit P (or the input holds inf / NaN): redo this
+            // query block with the exact online softmax
+            m0 = m1 = -INFINITY;
+            o[0] = o[1] = o[2] = o[3] = 0.f;
+            l[0] = l[1] = l[2] = l[3] = 0.f;
+#pragma unroll 1
+            for (int blk = 0; blk < nblk; ++blk) attn_exact_step<T>(Kf + blk * 256, Vf + blk * 256, lane, qa0, qa1, ones, m0, m1, o, l);
+        }
+        const float i0 = 1.0f / l[0], i1 = 1.0f / l[2];
+        T* ob = out + (size_t)n * S * C + head * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g) * C) = pack2<T>(o[0] * i0, o[1] * i0);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)(q0 + g + 8) * C) = pack2<T>(o[2] * i1, o[3] * i1);
+    }
+}
+
+template <typename T, uint32_t MASK>
+static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* out, dim3 grid, size_t smem, cudaStream_t s) {
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        PD_CHECK_CUDA(cudaFuncSetAttribute(attention_head_kernel<T, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    attention_head_kernel<T, MASK><<<grid, AH_WARPS * 32, smem, s>>>((const T*)qkv, S, C, qmul, (T*)out);
+    return 0;
+}
+
+// qfold: the factor the caller already folded into q (1 = raw q; AH_SL = the finalize-time fold of pd_api.cu)
+int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s) {
+    PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "attention_mma takes bf16 or fp16 activations");
+    PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
+    PD_REQUIRE(S % 64 == 0 && C % 8 == 0, "attention_mma needs S % 64 == 0");
+    static int variant = -1, polyv = -1;
+    if (variant < 0) {
+        const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL"); // "v2": the chunked per-128-query kernel; default v3
+        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : 3;
+        const char* pe = getenv("PHENDIFF_B200_ATTN_POLYPAIRS");   // v3: score pairs of 16 per step on the FMA/ALU pipes
+        polyv = pe ? atoi(pe) : -1;
+    }
+    const size_t smem = (size_t)S * 32;
+    if (variant == 2 || smem > 200 * 1024) return launch_attention_chunked(dt, qkv, N, S, C, d, AH_SL / qfold, out, s);
+    const float qmul = AH_SL / qfold;
+    const int heads = C / 8;
+    int split = 1;
+    while (split < 8 && (size_t)heads * N * split < 1184 && (S >> 4) / (split * 2) >= AH_WARPS) split *= 2;
+    dim3 grid(split, heads, N);
+    int pp = polyv;
+    if (pp < 0) pp = (dt == DT_F16) ? 6 : 4;   // measured flat between 4 and 8 (profiles/r1k_attention.md); the sum of pipe cycles is what counts
+#define PD_AH(MASK) PD_DISPATCH_HALF(dt, T, (launch_head<T, MASK>(qkv, N, S, C, qmul, out, grid, smem, s)))
+    switch (pp) {
+        case 0: PD_AH(0x0000u); break;
+        case 4: PD_AH(0x4242u); break;
+        case 6: PD_AH(0x6262u); break;
+        case 7: PD_AH(0x6662u); break;
+        case 10: PD_AH(0xE6E6u); break;
+        case 12: PD_AH(0xEEEEu); break;
+        default: PD_AH(0x6666u); break;
+    }
+#undef PD_AH
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

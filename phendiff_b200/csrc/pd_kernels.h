@@ -84,7 +84,10 @@ int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void*
 // ---- attention core: softmax(q k^T / sqrt(d)) v on packed qkv (N,S,3C) ------------------------------------------
 int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
                           cudaStream_t s);
-int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s);  // bf16 / fp16
+// bf16 / fp16 tensor-core path.  qfold = the factor already folded into q by the caller: 1 for raw q, PD_ATTN_QFOLD when
+// the q rows of the fused qkv weight were pre-multiplied at finalize (scores then leave the MMA in log2 units)
+constexpr float PD_ATTN_QFOLD = 0.35355339059327373f * 1.4426950408889634f;   // log2(e) / sqrt(8)
+int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s);
 
 // ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -318,26 +318,69 @@ def test_groupnorm(build_lib, bf, shape):
     assert err <= tol, f"groupnorm bf={bf} {shape}: {err:.3e}"
 
 
-@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "mma_bf16", "mma_fp16"])
-@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (1, 1024, 64)])
-def test_attention(build_lib, mode, shape):
-    n, s, c = shape
+QFOLD = math.log2(math.e) / math.sqrt(8)   # what pd_unet_finalize folds into the q rows of the fused qkv projection
+
+
+def _attention_case(build_lib, mode, qkv, n, s, c):
+    """mode: simt_* (raw q), mma_* (q pre-multiplied by QFOLD in fp32 before the one rounding to 16 bits, like the product),
+    mmaraw_* (tensor-core kernel on raw q: it rescales the 16-bit q itself, one extra rounding).  The reference is the fp64
+    softmax attention of exactly the 16-bit values the kernel reads."""
     L = build_lib.lib()
-    bf = {"fp32": 0, "bf16": 1, "fp16": 2}[mode.split("_")[1]]
+    kind, prec = mode.split("_")
+    bf = {"fp32": 0, "bf16": 1, "fp16": 2}[prec]
     dt = DT[bf]
-    g = torch.Generator().manual_seed(5)
-    qkv = torch.randn(n, s, 3 * c, generator=g) * 1.5
+    qkv = qkv.clone()
+    if kind == "mma":
+        qkv[..., :c] *= QFOLD
     qq = qkv.to(dt).double()
     h = c // 8
     q, k, v = [t.reshape(n, s, h, 8).transpose(1, 2) for t in qq.split(c, dim=-1)]
+    if kind == "mma":
+        q = q / QFOLD
     ref = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(8), -1) @ v
     ref = ref.transpose(1, 2).reshape(n, s, c).float()
     out = torch.empty(n, s, c, dtype=dt, device="cuda")
-    qd = qkv.to(dt).cuda()
-    build_lib.check(L.pd_test_attention(int(mode.startswith("mma")), bf, n, s, c, 8, _p(qd), _p(out), None))
-    err = (out.float().cpu() - ref).abs().max().item()
+    use = {"simt": 0, "mmaraw": 1, "mma": 2}[kind]
+    build_lib.check(L.pd_test_attention(use, bf, n, s, c, 8, _p(qkv.to(dt).cuda()), _p(out), None))
+    return out.float().cpu(), ref, bf
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "mma_bf16", "mma_fp16", "mmaraw_fp16"])
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (1, 1024, 64), (3, 1024, 512)])
+def test_attention(build_lib, mode, shape):
+    n, s, c = shape
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(n, s, 3 * c, generator=g) * 1.5
+    got, ref, bf = _attention_case(build_lib, mode, qkv, n, s, c)
+    err = (got - ref).abs().max().item()
     tol = {0: 1e-4, 1: 3e-2, 2: 4e-3}[bf]
+    if mode.startswith("mmaraw"):
+        tol = 1.2e-2   # q * log2(e)/sqrt(8) is rounded to fp16 a second time inside the kernel
     assert err <= tol, f"attention {mode} {shape}: {err:.3e}"
+
+
+@pytest.mark.parametrize("mode", ["mma_bf16", "mma_fp16"])
+@pytest.mark.parametrize("s", [256, 1024, 4096])
+def test_attention_stale_max_fallback(build_lib, mode, s):
+    """The head-resident kernel fixes each row's max after key block 0.  A late key whose score exceeds that max by more
+    than 2^16 (in probability) overflows the 16-bit P and must trigger the exact redo; a late key with a hugely negative
+    score must contribute exactly nothing (polynomial exp flushes to 0, not to its clamp value)."""
+    n, c = 1, 64
+    bf = {"bf16": 1, "fp16": 2}[mode.split("_")[1]]
+    g = torch.Generator().manual_seed(9)
+    qkv = torch.randn(n, s, 3 * c, generator=g) * 0.4
+    q = qkv[..., :c]
+    q += 1.5
+    q[:, ::2] *= -1.0                       # even rows: the hot key scores ~ -70 (log2 units); odd rows: ~ +70
+    hot = s - 37
+    qkv[:, hot, c:2 * c] = 12.0             # k of the hot key
+    qkv[:, hot, 2 * c:] = 3.0               # its value: odd rows must return ~3, even rows the average of the others
+    got, ref, _ = _attention_case(build_lib, mode, qkv, n, s, c)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    tol = {1: 3e-2, 2: 4e-3}[bf]
+    assert err <= tol, f"attention {mode} S={s}: {err:.3e}"
+    assert (got[:, 1::2] - 3.0).abs().max().item() <= tol
 
 
 @pytest.mark.parametrize("sched", ["3k_steps_clipping_rescaling", "1k_epsilon_pred", "SD_orig_config", "better_SD_config"])
