@@ -41,6 +41,7 @@ struct HaloParams {
     int m_tiles, n_tiles, phases, b_rows_per_phase;
     int Ho, Wo;                    // output extent (2x the tile-space extent in upsample mode)
     int upsample, use_base_offset;
+    int mt;                        // M halves per tile: 1 = 16x8 pixels, 2 = 16x16 pixels (two accumulators share every weight tile)
     TcEpi epi;
 };
 
@@ -56,11 +57,13 @@ constexpr int HL_EPI_BYTES = 8 * 4096;   // one 4 KB output slab per epilogue wa
 // epilogue warps that have work: two per TMEM lane quarter when the tile has >= 2 slabs of 64 output channels
 template <int BLOCK_N, int MODE> struct HaloEpiWarps { static constexpr int value = (MODE == TC_MODE_STD && BLOCK_N >= 128) ? 8 : 4; };
 
-template <int BLOCK_N, typename T, int MODE, int CW>
+template <int BLOCK_N, typename T, int MODE, int CW, int MT>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     constexpr int EPI_WARPS = HaloEpiWarps<BLOCK_N, MODE>::value;
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-    constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    constexpr int TMEM_COLS = (2 * MT * BLOCK_N < 32) ? 32 : 2 * MT * BLOCK_N;
+    static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
+    constexpr int TILE_W = HL_WT * MT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int SA = p.SA, SB = p.SB;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 const int phase = t2 % p.phases, m_tile = t2 / p.phases;
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
                 const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-                const int h0 = th * HL_HT, w0 = tw * HL_WT;
+                const int h0 = th * HL_HT, w0 = tw * TILE_W;
                 const int oh = p.off_h + (p.upsample ? (phase >> 1) : 0), ow = p.off_w + (p.upsample ? (phase & 1) : 0);
                 const int brow = phase * p.b_rows_per_phase + n_tile * BLOCK_N;
                 int kcol = 0;
@@ -156,12 +159,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 const uint32_t aphase = (iter >> 1) & 1;
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BLOCK_N);
                 uint32_t accum = 0;
                 for (int seg = 0; seg < 3; ++seg) {
                     const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
                     const int ntap = seg == 0 ? p.ntaps : 1;
-                    const int pitch = seg == 0 ? p.pitch_px : HL_WT;
+                    const int pitch = seg == 0 ? p.pitch_px : TILE_W;
                     const uint32_t sbo = (uint32_t)pitch * 128u;
                     for (int cb = 0; cb < nkb; ++cb) {
                         mbar_wait(&fullA[sa], pha);
@@ -172,13 +175,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                             tc_fence_after();
                             const int r = tap / p.kw, s = tap - r * p.kw;
                             const uint32_t row_off = (uint32_t)(r * pitch + s);
-                            const uint64_t a_desc = make_sw128_desc(a_base + row_off * 128u, sbo, p.use_base_offset ? row_off : 0u);
                             const uint64_t b_desc = make_sw128_desc(smem_u32(smB + (size_t)sb * B_BYTES));
 #pragma unroll
-                            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-                                umma_f16kind(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
-                                accum = 1;
+                            for (int half = 0; half < MT; ++half) {
+                                // the second 16x8-pixel half starts 8 pixel rows (one 1024-byte swizzle atom) further in the same halo tile
+                                const uint32_t ro = row_off + (uint32_t)(half * HL_WT);
+                                const uint64_t a_desc = make_sw128_desc(a_base + ro * 128u, sbo, p.use_base_offset ? ro : 0u);
+#pragma unroll
+                                for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                                    umma_f16kind(d_tmem + (uint32_t)(half * BLOCK_N), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                                 (accum | (uint32_t)k) ? 1u : 0u);
                             }
+                            accum = 1;
                             umma_commit(&emptyB[sb]);
                             if (++sb == SB) { sb = 0; phb ^= 1; }
                         }
@@ -209,17 +217,15 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             const int phase = t2 % p.phases, m_tile = t2 / p.phases;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
             const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-            const int h0 = th * HL_HT, w0 = tw * HL_WT;
-            int oh = h0 + hh, ow = w0 + ww;
-            if (p.upsample) { oh = 2 * oh + (phase >> 1); ow = 2 * ow + (phase & 1); }
-            const int hw = oh * p.Wo + ow;
-            const size_t pix = (size_t)img * p.Ho * p.Wo + hw;
+            const int h0 = th * HL_HT, w0 = tw * TILE_W;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BLOCK_N);
             if (MODE == TC_MODE_DDIM) {
+                int oh = h0 + hh, ow = w0 + ww;
+                const int hw = oh * p.Wo + ow;
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(t_addr, r);
                 tmem_ld_wait();
@@ -227,12 +233,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 mbar_arrive(&tempty[as]);      // accumulator is in registers: the MMA warp may overwrite this TMEM buffer
                 tc_epilogue_ddim(p.epi, r, img, hw);
             } else {
+                constexpr int SLABS = BLOCK_N >= 64 ? BLOCK_N / 64 : 1, ITEMS = MT * SLABS;
 #pragma unroll 1
-                for (int slab = slab0; slab < BLOCK_N / 64; slab += SLAB_STEP) {
+                for (int item = slab0; item < ITEMS; item += SLAB_STEP) {
+                    const int half = item / SLABS, slab = item - half * SLABS;
+                    const int wh = w0 + half * HL_WT;             // first output column of this 16x8-pixel half
+                    int oh = h0 + hh, ow = wh + ww;
+                    if (p.upsample) { oh = 2 * oh + (phase >> 1); ow = 2 * ow + (phase & 1); }
+                    const size_t pix = (size_t)img * p.Ho * p.Wo + (size_t)oh * p.Wo + ow;
                     const int col0 = n_tile * BLOCK_N + slab * 64;
+                    const uint32_t t_item = t_addr + (uint32_t)(half * BLOCK_N + slab * 64);
                     uint32_t r0[32], r1[32];
-                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(slab * 64), r0);
-                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(slab * 64 + 32), r1);
+                    tmem_ld_32x32b_x32(t_item, r0);
+                    tmem_ld_32x32b_x32(t_item + 32u, r1);
                     uint4 res[8];
                     const bool has_res = p.epi.residual != nullptr;
                     if (has_res) {
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const int i = (lane >> 3) + 4 * k;
-                            const size_t rp = (size_t)img * p.Ho * p.Wo + (size_t)(h0 + 4 * q + (i >> 3)) * p.Wo + (w0 + (i & 7));
+                            const size_t rp = (size_t)img * p.Ho * p.Wo + (size_t)(h0 + 4 * q + (i >> 3)) * p.Wo + (wh + (i & 7));
                             res[k] = __ldg(reinterpret_cast<const uint4*>(rbase + rp * p.epi.Cout));
                         }
                     }
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                         __syncwarp();
                     }
                     tmem_ld_wait();
-                    if (slab + SLAB_STEP >= BLOCK_N / 64) {   // last slab of this warp: its share of the accumulator is in registers
+                    if (item + SLAB_STEP >= ITEMS) {   // last item of this warp: its share of the accumulators is in registers
                         tc_fence_before();
                         mbar_arrive(&tempty[as]);
                     }
@@ -268,8 +281,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.upsample) tma_store_5d(&p.tmOut, buf, col0, phase & 1, w0, phase >> 1, img * (p.Ho >> 1) + h0 + 4 * q);
-                        else tma_store_4d(&p.tmOut, buf, col0, w0, h0 + 4 * q, img);
+                        if (p.upsample) tma_store_5d(&p.tmOut, buf, col0, phase & 1, wh, phase >> 1, img * (p.Ho >> 1) + h0 + 4 * q);
+                        else tma_store_4d(&p.tmOut, buf, col0, wh, h0 + 4 * q, img);
                         bulk_commit();
                     }
                 }
@@ -290,6 +303,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------------------
 static int halo_block_n(const ConvTcDesc& d) {
     if (d.mode == TC_MODE_DDIM) return d.Cout <= 16 ? 16 : 0;
+    // 1x1 / linear layers have K = C only: a 128x256 tile re-streams 384 KB from L2 per 33 MFLOP (the qkv projection sat at
+    // 660 TFLOP/s on the crossbar limit); 256 pixels x 128 channels on the dual-accumulator tile moves the same bytes for 2x the work
+    static const int lin128 = [] { const char* e = getenv("PHENDIFF_B200_HALO_LIN128"); return e ? atoi(e) : 1; }();
+    if (lin128 && d.ksize == 1 && !d.upsample && d.Cout % 128 == 0 && d.W % (2 * HL_WT) == 0) return 128;
     if (d.Cout % 256 == 0) return 256;
     if (d.Cout % 128 == 0) return 128;
     if (d.Cout % 64 == 0) return 64;
@@ -328,15 +345,23 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     // descriptor base offset to the row phase of the shifted start
     const char* pk = getenv("PHENDIFF_B200_HALO_PITCH");
     const bool pow2 = pk && std::string(pk) == "pow2";
-    p.pitch_px = (kw == 1) ? HL_WT : (pow2 ? 16 : HL_WT + kw - 1);
+    // M halves per tile: layers with <= 128 output channels per tile are bound by the L2 -> SM stream of the weight tiles
+    // (profiles/r1k_ncu_conv_halo128.md: 7.8 TB/s of crossbar reads, tensor pipe 47 % active): a 16x16-pixel tile feeds two
+    // accumulators from every weight tile and halves that stream.  TMEM holds 2 (double buffer) x mt x block_n fp32 columns.
+    int mt = 1;
+    if (d.mode == TC_MODE_STD && pl->block_n <= 128 && d.W % (2 * HL_WT) == 0 && !pow2) mt = 2;
+    if (const char* e = getenv("PHENDIFF_B200_HALO_MT")) mt = (atoi(e) == 2 && mt == 2) ? 2 : 1;
+    p.mt = mt;
+    const int tile_w = HL_WT * mt;
+    p.pitch_px = (kw == 1) ? tile_w : (pow2 ? 16 : tile_w + kw - 1);
     const char* bo = getenv("PHENDIFF_B200_HALO_BASEOFF");
     p.use_base_offset = bo ? (bo[0] != '0') : 0;
     const int rows = HL_HT + kh - 1;
     p.a_bytes_main = 128 * p.pitch_px * rows;
-    p.a_bytes_sc = 128 * HL_WT * HL_HT;
+    p.a_bytes_sc = 128 * tile_w * HL_HT;
     p.a_stage_bytes = ((std::max(p.a_bytes_main, p.a_bytes_sc) + 1023) / 1024) * 1024;
     p.C = d.C; p.kb_main = d.C / 64; p.kb_s1 = d.Csc1 / 64; p.kb_s2 = d.Csc2 / 64;
-    p.tilesW = d.W / HL_WT; p.tilesH = d.H / HL_HT;
+    p.tilesW = d.W / tile_w; p.tilesH = d.H / HL_HT;
     p.off_h = p.off_w = d.upsample ? -1 : -d.pad;
     p.m_tiles = d.N * p.tilesW * p.tilesH;
     p.phases = d.upsample ? 4 : 1;
@@ -352,7 +377,7 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     const int b_bytes = pl->block_n * 128;
     const int epi_bytes = d.mode == TC_MODE_STD ? HL_EPI_BYTES : 0;
     const int budget = 227 * 1024 - 1024 - 512 - epi_bytes;
-    p.SA = pl->block_n >= 256 ? 2 : 3;
+    p.SA = (pl->block_n >= 256 || mt == 2) ? 2 : 3;
     if (pl->block_n == 16) p.SA = 4;
     p.SB = std::min(16, (budget - p.SA * p.a_stage_bytes) / b_bytes);
     if (p.SB < 2) { delete pl; set_error("conv_halo: shared memory budget too small"); return 1; }
@@ -373,7 +398,7 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
         uint64_t Cs = cscs[i];
         uint64_t dims[4] = {Cs, W, H, N};
         uint64_t st[3] = {Cs * 2, W * Cs * 2, H * W * Cs * 2};
-        uint32_t box[4] = {64, HL_WT, HL_HT, 1};
+        uint32_t box[4] = {64, (uint32_t)tile_w, HL_HT, 1};
         if ((rc = tc_encode_map(tms[i], d.dt, scs[i], 4, dims, st, box))) { delete pl; return rc; }
     }
     {
@@ -406,17 +431,26 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
 
 void conv_halo_plan_destroy(ConvHaloPlan* p) { delete p; }
 
-template <int BLOCK_N, typename T, int MODE, int CW>
+template <int BLOCK_N, typename T, int MODE, int CW, int MT>
 static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t s) {
     static size_t attr_smem = 0;
     if (pl->smem > attr_smem) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE, CW, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)pl->smem));
         attr_smem = pl->smem;
     }
-    conv_halo_kernel<BLOCK_N, T, MODE, CW><<<pl->grid, HALO_THREADS, pl->smem, s>>>(p);
+    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT><<<pl->grid, HALO_THREADS, pl->smem, s>>>(p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int BLOCK_N, typename T>
+static int launch_halo_std(const ConvHaloPlan* pl, cudaStream_t s) {
+    const bool cw2 = pl->p.epi.stats != nullptr && pl->p.epi.stats_cw == 2;
+    if (BLOCK_N <= 128 && pl->p.mt == 2)
+        return cw2 ? launch_halo<(BLOCK_N <= 128 ? BLOCK_N : 128), T, TC_MODE_STD, 2, 2>(pl, pl->p, s)
+                   : launch_halo<(BLOCK_N <= 128 ? BLOCK_N : 128), T, TC_MODE_STD, 4, 2>(pl, pl->p, s);
+    return cw2 ? launch_halo<BLOCK_N, T, TC_MODE_STD, 2, 1>(pl, pl->p, s) : launch_halo<BLOCK_N, T, TC_MODE_STD, 4, 1>(pl, pl->p, s);
 }
 
 int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch* extra) {
@@ -430,14 +464,13 @@ int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch*
             PD_REQUIRE(extra->step->sigma == 0.f, "fused conv_out update requires eta == 0");
             p.epi.step = *extra->step;
         }
-        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM, 4>(pl, p, s); });
+        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM, 4, 1>(pl, p, s); });
     }
-    const bool cw2 = pl->p.epi.stats != nullptr && pl->p.epi.stats_cw == 2;
     PD_DISPATCH_HALF(pl->dt, T, {
         switch (pl->block_n) {
-            case 256: return cw2 ? launch_halo<256, T, TC_MODE_STD, 2>(pl, pl->p, s) : launch_halo<256, T, TC_MODE_STD, 4>(pl, pl->p, s);
-            case 128: return cw2 ? launch_halo<128, T, TC_MODE_STD, 2>(pl, pl->p, s) : launch_halo<128, T, TC_MODE_STD, 4>(pl, pl->p, s);
-            case 64: return cw2 ? launch_halo<64, T, TC_MODE_STD, 2>(pl, pl->p, s) : launch_halo<64, T, TC_MODE_STD, 4>(pl, pl->p, s);
+            case 256: return launch_halo_std<256, T>(pl, s);
+            case 128: return launch_halo_std<128, T>(pl, s);
+            case 64: return launch_halo_std<64, T>(pl, s);
         }
     });
     set_error("conv_halo: bad block_n");

@@ -216,6 +216,9 @@ HALO_CASES = [
     (1, 32, 32, 128, 128, 3, 1, dict(sc=(128, 64))),                        # conv2 + K-concatenated 1x1 shortcut over a concat
     (1, 16, 16, 1024, 512, 3, 1, dict(addvec=True)),                        # long K (up0.res0.conv1)
     (4, 16, 16, 64, 64, 3, 1, dict(addvec=True, addvec_rows=2)),            # time-embedding rows indexed by class label
+    (1, 16, 48, 128, 128, 3, 1, dict(addvec=True, residual=True)),          # 16x16-pixel dual-accumulator tiles, 3 tiles wide
+    (1, 16, 24, 64, 128, 3, 1, {}),                                         # W % 16 != 0: falls back to 16x8 tiles
+    (2, 32, 32, 256, 128, 1, 0, dict(residual=True)),                       # 1x1 on dual-accumulator tiles
 ]
 
 
