@@ -186,7 +186,8 @@ int pd_test_groupnorm(int32_t dtype, int32_t n, int32_t hw, int32_t c1, int32_t 
                       void* out, pd_stream_t stream);
 /* self-attention core on packed qkv (N, S, 3C) -> (N, S, C), head_dim d.  use_mma: 0 = SIMT kernel, 1 = tensor-core kernel on
    raw q, 2 = tensor-core kernel on q already multiplied by log2(e)/sqrt(d) (what pd_unet_finalize folds into the q rows of
-   the fused qkv projection, so that scores leave the MMA in log2 units) */
+   the fused qkv projection, so that scores leave the MMA in log2 units); 3 / 4 / 5 = as 2 but forcing the chunked warp-level /
+   head-resident warp-level / tcgen05 kernel */
 int pd_test_attention(int32_t use_mma, int32_t dtype, int32_t n, int32_t s, int32_t c, int32_t d, const void* qkv,
                       void* out, pd_stream_t stream);
 

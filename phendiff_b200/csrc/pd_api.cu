@@ -1234,7 +1234,7 @@ int pd_test_attention(int32_t use_mma, int32_t dt, int32_t n, int32_t s_len, int
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     if (use_mma) {
-        rc = launch_attention_mma(dt, qkv, n, s_len, c, d, use_mma == 2 ? PD_ATTN_QFOLD : 1.0f, out, s);
+        rc = launch_attention_mma(dt, qkv, n, s_len, c, d, use_mma >= 2 ? PD_ATTN_QFOLD : 1.0f, out, s, use_mma >= 3 ? use_mma - 1 : 0);
     } else {
         rc = launch_attention_simt(dt, dt == 0, qkv, n, s_len, c, d, out, s);
     }

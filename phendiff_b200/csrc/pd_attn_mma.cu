@@ -12,31 +12,13 @@
 //     64-key step with two 128-bit loads each (no bank conflicts, 4 instead of 16 load instructions per step);
 //   * one exponential in four is evaluated on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial,
 //     7.7e-5 relative error, below the 16-bit rounding of P) so the MUFU pipe and the issue slots run out together.
-#include "pd_kernels.h"
-#include <type_traits>
+#include "pd_attn_common.cuh"
 
 namespace pd {
 
 constexpr int AT_WARPS = 8;        // 16 queries per warp, 128 per CTA
 constexpr int AT_MAXS = 1024;      // keys resident in shared memory per pass
 
-__device__ __forceinline__ float ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// 2^x for x <= 0 on the FMA / ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial,
-// scaled by 2^n through the exponent field
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fminf(fmaxf(x, -100.0f), 128.0f);   // 128 -> exponent field 255 = +inf (overflow of a stale row max stays visible)
-    const float t = x + 12582912.0f;
-    const float f = x - (t - 12582912.0f);
-    float p = 0.05508868396282196f;
-    p = fmaf(p, f, 0.24260404706001282f);
-    p = fmaf(p, f, 0.6932762265205383f);
-    p = fmaf(p, f, 0.9999289512634277f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 template <typename T>
 __device__ __forceinline__ void mma_16x8x8(float c[4], uint32_t a0, uint32_t a1, uint32_t b0) {
     if (std::is_same<T, bf16>::value)
@@ -231,32 +213,6 @@ __device__ __forceinline__ void mma_16x8x8_c(float (&d)[4], uint32_t a0, uint32_
             : "r"(a0), "r"(a1), "r"(b0), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
 
-__device__ __forceinline__ uint32_t h2op_add(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t h2op_sub(uint32_t a, uint32_t b) { uint32_t d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t h2op_mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t h2op_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-__device__ __forceinline__ uint32_t h2op_min(uint32_t a, uint32_t b) { uint32_t d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t h2op_max(uint32_t a, uint32_t b) { uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-
-// (2^xa, 2^xb) as packed fp16 (low half = xa), on the FMA / ALU pipes.  x is clamped to [-15, 16]: n = round(x) rides in
-// the low mantissa bits of w = x + 1039 (ulp 1 in [1024, 2048)) as 15 + n = the fp16 exponent field of 2^n, so
-// x <= -14.5 gives exactly 0 and x >= 15.5 gives +inf (which is what flags the overflow of a stale row max).
-__device__ __forceinline__ uint32_t ex2_pair_h2(float xa, float xb) {
-    uint32_t x = pack_f16x2(xa, xb);
-    x = h2op_min(h2op_max(x, 0xCB80CB80u /* -15 */), 0x4C004C00u /* 16 */);
-    const uint32_t w = h2op_add(x, 0x640F640Fu /* 1039 */);
-    const uint32_t f = h2op_sub(x, h2op_sub(w, 0x640F640Fu));          // x - n in [-0.5, 0.5], exact
-    uint32_t p = h2op_fma(0x2B0D2B0Du /* 0.05508868 */, f, 0x33C333C3u /* 0.24260405 */);
-    p = h2op_fma(p, f, 0x398C398Cu /* 0.69327623 */);
-    p = h2op_fma(p, f, 0x3C003C00u /* 0.99992895 -> 1 */);
-    // exponent fields (15 + n) << 10 of both halves in one IMAD: (w - 0x64006400) * 1024, the subtraction folded into the addend
-    return h2op_mul(p, w * 1024u + (0u - 0x64006400u * 1024u));
-}
-
-template <typename T> __device__ __forceinline__ uint32_t ex2_pair_poly(float xa, float xb);
-template <> __device__ __forceinline__ uint32_t ex2_pair_poly<f16>(float xa, float xb) { return ex2_pair_h2(xa, xb); }
-template <> __device__ __forceinline__ uint32_t ex2_pair_poly<bf16>(float xa, float xb) { return pack_bf16x2(ex2_poly(xa), ex2_poly(xb)); }
-
 // One exact online-softmax step over a 64-key block (scores in log2 units): block 0 of every query block, and every block
 // of a query block whose fast pass overflowed.
 template <typename T>
@@ -303,7 +259,7 @@ __device__ __forceinline__ void attn_exact_step(const uint32_t* Kblk, const uint
 // POLY_MASK: bit 2*kb (2*kb+1) set = the score pair of accumulator rows g (g+8) of key octet kb goes to the polynomial
 template <typename T, uint32_t POLY_MASK>
 __global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_kernel(const T* __restrict__ qkv, int S, int C, float qmul,
-                                                                          T* __restrict__ out) {
+                                                                          T* __restrict__ out, const uint8_t* __restrict__ redo_flags) {
     extern __shared__ __align__(16) uint32_t ah_smem[];
     uint32_t* Kf = ah_smem;             // [S/64][2][32 lanes][4]: plane h, lane (g,t), word i = K[key 64 blk + 8 (4h+i) + g][dims 2t, 2t+1]
     uint32_t* Vf = ah_smem + S * 4;     // [S/64][2][32 lanes][4]: plane p, lane (g,t), word i = V[keys 64 blk + 16 (2p + (i>>1)) + 8 (i&1) + 2t, +1][dim g]
@@ -312,6 +268,13 @@ __global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_ker
     const int g = lane >> 2, t = lane & 3;
     const size_t rowp = (size_t)3 * C;
     const T* base = qkv + (size_t)n * S * rowp + head * 8;
+    // repair mode (after the tcgen05 kernel): only the 32-query groups it flagged (16-bit P overflow) are recomputed, exactly
+    const uint8_t* redo = redo_flags ? redo_flags + ((size_t)n * gridDim.y + head) * (size_t)(S >> 7) * 4 : nullptr;
+    if (redo) {
+        bool any = false;
+        for (int i = threadIdx.x; i < (S >> 7) * 4; i += blockDim.x) any = any || redo[i] != 0;
+        if (!__syncthreads_or(any)) return;
+    }
 
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
         const T* kp = base + (size_t)j * rowp + C;
@@ -348,6 +311,9 @@ __global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_ker
         }
         float o[4] = {0.f, 0.f, 0.f, 0.f}, l[4] = {0.f, 0.f, 0.f, 0.f};
         float m0 = -INFINITY, m1 = -INFINITY;
+        if (redo && !redo[(qb >> 3) * 4 + ((qb & 7) >> 1)]) continue;
+        bool need_exact = redo != nullptr;
+        if (!redo) {
         // key block 0: exact step, fixes the row maxima for the fast steps
         attn_exact_step<T>(Kf, Vf, lane, qa0, qa1, ones, m0, m1, o, l);
         {
@@ -415,7 +381,9 @@ __global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_ker
         }
         const bool bad = !(fabsf(l[0]) <= 3.0e38f) || !(fabsf(l[2]) <= 3.0e38f) || !(fabsf(o[0]) <= 3.0e38f) ||
                          !(fabsf(o[1]) <= 3.0e38f) || !(fabsf(o[2]) <= 3.0e38f) || !(fabsf(o[3]) <= 3.0e38f);
-        if (__any_sync(0xffffffffu, bad)) {
+        need_exact = __any_sync(0xffffffffu, bad);
+        }
+        if (need_exact) {
             // a score beyond the block-0 maximum by 2^16 overflowed the 16-bit P (or the input holds inf / NaN): redo this
             // query block with the exact online softmax
             m0 = m1 = -INFINITY;
@@ -432,30 +400,52 @@ __global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_ker
 }
 
 template <typename T, uint32_t MASK>
-static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* out, dim3 grid, size_t smem, cudaStream_t s) {
+static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* out, dim3 grid, size_t smem, cudaStream_t s,
+                       const uint8_t* redo = nullptr) {
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(attention_head_kernel<T, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    attention_head_kernel<T, MASK><<<grid, AH_WARPS * 32, smem, s>>>((const T*)qkv, S, C, qmul, (T*)out);
+    attention_head_kernel<T, MASK><<<grid, AH_WARPS * 32, smem, s>>>((const T*)qkv, S, C, qmul, (T*)out, redo);
     return 0;
 }
 
 // qfold: the factor the caller already folded into q (1 = raw q; AH_SL = the finalize-time fold of pd_api.cu)
-int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s) {
+int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s, int force_variant) {
     PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "attention_mma takes bf16 or fp16 activations");
     PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
     PD_REQUIRE(S % 64 == 0 && C % 8 == 0, "attention_mma needs S % 64 == 0");
     static int variant = -1, polyv = -1;
     if (variant < 0) {
-        const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL"); // "v2": the chunked per-128-query kernel; default v3
-        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : 3;
-        const char* pe = getenv("PHENDIFF_B200_ATTN_POLYPAIRS");   // v3: score pairs of 16 per step on the FMA/ALU pipes
+        // "v3" (default): warp-level head-resident kernel; "tc": tcgen05 / TMEM kernel + repair pass (functional, 1.3x slower
+        // than v3 in round 1: its two softmax warpgroups starve on three S buffers, profiles/r1o_attention_tc.md);
+        // "v2": chunked warp-level kernel (any S)
+        const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
+        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : ((e && e[0] == 't' && e[1] == 'c') ? 4 : 3);
+        const char* pe = getenv("PHENDIFF_B200_ATTN_POLYPAIRS");   // score pairs per 16 (v3) / per 8 (tc) on the FMA/ALU pipes
         polyv = pe ? atoi(pe) : -1;
     }
     const size_t smem = (size_t)S * 32;
-    if (variant == 2 || smem > 200 * 1024) return launch_attention_chunked(dt, qkv, N, S, C, d, AH_SL / qfold, out, s);
+    const int var = force_variant ? force_variant : variant;
+    if (var == 2 || smem > 200 * 1024) return launch_attention_chunked(dt, qkv, N, S, C, d, AH_SL / qfold, out, s);
+    if (var == 4 && S % 128 == 0 && attention_tc_smem_bytes(S) <= 110 * 1024) {
+        // flags: one byte per (image, head, 128-query tile, warp); grow-only scratch owned by the library
+        static uint8_t* flags = nullptr;
+        static size_t flags_cap = 0;
+        const size_t need = (size_t)N * (C / 8) * (S >> 7) * 4;
+        if (need > flags_cap) {
+            if (flags) PD_CHECK_CUDA(cudaFree(flags));
+            PD_CHECK_CUDA(cudaMalloc(&flags, need));
+            flags_cap = need;
+        }
+        int rc = launch_attention_tc(dt, qkv, N, S, C, AH_SL / qfold, out, flags, polyv < 0 ? (dt == DT_F16 ? 4 : 2) : polyv, s);
+        if (rc) return rc;
+        dim3 grid(1, C / 8, N);
+        PD_DISPATCH_HALF(dt, T, (launch_head<T, 0x0000u>(qkv, N, S, C, AH_SL / qfold, out, grid, smem, s, flags)));
+        PD_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     const float qmul = AH_SL / qfold;
     const int heads = C / 8;
     int split = 1;

@@ -87,7 +87,14 @@ int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, i
 // bf16 / fp16 tensor-core path.  qfold = the factor already folded into q by the caller: 1 for raw q, PD_ATTN_QFOLD when
 // the q rows of the fused qkv weight were pre-multiplied at finalize (scores then leave the MMA in log2 units)
 constexpr float PD_ATTN_QFOLD = 0.35355339059327373f * 1.4426950408889634f;   // log2(e) / sqrt(8)
-int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s);
+// force_variant: 0 = PHENDIFF_B200_ATTN_KERNEL / default, 2 = chunked warp-level, 3 = head-resident warp-level, 4 = tcgen05
+int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s,
+                         int force_variant = 0);
+// tcgen05 / TMEM kernel (pd_attn_tc.cu): q is multiplied by qmul while staging; flags[(n, head, 128-query tile, warp)] = 1 where
+// the 16-bit P overflowed and the rows must be recomputed by the exact warp-level pass
+size_t attention_tc_smem_bytes(int S);
+int launch_attention_tc(int dt, const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, int poly_pairs,
+                        cudaStream_t s);
 
 // ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
 #ifdef __CUDACC__
