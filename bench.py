@@ -289,7 +289,7 @@ def run_ours(args):
                 "share_by_class": {k: (v["ms"] / tot_ms if tot_ms else None) for k, v in prof.items() if isinstance(v, dict)},
                 "sampled_forwards": prof["samples"]}
         if gf:
-            model_tflops = value * 2 * n * gf / 1e3
+            model_tflops = value / world * 2 * n * gf / 1e3      # per GPU: the peaks below are single-GPU figures
             roof["whole_path_tflops"] = model_tflops
             roof["whole_path_frac_of_measured"] = model_tflops / pk["tflops"]
             roof["whole_path_frac_of_nominal_2250"] = model_tflops / 2250.0

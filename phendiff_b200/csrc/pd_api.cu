@@ -576,7 +576,7 @@ struct Rec {
                 const int N = mb;
                 const int dt = m->dt;
                 const bool precise = !m->half;
-                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, qfold, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C, "attention S=" + std::to_string(S) + " C=" + std::to_string(C));
+                if (use_mma) push([=](const Ctx&, cudaStream_t s) { return launch_attention_mma(dt, qp, N, S, C, d, qfold, op, s); }, attention_mma_launches(S), CLS_ATTN, 4.0 * N * (double)S * S * C, "attention S=" + std::to_string(S) + " C=" + std::to_string(C));
                 else push([=](const Ctx&, cudaStream_t s) { return launch_attention_simt(dt, precise, qp, N, S, C, d, op, s); }, 1, CLS_ATTN, 4.0 * N * (double)S * S * C);
             }
         }

@@ -411,6 +411,13 @@ static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* o
     return 0;
 }
 
+// kernel launches one launch_attention_mma call makes (the tcgen05 variant is followed by its repair pass)
+int attention_mma_launches(int S) {
+    const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
+    const bool tc = e && e[0] == 't' && e[1] == 'c';
+    return (tc && S % 128 == 0 && (size_t)S * 32 <= 200 * 1024 && attention_tc_smem_bytes(S) <= 110 * 1024) ? 2 : 1;
+}
+
 // qfold: the factor the caller already folded into q (1 = raw q; AH_SL = the finalize-time fold of pd_api.cu)
 int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s, int force_variant) {
     PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "attention_mma takes bf16 or fp16 activations");

@@ -16,7 +16,7 @@
 //     V'^T   : [S/64][16 rows][64 keys]: rows 0..7 = v dims, row 8 = ones (the PV product's column 8 is the softmax
 //              denominator, from the same rounded P the numerator uses), rows 9..15 = 0.
 //   TMEM: three S/P buffers of 64 fp32 columns (S = 128 queries x 64 keys; P overwrites columns 0..31 as packed 16-bit
-//         pairs = the A operand of the PV product, read straight from TMEM) + two O slots of 16 columns (O accumulates
+//         pairs [two halves of 16 columns, at columns 0 and 32] = the A operand of the PV product, read straight from TMEM) + two O slots of 16 columns (O accumulates
 //         over all key tiles of a query tile, the softmax threads read it once per query tile).
 //   warps 0-3: softmax (thread = one query row: row max / exponent pairs are thread-local, no shuffles);
 //   warp 4: MMA issuer; warp 5: TMEM allocator; warps 4-7 also stage.
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
     const int nqt = S >> 7, ntl = S >> 6, total = nqt * ntl;
 
     if (warp == ATC_SM_WARPS && lane == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pready[i], 128); mbar_init(&pvdone[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pready[i], 256); mbar_init(&pvdone[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&ofull[i], 1); mbar_init(&oread[i], 128); }
         mbar_init(qmready, 128);
         fence_barrier_init();
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
                 const uint32_t d = tmem_base + (uint32_t)(ATC_O_COL0 + 16 * (qt & 1));
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_f16kind_ts(d, tmem_base + (uint32_t)(buf * ATC_S_COLS + 8 * kk), atc_desc(v0 + (uint32_t)(j * 2048 + kk * 32)), idPV,
+                    umma_f16kind_ts(d, tmem_base + (uint32_t)(buf * ATC_S_COLS + 32 * (kk >> 1) + 8 * (kk & 1)), atc_desc(v0 + (uint32_t)(j * 2048 + kk * 32)), idPV,
                                     (j | kk) ? 1u : 0u);
                 if (j == ntl - 1) umma_commit(&ofull[qt & 1]);
                 if (i + 3 < total) {
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
             }
         }
     } else if (warp < ATC_SM_WARPS) {
-        // ===================== softmax: thread = query row; warpgroup wg takes the key tiles j = wg (mod 2) =====================
+        // ===================== softmax: two threads per query row (one per warpgroup, 32 keys of every tile each) =====================
         const int wg = warp >> 2, wq = warp & 3;          // TMEM lanes 32 wq .. 32 wq + 31 are this warp's
         const int row = wq * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
@@ -263,51 +263,52 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
             const bool anybad = __any_sync(0xffffffffu, bad);
             if (lane == 0) flags[(((size_t)n * gridDim.x + head) * nqt + qt) * 4 + wq] = anybad ? 1 : 0;
         };
-        for (int i = wg; i < total; i += 2) {
+        for (int i = 0; i < total; ++i) {
             const int qt = i / ntl, j = i - qt * ntl, buf = i % 3;
             mbar_wait(&sfull[buf], (uint32_t)(i / 3) & 1u);
             tc_fence_after();
+            // both warpgroups work on the SAME tile: warpgroup wg takes its keys 32 wg .. 32 wg + 31 (S columns 32 wg .. 32 wg + 31; its P
+            // overwrites the first 16 of those), so two whole tiles stay queued ahead of the softmax threads on the three buffers
             const uint32_t ts = lane_base + (uint32_t)(buf * ATC_S_COLS);
             uint32_t s[32], p[16];
-            float sub = 0.f;
             if (j == 0) {
-                // exact row max of key tile 0 -> Q' (so every later S tile arrives as s - m); this tile subtracts in registers
-                tmem_ld_32x32b_x32(ts + 32u, s);
+                // exact row max of key tile 0 -> Q' (so every later S tile arrives as s - m); this tile subtracts in registers.
+                // Both warpgroups read all 64 columns and get the same m; warpgroup 0 publishes it.
+                tmem_ld_32x32b_x32(ts + (uint32_t)(32 * (wg ^ 1)), s);
                 tmem_ld_wait();
                 float mx = __uint_as_float(s[0]);
 #pragma unroll
                 for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
-                tmem_ld_32x32b_x32(ts, s);
+                tmem_ld_32x32b_x32(ts + (uint32_t)(32 * wg), s);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
                 m = mx;
-                const T mh = from_f<T>(-m);
-                const T ml = from_f<T>(-m - to_f(mh));
-                *reinterpret_cast<uint4*>(smQ + (size_t)(qt >> 2) * 16384 + atc_tile_off(row, 2 * (qt & 3) + 1)) =
-                    make_uint4(atc_pack_raw<T>(mh, ml), 0u, 0u, 0u);
-                fence_proxy_async();
-                mbar_arrive(qmready);
-                sub = m;
+                if (wg == 0) {
+                    const T mh = from_f<T>(-m);
+                    const T ml = from_f<T>(-m - to_f(mh));
+                    *reinterpret_cast<uint4*>(smQ + (size_t)(qt >> 2) * 16384 + atc_tile_off(row, 2 * (qt & 3) + 1)) =
+                        make_uint4(atc_pack_raw<T>(mh, ml), 0u, 0u, 0u);
+                    fence_proxy_async();
+                    mbar_arrive(qmready);
+                }
+                atc_exp32<T, PP>(s, m, p);
+                // the other warpgroup may still be reading these S columns for its max: P is stored only after both are done
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             } else {
-                tmem_ld_32x32b_x32(ts, s);
+                tmem_ld_32x32b_x32(ts + (uint32_t)(32 * wg), s);
                 tmem_ld_wait();
+                atc_exp32_nosub<T, PP>(s, p);
             }
-            // P overwrites the S columns it was computed from: keys 0..31 -> columns 0..15, keys 32..63 -> columns 16..31
-            if (j == 0) atc_exp32<T, PP>(s, sub, p); else atc_exp32_nosub<T, PP>(s, p);
-            tmem_ld_32x32b_x32(ts + 32u, s);       // issued before the store below: column 32.. is untouched by it
-            tmem_st_32x32b_x16(ts, p);
-            tmem_ld_wait();
-            if (j == 0) atc_exp32<T, PP>(s, sub, p); else atc_exp32_nosub<T, PP>(s, p);
-            tmem_st_32x32b_x16(ts + 16u, p);
+            tmem_st_32x32b_x16(ts + (uint32_t)(32 * wg), p);      // P of keys 32 wg.. lands on the first 16 of this warpgroup's own S columns
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&pready[buf]);
             // O of the PREVIOUS query tile is collected one key tile into this one: waiting for it right after its last P
             // would deadlock (the MMA thread may be parked on qmready of the next query tile, which this thread signals)
-            if (j == 1 && qt >= 1) finish_qtile(qt - 1);
+            if (j == 1 && qt >= 1 && wg == 1) finish_qtile(qt - 1);
         }
-        if (wg == 1) finish_qtile(nqt - 1);      // the odd warpgroup collects every O (it owns j == 1)
+        if (wg == 1) finish_qtile(nqt - 1);      // warpgroup 1 collects every O
     }
     tc_fence_before();
     __syncthreads();

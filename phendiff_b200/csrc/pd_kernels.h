@@ -93,6 +93,7 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
 // tcgen05 / TMEM kernel (pd_attn_tc.cu): q is multiplied by qmul while staging; flags[(n, head, 128-query tile, warp)] = 1 where
 // the 16-bit P overflowed and the rows must be recomputed by the exact warp-level pass
 size_t attention_tc_smem_bytes(int S);
+int attention_mma_launches(int S);
 int launch_attention_tc(int dt, const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, int poly_pairs,
                         cudaStream_t s);
 

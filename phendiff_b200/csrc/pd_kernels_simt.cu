@@ -168,6 +168,12 @@ int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, f
 
 // normalise + affine (+SiLU) of concat(x1, x2): group statistics are finalised from the sources' chunk statistics in the
 // block prologue (per-channel scale / shift in shared memory), then every thread streams 8-channel vectors.
+
+// first-iteration prefetch of gn_apply: the raw 8 elements of a row (16-bit types: one 16-byte load; fp32: handled as two
+// loads folded into one uint4 pair by the fp32 specialisation below)
+template <typename T> __device__ __forceinline__ uint4 ld_raw8(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+template <typename T> __device__ __forceinline__ void unpack_raw8(const uint4& r, float v[8]) { unpack8<T>(r, v); }
+template <> __device__ __forceinline__ void unpack_raw8<float>(const uint4&, float v[8]) { for (int i = 0; i < 8; ++i) v[i] = 0.f; }   // fp32 rows are not prefetched
 template <typename T, bool kPrecise>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_block) {
     extern __shared__ float sm[];   // scale[C], shift[C], mean[groups], rstd[groups]
@@ -178,29 +184,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_bl
     float* s_rstd = s_mean + a.groups;
     const int n = blockIdx.y;
     const int cpg = C / a.groups, cw = a.stats_cw;
-    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
-    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-        float sum = 0.f, sq = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; c += cw) {
-            const float* st = (c < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + c / cw) * 2
-                                         : a.stats2 + ((size_t)n * (a.C2 / cw) + (c - a.C1) / cw) * 2;
-            sum += st[0]; sq += st[1];
-        }
-        const float mean = sum * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        s_mean[g] = mean;
-        s_rstd[g] = kPrecise ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float sc = s_rstd[g] * a.gamma[c];
-        s_sc[c] = sc;
-        s_sh[c] = a.beta[c] - s_mean[g] * sc;
-    }
-    __syncthreads();
+    // this thread's column of 8 channels and its rows; the first four 16-byte loads are issued BEFORE the statistics are
+    // finalised (they do not depend on them), so the block's prologue overlaps its first memory round trip
     const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
-    if (r0 >= rstep) return;
+    const bool worker = r0 < rstep;
     const int row_begin = blockIdx.x * rows_per_block;
     const int row_end = min(row_begin + rows_per_block, a.HW);
     const int c = cv * 8;
@@ -209,10 +196,52 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_bl
     if (c < a.C1) { src = (const T*)a.x1; pitch = a.C1; coff = c; } else { src = (const T*)a.x2; pitch = a.C2; coff = c - a.C1; }
     src += (size_t)n * a.HW * pitch + coff;
     T* dst = (T*)a.out + (size_t)n * a.HW * C + c;
+    int r = row_begin + r0;
+    uint4 pre[4];
+    const bool have_pre = sizeof(T) == 2 && worker && (r + 3 * rstep < row_end);
+    if (have_pre) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pre[u] = ld_raw8(src + (size_t)(r + u * rstep) * pitch);
+    }
+    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        float sum = 0.f, sq = 0.f;
+        for (int cc = g * cpg; cc < (g + 1) * cpg; cc += cw) {
+            const float* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
+                                          : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
+            sum += st[0]; sq += st[1];
+        }
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        s_mean[g] = mean;
+        s_rstd[g] = kPrecise ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+        const int g = cc / cpg;
+        const float scv = s_rstd[g] * a.gamma[cc];
+        s_sc[cc] = scv;
+        s_sh[cc] = a.beta[cc] - s_mean[g] * scv;
+    }
+    __syncthreads();
+    if (!worker) return;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = s_sc[c + i]; sh[i] = s_sh[c + i]; }
-    int r = row_begin + r0;
+    if (have_pre) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[8];
+            unpack_raw8<T>(pre[u], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float y = v[i] * sc[i] + sh[i];
+                v[i] = a.silu ? silu<kPrecise>(y) : y;
+            }
+            store8(dst + (size_t)(r + u * rstep) * C, v);
+        }
+        r += 4 * rstep;
+    }
     for (; r + 3 * rstep < row_end; r += 4 * rstep) {   // 4 independent 16-byte loads in flight per thread
         float v[4][8];
 #pragma unroll
@@ -248,7 +277,7 @@ int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s) {
     PD_REQUIRE(a.stats1 && (a.C2 == 0 || a.stats2), "GroupNorm sources need chunk statistics");
     const int block = gn_block(C);
     const int rstep = block / (C / 8);
-    int rows = rstep * 16;
+    int rows = rstep * (a.HW >= 4096 ? 32 : 16);   // 8 (4) iterations of 4 rows per thread: the prologue is amortised over >= 64 KB
     if (rows > a.HW) rows = a.HW;
     dim3 grid((a.HW + rows - 1) / rows, a.N);
     const size_t smem = (size_t)(2 * C + 2 * a.groups) * sizeof(float);
