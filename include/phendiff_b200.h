@@ -180,6 +180,13 @@ typedef struct pd_test_conv_args {
     const pd_step_coeffs_t* step;
 } pd_test_conv_args_t;
 int pd_test_conv_ex(const pd_test_conv_args_t* args, pd_stream_t stream);
+/* GroupNorm + SiLU of concat(x1, x2) fused INTO the 3x3 stride-1 convolution that consumes it (tcgen05 halo kernel, GN variant:
+ * the normalised tensor exists only as shared-memory tiles).  Same optional epilogue inputs as pd_test_conv_ex; dtype 1 / 2.
+ * Replaces the norm1/nonlinearity/conv1 and norm2/nonlinearity/conv2 pairs of diffusers ResnetBlock2D. */
+int pd_test_gn_conv(int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout, int32_t groups, float eps,
+                    const void* x1, const void* x2, const float* gamma, const float* beta, const float* weight, const float* bias,
+                    const float* addvec, const void* residual, const void* sc1, const void* sc2, int32_t csc1, int32_t csc2,
+                    const float* sc_w, float out_scale, void* out, float* stats_out, pd_stream_t stream);
 /* GroupNorm(+SiLU) over NHWC, two concatenated sources */
 int pd_test_groupnorm(int32_t dtype, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                       int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta,

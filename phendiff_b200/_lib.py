@@ -73,6 +73,7 @@ _SIGNATURES = {
     "pd_unet_profile_op": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "pd_test_conv": (C.c_int, [C.c_int32] * 11 + [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_float, _P, _P]),
     "pd_test_conv_ex": (C.c_int, [C.POINTER(TestConvArgs), _P]),
+    "pd_test_gn_conv": (C.c_int, [C.c_int32] * 8 + [C.c_float] + [_P] * 10 + [C.c_int32, C.c_int32, _P, C.c_float, _P, _P, _P]),
     "pd_test_groupnorm": (C.c_int, [C.c_int32] * 6 + [C.c_float, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "pd_test_attention": (C.c_int, [C.c_int32] * 6 + [_P, _P, _P]),
 }

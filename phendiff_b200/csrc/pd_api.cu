@@ -395,7 +395,14 @@ struct ConvOpt {
     Tensor *s1 = nullptr, *s2 = nullptr;   // fused 1x1 shortcut sources
     const ConvL* scL = nullptr;
     bool want_stats = true;          // the output feeds a GroupNorm
+    // fused GroupNorm + SiLU of concat(x, x2) applied by the conv to its own input tiles (tcgen05 halo kernel, GN variant):
+    // the normalised tensor is never written.  Only set after gn_fusable() said yes.
+    const GNL* gn = nullptr;
+    Tensor* x2 = nullptr;
 };
+
+// non-null stand-in for ConvTcDesc::gn_coef while only the shape is being checked (never dereferenced)
+static const float2* const kGnCoefProbe = reinterpret_cast<const float2*>(uintptr_t(64));
 
 struct Rec {
     pd_unet* m;
@@ -465,21 +472,41 @@ struct Rec {
         const int Ho = upsample ? 2 * x->H : ((L.stride == 2) ? x->H / 2 : x->H);
         const int Wo = upsample ? 2 * x->W : ((L.stride == 2) ? x->W / 2 : x->W);
         Tensor* o = alloc(L.cout, Ho, Wo);
+        const int Cmain = x->C + (c.x2 ? c.x2->C : 0);
         ConvTcDesc d{};
-        d.dt = m->dt; d.C = x->C; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = L.k; d.stride = L.stride; d.pad = L.pad;
+        d.dt = m->dt; d.C = Cmain; d.C2 = c.x2 ? c.x2->C : 0; d.N = mb; d.H = x->H; d.W = x->W; d.ksize = L.k; d.stride = L.stride; d.pad = L.pad;
         d.Ho = Ho; d.Wo = Wo; d.Cout = L.cout; d.upsample = upsample ? 1 : 0; d.mode = TC_MODE_STD;
         d.Csc1 = c.s1 ? c.s1->C : 0; d.Csc2 = c.s2 ? c.s2->C : 0;
         d.stats_cw = m->stats_cw;
+        d.gn_coef = c.gn ? kGnCoefProbe : nullptr;   // shape checks only look at null / non-null; the real table is bound below
         const bool want_tc = m->half && m->cfg.conv_impl == 0 && c.w_tc != nullptr;
-        bool use_tc = want_tc && (conv_halo_supported(d, nullptr) || conv_tc_supported(d, nullptr));
+        bool use_tc = want_tc && (conv_halo_supported(d, nullptr) || (!c.gn && !c.x2 && conv_tc_supported(d, nullptr)));
         last_used_tc = use_tc;
         if (upsample && !use_tc) { rc = 1; set_error("internal: fused upsample conv requested for an unsupported shape"); return o; }
+        if ((c.gn || c.x2) && !use_tc) { rc = 1; set_error("internal: fused GroupNorm conv requested for an unsupported shape"); return o; }
+        // per-image per-channel (scale, shift) of the fused GroupNorm: one tiny kernel ahead of the conv
+        size_t coef_off = 0, coef_bytes = 0;
+        if (c.gn) {
+            if (x->stats_off == (size_t)-1 || (c.x2 && c.x2->stats_off == (size_t)-1)) { rc = 1; set_error("internal: GroupNorm source without statistics"); return o; }
+            coef_bytes = (size_t)mb * Cmain * sizeof(float2);
+            coef_off = m->arena.alloc(coef_bytes);
+            if (!dry) {
+                GNArgs ga{};
+                ga.C1 = x->C; ga.C2 = c.x2 ? c.x2->C : 0; ga.N = mb; ga.HW = x->H * x->W; ga.groups = m->cfg.norm_num_groups;
+                ga.eps = m->cfg.norm_eps; ga.gamma = c.gn->g->dev; ga.beta = c.gn->b->dev; ga.silu = 1; ga.stats_cw = m->stats_cw;
+                ga.stats1 = stats_ptr(x); ga.stats2 = c.x2 ? stats_ptr(c.x2) : nullptr;
+                float2* cf = (float2*)raw(coef_off);
+                push([ga, cf](const Ctx&, cudaStream_t s) { return launch_gn_coef(ga, cf, s); }, 1, CLS_GN, 0.0,
+                     "gn_coef C=" + std::to_string(Cmain) + " @" + std::to_string(x->H) + "x" + std::to_string(x->W));
+            }
+        }
         if (use_tc) {
             const bool fused_stats = c.want_stats && m->stats_cw >= 2 && (conv_halo_supported(d, nullptr) || conv_tc_can_emit_stats(d));
             if (fused_stats) stats_alloc(o);
             m->tc_layers += dry ? 0 : 1;
             if (!dry) {
-                d.x = ptr(x); d.sc1 = c.s1 ? ptr(c.s1) : nullptr; d.sc2 = c.s2 ? ptr(c.s2) : nullptr;
+                d.x = ptr(x); d.x2 = c.x2 ? ptr(c.x2) : nullptr; d.gn_coef = c.gn ? (const float2*)raw(coef_off) : nullptr;
+                d.sc1 = c.s1 ? ptr(c.s1) : nullptr; d.sc2 = c.s2 ? ptr(c.s2) : nullptr;
                 d.wmat = c.w_tc; d.bias = c.s1 ? c.bias_fused : (c.bias_tc ? c.bias_tc : c.bias); d.addvec = c.addvec; d.addvec_stride = c.addvec_stride;
                 d.addvec_row = c.addvec ? (const int32_t*)raw(m->rowidx_off) : nullptr;
                 d.residual = c.residual ? ptr(c.residual) : nullptr; d.out_scale = c.out_scale; d.out = ptr(o);
@@ -488,15 +515,16 @@ struct Rec {
                 int r = conv_tc_plan_create(d, &pl);
                 if (r) { rc = r; return o; }
                 m->tc_plans.push_back(pl);
-                const double ktot = upsample ? 4.0 * x->C : (double)(L.k * L.k * x->C + d.Csc1 + d.Csc2);
-                const std::string nm = std::string(upsample ? "up+conv" : "conv") + std::to_string(L.k) + "x" + std::to_string(L.k) + (L.stride == 2 ? "s2 " : " ") +
-                                       std::to_string(x->C) + (d.Csc1 + d.Csc2 ? "+sc" + std::to_string(d.Csc1 + d.Csc2) : std::string()) + "->" +
+                const double ktot = upsample ? 4.0 * x->C : (double)(L.k * L.k * Cmain + d.Csc1 + d.Csc2);
+                const std::string nm = std::string(c.gn ? "gn+" : "") + std::string(upsample ? "up+conv" : "conv") + std::to_string(L.k) + "x" + std::to_string(L.k) + (L.stride == 2 ? "s2 " : " ") +
+                                       std::to_string(Cmain) + (d.Csc1 + d.Csc2 ? "+sc" + std::to_string(d.Csc1 + d.Csc2) : std::string()) + "->" +
                                        std::to_string(L.cout) + " @" + std::to_string(Ho) + "x" + std::to_string(Wo) +
                                        (conv_halo_supported(d, nullptr) ? " halo" : " tap");
                 push([pl](const Ctx&, cudaStream_t s) { return conv_tc_launch(pl, s); }, 1, CLS_CONV_TC,
                      2.0 * mb * Ho * Wo * (double)L.cout * ktot, nm);
             }
             if (c.want_stats && !fused_stats) stats_kernel(o);
+            if (c.gn) m->arena.release(coef_off, coef_bytes);
             return o;
         }
         // SIMT path; a fused shortcut request is split into (1x1 conv -> tmp) + (conv with residual = tmp)
@@ -532,17 +560,37 @@ struct Rec {
     }
 
     // ResnetBlock2D (A.1) on concat(a, b); returns the block output (refs = 1)
+    // can GroupNorm + SiLU of concat(a, b) ride inside the conv that consumes it (tcgen05 halo kernel, GN variant)?
+    bool gn_fusable(const ConvL& L, const void* w_tc, const Tensor* a, const Tensor* b, const Tensor* s1, const Tensor* s2) const {
+        static const int on = [] { const char* e = getenv("PHENDIFF_B200_GNFUSE"); return e ? atoi(e) : 1; }();
+        if (!on || !m->half || m->cfg.conv_impl != 0 || !w_tc || L.stride != 1) return false;
+        ConvTcDesc d{};
+        d.dt = m->dt; d.C = a->C + (b ? b->C : 0); d.C2 = b ? b->C : 0; d.N = mb; d.H = a->H; d.W = a->W; d.ksize = L.k; d.stride = 1;
+        d.pad = L.pad; d.Ho = a->H; d.Wo = a->W; d.Cout = L.cout; d.mode = TC_MODE_STD; d.stats_cw = m->stats_cw;
+        d.Csc1 = s1 ? s1->C : 0; d.Csc2 = s2 ? s2->C : 0; d.gn_coef = kGnCoefProbe;
+        return conv_halo_supported(d, nullptr);
+    }
+
     Tensor* resnet(ResL& R, Tensor* a, Tensor* b) {
-        Tensor* hn = gn(R.n1, a, b, true);
         // conv1 (+ time embedding row; conv1.bias is folded into that row at finalize)
         ConvOpt o1;
         o1.w_simt = R.c1.w_simt; o1.w_tc = R.c1.w_tc;
         o1.addvec = dry ? nullptr : (const float*)raw(m->temb_off) + R.temb_off; o1.addvec_stride = m->J;
-        Tensor* h1 = conv(R.c1, hn, o1);
-        release(hn);
-        Tensor* h1n = gn(R.n2, h1, nullptr, true);
-        release(h1);
+        Tensor* h1;
+        if (gn_fusable(R.c1, R.c1.w_tc, a, b, nullptr, nullptr)) {
+            o1.gn = &R.n1; o1.x2 = b;
+            h1 = conv(R.c1, a, o1);
+        } else {
+            Tensor* hn = gn(R.n1, a, b, true);
+            h1 = conv(R.c1, hn, o1);
+            release(hn);
+        }
+        const void* w2 = R.has_sc ? R.w2sc_tc : R.c2.w_tc;
+        const bool fuse2 = gn_fusable(R.c2, w2, h1, nullptr, R.has_sc ? a : nullptr, R.has_sc ? b : nullptr);
+        Tensor* h1n = fuse2 ? h1 : gn(R.n2, h1, nullptr, true);
+        if (!fuse2) release(h1);
         ConvOpt o2;
+        if (fuse2) o2.gn = &R.n2;
         o2.w_simt = R.c2.w_simt; o2.bias = R.c2.b->dev; o2.out_scale = 1.0f / R.scale;
         if (R.has_sc) {
             // out = (conv2(h) + conv_shortcut(x)) / scale: one K-concatenated GEMM on the tensor-core path
@@ -1190,6 +1238,50 @@ int pd_test_conv_ex(const pd_test_conv_args_t* a, pd_stream_t stream) {
     if (tmp) cudaFree(tmp);
     if (wsc) cudaFree(wsc);
     if (!rc && e != cudaSuccess) { set_error(std::string("conv_simt kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
+    return rc;
+}
+
+int pd_test_gn_conv(int32_t dt, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout, int32_t groups, float eps,
+                    const void* x1, const void* x2, const float* gamma, const float* beta, const float* weight, const float* bias,
+                    const float* addvec, const void* residual, const void* sc1, const void* sc2, int32_t csc1, int32_t csc2,
+                    const float* sc_w, float out_scale, void* out, float* stats_out, pd_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "fused GroupNorm convolution takes bf16 / fp16 activations");
+    PD_REQUIRE(x1 && gamma && beta && weight && out, "null argument");
+    const int ct = c1 + c2, hw = h * w;
+    PD_REQUIRE(groups > 0 && ct % groups == 0, "channels not divisible by groups");
+    int cw = 4;
+    while (cw > 1 && ((ct / groups) % cw != 0 || c1 % cw != 0)) cw >>= 1;
+    const int ktot = 9 * ct + csc1 + csc2;
+    const size_t n1 = (size_t)n * (c1 / cw) * 2, n2 = (size_t)n * (c2 / cw) * 2;
+    float* stats = nullptr;
+    float2* coef = nullptr;
+    void* wm = nullptr;
+    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (n1 + n2 + 2) * sizeof(float)));
+    PD_CHECK_CUDA(cudaMalloc((void**)&coef, (size_t)n * ct * sizeof(float2)));
+    PD_CHECK_CUDA(cudaMalloc(&wm, (size_t)cout * ktot * 2));
+    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (n1 + n2 + 2) * sizeof(float), s));
+    PD_CHECK_CUDA(cudaMemsetAsync(wm, 0, (size_t)cout * ktot * 2, s));
+    GNArgs ga{};
+    ga.C1 = c1; ga.C2 = c2; ga.N = n; ga.HW = hw; ga.groups = groups; ga.eps = eps; ga.gamma = gamma; ga.beta = beta; ga.silu = 1;
+    ga.stats_cw = cw; ga.stats1 = stats; ga.stats2 = c2 ? stats + n1 : nullptr;
+    int rc = launch_gn_chunk_stats(dt, x1, n, hw, c1, cw, stats, s);
+    if (!rc && c2) rc = launch_gn_chunk_stats(dt, x2, n, hw, c2, cw, stats + n1, s);
+    if (!rc) rc = launch_gn_coef(ga, coef, s);
+    if (!rc) rc = launch_relayout_tc(dt, weight, cout, ct, 3, wm, ktot, 0, s);
+    if (!rc && (csc1 + csc2)) rc = launch_relayout_tc(dt, sc_w, cout, csc1 + csc2, 1, wm, ktot, 9 * ct, s);
+    ConvTcDesc d{};
+    d.dt = dt; d.x = x1; d.x2 = x2; d.C = ct; d.C2 = c2; d.gn_coef = coef; d.N = n; d.H = h; d.W = w; d.ksize = 3; d.stride = 1; d.pad = 1;
+    d.Ho = h; d.Wo = w; d.Cout = cout; d.sc1 = sc1; d.Csc1 = csc1; d.sc2 = sc2; d.Csc2 = csc2; d.wmat = wm; d.bias = bias;
+    d.addvec = addvec; d.addvec_stride = cout; d.residual = residual; d.out_scale = out_scale; d.out = out; d.stats_out = stats_out;
+    d.stats_cw = 4; d.mode = TC_MODE_STD;
+    ConvHaloPlan* hp = nullptr;
+    if (!rc) rc = conv_halo_plan_create(d, &hp);
+    if (!rc) rc = conv_halo_launch(hp, s, nullptr);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (hp) conv_halo_plan_destroy(hp);
+    cudaFree(stats); cudaFree(coef); cudaFree(wm);
+    if (!rc && e != cudaSuccess) { set_error(std::string("fused GroupNorm conv kernel failed: ") + cudaGetErrorString(e)); rc = 2; }
     return rc;
 }
 

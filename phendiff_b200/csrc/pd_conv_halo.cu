@@ -19,9 +19,16 @@
 //   upsample mode: nearest-2x + 3x3 conv (Upsample2D) = four 2x2 sub-pixel phase convs on the low-res input (2.25x
 //   fewer MACs, no 4x tensor): phase (a,b) reads rows {i-1+a, i+a}, cols {j-1+b, j+b} and writes pixel (2i+a, 2j+b).
 //   TC_MODE_DDIM: conv_out (Cout = 3 padded to 16); the epilogue applies the scheduler update to x_t in place.
-// Warp roles (384 threads, 1 CTA/SM, persistent): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM
-// allocator, warps 4-11 epilogue (two per TMEM lane quarter; TMA-store of swizzled 64-channel slabs).  Rings: A (halo tiles, SA stages) and B (weight tiles, SB stages) are decoupled: one A
+// Warp roles (384 threads, 1 CTA/SM, persistent): warp 0 TMA producer of weight tiles, warp 3 TMA producer of halo tiles,
+// warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-11 epilogue (two per TMEM lane quarter; TMA-store of swizzled 64-channel slabs).  Rings: A (halo tiles, SA stages) and B (weight tiles, SB stages) are decoupled: one A
 // stage lives through `taps` B stages.  The fp32 accumulator is double buffered in TMEM.
+//
+// GN variant (template flag, 512 threads): the conv's input is GroupNorm(+SiLU) of concat(x, x2) and the normalised tensor
+// is NEVER written to HBM.  The producer loads the RAW halo tile; four extra warps (12-15) apply y = silu(x * a[n,c] + b[n,c])
+// to it in place in shared memory (per-image per-channel coefficients from gn_coef_kernel; halo pixels outside the image
+// stay zero = the conv's zero padding of the NORMALISED tensor), fence the generic-proxy writes towards the async proxy
+// and hand the stage to the MMA issuer through a third barrier ring (readyA).  The transform of stage k+1 runs under the
+// 36 MMAs of stage k.  Registers are re-split with setmaxnreg (control 96, epilogue 168, transform 80 per thread).
 #include "pd_tc_common.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -31,7 +38,7 @@
 namespace pd {
 
 struct HaloParams {
-    CUtensorMap tmA, tmS1, tmS2, tmB;
+    CUtensorMap tmA, tmA2, tmS1, tmS2, tmB;   // tmA2: second main-segment source (channel concat), GN variant only
     CUtensorMap tmOut;             // output: 4-D {C, Wo, Ho, N} box {64, 8, 4, 1}; upsample: 5-D {C, 2, W, 2, N*H} box {64, 1, 8, 1, 4}
     int ntaps, kw, pitch_px;
     int a_bytes_main, a_bytes_sc, a_stage_bytes, SA, SB;
@@ -42,12 +49,16 @@ struct HaloParams {
     int Ho, Wo;                    // output extent (2x the tile-space extent in upsample mode)
     int upsample, use_base_offset;
     int mt;                        // M halves per tile: 1 = 16x8 pixels, 2 = 16x16 pixels (two accumulators share every weight tile)
+    int kb_a1;                     // 64-channel blocks of the main segment that come from tmA (the rest from tmA2)
+    const float2* gn_coef;         // GN variant: (N, C) (scale, shift) of the fused GroupNorm, SiLU follows; else null
+    int H, W;                      // input extent (halo mask of the GN variant)
+    int gn_tanh;                   // SiLU of the GN variant through tanh.approx (1 MUFU / element) instead of ex2 + rcp
     TcEpi epi;
 };
 
 struct ConvHaloPlan {
     HaloParams p;
-    int dt, block_n, grid, mode;
+    int dt, block_n, grid, mode, gn;
     size_t smem;
 };
 
@@ -57,8 +68,69 @@ constexpr int HL_EPI_BYTES = 8 * 4096;   // one 4 KB output slab per epilogue wa
 // epilogue warps that have work: two per TMEM lane quarter when the tile has >= 2 slabs of 64 output channels
 template <int BLOCK_N, int MODE> struct HaloEpiWarps { static constexpr int value = (MODE == TC_MODE_STD && BLOCK_N >= 128) ? 8 : 4; };
 
-template <int BLOCK_N, typename T, int MODE, int CW, int MT>
-__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// y = silu(x * a + b) on 8 packed 16-bit values.  TANH = false: cf = (a0,b0,a1,b1) pairs, silu(y) = y / (1 + 2^(-y log2 e))
+// (MUFU.EX2 + MUFU.RCP per element).  TANH = true: cf holds (a/2, b/2), silu(y) = h + h tanh(h) with h = y/2: ONE MUFU per
+// element; tanh.approx.f32 is good to 2^-11 relative, i.e. the same size as the fp16 rounding of the stored activation.
+template <typename T, bool TANH> __device__ __forceinline__ uint4 gn_silu8(const uint4& raw, const float4 (&cf)[4]) {
+    float v[8];
+    unpack8<T>(raw, v);
+    const float a[8] = {cf[0].x, cf[0].z, cf[1].x, cf[1].z, cf[2].x, cf[2].z, cf[3].x, cf[3].z};
+    const float b[8] = {cf[0].y, cf[0].w, cf[1].y, cf[1].w, cf[2].y, cf[2].w, cf[3].y, cf[3].w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(v[i], a[i], b[i]);
+        if (TANH) {
+            float t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y));
+            v[i] = fmaf(y, t, y);
+        } else {
+            v[i] = silu<false>(y);
+        }
+    }
+    uint4 o;
+    o.x = pack2<T>(v[0], v[1]); o.y = pack2<T>(v[2], v[3]); o.z = pack2<T>(v[4], v[5]); o.w = pack2<T>(v[6], v[7]);
+    return o;
+}
+
+// GroupNorm + SiLU of one raw halo tile in place (128 threads; see the GN-variant note in the file header).  Thread ->
+// 16-byte chunk column `col` of rows r0, r0+16, ...; two rows (16 values) are in flight per iteration so that the MUFU
+// latency of one hides under the other.  Rows outside the image keep their TMA zero fill: they are the conv's padding.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T, bool TANH>
+__device__ __forceinline__ void gn_transform_tile(uint32_t col, int r0, int nrows, int pitch, int qstep, int rstep, int hy, int hx,
+                                                  int gy0, int gx0, int H, int W, const float4 (&cf)[4]) {
+#pragma unroll 1
+    for (int rho = r0; rho < nrows; rho += 32) {
+        const bool ok0 = (unsigned)(gy0 + hy) < (unsigned)H && (unsigned)(gx0 + hx) < (unsigned)W;
+        hy += qstep; hx += rstep;
+        if (hx >= pitch) { hx -= pitch; ++hy; }
+        const bool in1 = rho + 16 < nrows;
+        const bool ok1 = in1 && (unsigned)(gy0 + hy) < (unsigned)H && (unsigned)(gx0 + hx) < (unsigned)W;
+        hy += qstep; hx += rstep;
+        if (hx >= pitch) { hx -= pitch; ++hy; }
+        const uint32_t q0 = col + (uint32_t)rho * 128u, q1 = q0 + 2048u;
+        const uint4 v0 = lds128(q0);
+        const uint4 v1 = in1 ? lds128(q1) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 o0 = gn_silu8<T, TANH>(v0, cf);
+        const uint4 o1 = gn_silu8<T, TANH>(v1, cf);
+        if (ok0) sts128(q0, o0);
+        if (ok1) sts128(q1, o1);
+    }
+}
+
+template <int BLOCK_N, typename T, int MODE, int CW, int MT, bool GN>
+__global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     constexpr int EPI_WARPS = HaloEpiWarps<BLOCK_N, MODE>::value;
     constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
     constexpr int TMEM_COLS = (2 * MT * BLOCK_N < 32) ? 32 : 2 * MT * BLOCK_N;
@@ -77,13 +149,15 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     uint64_t* emptyB = fullB + SB;
     uint64_t* tfull = emptyB + SB;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* readyA = tempty + 2;   // GN variant: stage transformed (or passed through) by warps 12-15
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(readyA + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&p.tmA);
         prefetch_tmap(&p.tmB);
+        if (p.kb_a1 < p.kb_main) prefetch_tmap(&p.tmA2);
         if (p.kb_s1) prefetch_tmap(&p.tmS1);
         if (p.kb_s2) prefetch_tmap(&p.tmS2);
         if (MODE == TC_MODE_STD) prefetch_tmap(&p.tmOut);
@@ -92,6 +166,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * EPI_WARPS); }
+        if (GN) for (int i = 0; i < SA; ++i) mbar_init(&readyA[i], 128);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -106,19 +181,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     const int total_tiles = p.m_tiles * p.phases * p.n_tiles;
     const int tiles_per_img = p.tilesW * p.tilesH;
 
-    if (warp == 0) {
+    // GN variant: 512 threads start at 128 registers each; every role branch opens with the setmaxnreg of its warpgroup
+    // (control 96, transform 80, epilogue 168) so that ptxas allocates each region against its own budget
+    if (warp < 4) {
+      if (GN) setmaxnreg_dec<96>();
+      if (warp == 0) {
         if (elect_one()) {
-            // ===================== TMA producer =====================
-            int sa = 0, sb = 0;
-            uint32_t pha = 0, phb = 0;
+            // ===================== TMA producer, weight tiles (B ring) =====================
+            int sb = 0;
+            uint32_t phb = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles;
-                const int t2 = tile / p.n_tiles;
-                const int phase = t2 % p.phases, m_tile = t2 / p.phases;
-                const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
-                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
-                const int h0 = th * HL_HT, w0 = tw * TILE_W;
-                const int oh = p.off_h + (p.upsample ? (phase >> 1) : 0), ow = p.off_w + (p.upsample ? (phase & 1) : 0);
+                const int phase = (tile / p.n_tiles) % p.phases;
                 const int brow = phase * p.b_rows_per_phase + n_tile * BLOCK_N;
                 int kcol = 0;
                 for (int seg = 0; seg < 3; ++seg) {
@@ -126,16 +200,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                     const int ntap = seg == 0 ? p.ntaps : 1;
                     const int segC = nkb * TC_BLOCK_K;
                     for (int cb = 0; cb < nkb; ++cb) {
-                        mbar_wait(&emptyA[sa], pha ^ 1);
-                        uint8_t* dstA = smA + (size_t)sa * p.a_stage_bytes;
-                        if (seg == 0) {
-                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_main);
-                            tma_load_4d(&p.tmA, &fullA[sa], dstA, cb * TC_BLOCK_K, w0 + ow, h0 + oh, img);
-                        } else {
-                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_sc);
-                            tma_load_4d(seg == 1 ? &p.tmS1 : &p.tmS2, &fullA[sa], dstA, cb * TC_BLOCK_K, w0, h0, img);
-                        }
-                        if (++sa == SA) { sa = 0; pha ^= 1; }
                         for (int tap = 0; tap < ntap; ++tap) {
                             mbar_wait(&emptyB[sb], phb ^ 1);
                             mbar_arrive_expect_tx(&fullB[sb], B_BYTES);
@@ -147,7 +211,40 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 3) {
+        if (elect_one()) {
+            // ===================== TMA producer, activation halo tiles (A ring) =====================
+            // Its own thread: an A stage is requested the moment the MMAs that read its previous content retire, not when
+            // the weight producer gets round to it (with one producer the request went out only SB taps before the
+            // tile was needed, which left no room for the GN variant's in-place transform).
+            int sa = 0;
+            uint32_t pha = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int t2 = tile / p.n_tiles;
+                const int phase = t2 % p.phases, m_tile = t2 / p.phases;
+                const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+                const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+                const int h0 = th * HL_HT, w0 = tw * TILE_W;
+                const int oh = p.off_h + (p.upsample ? (phase >> 1) : 0), ow = p.off_w + (p.upsample ? (phase & 1) : 0);
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
+                    for (int cb = 0; cb < nkb; ++cb) {
+                        mbar_wait(&emptyA[sa], pha ^ 1);
+                        uint8_t* dstA = smA + (size_t)sa * p.a_stage_bytes;
+                        if (seg == 0) {
+                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_main);
+                            if (cb < p.kb_a1) tma_load_4d(&p.tmA, &fullA[sa], dstA, cb * TC_BLOCK_K, w0 + ow, h0 + oh, img);
+                            else tma_load_4d(&p.tmA2, &fullA[sa], dstA, (cb - p.kb_a1) * TC_BLOCK_K, w0 + ow, h0 + oh, img);
+                        } else {
+                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_sc);
+                            tma_load_4d(seg == 1 ? &p.tmS1 : &p.tmS2, &fullA[sa], dstA, cb * TC_BLOCK_K, w0, h0, img);
+                        }
+                        if (++sa == SA) { sa = 0; pha ^= 1; }
+                    }
+                }
+            }
+        }
+      } else if (warp == 1) {
         if (elect_one()) {
             // ===================== MMA issuer (single thread) =====================
             constexpr uint32_t idesc = make_idesc<T, BLOCK_N>();
@@ -167,7 +264,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                     const int pitch = seg == 0 ? p.pitch_px : TILE_W;
                     const uint32_t sbo = (uint32_t)pitch * 128u;
                     for (int cb = 0; cb < nkb; ++cb) {
-                        mbar_wait(&fullA[sa], pha);
+                        mbar_wait(GN ? &readyA[sa] : &fullA[sa], pha);
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(smA + (size_t)sa * p.a_stage_bytes);
                         for (int tap = 0; tap < ntap; ++tap) {
@@ -197,7 +294,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 umma_commit(&tfull[as]);
             }
         }
-    } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
+      }
+    } else if (warp < 12) {
+      if (GN) setmaxnreg_inc<168>();
+      if (warp < 4 + EPI_WARPS) {
         // ===================== epilogue (8 warps: two per TMEM lane quarter, alternating 64-channel slabs) =====================
         // Accumulator row = output pixel.  A warp owns 32 rows = a 4 x 8-pixel box of the tile; it stages 64 output channels
         // at a time as a SWIZZLE_128B slab (32 x 128 B) in its private shared-memory buffer and one elected lane writes it
@@ -289,6 +389,55 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             }
         }
         if (MODE == TC_MODE_STD && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last store's reads
+      }
+    } else if (GN) {
+        setmaxnreg_dec<80>();
+        // ===================== GroupNorm + SiLU on the raw halo tile, in place (GN variant) =====================
+        // 128 threads; thread -> 16-byte chunk j of rows r0, r0+16, ...  Rows are 128 B and stage bases 1024-aligned, so the
+        // swizzle phase (row & 7) of a thread's rows is constant and so is its logical chunk = 8 channels: the coefficients
+        // are loaded once per stage.
+        const int t = threadIdx.x - 384;
+        const int j = t & 7, r0 = t >> 3;
+        const int lc = j ^ (r0 & 7);
+        const int pitch = p.pitch_px;
+        const int nrows = pitch * (HL_HT + 2);
+        const int qstep = 16 / pitch, rstep = 16 - qstep * pitch;   // row + 16 -> (hy + qstep, hx + rstep) before the carry
+        int hy0 = 0, hx0 = r0;
+        while (hx0 >= pitch) { hx0 -= pitch; ++hy0; }
+        int sa = 0;
+        uint32_t pha = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int t2 = tile / p.n_tiles;
+            const int m_tile = t2 / p.phases;
+            const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
+            const int th = rem / p.tilesW, tw = rem - th * p.tilesW;
+            const int gy0 = th * HL_HT + p.off_h, gx0 = tw * TILE_W + p.off_w;
+            const float2* crow = p.gn_coef + (size_t)img * p.C + lc * 8;
+            for (int seg = 0; seg < 3; ++seg) {
+                const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
+                for (int cb = 0; cb < nkb; ++cb) {
+                    float4 cf[4];
+                    if (seg == 0) {
+                        const float4* cp = reinterpret_cast<const float4*>(crow + cb * TC_BLOCK_K);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cf[i] = __ldg(cp + i);
+                        if (p.gn_tanh) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { cf[i].x *= 0.5f; cf[i].y *= 0.5f; cf[i].z *= 0.5f; cf[i].w *= 0.5f; }
+                        }
+                    }
+                    mbar_wait(&fullA[sa], pha);
+                    if (seg == 0) {
+                        const uint32_t col = smem_u32(smA + (size_t)sa * p.a_stage_bytes + j * 16);
+                        if (p.gn_tanh) gn_transform_tile<T, true>(col, r0, nrows, pitch, qstep, rstep, hy0, hx0, gy0, gx0, p.H, p.W, cf);
+                        else gn_transform_tile<T, false>(col, r0, nrows, pitch, qstep, rstep, hy0, hx0, gy0, gx0, p.H, p.W, cf);
+                        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    }
+                    mbar_arrive(&readyA[sa]);
+                    if (++sa == SA) { sa = 0; pha ^= 1; }
+                }
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -317,7 +466,10 @@ bool conv_halo_supported(const ConvTcDesc& d, std::string* why) {
     auto no = [&](const char* m) { if (why) *why = m; return false; };
     if (const char* off = getenv("PHENDIFF_B200_HALO")) if (off[0] == '0') return no("halo kernel disabled by PHENDIFF_B200_HALO=0");
     if (d.dt != DT_BF16 && d.dt != DT_F16) return no("tcgen05 path takes bf16 or fp16 activations");
-    if (d.C % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
+    if (d.C % 64 != 0 || d.C2 % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
+    if (d.C2 < 0 || d.C2 >= d.C + (d.C == 0)) return no("second main-segment source must leave channels for the first");
+    if (d.gn_coef && (d.ksize != 3 || d.upsample || d.mode != TC_MODE_STD)) return no("fused GroupNorm: plain 3x3 convolution only");
+    if (d.gn_coef && halo_block_n(d) < 128) return no("fused GroupNorm: Cout must be a multiple of 128");
     if (halo_block_n(d) == 0) return no("Cout must be a multiple of 64 (or <= 16 for the conv_out mode)");
     if (d.stride != 1) return no("halo kernel takes stride-1 convolutions");
     if (!(d.ksize == 1 || d.ksize == 3)) return no("kernel size must be 1 or 3");
@@ -337,7 +489,12 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     ConvHaloPlan* pl = new ConvHaloPlan();
     HaloParams& p = pl->p;
     memset(&p, 0, sizeof(p));
-    pl->dt = d.dt; pl->mode = d.mode; pl->block_n = halo_block_n(d);
+    pl->dt = d.dt; pl->mode = d.mode; pl->block_n = halo_block_n(d); pl->gn = d.gn_coef != nullptr;
+    p.gn_coef = d.gn_coef; p.H = d.H; p.W = d.W;
+    {   // PHENDIFF_B200_GN_SILU=exp|tanh (default below): which SiLU the GN variant's transform warps evaluate
+        const char* e = getenv("PHENDIFF_B200_GN_SILU");
+        p.gn_tanh = e ? (std::string(e) == "tanh") : 0;
+    }
     const int kh = d.upsample ? 2 : d.ksize, kw = kh;
     p.ntaps = kh * kw; p.kw = kw;
     // probe knobs for the descriptor semantics (see file header; defaults = the measured-correct variant):
@@ -361,6 +518,7 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     p.a_bytes_sc = 128 * tile_w * HL_HT;
     p.a_stage_bytes = ((std::max(p.a_bytes_main, p.a_bytes_sc) + 1023) / 1024) * 1024;
     p.C = d.C; p.kb_main = d.C / 64; p.kb_s1 = d.Csc1 / 64; p.kb_s2 = d.Csc2 / 64;
+    p.kb_a1 = (d.C - d.C2) / 64;
     p.tilesW = d.W / tile_w; p.tilesH = d.H / HL_HT;
     p.off_h = p.off_w = d.upsample ? -1 : -d.pad;
     p.m_tiles = d.N * p.tilesW * p.tilesH;
@@ -379,16 +537,28 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     const int budget = 227 * 1024 - 1024 - 512 - epi_bytes;
     p.SA = (pl->block_n >= 256 || mt == 2) ? 2 : 3;
     if (pl->block_n == 16) p.SA = 4;
+    if (d.gn_coef) {
+        // TMA latency + transform must fit under (SA - 1) K-blocks of MMAs; the 41 KB stages of the dual-accumulator tile take
+        // the longest to transform and leave room for a third stage beside a 4-deep weight ring
+        if (mt == 2) p.SA = 3;
+        if (const char* e = getenv("PHENDIFF_B200_HALO_GN_SA")) p.SA = std::min(4, std::max(2, atoi(e)));
+    }
     p.SB = std::min(16, (budget - p.SA * p.a_stage_bytes) / b_bytes);
     if (p.SB < 2) { delete pl; set_error("conv_halo: shared memory budget too small"); return 1; }
     pl->smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * b_bytes + epi_bytes + 1024 + 512;
     const uint64_t C = d.C, H = d.H, W = d.W, N = d.N;
     int rc;
     {
-        uint64_t dims[4] = {C, W, H, N};
-        uint64_t st[3] = {C * 2, W * C * 2, H * W * C * 2};
-        uint32_t box[4] = {64, (uint32_t)p.pitch_px, (uint32_t)rows, 1};
-        if ((rc = tc_encode_map(&p.tmA, d.dt, d.x, 4, dims, st, box))) { delete pl; return rc; }
+        const void* srcs[2] = {d.x, d.x2};
+        const uint64_t cs[2] = {C - (uint64_t)d.C2, (uint64_t)d.C2};
+        CUtensorMap* tms[2] = {&p.tmA, &p.tmA2};
+        for (int i = 0; i < 2; ++i) {
+            if (!cs[i]) continue;
+            uint64_t dims[4] = {cs[i], W, H, N};
+            uint64_t st[3] = {cs[i] * 2, W * cs[i] * 2, H * W * cs[i] * 2};
+            uint32_t box[4] = {64, (uint32_t)p.pitch_px, (uint32_t)rows, 1};
+            if ((rc = tc_encode_map(tms[i], d.dt, srcs[i], 4, dims, st, box))) { delete pl; return rc; }
+        }
     }
     const void* scs[2] = {d.sc1, d.sc2};
     const int cscs[2] = {d.Csc1, d.Csc2};
@@ -431,26 +601,26 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
 
 void conv_halo_plan_destroy(ConvHaloPlan* p) { delete p; }
 
-template <int BLOCK_N, typename T, int MODE, int CW, int MT>
+template <int BLOCK_N, typename T, int MODE, int CW, int MT, bool GN>
 static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t s) {
     static size_t attr_smem = 0;
     if (pl->smem > attr_smem) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE, CW, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)pl->smem));
         attr_smem = pl->smem;
     }
-    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT><<<pl->grid, HALO_THREADS, pl->smem, s>>>(p);
+    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN><<<pl->grid, GN ? HALO_THREADS_GN : HALO_THREADS, pl->smem, s>>>(p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-template <int BLOCK_N, typename T>
+template <int BLOCK_N, typename T, bool GN>
 static int launch_halo_std(const ConvHaloPlan* pl, cudaStream_t s) {
     const bool cw2 = pl->p.epi.stats != nullptr && pl->p.epi.stats_cw == 2;
     if (BLOCK_N <= 128 && pl->p.mt == 2)
-        return cw2 ? launch_halo<(BLOCK_N <= 128 ? BLOCK_N : 128), T, TC_MODE_STD, 2, 2>(pl, pl->p, s)
-                   : launch_halo<(BLOCK_N <= 128 ? BLOCK_N : 128), T, TC_MODE_STD, 4, 2>(pl, pl->p, s);
-    return cw2 ? launch_halo<BLOCK_N, T, TC_MODE_STD, 2, 1>(pl, pl->p, s) : launch_halo<BLOCK_N, T, TC_MODE_STD, 4, 1>(pl, pl->p, s);
+        return cw2 ? launch_halo<(BLOCK_N <= 128 ? BLOCK_N : 128), T, TC_MODE_STD, 2, 2, GN>(pl, pl->p, s)
+                   : launch_halo<(BLOCK_N <= 128 ? BLOCK_N : 128), T, TC_MODE_STD, 4, 2, GN>(pl, pl->p, s);
+    return cw2 ? launch_halo<BLOCK_N, T, TC_MODE_STD, 2, 1, GN>(pl, pl->p, s) : launch_halo<BLOCK_N, T, TC_MODE_STD, 4, 1, GN>(pl, pl->p, s);
 }
 
 int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch* extra) {
@@ -464,13 +634,23 @@ int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch*
             PD_REQUIRE(extra->step->sigma == 0.f, "fused conv_out update requires eta == 0");
             p.epi.step = *extra->step;
         }
-        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM, 4, 1>(pl, p, s); });
+        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM, 4, 1, false>(pl, p, s); });
+    }
+    if (pl->gn) {
+        PD_DISPATCH_HALF(pl->dt, T, {
+            switch (pl->block_n) {
+                case 256: return launch_halo_std<256, T, true>(pl, s);
+                case 128: return launch_halo_std<128, T, true>(pl, s);
+            }
+        });
+        set_error("conv_halo: fused GroupNorm needs a 128- or 256-channel output tile");
+        return 1;
     }
     PD_DISPATCH_HALF(pl->dt, T, {
         switch (pl->block_n) {
-            case 256: return launch_halo_std<256, T>(pl, s);
-            case 128: return launch_halo_std<128, T>(pl, s);
-            case 64: return launch_halo_std<64, T>(pl, s);
+            case 256: return launch_halo_std<256, T, false>(pl, s);
+            case 128: return launch_halo_std<128, T, false>(pl, s);
+            case 64: return launch_halo_std<64, T, false>(pl, s);
         }
     });
     set_error("conv_halo: bad block_n");

@@ -45,6 +45,8 @@ struct GNArgs {
 // standalone producer of chunk statistics for one NHWC tensor (stats zero on entry)
 int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, float* stats, cudaStream_t s);
 int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s);
+// GroupNorm as (scale, shift) per (image, channel) for a consumer that normalises its own input tiles (x1/x2/out/silu unused)
+int launch_gn_coef(const GNArgs& a, float2* coef, cudaStream_t s);
 
 // ---- generic SIMT convolution (fp32 validation path; odd shapes of the bf16 path) -------------------------------
 struct ConvArgs {
@@ -143,7 +145,13 @@ enum { TC_MODE_STD = 0, TC_MODE_DDIM = 1 };
 struct ConvTcDesc {
     // main segment: ksize x ksize conv over `x` (N,H,W,C) bf16/fp16 NHWC (already normalised / concatenated)
     int dt;                           // DT_BF16 or DT_F16
-    const void* x; int C;
+    const void* x; int C;             // C = channels of the main segment (both sources together)
+    // halo kernel only: the last C2 of the C channels come from x2 (channel concat that is never materialised)
+    const void* x2; int C2;
+    // halo kernel, 3x3 stride-1 only: the conv input is silu(v * gn_coef[n,c].x + gn_coef[n,c].y) of the raw main-segment
+    // values v (GroupNorm + SiLU folded into per-image per-channel coefficients, launch_gn_coef); applied to the halo
+    // tiles in shared memory, the normalised tensor is never written to HBM.  (N, C) float2 or null.
+    const float2* gn_coef;
     int N, H, W, ksize, stride, pad, Ho, Wo, Cout;
     // upsample != 0: nearest-2x upsample followed by the 3x3 conv (Upsample2D), executed as four 2x2 sub-pixel phase
     // convolutions on the LOW-resolution input (H,W); Ho = 2H, Wo = 2W; wmat = (4*Cout, 4*C) phase weights

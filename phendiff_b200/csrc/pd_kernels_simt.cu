@@ -287,6 +287,47 @@ int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s) {
     return 0;
 }
 
+// GroupNorm folded to per-image per-channel coefficients for the convolution that applies it to its own input tiles
+// (pd_conv_halo.cu, GN variant): coef[n, c] = (rstd[n,g] * gamma[c], beta[c] - mean[n,g] * rstd[n,g] * gamma[c]).  Same
+// finalisation of the producers' chunk statistics as gn_apply_kernel's prologue (groups may straddle the two sources).
+__global__ void __launch_bounds__(256) gn_coef_kernel(GNArgs a, float2* coef) {
+    extern __shared__ float sm[];   // mean[groups], rstd[groups]
+    float* s_mean = sm;
+    float* s_rstd = sm + a.groups;
+    const int C = a.C1 + a.C2, n = blockIdx.x;
+    const int cpg = C / a.groups, cw = a.stats_cw;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        float sum = 0.f, sq = 0.f;
+        for (int cc = g * cpg; cc < (g + 1) * cpg; cc += cw) {
+            const float* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
+                                          : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
+            sum += st[0]; sq += st[1];
+        }
+        const float mean = sum * inv_cnt;
+        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        s_mean[g] = mean;
+        s_rstd[g] = rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+        const int g = cc / cpg;
+        const float scv = s_rstd[g] * a.gamma[cc];
+        coef[(size_t)n * C + cc] = make_float2(scv, a.beta[cc] - s_mean[g] * scv);
+    }
+}
+
+int launch_gn_coef(const GNArgs& a, float2* coef, cudaStream_t s) {
+    const int C = a.C1 + a.C2;
+    PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
+    const int cw = a.stats_cw;
+    PD_REQUIRE((cw == 4 || cw == 2 || cw == 1) && (C / a.groups) % cw == 0 && a.C1 % cw == 0, "statistics chunk width must divide the group width");
+    PD_REQUIRE(a.stats1 && (a.C2 == 0 || a.stats2), "GroupNorm sources need chunk statistics");
+    gn_coef_kernel<<<a.N, 256, 2 * a.groups * sizeof(float), s>>>(a, coef);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // =====================================================================================================================
 // SIMT implicit-GEMM convolution, fp32 FMA.  M = N*Ho*Wo output pixels, Ncol = Cout, K = k*k*(C1+C2).
 // 64x64x16 tiles, 256 threads, 4x4 register micro-tile.  This is the fp32 validation path (<= 1e-4 vs the oracle)

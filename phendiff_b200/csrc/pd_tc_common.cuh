@@ -12,6 +12,7 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;
 constexpr int TC_THREADS = 256;        // per-tap kernel: 4 control warps + 4 epilogue warps
 constexpr int HALO_THREADS = 384;      // halo kernel: 4 control warps + 8 epilogue warps
+constexpr int HALO_THREADS_GN = 512;   // + 4 warps that apply GroupNorm + SiLU to the raw halo tiles in shared memory
 
 struct TcEpi {
     const float* bias;          // (Cout) or null

@@ -233,6 +233,85 @@ def test_conv_halo(build_lib, case, dtype):
     assert err <= tol, f"conv_halo dt={dtype} {case}: max abs err {err:.3e} (tol {tol:.3e})"
 
 
+GN_CONV_CASES = [
+    # n, h, w, c1, c2, cout, groups, kwargs
+    (2, 16, 16, 128, 0, 128, 32, {}),                                           # one 16x16 tile per image: every halo pixel is padding
+    (1, 32, 32, 128, 0, 256, 32, dict(addvec=True)),                            # BLOCK_N 256 (16x8 tiles), interior halos
+    (2, 32, 48, 256, 128, 128, 32, dict(addvec=True)),                          # concat of two sources, group width 12 straddles them
+    (1, 32, 32, 128, 0, 128, 32, dict(sc=(128, 64))),                           # conv2 + K-concatenated shortcut (shortcut stays raw)
+    (1, 16, 16, 512, 512, 512, 32, dict(addvec=True)),                          # up0.res0.conv1: 16 channel blocks, two N tiles
+    (3, 16, 24, 128, 0, 128, 32, dict(residual=True, out_scale=0.5)),           # W % 16 != 0: 16x8 tiles with BLOCK_N 128
+    (2, 128, 128, 128, 0, 128, 32, dict(addvec=True, stats=True)),              # the bench's top resolution, many tiles per CTA
+    (1, 64, 64, 256, 128, 256, 32, dict(addvec=True, stats=True)),              # up1-like concat at 64x64
+]
+
+
+@pytest.mark.parametrize("dtype", [1, 2])
+@pytest.mark.parametrize("case", GN_CONV_CASES)
+def test_conv_halo_fused_groupnorm(build_lib, case, dtype):
+    """GroupNorm + SiLU applied by the conv to its own shared-memory input tiles (pd_conv_halo.cu, GN variant) against
+    F.group_norm -> F.silu -> (16-bit rounding, as the kernel feeds the tensor core) -> F.conv2d in float64."""
+    n, h, w, c1, c2, cout, groups, kw = case
+    L = build_lib.lib()
+    g = torch.Generator().manual_seed(7)
+    dt = DT[dtype]
+    ct = c1 + c2
+    # per-channel offsets and scales so that the normalisation actually matters
+    x = torch.randn(n, ct, h, w, generator=g) * (0.5 + torch.rand(1, ct, 1, 1, generator=g)) + torch.randn(1, ct, 1, 1, generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(ct, generator=g)
+    beta = 0.3 * torch.randn(ct, generator=g)
+    wt = torch.randn(cout, ct, 3, 3, generator=g) / math.sqrt(ct * 9)
+    b = torch.randn(cout, generator=g) * 0.1
+    av = torch.randn(n, cout, generator=g) * 0.5 if kw.get("addvec") else None
+    res = torch.randn(n, cout, h, w, generator=g) if kw.get("residual") else None
+    out_scale = kw.get("out_scale", 1.0)
+    csc1 = csc2 = 0
+    scx = scw = None
+    if kw.get("sc"):
+        csc1, csc2 = kw["sc"]
+        scx = torch.randn(n, csc1 + csc2, h, w, generator=g)
+        scw = torch.randn(cout, csc1 + csc2, 1, 1, generator=g) / math.sqrt(csc1 + csc2)
+    q = lambda t: t.to(dt).float() if t is not None else None
+    xn = q(F.silu(F.group_norm(q(x), groups, gamma, beta, eps=1e-5)))
+    ref = F.conv2d(xn.double(), q(wt).double(), b.double(), padding=1)
+    if av is not None:
+        ref = ref + av.double()[:, :, None, None]
+    if res is not None:
+        ref = ref + q(res).double()
+    if scx is not None:
+        ref = ref + F.conv2d(q(scx).double(), q(scw).double())
+    ref = (ref * out_scale).float()
+    keep = []
+
+    def dp(t):
+        if t is None:
+            return None
+        t = t.contiguous().to("cuda")
+        keep.append(t)
+        return C.c_void_p(t.data_ptr())
+
+    out = torch.zeros(n, h, w, cout, dtype=dt, device="cuda")
+    stats = torch.zeros(n, cout // 4, 2, dtype=torch.float32, device="cuda") if kw.get("stats") else None
+    build_lib.check(L.pd_test_gn_conv(
+        dtype, n, h, w, c1, c2, cout, groups, 1e-5, dp(nhwc(x[:, :c1], dt)), dp(nhwc(x[:, c1:], dt)) if c2 else None,
+        dp(gamma), dp(beta), dp(wt), dp(b), dp(av), dp(nhwc(res, dt)) if res is not None else None,
+        dp(nhwc(scx[:, :csc1], dt)) if scx is not None else None, dp(nhwc(scx[:, csc1:], dt)) if csc2 else None, csc1, csc2,
+        dp(scw.reshape(cout, -1)) if scw is not None else None, out_scale, C.c_void_p(out.data_ptr()),
+        C.c_void_p(stats.data_ptr()) if stats is not None else None, None))
+    torch.cuda.synchronize()
+    got = nchw(out.cpu())
+    # one 16-bit rounding of the output + a few last-place flips of the normalised input (fast exp vs torch's)
+    rel = 1.5e-2 if dtype == 1 else 3e-3
+    tol = rel * max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    assert err <= tol, f"gn+conv dt={dtype} {case}: max abs err {err:.3e} (tol {tol:.3e})"
+    if stats is not None:
+        o = ref.permute(0, 2, 3, 1).reshape(n, h * w, cout // 4, 4).double()
+        sref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).float()
+        serr = ((stats.cpu() - sref).abs() / (sref.abs() + 1e-3 * sref.abs().max())).max().item()
+        assert serr <= 2e-2, f"gn+conv chunk statistics rel err {serr:.3e}"
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 32, 32, 128, 256), (1, 64, 64, 256, 256)])
 def test_conv_halo_fused_upsample(build_lib, case):
     """Upsample2D = nearest 2x + conv3x3 run as four sub-pixel phase convs on the low-res input."""
