@@ -47,7 +47,7 @@ struct HaloParams {
     int off_h, off_w;              // box origin relative to the tile origin (-pad); upsample adds the phase
     int m_tiles, n_tiles, phases, b_rows_per_phase;
     int Ho, Wo;                    // output extent (2x the tile-space extent in upsample mode)
-    int upsample, use_base_offset;
+    int upsample;
     int mt;                        // M halves per tile: 1 = 16x8 pixels, 2 = 16x16 pixels (two accumulators share every weight tile)
     int kb_a1;                     // 64-channel blocks of the main segment that come from tmA (the rest from tmA2)
     const float2* gn_coef;         // GN variant: (N, C) (scale, shift) of the fused GroupNorm, SiLU follows; else null
@@ -247,51 +247,68 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
       } else if (warp == 1) {
         if (elect_one()) {
             // ===================== MMA issuer (single thread) =====================
+            // Everything a tap needs is an add away: ncu on conv_out (profiles/r1y_ncu_conv_out.md) showed this thread — not a
+            // barrier — as the critical path of the kernel at ~510 cycles of dependent scalar work per tap (an integer division
+            // by the runtime kernel width, 64-bit descriptor assembly, generic->shared conversions and constant-bank reloads),
+            // i.e. as long as the four N = 256 MMAs of a tap keep the tensor pipe busy.  Descriptors are now (constant high
+            // word, running low word = address >> 4), barrier addresses are 32-bit shared addresses advanced by 8.
             constexpr uint32_t idesc = make_idesc<T, BLOCK_N>();
+            constexpr uint32_t B_HI = sw128_desc_hi(1024u);
+            constexpr uint32_t B_LO_STEP = (uint32_t)B_BYTES >> 4;
+            const int kw = p.kw, ntaps = p.ntaps, pitch_main = p.pitch_px;
+            const int nkbs[3] = {p.kb_main, p.kb_s1, p.kb_s2};
+            const uint32_t a_lo0 = (smem_u32(smA) & 0x3FFFFu) >> 4, a_lo_step = (uint32_t)p.a_stage_bytes >> 4;
+            const uint32_t b_lo0 = (smem_u32(smB) & 0x3FFFFu) >> 4;
+            const uint32_t bar_fullA = smem_u32(GN ? readyA : fullA), bar_emptyA = smem_u32(emptyA);
+            const uint32_t bar_fullB = smem_u32(fullB), bar_emptyB = smem_u32(emptyB);
+            const uint32_t bar_tfull = smem_u32(tfull), bar_tempty = smem_u32(tempty);
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
             int iter = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int as = iter & 1;
                 const uint32_t aphase = (iter >> 1) & 1;
-                mbar_wait(&tempty[as], aphase ^ 1);
+                mbar_wait_addr(bar_tempty + as * 8, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BLOCK_N);
                 uint32_t accum = 0;
+#pragma unroll 1
                 for (int seg = 0; seg < 3; ++seg) {
-                    const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
-                    const int ntap = seg == 0 ? p.ntaps : 1;
-                    const int pitch = seg == 0 ? p.pitch_px : TILE_W;
-                    const uint32_t sbo = (uint32_t)pitch * 128u;
+                    const int nkb = nkbs[seg];
+                    const int ntap = seg == 0 ? ntaps : 1;
+                    const int pitch = seg == 0 ? pitch_main : TILE_W;
+                    const uint32_t a_hi = sw128_desc_hi((uint32_t)pitch * 128u);   // SBO = one pixel row of the tile per 8-row group step
+                    const uint32_t row_wrap = (uint32_t)(pitch - kw) * 8u;
+#pragma unroll 1
                     for (int cb = 0; cb < nkb; ++cb) {
-                        mbar_wait(GN ? &readyA[sa] : &fullA[sa], pha);
+                        mbar_wait_addr(bar_fullA + sa * 8, pha);
                         tc_fence_after();
-                        const uint32_t a_base = smem_u32(smA + (size_t)sa * p.a_stage_bytes);
+                        uint32_t a_lo = a_lo0 + (uint32_t)sa * a_lo_step;   // + 8 per pixel row of 128 B
+                        int sx = 0;
+#pragma unroll 1
                         for (int tap = 0; tap < ntap; ++tap) {
-                            mbar_wait(&fullB[sb], phb);
+                            mbar_wait_addr(bar_fullB + sb * 8, phb);
                             tc_fence_after();
-                            const int r = tap / p.kw, s = tap - r * p.kw;
-                            const uint32_t row_off = (uint32_t)(r * pitch + s);
-                            const uint64_t b_desc = make_sw128_desc(smem_u32(smB + (size_t)sb * B_BYTES));
+                            const uint32_t b_lo = b_lo0 + (uint32_t)sb * B_LO_STEP;
 #pragma unroll
                             for (int half = 0; half < MT; ++half) {
                                 // the second 16x8-pixel half starts 8 pixel rows (one 1024-byte swizzle atom) further in the same halo tile
-                                const uint32_t ro = row_off + (uint32_t)(half * HL_WT);
-                                const uint64_t a_desc = make_sw128_desc(a_base + ro * 128u, sbo, p.use_base_offset ? ro : 0u);
 #pragma unroll
                                 for (int k = 0; k < TC_BLOCK_K / 16; ++k)
-                                    umma_f16kind(d_tmem + (uint32_t)(half * BLOCK_N), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                                 (accum | (uint32_t)k) ? 1u : 0u);
+                                    umma_f16kind(d_tmem + (uint32_t)(half * BLOCK_N), desc64(a_hi, a_lo + (uint32_t)(half * HL_WT * 8 + 2 * k)),
+                                                 desc64(B_HI, b_lo + (uint32_t)(2 * k)), idesc, (accum | (uint32_t)k) ? 1u : 0u);
                             }
                             accum = 1;
-                            umma_commit(&emptyB[sb]);
+                            umma_commit_addr(bar_emptyB + sb * 8);
                             if (++sb == SB) { sb = 0; phb ^= 1; }
+                            a_lo += 8u;                                   // next tap: one pixel to the right ...
+                            if (++sx == kw) { sx = 0; a_lo += row_wrap; }   // ... or the first pixel of the next halo row
                         }
-                        umma_commit(&emptyA[sa]);
+                        umma_commit_addr(bar_emptyA + sa * 8);
                         if (++sa == SA) { sa = 0; pha ^= 1; }
                     }
                 }
-                umma_commit(&tfull[as]);
+                umma_commit_addr(bar_tfull + as * 8);
             }
         }
       }
@@ -500,8 +517,8 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     const int kh = d.upsample ? 2 : d.ksize, kw = kh;
     p.ntaps = kh * kw; p.kw = kw;
     // probe knobs for the descriptor semantics (see file header; defaults = the measured-correct variant):
-    // PHENDIFF_B200_HALO_PITCH=pow2 pads the halo row to 16 pixels (SBO 2048); PHENDIFF_B200_HALO_BASEOFF=1 sets the
-    // descriptor base offset to the row phase of the shifted start
+    // PHENDIFF_B200_HALO_PITCH=pow2 pads the halo row to 16 pixels (SBO 2048).  (The r1b probe also had a knob that set the
+    // descriptor's base-offset field to the row phase of the shifted start; it addressed the wrong rows and was removed.)
     const char* pk = getenv("PHENDIFF_B200_HALO_PITCH");
     const bool pow2 = pk && std::string(pk) == "pow2";
     // M halves per tile: layers with <= 128 output channels per tile are bound by the L2 -> SM stream of the weight tiles
@@ -513,8 +530,6 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     p.mt = mt;
     const int tile_w = HL_WT * mt;
     p.pitch_px = (kw == 1) ? tile_w : (pow2 ? 16 : tile_w + kw - 1);
-    const char* bo = getenv("PHENDIFF_B200_HALO_BASEOFF");
-    p.use_base_offset = bo ? (bo[0] != '0') : 0;
     const int rows = HL_HT + kh - 1;
     p.a_bytes_main = 128 * p.pitch_px * rows;
     p.a_bytes_sc = 128 * tile_w * HL_HT;

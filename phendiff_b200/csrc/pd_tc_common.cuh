@@ -46,6 +46,13 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
     return d;
 }
 
+// The same descriptor as (high word, low word): the high word (SBO, version, layout; base offset 0) is constant per operand,
+// the low word is the 16-byte-granular shared-memory address, so stepping through taps / K slices / ring stages is one 32-bit add.
+__host__ __device__ constexpr uint32_t sw128_desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
 // instruction descriptor, kind::f16: D fp32 (bit 4), A/B format at bits 7/10 (0 = fp16, 1 = bf16), both K-major,
 // N >> 3 at bits 17.., M >> 4 at bits 24..
 template <typename T, int BLOCK_N> __device__ __forceinline__ constexpr uint32_t make_idesc() {
