@@ -290,11 +290,13 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
                             mbar_wait_addr(bar_fullB + sb * 8, phb);
                             tc_fence_after();
                             const uint32_t b_lo = b_lo0 + (uint32_t)sb * B_LO_STEP;
+                            // K slice outer, tile half inner: consecutive MMAs alternate between the two accumulators instead of
+                            // chaining four dependent accumulations into the same TMEM columns
 #pragma unroll
-                            for (int half = 0; half < MT; ++half) {
-                                // the second 16x8-pixel half starts 8 pixel rows (one 1024-byte swizzle atom) further in the same halo tile
+                            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
 #pragma unroll
-                                for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+                                for (int half = 0; half < MT; ++half)
+                                    // the second 16x8-pixel half starts 8 pixel rows (one 1024-byte swizzle atom) further in the same halo tile
                                     umma_f16kind(d_tmem + (uint32_t)(half * BLOCK_N), desc64(a_hi, a_lo + (uint32_t)(half * HL_WT * 8 + 2 * k)),
                                                  desc64(B_HI, b_lo + (uint32_t)(2 * k)), idesc, (accum | (uint32_t)k) ? 1u : 0u);
                             }
