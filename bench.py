@@ -30,6 +30,18 @@ GFLOP_PER_IMAGE_FORWARD = {("small_denoiser_config", 128): 285.58, ("small_denoi
 METRIC = "images/sec, DDIM invert+regenerate 128x128 100 steps"
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the roofline's kernel class from the committed ncu pass (tools/summarize_profile.py writes
+    profiles/traffic.json from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over whole forwards at the bench's
+    micro-batch); None when no capture has been committed."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["conv_tcgen05"]
+    except Exception:
+        return None
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -283,11 +295,15 @@ def run_ours(args):
         tot_ms = sum(v["ms"] for k, v in prof.items() if isinstance(v, dict))
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": None,
-                "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/linear)", "peak_source": pk["src"] + " sustained bf16 cuBLAS",
+                "kernel": "conv_halo_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv/linear class)", "peak_source": pk["src"] + " sustained bf16 cuBLAS",
                 "avg_launch_ms": tc["ms"] / tc["launches"] if tc["launches"] else None,
                 "kernel_share_of_step": tc["ms"] / tot_ms if tot_ms else None,
                 "share_by_class": {k: (v["ms"] / tot_ms if tot_ms else None) for k, v in prof.items() if isinstance(v, dict)},
                 "sampled_forwards": prof["samples"]}
+        tr = measured_traffic()
+        if tr:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_note"] = tr["note"]
         if gf:
             model_tflops = value / world * 2 * n * gf / 1e3      # per GPU: the peaks below are single-GPU figures
             roof["whole_path_tflops"] = model_tflops

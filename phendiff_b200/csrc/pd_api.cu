@@ -761,16 +761,38 @@ struct Rec {
             if (rc) return rc;
         }
         // out (cond_unet_2d.py:346-348) + optional fused scheduler update (A.5)
-        Tensor* xn = gn(M->norm_out, x, nullptr, true);
-        release(x);
         bool out_tc = false;
         ConvTcDesc od{};
         od.dt = M->dt; od.C = C0; od.N = mb; od.H = H; od.W = W; od.ksize = 3; od.stride = 1; od.pad = 1; od.Ho = H; od.Wo = W;
         od.Cout = c.out_channels; od.mode = TC_MODE_DDIM;
         if (M->half && c.conv_impl == 0 && M->w_out_tc) out_tc = conv_halo_supported(od, nullptr);
+        // conv_norm_out + SiLU inside conv_out's own halo tiles when the tensor-core path runs (same GN variant as the ResNet convs)
+        static const int gnfuse = [] { const char* e = getenv("PHENDIFF_B200_GNFUSE"); return e ? atoi(e) : 1; }();
+        bool out_gn = false;
+        if (out_tc && gnfuse && x->stats_off != (size_t)-1) {
+            ConvTcDesc pd_ = od;
+            pd_.gn_coef = kGnCoefProbe;
+            out_gn = conv_halo_supported(pd_, nullptr);
+        }
+        Tensor* xn = out_gn ? x : gn(M->norm_out, x, nullptr, true);
+        if (!out_gn) release(x);
+        size_t coef_off = 0, coef_bytes = 0;
+        if (out_gn) {
+            coef_bytes = (size_t)mb * C0 * sizeof(float2);
+            coef_off = M->arena.alloc(coef_bytes);
+            if (!dry) {
+                GNArgs ga{};
+                ga.C1 = C0; ga.C2 = 0; ga.N = mb; ga.HW = H * W; ga.groups = c.norm_num_groups; ga.eps = c.norm_eps;
+                ga.gamma = M->norm_out.g->dev; ga.beta = M->norm_out.b->dev; ga.silu = 1; ga.stats_cw = M->stats_cw; ga.stats1 = stats_ptr(x);
+                float2* cf = (float2*)raw(coef_off);
+                push([ga, cf](const Ctx&, cudaStream_t s) { return launch_gn_coef(ga, cf, s); }, 1, CLS_GN, 0.0,
+                     "gn_coef C=" + std::to_string(C0) + " @" + std::to_string(H) + "x" + std::to_string(W));
+            }
+        }
         if (out_tc) {
             if (!dry) {
                 od.x = ptr(xn); od.wmat = M->w_out_tc; od.bias = M->conv_out.b->dev; od.out_scale = 1.f;
+                od.gn_coef = out_gn ? (const float2*)raw(coef_off) : nullptr;
                 ConvTcPlan* pl = nullptr;
                 int r = conv_tc_plan_create(od, &pl);
                 if (r) return r;
@@ -779,7 +801,7 @@ struct Rec {
                 push([pl](const Ctx& cx, cudaStream_t s) {
                     ConvTcLaunch ex{cx.model_out, cx.x_update, cx.step};
                     return conv_tc_launch(pl, s, &ex);
-                }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels);
+                }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels, out_gn ? "gn+conv_out+ddim" : "conv_out+ddim");
             }
         } else if (!dry) {
             ConvOutArgs oa{};
@@ -792,6 +814,7 @@ struct Rec {
                 return launch_conv_out(dt, a, s);
             }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels);
         }
+        if (out_gn) M->arena.release(coef_off, coef_bytes);
         release(xn);
         M->stats_needed = stats_bump;
         if (!dry && stats_bump > M->stats_bytes) { set_error("internal: statistics region too small"); return 1; }

@@ -343,14 +343,19 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BLOCK_N);
             if (MODE == TC_MODE_DDIM) {
-                int oh = h0 + hh, ow = w0 + ww;
-                const int hw = oh * p.Wo + ow;
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(t_addr, r);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&tempty[as]);      // accumulator is in registers: the MMA warp may overwrite this TMEM buffer
-                tc_epilogue_ddim(p.epi, r, img, hw);
+#pragma unroll
+                for (int half = 0; half < MT; ++half) {
+                    const int oh = h0 + hh, ow = w0 + half * HL_WT + ww;
+                    const int hw = oh * p.Wo + ow;
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(t_addr + (uint32_t)(half * BLOCK_N), r);
+                    tmem_ld_wait();
+                    if (half == MT - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&tempty[as]);      // accumulators are in registers: the MMA warp may overwrite this TMEM buffer
+                    }
+                    tc_epilogue_ddim(p.epi, r, img, hw);
+                }
             } else {
                 constexpr int SLABS = BLOCK_N >= 64 ? BLOCK_N / 64 : 1, ITEMS = MT * SLABS;
 #pragma unroll 1
@@ -487,8 +492,8 @@ bool conv_halo_supported(const ConvTcDesc& d, std::string* why) {
     if (d.dt != DT_BF16 && d.dt != DT_F16) return no("tcgen05 path takes bf16 or fp16 activations");
     if (d.C % 64 != 0 || d.C2 % 64 != 0 || d.Csc1 % 64 != 0 || d.Csc2 % 64 != 0) return no("channel counts must be multiples of 64");
     if (d.C2 < 0 || d.C2 >= d.C + (d.C == 0)) return no("second main-segment source must leave channels for the first");
-    if (d.gn_coef && (d.ksize != 3 || d.upsample || d.mode != TC_MODE_STD)) return no("fused GroupNorm: plain 3x3 convolution only");
-    if (d.gn_coef && halo_block_n(d) < 128) return no("fused GroupNorm: Cout must be a multiple of 128");
+    if (d.gn_coef && (d.ksize != 3 || d.upsample)) return no("fused GroupNorm: plain 3x3 convolution only");
+    if (d.gn_coef && d.mode == TC_MODE_STD && halo_block_n(d) < 128) return no("fused GroupNorm: Cout must be a multiple of 128");
     if (halo_block_n(d) == 0) return no("Cout must be a multiple of 64 (or <= 16 for the conv_out mode)");
     if (d.stride != 1) return no("halo kernel takes stride-1 convolutions");
     if (!(d.ksize == 1 || d.ksize == 3)) return no("kernel size must be 1 or 3");
@@ -527,7 +532,7 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     // (profiles/r1k_ncu_conv_halo128.md: 7.8 TB/s of crossbar reads, tensor pipe 47 % active): a 16x16-pixel tile feeds two
     // accumulators from every weight tile and halves that stream.  TMEM holds 2 (double buffer) x mt x block_n fp32 columns.
     int mt = 1;
-    if (d.mode == TC_MODE_STD && pl->block_n <= 128 && d.W % (2 * HL_WT) == 0 && !pow2) mt = 2;
+    if (pl->block_n <= 128 && d.W % (2 * HL_WT) == 0 && !pow2) mt = 2;   // conv_out (N = 16) too: its cost is the per-tap issue overhead
     if (const char* e = getenv("PHENDIFF_B200_HALO_MT")) mt = (atoi(e) == 2 && mt == 2) ? 2 : 1;
     p.mt = mt;
     const int tile_w = HL_WT * mt;
@@ -559,7 +564,7 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     if (d.gn_coef) {
         // TMA latency + transform must fit under (SA - 1) K-blocks of MMAs; the 41 KB stages of the dual-accumulator tile take
         // the longest to transform and leave room for a third stage beside a 4-deep weight ring
-        if (mt == 2) p.SA = 3;
+        if (mt == 2 && pl->block_n != 16) p.SA = 3;
         if (const char* e = getenv("PHENDIFF_B200_HALO_GN_SA")) p.SA = std::min(4, std::max(2, atoi(e)));
     }
     p.SB = std::min(16, (budget - p.SA * p.a_stage_bytes) / b_bytes);
@@ -653,7 +658,10 @@ int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch*
             PD_REQUIRE(extra->step->sigma == 0.f, "fused conv_out update requires eta == 0");
             p.epi.step = *extra->step;
         }
-        PD_DISPATCH_HALF(pl->dt, T, { return launch_halo<16, T, TC_MODE_DDIM, 4, 1, false>(pl, p, s); });
+        PD_DISPATCH_HALF(pl->dt, T, {
+            if (pl->gn) return p.mt == 2 ? launch_halo<16, T, TC_MODE_DDIM, 4, 2, true>(pl, p, s) : launch_halo<16, T, TC_MODE_DDIM, 4, 1, true>(pl, p, s);
+            return p.mt == 2 ? launch_halo<16, T, TC_MODE_DDIM, 4, 2, false>(pl, p, s) : launch_halo<16, T, TC_MODE_DDIM, 4, 1, false>(pl, p, s);
+        });
     }
     if (pl->gn) {
         PD_DISPATCH_HALF(pl->dt, T, {

@@ -54,6 +54,45 @@ def launches(tag):
     print("wrote", f"profiles/{tag}_launches.md")
 
 
+def dram(tag):
+    """gpurun_out/dram_<tag>.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum over whole
+    forwards at the bench's micro-batch -> profiles/<tag>_dram.md and profiles/traffic.json (read by bench.py's roofline)."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", f"dram_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.defaultdict(lambda: collections.defaultdict(float))   # kernel -> metric -> sum (bytes / us)
+    cnt = collections.Counter()
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except Exception:
+            continue
+        u, m = row["Metric Unit"], row["Metric Name"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(u, 1.0)
+        name = row["Kernel Name"].split("(")[0]
+        per[name][m] += v * scale
+        if m == "gpu__time_duration.sum":
+            cnt[name] += 1
+    conv = [k for k in per if "conv_halo_kernel" in k or "conv_tc_kernel" in k]
+    with open(os.path.join(ROOT, "profiles", f"{tag}_dram.md"), "w") as f:
+        f.write(f"# ncu DRAM traffic per kernel `{tag}` (dram__bytes_read.sum + dram__bytes_write.sum; whole forwards at micro-batch 64)\n\n")
+        f.write("| kernel | launches | read MB / launch | write MB / launch | avg us | GB/s |\n|---|---:|---:|---:|---:|---:|\n")
+        for k in sorted(per, key=lambda k: -per[k]["gpu__time_duration.sum"]):
+            n = max(cnt[k], 1)
+            r, w, t = per[k]["dram__bytes_read.sum"] / n, per[k]["dram__bytes_write.sum"] / n, per[k]["gpu__time_duration.sum"] / n
+            f.write(f"| `{k}` | {n} | {r / 1e6:.1f} | {w / 1e6:.1f} | {t:.1f} | {(r + w) / max(t, 1e-9) / 1e3:.0f} |\n")
+    nconv = sum(cnt[k] for k in conv)
+    if nconv:
+        tot = sum(per[k]["dram__bytes_read.sum"] + per[k]["dram__bytes_write.sum"] for k in conv)
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            json.dump({"conv_tcgen05": {"dram_bytes_per_launch": tot / nconv, "launches": nconv,
+                                        "note": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over {nconv} tcgen05 conv launches of whole forwards "
+                                                f"at micro-batch 64 (profiles/{tag}_dram.md)"}}, f, indent=1)
+    print("wrote", f"profiles/{tag}_dram.md")
+
+
 def full(tag):
     for rep in glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_*_{tag}.ncu-rep")):
         name = os.path.basename(rep)[len("prof_"):-len(f"_{tag}.ncu-rep")]
@@ -76,6 +115,7 @@ def full(tag):
 if __name__ == "__main__":
     t = sys.argv[1]
     launches(t)
+    dram(t)
     full(t)
     b = os.path.join(ROOT, "gpurun_out", f"bench_{t}.json")
     if os.path.exists(b) and os.path.getsize(b):
