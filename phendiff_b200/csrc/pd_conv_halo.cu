@@ -50,6 +50,8 @@ struct HaloParams {
     int upsample;
     int mt;                        // M halves per tile: 1 = 16x8 pixels, 2 = 16x16 pixels (two accumulators share every weight tile)
     int kb_a1;                     // 64-channel blocks of the main segment that come from tmA (the rest from tmA2)
+    int sc_per_stage;              // 1x1-shortcut K blocks that share one A stage (1 or 2): a shortcut block is ONE tap (~0.5 k cycles
+                                   // of MMAs), shorter than a TMA round trip, so two of them travel per stage where shared memory allows
     const float2* gn_coef;         // GN variant: (N, C) (scale, shift) of the fused GroupNorm, SiLU follows; else null
     int H, W;                      // input extent (halo mask of the GN variant)
     int gn_tanh;                   // SiLU of the GN variant through tanh.approx (1 MUFU / element) instead of ex2 + rcp
@@ -228,7 +230,8 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
                 const int oh = p.off_h + (p.upsample ? (phase >> 1) : 0), ow = p.off_w + (p.upsample ? (phase & 1) : 0);
                 for (int seg = 0; seg < 3; ++seg) {
                     const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
-                    for (int cb = 0; cb < nkb; ++cb) {
+                    const int per = seg == 0 ? 1 : p.sc_per_stage;   // K blocks per stage
+                    for (int cb = 0; cb < nkb; cb += per) {
                         mbar_wait(&emptyA[sa], pha ^ 1);
                         uint8_t* dstA = smA + (size_t)sa * p.a_stage_bytes;
                         if (seg == 0) {
@@ -236,8 +239,10 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
                             if (cb < p.kb_a1) tma_load_4d(&p.tmA, &fullA[sa], dstA, cb * TC_BLOCK_K, w0 + ow, h0 + oh, img);
                             else tma_load_4d(&p.tmA2, &fullA[sa], dstA, (cb - p.kb_a1) * TC_BLOCK_K, w0 + ow, h0 + oh, img);
                         } else {
-                            mbar_arrive_expect_tx(&fullA[sa], p.a_bytes_sc);
-                            tma_load_4d(seg == 1 ? &p.tmS1 : &p.tmS2, &fullA[sa], dstA, cb * TC_BLOCK_K, w0, h0, img);
+                            const int nb = min(per, nkb - cb);
+                            mbar_arrive_expect_tx(&fullA[sa], nb * p.a_bytes_sc);
+                            for (int b = 0; b < nb; ++b)
+                                tma_load_4d(seg == 1 ? &p.tmS1 : &p.tmS2, &fullA[sa], dstA + (size_t)b * p.a_bytes_sc, (cb + b) * TC_BLOCK_K, w0, h0, img);
                         }
                         if (++sa == SA) { sa = 0; pha ^= 1; }
                     }
@@ -257,6 +262,8 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
             constexpr uint32_t B_LO_STEP = (uint32_t)B_BYTES >> 4;
             const int kw = p.kw, ntaps = p.ntaps, pitch_main = p.pitch_px;
             const int nkbs[3] = {p.kb_main, p.kb_s1, p.kb_s2};
+            const int sc_per_stage = p.sc_per_stage;
+            const uint32_t sc_blk_lo = (uint32_t)p.a_bytes_sc >> 4;
             const uint32_t a_lo0 = (smem_u32(smA) & 0x3FFFFu) >> 4, a_lo_step = (uint32_t)p.a_stage_bytes >> 4;
             const uint32_t b_lo0 = (smem_u32(smB) & 0x3FFFFu) >> 4;
             const uint32_t bar_fullA = smem_u32(GN ? readyA : fullA), bar_emptyA = smem_u32(emptyA);
@@ -275,12 +282,17 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
 #pragma unroll 1
                 for (int seg = 0; seg < 3; ++seg) {
                     const int nkb = nkbs[seg];
-                    const int ntap = seg == 0 ? ntaps : 1;
                     const int pitch = seg == 0 ? pitch_main : TILE_W;
                     const uint32_t a_hi = sw128_desc_hi((uint32_t)pitch * 128u);   // SBO = one pixel row of the tile per 8-row group step
+                    // a shortcut stage holds up to sc_per_stage K blocks of ONE tap each: it runs through the same loop as the taps
+                    // of a main block, stepping a whole block (a_bytes_sc) instead of one pixel row and never wrapping
+                    const int per = seg == 0 ? 1 : sc_per_stage;
+                    const uint32_t tap_step = seg == 0 ? 8u : sc_blk_lo;
+                    const int wrap_at = seg == 0 ? kw : (1 << 30);
                     const uint32_t row_wrap = (uint32_t)(pitch - kw) * 8u;
 #pragma unroll 1
-                    for (int cb = 0; cb < nkb; ++cb) {
+                    for (int cb = 0; cb < nkb; cb += per) {
+                        const int ntap = seg == 0 ? ntaps : min(per, nkb - cb);
                         mbar_wait_addr(bar_fullA + sa * 8, pha);
                         tc_fence_after();
                         uint32_t a_lo = a_lo0 + (uint32_t)sa * a_lo_step;   // + 8 per pixel row of 128 B
@@ -303,8 +315,8 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
                             accum = 1;
                             umma_commit_addr(bar_emptyB + sb * 8);
                             if (++sb == SB) { sb = 0; phb ^= 1; }
-                            a_lo += 8u;                                   // next tap: one pixel to the right ...
-                            if (++sx == kw) { sx = 0; a_lo += row_wrap; }   // ... or the first pixel of the next halo row
+                            a_lo += tap_step;                                  // next tap: one pixel to the right ...
+                            if (++sx == wrap_at) { sx = 0; a_lo += row_wrap; }   // ... or the first pixel of the next halo row
                         }
                         umma_commit_addr(bar_emptyA + sa * 8);
                         if (++sa == SA) { sa = 0; pha ^= 1; }
@@ -439,7 +451,8 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
             const float2* crow = p.gn_coef + (size_t)img * p.C + lc * 8;
             for (int seg = 0; seg < 3; ++seg) {
                 const int nkb = seg == 0 ? p.kb_main : (seg == 1 ? p.kb_s1 : p.kb_s2);
-                for (int cb = 0; cb < nkb; ++cb) {
+                const int per = seg == 0 ? 1 : p.sc_per_stage;
+                for (int cb = 0; cb < nkb; cb += per) {
                     float4 cf[4];
                     if (seg == 0) {
                         const float4* cp = reinterpret_cast<const float4*>(crow + cb * TC_BLOCK_K);
@@ -540,6 +553,7 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     const int rows = HL_HT + kh - 1;
     p.a_bytes_main = 128 * p.pitch_px * rows;
     p.a_bytes_sc = 128 * tile_w * HL_HT;
+    p.sc_per_stage = 1;
     p.a_stage_bytes = ((std::max(p.a_bytes_main, p.a_bytes_sc) + 1023) / 1024) * 1024;
     p.C = d.C; p.kb_main = d.C / 64; p.kb_s1 = d.Csc1 / 64; p.kb_s2 = d.Csc2 / 64;
     p.kb_a1 = (d.C - d.C2) / 64;
@@ -566,6 +580,15 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
         // the longest to transform and leave room for a third stage beside a 4-deep weight ring
         if (mt == 2 && pl->block_n != 16) p.SA = 3;
         if (const char* e = getenv("PHENDIFF_B200_HALO_GN_SA")) p.SA = std::min(4, std::max(2, atoi(e)));
+    }
+    if (d.Csc1 >= 128 || d.Csc2 >= 128) {
+        // two shortcut blocks per A stage where that keeps the stage count and a 4-deep weight ring: the 16x8-pixel tiles
+        // (2 x 16 KB beside a 23 KB halo tile).  Same-box A/B (profiles/r2f): fused conv2+shortcut layers +8..14 %.  On the
+        // 16x16-pixel tiles it would cost the GN variant its third A stage (2 x 64 KB): measured slower, not done.
+        // PHENDIFF_B200_HALO_SC2=0 keeps one block per stage.
+        static const int sc2 = [] { const char* e = getenv("PHENDIFF_B200_HALO_SC2"); return e ? atoi(e) : 1; }();
+        const int stage2 = ((std::max(p.a_bytes_main, 2 * p.a_bytes_sc) + 1023) / 1024) * 1024;
+        if (sc2 && stage2 <= 48 * 1024 && (budget - p.SA * stage2) / b_bytes >= 4) { p.sc_per_stage = 2; p.a_stage_bytes = stage2; }
     }
     p.SB = std::min(16, (budget - p.SA * p.a_stage_bytes) / b_bytes);
     if (p.SB < 2) { delete pl; set_error("conv_halo: shared memory budget too small"); return 1; }
