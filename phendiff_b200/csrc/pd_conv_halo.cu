@@ -575,6 +575,12 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
     const int budget = 227 * 1024 - 1024 - 512 - epi_bytes;
     p.SA = (pl->block_n >= 256 || mt == 2) ? 2 : 3;
     if (pl->block_n == 16) p.SA = 4;
+    // 1x1 / linear layers: an A stage lives for ONE weight tile (~0.5 k cycles of MMAs), less than a TMA round trip, so the ring
+    // has to be deep in stages, not in bytes.  PHENDIFF_B200_HALO_LIN_SA overrides.
+    if (d.ksize == 1 && d.mode == TC_MODE_STD && d.C >= 128) {   // (conv_in's K = 64 GEMM is one block per tile: HBM-bound, measured no gain)
+        static const int lin_sa = [] { const char* e = getenv("PHENDIFF_B200_HALO_LIN_SA"); return e ? atoi(e) : 4; }();
+        p.SA = std::min(4, std::max(2, lin_sa));
+    }
     if (d.gn_coef) {
         // TMA latency + transform must fit under (SA - 1) K-blocks of MMAs; the 41 KB stages of the dual-accumulator tile take
         // the longest to transform and leave room for a third stage beside a 4-deep weight ring
