@@ -442,6 +442,8 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
         while (hx0 >= pitch) { hx0 -= pitch; ++hy0; }
         int sa = 0;
         uint32_t pha = 0;
+        // the coefficient table is written by the kernel this grid may have overtaken (programmatic dependent launch, see launch_halo)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int t2 = tile / p.n_tiles;
             const int m_tile = t2 / p.phases;
@@ -662,7 +664,22 @@ static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t
                                            (int)pl->smem));
         attr_smem = pl->smem;
     }
-    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN><<<pl->grid, GN ? HALO_THREADS_GN : HALO_THREADS, pl->smem, s>>>(p);
+    if (GN) {
+        // Programmatic dependent launch: the kernel ahead of a GN-variant conv is its gn_coef_kernel, which releases its
+        // dependents at once (griddepcontrol.launch_dependents).  This grid may therefore start while the coefficients are
+        // still being computed: barrier init, TMEM allocation, the first weight and halo-tile loads all run under gn_coef;
+        // only the transform warps wait (griddepcontrol.wait) before they read the table.  PHENDIFF_B200_PDL=0 disables.
+        static const int pdl = [] { const char* e = getenv("PHENDIFF_B200_PDL"); return e ? atoi(e) : 1; }();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(HALO_THREADS_GN); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+        PD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN>, p));
+        return 0;
+    }
+    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN><<<pl->grid, HALO_THREADS, pl->smem, s>>>(p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -291,6 +291,9 @@ int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s) {
 // (pd_conv_halo.cu, GN variant): coef[n, c] = (rstd[n,g] * gamma[c], beta[c] - mean[n,g] * rstd[n,g] * gamma[c]).  Same
 // finalisation of the producers' chunk statistics as gn_apply_kernel's prologue (groups may straddle the two sources).
 __global__ void __launch_bounds__(256) gn_coef_kernel(GNArgs a, float2* coef) {
+    // let the consuming convolution (launched with programmatic stream serialization) start its prologue and first tile
+    // loads now; its transform warps wait for this grid to finish before they read `coef`
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ float sm[];   // mean[groups], rstd[groups]
     float* s_mean = sm;
     float* s_rstd = sm + a.groups;
