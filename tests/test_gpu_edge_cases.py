@@ -1,0 +1,113 @@
+"""GPU parity tests, edge cases of the path: ragged / prime batches against the micro-batch planner, batch 1, extents the
+tensor-core tiles do not cover (the in-CUDA fallback routes), non-square samples, more than two classes, per-sample
+timesteps and `class_emb` conditioning (`timestep` scalar / 0-dim / 1-D, labels xor embedding).
+
+Same bars as tests/test_gpu_unet.py: fp32 validation mode <= 1e-4 per-step eps, 16-bit modes <= 1e-2 (fp16), images >= 40 dB.
+"""
+import pytest
+import torch
+
+from tests.util import make_pair, psnr, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _sched(name="3k_steps_clipping_rescaling"):
+    from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+
+    return SCHEDULER_CONFIGS[name]
+
+
+@pytest.mark.parametrize("batch,cap,expect_mb", [(1, 64, 1), (7, 4, 1), (6, 4, 3), (10, 64, 10), (12, 8, 6)])
+def test_ddib_batches_against_the_microbatch_planner(build_lib, batch, cap, expect_mb):
+    """The planner runs the largest divisor of the batch that fits the cap (prime batches degrade to 1, never to a ragged
+    tail): every image's trajectory must be the one it has when transferred alone in the oracle."""
+    from oracle import OracleDDIMScheduler, OraclePipeline, oracle_ddib
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, ddib_transfer
+
+    oracle, model = make_pair("super_small", 32, "fp16", max_microbatch=cap)
+    x, src = synth_images(batch, 32)
+    tgt = 1 - src
+    o_pipe = OraclePipeline(oracle, OracleDDIMScheduler.from_config(_sched()))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched()))
+    got = ddib_transfer(pipe, x, src, tgt, 5).cpu()
+    assert model.plan_info()["microbatch"] == expect_mb
+    ref = oracle_ddib(o_pipe, x, src, tgt, 5, return_raw=True)
+    assert got.shape == ref.shape == (batch, 3, 32, 32)
+    for i in range(batch):
+        p = psnr(ref[i], got[i])
+        assert p >= 40.0, f"batch {batch} cap {cap}: image {i} PSNR {p:.1f} dB"
+
+
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-4), ("fp16", 1e-2)])
+@pytest.mark.parametrize("h,w", [(40, 40), (32, 64), (48, 16), (24, 24)])
+def test_forward_extents_outside_the_tensor_core_tiles(build_lib, h, w, precision, bar):
+    """Extents whose levels are not multiples of the 16x8-pixel halo tile (40 -> 20 -> 10, 24 -> 12 -> 6) or are not
+    square: layers the tcgen05 kernels do not tile take the in-CUDA fallback (per-tap tcgen05 or SIMT fp32 accumulate),
+    never the CPU; the result must not depend on which kernel ran."""
+    oracle, model = make_pair("super_small", 32, precision)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(2, 3, h, w, generator=g) * 0.5).clamp(-1, 1)
+    labels = torch.tensor([1, 0])
+    for t in (3, 2500):
+        with torch.no_grad():
+            ref = oracle(x, torch.tensor(t), labels).sample
+        got = model(x.cuda(), torch.tensor(t), labels.cuda()).sample.cpu()
+        assert got.shape == ref.shape
+        err = (got - ref).abs().max().item()
+        assert err <= bar, f"{h}x{w} {precision} t={t}: eps max-abs err {err:.3e}"
+
+
+def test_many_classes_per_sample_timesteps_and_class_emb(build_lib):
+    """num_class_embeds > 2 with repeated / missing labels (the embedding rows are de-duplicated per class on the DDIB
+    route), a 1-D per-sample `timestep`, and conditioning through `class_emb` instead of labels."""
+    from oracle import OracleCondUNet2D
+    from phendiff_b200 import CustomCondUNet2DModel
+    from phendiff_b200.reference_configs import DENOISER_CONFIGS
+
+    cfg = dict(DENOISER_CONFIGS["super_small"], sample_size=32, num_class_embeds=5)
+    torch.manual_seed(3)
+    oracle = OracleCondUNet2D(**cfg).eval()
+    model = CustomCondUNet2DModel.from_config(cfg, precision="fp32")
+    model.load_state_dict(oracle.state_dict())
+    model = model.to("cuda").eval()
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(6, 3, 32, 32, generator=g) * 0.5).clamp(-1, 1)
+    labels = torch.tensor([4, 0, 4, 2, 2, 4])                      # classes 1 and 3 absent, 4 three times
+    with torch.no_grad():
+        ref = oracle(x, torch.tensor(700), labels).sample
+    got = model(x.cuda(), torch.tensor(700), labels.cuda()).sample.cpu()
+    assert (got - ref).abs().max().item() <= 1e-4
+    ts = torch.tensor([0, 10, 999, 1500, 2999, 7])                  # one timestep per sample
+    with torch.no_grad():
+        ref = oracle(x, ts, labels).sample
+    got = model(x.cuda(), ts.cuda(), labels.cuda()).sample.cpu()
+    assert (got - ref).abs().max().item() <= 1e-4
+    emb = torch.randn(6, model.time_embed_dim, generator=g) * 0.1   # class_emb xor class_labels (cond_unet_2d.py:268-269)
+    with torch.no_grad():
+        ref = oracle(x, torch.tensor(42), class_emb=emb).sample
+    got = model(x.cuda(), torch.tensor(42), class_emb=emb.cuda()).sample.cpu()
+    assert (got - ref).abs().max().item() <= 1e-4
+    with pytest.raises(ValueError):
+        model(x.cuda(), torch.tensor(42), labels.cuda(), class_emb=emb.cuda())
+    with pytest.raises(ValueError):
+        model(x.cuda(), torch.tensor(42))
+
+
+def test_single_step_and_same_class_transfer(build_lib):
+    """n = 1 (one inversion step lands exactly on eps-hat for the 0.18.2 inverse scheduler) and a same-class
+    transfer, which must reconstruct the input up to the discretisation error the oracle shows too."""
+    from oracle import OracleDDIMScheduler, OraclePipeline, oracle_ddib
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, ddib_transfer
+
+    oracle, model = make_pair("super_small", 32, "fp32")
+    x, src = synth_images(2, 32)
+    o_pipe = OraclePipeline(oracle, OracleDDIMScheduler.from_config(_sched("1k_epsilon_pred")))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched("1k_epsilon_pred")))
+    for n, tgt in ((1, 1 - src), (8, src)):
+        ref = oracle_ddib(o_pipe, x, src, tgt, n, return_raw=True)
+        got = ddib_transfer(pipe, x, src, tgt, n).cpu()
+        ok = ~(torch.isnan(ref) | torch.isnan(got))
+        assert torch.equal(torch.isnan(ref), torch.isnan(got))
+        p = psnr(ref[ok], got[ok])
+        assert p >= 40.0, f"n={n}: PSNR {p:.1f} dB"
