@@ -1,4 +1,5 @@
-"""ORACLE — CPU restatement of the reference's hot path (test infrastructure only; PARITY UNPINNED).
+"""ORACLE — CPU restatement of the reference's hot path (test infrastructure only; blocks and schedulers pinned against the
+third-party package's published known-answer tests, tests/test_oracle_published_kats.py; the 0.18.2 inverse-scheduler pairing unpinned).
 
 See oracle/unet.py, oracle/schedulers.py, oracle/pipeline.py for the per-function reference citations.
 Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline and --impl reference legs).

@@ -4,7 +4,8 @@ Restatement of the reference's denoising loop and DDIB drivers on top of the ora
   * ConditionalDDIMPipeline.__call__  src/pipeline_conditional_ddim/pipeline_conditionial_ddim.py:139-361
   * _inversion                        src/utils_Img2Img.py:763-800
   * _ddib                             src/utils_Img2Img.py:566-612
-PARITY UNPINNED (see oracle/unet.py, oracle/schedulers.py).
+Parity status: blocks and schedulers are pinned against diffusers' published known answers, the loop itself follows the
+reference lines cited above (see oracle/unet.py, oracle/schedulers.py, tests/test_oracle_published_kats.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """

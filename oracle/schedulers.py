@@ -5,12 +5,17 @@ calls: `diffusers==0.18.2` `DDIMScheduler` and `DDIMInverseScheduler` (pinned by
 environment.yaml:80; the package itself is absent from /root/reference and from this image, so this
 is a restatement of its published algorithm).
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or KATs for this path and
-diffusers cannot be imported here, so this oracle is anchored on the reference's call sites only:
+PARITY PINNED FOR `DDIMScheduler` AND THE >= 0.19 `DDIMInverseScheduler`, UNPINNED FOR THE 0.18.2 INVERSE PAIRING:
+the reference itself ships no tests, golden vectors or KATs for this path and diffusers cannot be imported
+here, but diffusers' own test-suite publishes full-loop known answers (tests/schedulers/test_scheduler_ddim.py and
+test_scheduler_ddim_inverse.py: epsilon / v-prediction / set_alpha_to_one on and off); this restatement reproduces all
+eight (tests/test_oracle_published_kats.py).  The 0.18.2 inverse scheduler differs from the pinned >= 0.19 one only in
+which (alpha-bar_t, alpha-bar_next) pair a step reads (`step`, ~10 lines) — that pairing is restated from SURVEY A.4 and no
+published vector could be matched to it.  Further anchors:
   * generation:  src/pipeline_conditional_ddim/pipeline_conditionial_ddim.py:45,248,267,340-347
   * inversion:   src/utils_Img2Img.py:776-798
   * configs:     models_configs/noise_scheduler/*.json
-and on the derived known-answer values of SURVEY.md Appendix A.6 (tests/test_oracle_schedulers.py).
+and the derived known-answer values of SURVEY.md Appendix A.6 (tests/test_oracle.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """

@@ -7,8 +7,13 @@ Plain-PyTorch fp32 restatement of the reference's conditional UNet:
     Attention(AttnProcessor2_0), Downsample2D, Upsample2D, Timesteps, TimestepEmbedding.
     Their behaviour is restated from SURVEY.md Appendix A.1/A.2 with torch functional ops only.
 
-PARITY UNPINNED (no reference tests / golden tensors exist for this path, SURVEY.md §4, and diffusers is not
-importable here).  Parameter names follow the diffusers checkpoint layout (Appendix A.7) so a real PhenDiff
+PARITY PINNED PER BLOCK: the reference has no tests / golden tensors for this path and diffusers is not
+importable here, but diffusers' own test-suite (tests/models/test_layers_utils.py) publishes known answers for exactly
+these blocks under `torch.manual_seed(0)` + default initialisation: ResnetBlock2D (with and without the 1x1 shortcut),
+the attention block (32 heads of dim 1; one head of dim 512), Upsample2D / Downsample2D with conv, and the sinusoid
+embedding in the reference's (flip_sin_to_cos, freq_shift 0) setting.  Every block here reproduces its vector to the
+printed precision (tests/test_oracle_published_kats.py).  The assembly of the blocks into the UNet follows the
+reference's own constructor / forward (citations above) and has no published vector.  Parameter names follow the diffusers checkpoint layout (Appendix A.7) so a real PhenDiff
 state_dict loads; parameter counts are pinned to SURVEY §8 (62 826 243 / 15 725 443).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.

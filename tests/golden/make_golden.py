@@ -1,5 +1,5 @@
-"""Generates the committed golden fixtures from the ORACLE (parity unpinned: the reference has no vectors of its own;
-diffusers 0.18.2 is not importable here, see oracle/ headers).  Run from the repo root:  python tests/golden/make_golden.py
+"""Generates the committed golden fixtures from the ORACLE (the reference has no vectors of its own and diffusers 0.18.2 is
+not importable here; the oracle's blocks and schedulers are pinned by tests/test_oracle_published_kats.py, see oracle/ headers).  Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys

@@ -1,6 +1,7 @@
 """CPU tests of the oracle itself: known-answer values, committed golden fixtures, parameter
-counts and the structural properties of the restated schedulers.  (Parity is unpinned by the reference —
-it has no tests or vectors — so these pin the oracle to the derived KATs and to its own committed outputs.)"""
+counts and the structural properties of the restated schedulers.  (The reference has no tests or vectors of
+its own; the third-party package's PUBLISHED known answers are in tests/test_oracle_published_kats.py, these tests add the
+derived KATs and guard the oracle against drift from its committed outputs.)"""
 import os
 
 import pytest
