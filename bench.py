@@ -8,6 +8,9 @@ scheduler 3k_steps_clipping_rescaling; synthetic images, seed-0 random-init weig
 
   python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA path through the C ABI)
   python bench.py --impl reference [...]                     reference arm: the CPU oracle on the host cores
+  python bench.py --workload cfg [...]                       secondary line: classifier-free-guidance forward
+                                                             start, guidance scale 2.5, half of the trajectory skipped (the reference's
+                                                             example config), through `_classifier_free_guidance_forward_start`
 Under torchrun (N > 1): one rank per GPU, batch-sharded (weak scaling), one final NCCL all-gather of the outputs.
 Prints ONE JSON line on rank 0.
 """
@@ -48,6 +51,10 @@ def parse():
     p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="ddib", choices=["ddib", "cfg"],
+                   help="ddib (default, the BASELINE.json metric) or cfg: SURVEY §8 row f1, classifier-free-guidance forward start")
+    p.add_argument("--guidance-scale", type=float, default=2.5)
+    p.add_argument("--frac-diffusion-skipped", type=float, default=0.5)
     p.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     p.add_argument("--size", type=int, default=128)
     p.add_argument("--num-inference-steps", type=int, default=100)
@@ -58,7 +65,7 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=1)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--dump-ops", default="", help="write the per-op device-time table (sampled forwards) to this markdown file")
-    p.add_argument("--cpu-sample-images", type=int, default=4)
+    p.add_argument("--cpu-sample-images", type=int, default=12)   # ~12 s of 16-thread CPU work on the GPU box (4 images took 4.2 s)
     p.add_argument("--cpu-sample-steps", type=int, default=1)
     return p.parse_args()
 
@@ -224,6 +231,9 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     total = args.batch * world
 
+    if args.workload == "cfg":
+        return run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local)
+
     def step():
         out = ddib_transfer(pipe, x_dev, src_d, tgt_d, n)
         if world > 1:
@@ -321,6 +331,90 @@ def run_ours(args):
                 line["cpu_baseline"] = cpu_sample(args)
             except Exception as ex:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local):
+    """Secondary workload (reference utils_Img2Img.py:615-648 with the example config's guidance_scale 2.5 /
+    frac_diffusion_skipped 0.5): forward-noise the images to the middle of the trajectory, then per kept step one conditional
+    and one unconditional UNet forward, the guidance combine and the DDIM update, through the per-op route of the C ABI.
+    Both figures go through the drop-in call and end in PIL images; `value` starts from device-resident images and is timed
+    with CUDA events, `e2e` starts from pinned host images and is timed on the host clock."""
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace as NS
+
+    from phendiff_b200 import _classifier_free_guidance_forward_start as cfg_start
+
+    n = args.num_inference_steps
+    cfg = NS(class_transfer_method=NS(classifier_free_guidance_forward_start=NS(
+        guidance_scale=args.guidance_scale, frac_diffusion_skipped=args.frac_diffusion_skipped)))
+    pipe.set_progress_bar_config(disable=True)
+    pipe.scheduler.set_timesteps(n)
+    kept = int((pipe.scheduler.timesteps <= pipe.scheduler.config.num_train_timesteps * (1 - args.frac_diffusion_skipped)).sum())
+    total = args.batch * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        cfg_start(pipe, x_dev, tgt_d, cfg, n)
+    sync()
+    l0 = unet.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        imgs = cfg_start(pipe, x_dev, tgt_d, cfg, n)
+    e1.record()
+    sync()
+    assert len(imgs) == args.batch
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = unet.launch_count() - l0
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total * args.steps / (ms / 1000.0)
+    sync()
+    t0 = time.perf_counter()
+    imgs = cfg_start(pipe, x_host, tgt, cfg, n)
+    sync()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        gf = GFLOP_PER_IMAGE_FORWARD.get((args.denoiser, args.size))
+        line = {"metric": f"images/sec, classifier-free-guidance forward-start class transfer {args.size}x{args.size}, "
+                          f"{kept} of {n} steps, 2 UNet forwards per step",
+                "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": dict(workload_config(args, unet.plan_info()),
+                               workload=f"CondUNet2D {args.denoiser} {args.size}x{args.size} RGB, 2 classes, CFG forward start "
+                                        f"(guidance_scale {args.guidance_scale}, frac_diffusion_skipped {args.frac_diffusion_skipped}, "
+                                        f"{n} inference steps -> {kept} kept), batch {args.batch}/GPU (SURVEY §8 row f1)"),
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": total / float(t_e2e.item()), "unit": "images/s",
+                        "h2d_bytes_per_step": x_host.numel() * 4 + tgt.numel() * 8,
+                        "d2h_bytes_per_step": args.batch * args.size * args.size * 3 * 4, "steps": 1,
+                        "api": "phendiff_b200._classifier_free_guidance_forward_start(pipe, pinned_host_images, tgt, cfg, n) -> PIL images"}}
+        if gf:
+            tf = value / world * 2 * kept * gf / 1e3
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf / pk["tflops"],
+                                "traffic": None, "kernel": "whole path (2 x kept UNet forwards per image, SURVEY §8d algorithmic FLOPs)",
+                                "peak_source": pk["src"] + " sustained bf16 cuBLAS"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

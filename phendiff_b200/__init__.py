@@ -7,8 +7,9 @@ from .cond_unet_2d import CustomCondUNet2DModel, UNet2DOutput
 from .custom_embedding import CustomEmbedding
 from .pipeline_conditional_ddim import ConditionalDDIMPipeline, ImagePipelineOutput
 from .schedulers import DDIMInverseScheduler, DDIMScheduler
-from .utils_img2img import _ddib, _inversion, ddib_transfer
+from .utils_img2img import _classifier_free_guidance_forward_start, _ddib, _inversion, ddib_transfer
 from ._lib import PhenDiffB200Error
 
 __all__ = ["CustomCondUNet2DModel", "UNet2DOutput", "CustomEmbedding", "ConditionalDDIMPipeline", "ImagePipelineOutput",
-           "DDIMScheduler", "DDIMInverseScheduler", "_ddib", "_inversion", "ddib_transfer", "PhenDiffB200Error"]
+           "DDIMScheduler", "DDIMInverseScheduler", "_ddib", "_inversion", "ddib_transfer",
+           "_classifier_free_guidance_forward_start", "PhenDiffB200Error"]

@@ -1,5 +1,6 @@
-"""DDIB drivers — drop-ins for the reference's `_inversion` and `_ddib`
-(reference: src/utils_Img2Img.py:763-800 and :566-612; called from perform_class_transfer_experiment :365-384).
+"""Class-transfer drivers — drop-ins for the reference's `_inversion`, `_ddib` and
+`_classifier_free_guidance_forward_start`
+(reference: src/utils_Img2Img.py:763-800, :566-612 and :615-648; called from perform_class_transfer_experiment :365-384).
 
 `_ddib` = invert the real images to noise with the SOURCE class, regenerate with the TARGET class.  Here both loops
 (2 x num_inference_steps UNet forwards + scheduler updates) run inside ONE C-ABI call on the current CUDA stream; x_t
@@ -78,3 +79,26 @@ def _ddib(pipe: ConditionalDDIMPipeline, clean_images: Tensor, orig_class_labels
     inverted_gauss = _inversion(pipe, clean_images, orig_class_labels, num_inference_steps, process_idx)
     return pipe(class_labels=target_class_labels, w=0, num_inference_steps=num_inference_steps,
                 start_image=inverted_gauss, add_forward_noise_to_image=False, frac_diffusion_skipped=0).images
+
+
+def _cfg_lookup(cfg, *path):
+    """`cfg.a.b.c` for attribute-style configs (the reference's omegaconf DictConfig) and plain nested dicts alike."""
+    node = cfg
+    for key in path:
+        node = node[key] if isinstance(node, dict) else getattr(node, key)
+    return node
+
+
+@torch.no_grad()
+def _classifier_free_guidance_forward_start(pipe: ConditionalDDIMPipeline, clean_images: Tensor, target_class_labels: Tensor,
+                                            cfg, num_inference_steps: int) -> List:
+    """Forward-noise the real images part of the way, then denoise them with classifier-free guidance towards the target
+    class (utils_Img2Img.py:615-648).  `cfg` is read exactly where the reference reads it:
+    `cfg.class_transfer_method.classifier_free_guidance_forward_start.{guidance_scale, frac_diffusion_skipped}`."""
+    this_exp_cfg = _cfg_lookup(cfg, "class_transfer_method", "classifier_free_guidance_forward_start")
+    guidance_scale = _cfg_lookup(this_exp_cfg, "guidance_scale")
+    frac_diffusion_skipped = _cfg_lookup(this_exp_cfg, "frac_diffusion_skipped")
+    if not isinstance(pipe, ConditionalDDIMPipeline):
+        raise NotImplementedError("only the pixel-space ConditionalDDIMPipeline path is implemented (SURVEY §8)")
+    return pipe(class_labels=target_class_labels, w=guidance_scale, num_inference_steps=num_inference_steps,
+                start_image=clean_images, frac_diffusion_skipped=frac_diffusion_skipped).images

@@ -190,3 +190,40 @@ def test_pipeline_call_matches_oracle_with_cfg(build_lib):
         pipe(labels, class_emb=torch.zeros(2, 256))
     with pytest.raises(AssertionError):
         pipe(labels, start_image=x.cuda())  # frac_diffusion_skipped missing
+
+
+def test_classifier_free_guidance_forward_start_dropin(build_lib):
+    """SURVEY §8 row f1 (utils_Img2Img.py:615-648): forward-noise the real images half of the way, denoise with
+    classifier-free guidance towards the target class.  (1) the free function is the pipeline call the reference makes;
+    (2) with the forward noise drawn from a CPU generator on both sides the whole route is comparable with the oracle."""
+    from types import SimpleNamespace as NS
+
+    import numpy as np
+
+    from oracle import OracleDDIMScheduler, OraclePipeline
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, _classifier_free_guidance_forward_start
+
+    oracle, model = make_pair("super_small", 32, "fp32")
+    x, labels = synth_images(2, 32)
+    tgt = 1 - labels
+    o_pipe = OraclePipeline(oracle, OracleDDIMScheduler.from_config(_sched("3k_steps_clipping_rescaling")))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched("3k_steps_clipping_rescaling")))
+    cfg = NS(class_transfer_method=NS(classifier_free_guidance_forward_start=NS(guidance_scale=2.5, frac_diffusion_skipped=0.5)))
+    torch.manual_seed(5)
+    imgs = _classifier_free_guidance_forward_start(pipe, x.cuda(), tgt, cfg, 6)
+    torch.manual_seed(5)
+    same = pipe(class_labels=tgt, w=2.5, num_inference_steps=6, start_image=x.cuda(), frac_diffusion_skipped=0.5).images
+    assert len(imgs) == 2 and imgs[0].size == (32, 32)
+    assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(imgs, same))
+    # dict-style config, as a plain YAML load would give it
+    cfg_d = {"class_transfer_method": {"classifier_free_guidance_forward_start": {"guidance_scale": 2.5, "frac_diffusion_skipped": 0.5}}}
+    torch.manual_seed(5)
+    imgs_d = _classifier_free_guidance_forward_start(pipe, x.cuda(), tgt, cfg_d, 6)
+    assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(imgs, imgs_d))
+
+    ref = o_pipe(tgt, w=2.5, num_inference_steps=6, start_image=x, frac_diffusion_skipped=0.5,
+                 generator=torch.Generator().manual_seed(9)).images
+    got = pipe(tgt, w=2.5, num_inference_steps=6, start_image=x.cuda(), frac_diffusion_skipped=0.5,
+               generator=torch.Generator().manual_seed(9), output_type="numpy").images
+    err = float(abs(ref - got).max())
+    assert err <= 1e-3, f"forward-noised CFG route vs oracle: {err:.3e}"
