@@ -206,3 +206,52 @@ def test_shard_ranges():
             assert max(shard_sizes(total, world)) - min(shard_sizes(total, world)) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) on a tiny configuration: one JSON line carrying the
+    keys the bench contract names for the reference arm."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--denoiser", "super_small", "--size", "32", "--batch", "4", "--num-inference-steps", "4",
+                          "--cpu-sample-images", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("images/sec, DDIM invert+regenerate")
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_bench_reference_arm_other_ranks_exit_without_work():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_cfg_lookup_reads_attribute_and_dict_configs():
+    from types import SimpleNamespace as NS
+
+    from phendiff_b200.utils_img2img import _cfg_lookup
+
+    a = NS(class_transfer_method=NS(classifier_free_guidance_forward_start=NS(guidance_scale=2.5, frac_diffusion_skipped=0.5)))
+    d = {"class_transfer_method": {"classifier_free_guidance_forward_start": {"guidance_scale": 2.5, "frac_diffusion_skipped": 0.5}}}
+    for c in (a, d):
+        node = _cfg_lookup(c, "class_transfer_method", "classifier_free_guidance_forward_start")
+        assert _cfg_lookup(node, "guidance_scale") == 2.5 and _cfg_lookup(node, "frac_diffusion_skipped") == 0.5
+    with pytest.raises((AttributeError, KeyError)):
+        _cfg_lookup(a, "class_transfer_method", "ddib")
