@@ -380,7 +380,8 @@ def run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local
     assert len(imgs) == args.batch
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = unet.launch_count() - l0
+    # UNet kernels (counted by the library) + per call: add_noise, denorm, and per kept step the guidance combine and the DDIM update
+    launches = unet.launch_count() - l0 + args.steps * (2 + 2 * kept)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

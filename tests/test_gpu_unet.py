@@ -214,12 +214,19 @@ def test_classifier_free_guidance_forward_start_dropin(build_lib):
     torch.manual_seed(5)
     same = pipe(class_labels=tgt, w=2.5, num_inference_steps=6, start_image=x.cuda(), frac_diffusion_skipped=0.5).images
     assert len(imgs) == 2 and imgs[0].size == (32, 32)
-    assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(imgs, same))
+
+    def lsb_diff(a, b):   # GroupNorm statistics are accumulated with atomics: two runs may differ in the last uint8 step
+        return max(int(np.abs(np.asarray(p, dtype=np.int16) - np.asarray(q, dtype=np.int16)).max()) for p, q in zip(a, b))
+
+    assert lsb_diff(imgs, same) <= 2, lsb_diff(imgs, same)
     # dict-style config, as a plain YAML load would give it
     cfg_d = {"class_transfer_method": {"classifier_free_guidance_forward_start": {"guidance_scale": 2.5, "frac_diffusion_skipped": 0.5}}}
     torch.manual_seed(5)
     imgs_d = _classifier_free_guidance_forward_start(pipe, x.cuda(), tgt, cfg_d, 6)
-    assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(imgs, imgs_d))
+    assert lsb_diff(imgs, imgs_d) <= 2, lsb_diff(imgs, imgs_d)
+    torch.manual_seed(6)   # a different forward noise gives a visibly different image: the seed comparison above is meaningful
+    other = _classifier_free_guidance_forward_start(pipe, x.cuda(), tgt, cfg, 6)
+    assert lsb_diff(imgs, other) > 8
 
     ref = o_pipe(tgt, w=2.5, num_inference_steps=6, start_image=x, frac_diffusion_skipped=0.5,
                  generator=torch.Generator().manual_seed(9)).images
