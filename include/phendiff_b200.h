@@ -97,7 +97,11 @@ int pd_unet_load_weight(pd_unet_t* h, const char* name, const float* data, const
 int pd_unet_finalize(pd_unet_t* h, pd_stream_t stream);
 int pd_unet_time_embed_dim(pd_unet_t* h, int32_t* dim);
 
-/* ---- planning: static buffer plan for (batch, H, W); the caller then provides the workspace ---- */
+/* ---- planning: static buffer plan for (batch, H, W); the caller then provides the workspace.
+ *      The batch runs in micro-batches of `microbatch` images (pd_unet_plan_info): the largest divisor of the batch within
+ *      max_microbatch (default 64) when one exists within a factor 2 of it, else even micro-batches whose ragged last one runs
+ *      on padded scratch copies inside the workspace (the padding images are copies of a real image; only real outputs are
+ *      written back). ---- */
 int pd_unet_plan(pd_unet_t* h, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes);
 int pd_unet_bind_workspace(pd_unet_t* h, void* workspace, size_t bytes);
 

@@ -156,6 +156,8 @@ struct pd_unet {
     std::vector<void*> owned;   // derived device buffers
     // plan
     int B = 0, H = 0, W = 0, mb = 0;
+    int tail = 0;               // images in the last micro-batch when the batch is ragged (B % mb), else 0
+    size_t tail_x_off = 0, tail_out_off = 0, tail_t_off = 0, tail_lab_off = 0, tail_emb_off = 0;   // padded scratch copies of the tail
     size_t ws_bytes = 0;
     Arena arena;
     std::vector<Op> ops;
@@ -647,6 +649,15 @@ struct Rec {
         M->emb_off = M->arena.alloc((size_t)rows_max * M->D * sizeof(float));
         M->temb_off = M->arena.alloc((size_t)rows_max * M->J * sizeof(float));
         M->rowidx_off = M->arena.alloc((size_t)mb * sizeof(int32_t));
+        if (M->tail) {
+            // ragged batch: the last micro-batch runs on scratch copies of its inputs, padded to mb images with its first image
+            const size_t hw = (size_t)H * W;
+            M->tail_x_off = M->arena.alloc((size_t)mb * c.in_channels * hw * sizeof(float));
+            M->tail_out_off = M->arena.alloc((size_t)mb * c.out_channels * hw * sizeof(float));
+            M->tail_t_off = M->arena.alloc((size_t)mb * sizeof(float));
+            M->tail_lab_off = M->arena.alloc((size_t)2 * mb * sizeof(int64_t));
+            M->tail_emb_off = M->arena.alloc((size_t)mb * M->D * sizeof(float));
+        }
         if (!dry) {
             float* stats = (float*)raw(M->stats_off);
             const size_t sb = M->stats_bytes;
@@ -868,6 +879,15 @@ static int run_program(pd_unet* m, const Ctx& c, cudaStream_t s) {
     return 0;
 }
 
+// Copies `n` items of `item` bytes from src into a scratch array of `mb` items and fills items n..mb-1 with item 0
+// (the padding images of a ragged tail must be VALID inputs: real pixels, labels inside the class table).
+static int copy_padded(void* dst, const void* src, size_t item, int n, int mb, cudaStream_t s) {
+    PD_CHECK_CUDA(cudaMemcpyAsync(dst, src, item * n, cudaMemcpyDeviceToDevice, s));
+    for (int j = n; j < mb; ++j)
+        PD_CHECK_CUDA(cudaMemcpyAsync((uint8_t*)dst + item * j, src, item, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 }  // namespace pd
 
 // =====================================================================================================================
@@ -1018,9 +1038,16 @@ int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, siz
     clear_plan(m);
     m->B = batch; m->H = height; m->W = width;
     int cap = m->cfg.max_microbatch > 0 ? m->cfg.max_microbatch : 64;   // 64 images: >= 6.9 waves of 148 CTAs at every UNet level
+    const int lim = std::min(cap, batch);
     int mb = 1;
-    for (int d = 1; d <= std::min(cap, batch); ++d) if (batch % d == 0) mb = d;
+    for (int d = 1; d <= lim; ++d) if (batch % d == 0) mb = d;
+    if (mb * 2 < lim) {
+        // no divisor of the batch within a factor 2 of the cap (prime batches: 1): even micro-batches and a padded ragged tail
+        const int k = (batch + lim - 1) / lim;
+        mb = (batch + k - 1) / k;
+    }
     m->mb = mb;
+    m->tail = batch % mb;
     // dry pass 1 sizes the statistics region, dry pass 2 gives the arena peak with that region in place
     m->stats_bytes = 0;
     int rc = 0;
@@ -1062,6 +1089,7 @@ int pd_unet_forward(pd_unet_t* m, const float* sample, const float* timesteps, c
     PD_REQUIRE(!(class_labels && class_emb), "Cannot specify both class_labels and class_emb");
     PD_REQUIRE(!(m->cls && !class_labels && !class_emb), "either class_labels or class_emb should be provided when doing class conditioning");
     const size_t per_in = (size_t)m->cfg.in_channels * m->H * m->W, per_out = (size_t)m->cfg.out_channels * m->H * m->W;
+    cudaStream_t s = (cudaStream_t)stream;
     for (int i = 0; i < m->B; i += m->mb) {
         Ctx c;
         c.x = sample + (size_t)i * per_in;
@@ -1069,7 +1097,27 @@ int pd_unet_forward(pd_unet_t* m, const float* sample, const float* timesteps, c
         c.labels = class_labels ? class_labels + i : nullptr;
         c.class_emb = class_emb ? class_emb + (size_t)i * m->D : nullptr;
         c.model_out = out + (size_t)i * per_out;
-        int rc = run_program(m, c, (cudaStream_t)stream);
+        const int n = std::min(m->mb, m->B - i);
+        if (n < m->mb) {   // ragged tail on padded scratch copies
+            uint8_t* base = m->arena.base;
+            float* sx = (float*)(base + m->tail_x_off);
+            float* so = (float*)(base + m->tail_out_off);
+            int rc = copy_padded(sx, c.x, per_in * sizeof(float), n, m->mb, s);
+            if (rc) return rc;
+            if ((rc = copy_padded(base + m->tail_t_off, c.timesteps, sizeof(float), n, m->mb, s))) return rc;
+            if (c.labels && (rc = copy_padded(base + m->tail_lab_off, c.labels, sizeof(int64_t), n, m->mb, s))) return rc;
+            if (c.class_emb && (rc = copy_padded(base + m->tail_emb_off, c.class_emb, (size_t)m->D * sizeof(float), n, m->mb, s))) return rc;
+            Ctx t = c;
+            t.x = sx;
+            t.timesteps = (const float*)(base + m->tail_t_off);
+            if (c.labels) t.labels = (const int64_t*)(base + m->tail_lab_off);
+            if (c.class_emb) t.class_emb = (const float*)(base + m->tail_emb_off);
+            t.model_out = so;
+            if ((rc = run_program(m, t, s))) return rc;
+            PD_CHECK_CUDA(cudaMemcpyAsync(c.model_out, so, per_out * sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+            continue;
+        }
+        int rc = run_program(m, c, s);
         if (rc) return rc;
     }
     return 0;
@@ -1108,20 +1156,35 @@ int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const in
     PD_REQUIRE(m->cfg.in_channels == m->cfg.out_channels, "in/out channels must match for sampling");
     PD_REQUIRE(!m->cls || ((n_inv == 0 || src_labels) && (n_gen == 0 || tgt_labels)), "class-conditioned model needs source labels for inversion steps and target labels for generation steps");
     const size_t per = (size_t)m->cfg.in_channels * m->H * m->W;
+    cudaStream_t s = (cudaStream_t)stream;
     for (int i = 0; i < m->B; i += m->mb) {
+        const int n = std::min(m->mb, m->B - i);
+        float* xi = x + (size_t)i * per;
+        const int64_t* src_i = src_labels ? src_labels + i : nullptr;
+        const int64_t* tgt_i = tgt_labels ? tgt_labels + i : nullptr;
+        if (n < m->mb) {   // ragged tail: the whole trajectory runs on a padded scratch copy, the n real images are copied back
+            uint8_t* base = m->arena.base;
+            int64_t* sl = (int64_t*)(base + m->tail_lab_off);
+            int rc = copy_padded(base + m->tail_x_off, xi, per * sizeof(float), n, m->mb, s);
+            if (rc) return rc;
+            if (src_i && n_inv > 0) { if ((rc = copy_padded(sl, src_i, sizeof(int64_t), n, m->mb, s))) return rc; src_i = sl; }
+            if (tgt_i && n_gen > 0) { if ((rc = copy_padded(sl + m->mb, tgt_i, sizeof(int64_t), n, m->mb, s))) return rc; tgt_i = sl + m->mb; }
+            xi = (float*)(base + m->tail_x_off);
+        }
         for (int sidx = 0; sidx < n_inv + n_gen; ++sidx) {
             Ctx c;
-            c.x = x + (size_t)i * per;
+            c.x = xi;
             c.timesteps = nullptr;
             c.t_scalar = steps_host[sidx].timestep;
-            const int64_t* lab = sidx < n_inv ? src_labels : tgt_labels;
-            c.labels = lab ? lab + i : nullptr;
+            c.labels = sidx < n_inv ? src_i : tgt_i;
             c.model_out = nullptr;
-            c.x_update = x + (size_t)i * per;
+            c.x_update = xi;
             c.step = &steps_host[sidx];
-            int rc = run_program(m, c, (cudaStream_t)stream);
+            int rc = run_program(m, c, s);
             if (rc) return rc;
         }
+        if (n < m->mb)
+            PD_CHECK_CUDA(cudaMemcpyAsync(x + (size_t)i * per, xi, per * sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
     }
     return 0;
 }

@@ -18,10 +18,11 @@ def _sched(name="3k_steps_clipping_rescaling"):
     return SCHEDULER_CONFIGS[name]
 
 
-@pytest.mark.parametrize("batch,cap,expect_mb", [(1, 64, 1), (7, 4, 1), (6, 4, 3), (10, 64, 10), (12, 8, 6)])
+@pytest.mark.parametrize("batch,cap,expect_mb", [(1, 64, 1), (7, 4, 4), (6, 4, 3), (10, 64, 10), (12, 8, 6), (11, 4, 4), (13, 8, 7)])
 def test_ddib_batches_against_the_microbatch_planner(build_lib, batch, cap, expect_mb):
-    """The planner runs the largest divisor of the batch that fits the cap (prime batches degrade to 1, never to a ragged
-    tail): every image's trajectory must be the one it has when transferred alone in the oracle."""
+    """The planner runs the largest divisor of the batch that fits the cap when one exists within a factor 2 of it; otherwise
+    (prime batches) even micro-batches whose ragged last one runs on padded scratch copies: every image's trajectory must be
+    the one it has when transferred alone in the oracle, and the padding must never leak into the real outputs."""
     from oracle import OracleDDIMScheduler, OraclePipeline, oracle_ddib
     from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler, ddib_transfer
 
@@ -111,3 +112,26 @@ def test_single_step_and_same_class_transfer(build_lib):
         assert torch.equal(torch.isnan(ref), torch.isnan(got))
         p = psnr(ref[ok], got[ok])
         assert p >= 40.0, f"n={n}: PSNR {p:.1f} dB"
+
+
+def test_forward_ragged_tail_per_sample_inputs(build_lib):
+    """Per-op route on a ragged batch (7 images, cap 4 -> micro-batches 4 + 3 padded to 4): per-sample timesteps with integer
+    labels, then with `class_emb`; every real image must match the oracle and the caller's buffers beyond the batch stay
+    untouched (the tail is computed on scratch copies)."""
+    oracle, model = make_pair("super_small", 32, "fp32", max_microbatch=4)
+    x, labels = synth_images(7, 32)
+    t = torch.tensor([3, 250, 1000, 1999, 2999, 7, 1500])
+    with torch.no_grad():
+        ref = oracle(x, t, labels).sample
+    got = model(x.cuda(), t.cuda(), labels.cuda()).sample.cpu()
+    assert model.plan_info()["microbatch"] == 4
+    assert got.shape == ref.shape == (7, 3, 32, 32)
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-4, f"ragged forward with labels: {err:.3e}"
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(7, oracle.time_embed_dim, generator=g) * 0.1
+    with torch.no_grad():
+        ref = oracle(x, t, class_emb=emb).sample
+    got = model(x.cuda(), t.cuda(), class_emb=emb.cuda()).sample.cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-4, f"ragged forward with class_emb: {err:.3e}"
