@@ -73,6 +73,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16b(uint32_t taddr, uint32_t (&r
         : "r"(taddr));
 }
 
+// mbarrier wait of the softmax / issuer loops: same bounded-wait contract as mbar_wait (a protocol bug traps instead of hanging
+// the box), but the 64-bit clock is read once per 64 polls — in the r3b capture the watchdog arithmetic of the shared helper was
+// 8 % of this kernel's issued instructions, competing with the exponentials for issue slots.
+__device__ __forceinline__ void atc_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int k = 0; k < 64; ++k)
+            if (mbar_try_wait(bar, parity)) return;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("phendiff_b200: attention_tc mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // K-major SWIZZLE_128B descriptor, 8-row groups 1024 B apart (same encoding as the convolution kernels)
 __device__ __forceinline__ uint64_t atc_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -199,9 +216,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
             // ===================== MMA issuer =====================
             constexpr uint32_t idS = atc_idesc<T, 64>(), idPV = atc_idesc<T, 16>();
             const uint32_t q0 = smem_u32(smQ), k0 = smem_u32(smK), v0 = smem_u32(smV);
-            auto issue_S = [&](int i) {
-                const int qt = i / ntl, j = i - qt * ntl, buf = i % 3;
-                if (j == 1) { mbar_wait(qmready, qt & 1); tc_fence_after(); }
+            // tile counters are advanced incrementally: ncu's source view (profiles/r3b_attention_tc.md) showed the
+            // software division by the runtime ntl (I2F / MUFU.RCP / F2I chains) of `i / ntl`, `i % 3` on every tile
+            int s_qt = 0, s_j = 0, s_buf = 0;       // the S tile issue_S() issues next
+            auto issue_S = [&]() {
+                const int qt = s_qt, j = s_j, buf = s_buf;
+                if (++s_j == ntl) { s_j = 0; ++s_qt; }
+                if (++s_buf == 3) s_buf = 0;
+                if (j == 1) { atc_wait(qmready, qt & 1); tc_fence_after(); }
                 const int kb = j >> 1;                                                  // 128-token block of the key tile
                 const uint64_t a = atc_desc(q0 + (uint32_t)((qt >> 2) * 16384 + (qt & 3) * 32));
                 const uint64_t b = atc_desc(k0 + (uint32_t)((kb >> 2) * 16384 + (j & 1) * 8192 + (kb & 3) * 32));
@@ -209,13 +231,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
                 umma_commit(&sfull[buf]);
             };
             const int pro = total < 3 ? total : 3;
-            for (int i = 0; i < pro; ++i) issue_S(i);
+            for (int i = 0; i < pro; ++i) issue_S();
+            int qt = 0, j = 0, buf = 0;
+            uint32_t use = 0;                       // parity of the buffer's use count: (i / 3) & 1
             for (int i = 0; i < total; ++i) {
-                const int qt = i / ntl, j = i - qt * ntl, buf = i % 3;
-                const uint32_t use = (uint32_t)(i / 3) & 1u;
-                mbar_wait(&pready[buf], use);
+                atc_wait(&pready[buf], use);
                 tc_fence_after();
-                if (j == 0 && qt >= 2) { mbar_wait(&oread[qt & 1], (uint32_t)((qt >> 1) - 1) & 1u); tc_fence_after(); }
+                if (j == 0 && qt >= 2) { atc_wait(&oread[qt & 1], (uint32_t)((qt >> 1) - 1) & 1u); tc_fence_after(); }
                 const uint32_t d = tmem_base + (uint32_t)(ATC_O_COL0 + 16 * (qt & 1));
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
@@ -228,11 +250,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
                     // conservative variant (commit + wait) for A/B checks.
                     if (ATC_WAIT_PV) {
                         umma_commit(&pvdone[buf]);
-                        mbar_wait(&pvdone[buf], use);
+                        atc_wait(&pvdone[buf], use);
                         tc_fence_after();
                     }
-                    issue_S(i + 3);
+                    issue_S();
                 }
+                if (++j == ntl) { j = 0; ++qt; }
+                if (++buf == 3) { buf = 0; use ^= 1u; }
             }
         }
     } else if (warp < ATC_SM_WARPS) {
@@ -242,7 +266,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
         float m = 0.f;
         auto finish_qtile = [&](int qt) {
-            mbar_wait(&ofull[qt & 1], (uint32_t)(qt >> 1) & 1u);
+            atc_wait(&ofull[qt & 1], (uint32_t)(qt >> 1) & 1u);
             tc_fence_after();
             uint32_t o[16];
             tmem_ld_32x32b_x16b(lane_base + (uint32_t)(ATC_O_COL0 + 16 * (qt & 1)), o);
@@ -263,9 +287,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
             const bool anybad = __any_sync(0xffffffffu, bad);
             if (lane == 0) flags[(((size_t)n * gridDim.x + head) * nqt + qt) * 4 + wq] = anybad ? 1 : 0;
         };
+        int qt = 0, j = 0, buf = 0;
+        uint32_t use = 0;                           // (i / 3) & 1, advanced incrementally (no division by the runtime ntl)
         for (int i = 0; i < total; ++i) {
-            const int qt = i / ntl, j = i - qt * ntl, buf = i % 3;
-            mbar_wait(&sfull[buf], (uint32_t)(i / 3) & 1u);
+            atc_wait(&sfull[buf], use);
             tc_fence_after();
             // both warpgroups work on the SAME tile: warpgroup wg takes its keys 32 wg .. 32 wg + 31 (S columns 32 wg .. 32 wg + 31; its P
             // overwrites the first 16 of those), so two whole tiles stay queued ahead of the softmax threads on the three buffers
@@ -307,6 +332,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc_kernel(const T* _
             // O of the PREVIOUS query tile is collected one key tile into this one: waiting for it right after its last P
             // would deadlock (the MMA thread may be parked on qmready of the next query tile, which this thread signals)
             if (j == 1 && qt >= 1 && wg == 1) finish_qtile(qt - 1);
+            if (++j == ntl) { j = 0; ++qt; }
+            if (++buf == 3) { buf = 0; use ^= 1u; }
         }
         if (wg == 1) finish_qtile(nqt - 1);      // warpgroup 1 collects every O
     }

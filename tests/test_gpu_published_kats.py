@@ -54,3 +54,31 @@ def test_product_ddim_inverse_scheduler_published_full_loops(build_lib, override
 
     s, m = _full_loop(DDIMInverseScheduler(variant=">=0.19", **dict(_BASE, **overrides)))
     assert abs(s - exp_sum) < 1e-2 and abs(m - exp_mean) < 1e-3, (s, m)
+
+
+@pytest.mark.parametrize("precision,atol", [("fp32", 1e-3), ("fp16", 2e-2)])
+def test_product_unet_and_ddim_loop_published_pipeline_vector(build_lib, precision, atol):
+    """diffusers tests/pipelines/ddim/test_ddim.py::DDIMPipelineFastTests::test_inference through the PRODUCT: the CUDA UNet
+    (unconditional here: the reference's graph without the class embedding) with the seed-0 weights diffusers' constructor
+    draws, two DDIM steps on the device, de-normalisation kernel; compared with the published corner of the image at
+    diffusers' own tolerance (fp32 validation mode) / a 16-bit bound (fp16 storage)."""
+    import numpy as np
+
+    from oracle.unet import OracleCondUNet2D
+    from phendiff_b200 import CustomCondUNet2DModel, DDIMScheduler
+    from tests.util import DDIM_FAST_TEST_SLICE, DDIM_FAST_TEST_UNET, diffusers_order_init
+
+    oracle = diffusers_order_init(OracleCondUNet2D(**DDIM_FAST_TEST_UNET).eval(), 0)
+    model = CustomCondUNet2DModel.from_config(dict(DDIM_FAST_TEST_UNET), precision=precision)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to("cuda").eval()
+    sched = DDIMScheduler()
+    torch.manual_seed(0)
+    image = torch.randn(1, 3, 32, 32).cuda()
+    sched.set_timesteps(2)
+    with torch.no_grad():
+        for t in sched.timesteps:
+            image = sched.step(model(image, t).sample, t, image, eta=0.0, use_clipped_model_output=None).prev_sample
+    out = (image / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).cpu().numpy()
+    got = out[0, -3:, -3:, -1].flatten()
+    assert np.abs(got - np.array(DDIM_FAST_TEST_SLICE)).max() < atol, got.tolist()

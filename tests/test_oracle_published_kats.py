@@ -146,3 +146,30 @@ def test_ddim_scheduler_full_loops(overrides, exp_sum, exp_mean):
 def test_ddim_inverse_scheduler_full_loops_later_release(overrides, exp_sum, exp_mean):
     s, m = _full_loop(functools.partial(OracleDDIMInverseScheduler, ">=0.19"), **overrides)
     assert abs(s - exp_sum) < 1e-2 and abs(m - exp_mean) < 1e-3, (s, m)
+
+
+# ---- tests/pipelines/ddim/test_ddim.py: the whole UNet graph + the DDIM loop --------------------------------------------
+
+@torch.no_grad()
+def test_ddim_pipeline_fast_test_whole_unet():
+    """DDIMPipelineFastTests.test_inference: `torch.manual_seed(0)`; UNet2DModel(block_out_channels=(32, 64), layers_per_block=2,
+    sample_size=32, DownBlock2D + AttnDownBlock2D / AttnUpBlock2D + UpBlock2D); DDIMScheduler(); generator seed 0; 2 steps;
+    numpy output.  The UNet is the reference's graph without the class embedding (cond_unet_2d.py builds exactly these
+    blocks), so this pins the ASSEMBLY — skip connections, attention placement, time embedding, conv_in / conv_norm_out /
+    conv_out — together with the scheduler loop and the (x / 2 + 0.5).clamp(0, 1) post-processing."""
+    import numpy as np
+
+    from oracle.unet import OracleCondUNet2D
+    from tests.util import DDIM_FAST_TEST_SLICE, DDIM_FAST_TEST_UNET, diffusers_order_init
+
+    unet = diffusers_order_init(OracleCondUNet2D(**DDIM_FAST_TEST_UNET).eval(), 0)
+    sched = OracleDDIMScheduler()
+    torch.manual_seed(0)
+    image = torch.randn(1, 3, 32, 32)
+    sched.set_timesteps(2)
+    for t in sched.timesteps:
+        image = sched.step(unet(image, t).sample, t, image, eta=0.0, use_clipped_model_output=None).prev_sample
+    out = (image / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).numpy()
+    assert out.shape == (1, 32, 32, 3)
+    got = out[0, -3:, -3:, -1].flatten()
+    assert np.abs(got - np.array(DDIM_FAST_TEST_SLICE)).max() < 1e-4, got.tolist()   # diffusers' own tolerance: 1e-3
