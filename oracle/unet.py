@@ -12,8 +12,10 @@ importable here, but diffusers' own test-suite (tests/models/test_layers_utils.p
 these blocks under `torch.manual_seed(0)` + default initialisation: ResnetBlock2D (with and without the 1x1 shortcut),
 the attention block (32 heads of dim 1; one head of dim 512), Upsample2D / Downsample2D with conv, and the sinusoid
 embedding in the reference's (flip_sin_to_cos, freq_shift 0) setting.  Every block here reproduces its vector to the
-printed precision (tests/test_oracle_published_kats.py).  The assembly of the blocks into the UNet follows the
-reference's own constructor / forward (citations above) and has no published vector.  Parameter names follow the diffusers checkpoint layout (Appendix A.7) so a real PhenDiff
+printed precision (tests/test_oracle_published_kats.py).  The ASSEMBLY of the blocks into the UNet is pinned too: with the
+weights re-drawn in diffusers' module-creation order (tests/util.py::diffusers_order_init) the whole graph + DDIM loop
+reproduces the image corner published in tests/pipelines/ddim/test_ddim.py (DDIMPipelineFastTests.test_inference).  What
+that vector cannot cover is the reference's own class conditioning (emb + class_embedding(labels), cond_unet_2d.py:297-309).  Parameter names follow the diffusers checkpoint layout (Appendix A.7) so a real PhenDiff
 state_dict loads; parameter counts are pinned to SURVEY §8 (62 826 243 / 15 725 443).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.

@@ -11,10 +11,11 @@ for exactly the layers and schedulers on this path:
   * tests/schedulers/test_scheduler_ddim.py: test_full_loop_no_noise / _with_v_prediction / _with_set_alpha_to_one /
     _with_no_set_alpha_to_one
   * tests/schedulers/test_scheduler_ddim_inverse.py (the >= 0.19 scheduler): the same four loops
+  * tests/pipelines/ddim/test_ddim.py: DDIMPipelineFastTests.test_inference (whole seed-0 UNet2DModel + DDIMScheduler loop)
 
 Provenance: the expected numbers below are those published constants, restated (the test files are not in this container);
 the inputs are fully determined by `torch.manual_seed(0)` + PyTorch's default layer initialisation in diffusers' parameter
-creation order, or by closed-form tensors.  An independently written restatement reproducing all 17 vectors to the printed
+creation order, or by closed-form tensors.  An independently written restatement reproducing all 18 vectors to the printed
 precision is what pins it; a wrong block (or a wrong recollection of a constant) fails here.
 
 What stays unpinned: the 0.18.2 `DDIMInverseScheduler` index pairing (t -> t + r, `set_alpha_to_zero`), for which no
