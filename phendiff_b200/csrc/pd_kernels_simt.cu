@@ -600,7 +600,7 @@ int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s) {
     PD_REQUIRE(a.Cout <= 3, "conv_out supports out_channels <= 3");
     PD_REQUIRE(a.Cin % 32 == 0, "conv_out needs block_out_channels[0] % 32 == 0");
     const int cpl = a.Cin / 32;
-    PD_REQUIRE(cpl == 2 || cpl == 4 || cpl == 8, "conv_out: block_out_channels[0] must be 64, 128 or 256");
+    PD_REQUIRE(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8, "conv_out: block_out_channels[0] must be 32, 64, 128 or 256");
     pd_step_coeffs_t st{};
     int has = 0;
     if (a.step) { st = *a.step; has = 1; PD_REQUIRE(st.sigma == 0.f, "fused conv_out update requires eta == 0"); }
@@ -608,7 +608,8 @@ int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s) {
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 8);
     if (grid < 1) grid = 1;
     PD_DISPATCH_DT(dt, T, {
-        if (cpl == 2) conv_out_kernel<T, 2><<<grid, 256, 0, s>>>(a, st, has);
+        if (cpl == 1) conv_out_kernel<T, 1><<<grid, 256, 0, s>>>(a, st, has);
+        else if (cpl == 2) conv_out_kernel<T, 2><<<grid, 256, 0, s>>>(a, st, has);
         else if (cpl == 4) conv_out_kernel<T, 4><<<grid, 256, 0, s>>>(a, st, has);
         else conv_out_kernel<T, 8><<<grid, 256, 0, s>>>(a, st, has);
     });
