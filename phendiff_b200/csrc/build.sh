@@ -8,5 +8,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
   -Xcompiler -fPIC -shared \
   ${PD_NVCC_EXTRA:-} \
   -o "${out}" \
-  "${here}/pd_api.cu" "${here}/pd_kernels_simt.cu" "${here}/pd_conv_tc.cu" "${here}/pd_conv_halo.cu" "${here}/pd_attn_mma.cu" "${here}/pd_attn_tc.cu"
+  "${here}/pd_api.cu" "${here}/pd_kernels_simt.cu" "${here}/pd_conv_tc.cu" "${here}/pd_conv_halo.cu" "${here}/pd_attn_mma.cu" "${here}/pd_attn_tc.cu" "${here}/pd_attn_tc2.cu"
 echo "built ${out}"

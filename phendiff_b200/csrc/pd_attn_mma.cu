@@ -429,14 +429,15 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
         // than v3 in round 1: its two softmax warpgroups starve on three S buffers, profiles/r1o_attention_tc.md);
         // "v2": chunked warp-level kernel (any S)
         const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
-        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : ((e && e[0] == 't' && e[1] == 'c') ? 4 : 3);
+        // "tc2": experimental second tcgen05 kernel (pd_attn_tc2.cu: softmax warpgroups on alternate tiles), unmeasured at the end of round 1
+        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : ((e && e[0] == 't' && e[1] == 'c') ? (e[2] == '2' ? 5 : 4) : 3);
         const char* pe = getenv("PHENDIFF_B200_ATTN_POLYPAIRS");   // score pairs per 16 (v3) / per 8 (tc) on the FMA/ALU pipes
         polyv = pe ? atoi(pe) : -1;
     }
     const size_t smem = (size_t)S * 32;
     const int var = force_variant ? force_variant : variant;
     if (var == 2 || smem > 200 * 1024) return launch_attention_chunked(dt, qkv, N, S, C, d, AH_SL / qfold, out, s);
-    if (var == 4 && S % 128 == 0 && attention_tc_smem_bytes(S) <= 110 * 1024) {
+    if ((var == 4 || var == 5) && S % 128 == 0 && attention_tc_smem_bytes(S) <= 110 * 1024) {
         // flags: one byte per (image, head, 128-query tile, warp); grow-only scratch owned by the library
         static uint8_t* flags = nullptr;
         static size_t flags_cap = 0;
@@ -446,7 +447,9 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
             PD_CHECK_CUDA(cudaMalloc(&flags, need));
             flags_cap = need;
         }
-        int rc = launch_attention_tc(dt, qkv, N, S, C, AH_SL / qfold, out, flags, polyv < 0 ? (dt == DT_F16 ? 4 : 2) : polyv, s);
+        const int tc_pp = polyv < 0 ? (dt == DT_F16 ? 4 : 2) : polyv;
+        int rc = var == 5 ? launch_attention_tc2(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s)
+                          : launch_attention_tc(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s);
         if (rc) return rc;
         dim3 grid(1, C / 8, N);
         PD_DISPATCH_HALF(dt, T, (launch_head<T, 0x0000u>(qkv, N, S, C, AH_SL / qfold, out, grid, smem, s, flags)));

@@ -98,6 +98,9 @@ size_t attention_tc_smem_bytes(int S);
 int attention_mma_launches(int S);
 int launch_attention_tc(int dt, const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, int poly_pairs,
                         cudaStream_t s);
+// experimental variant (pd_attn_tc2.cu): same contract
+int launch_attention_tc2(int dt, const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, int poly_pairs,
+                        cudaStream_t s);
 
 // ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
 #ifdef __CUDACC__

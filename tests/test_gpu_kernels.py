@@ -6,6 +6,7 @@ relative bound that reflects one bf16 rounding of the output plus fp32 accumulat
 """
 import ctypes as C
 import math
+import os
 
 import pytest
 import torch
@@ -422,7 +423,7 @@ def _attention_case(build_lib, mode, qkv, n, s, c):
     ref = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(8), -1) @ v
     ref = ref.transpose(1, 2).reshape(n, s, c).float()
     out = torch.empty(n, s, c, dtype=dt, device="cuda")
-    use = {"simt": 0, "mmaraw": 1, "mma": 2, "mmav2": 3, "mmav3": 4, "mmatc": 5}[kind]
+    use = {"simt": 0, "mmaraw": 1, "mma": 2, "mmav2": 3, "mmav3": 4, "mmatc": 5, "mmatc2": 6}[kind]
     build_lib.check(L.pd_test_attention(use, bf, n, s, c, 8, _p(qkv.to(dt).cuda()), _p(out), None))
     return out.float().cpu(), ref, bf
 
@@ -539,3 +540,19 @@ def test_add_noise_velocity_cfg_denorm(build_lib):
     xxd = xx.cuda()
     build_lib.check(L.pd_denorm_nhwc(_p(xxd), _p(out), 4, 3, 8, 8, None))
     assert (out.cpu() - (xx / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)).abs().max() <= 1e-7
+
+
+@pytest.mark.skipif(os.environ.get("PHENDIFF_B200_EXPERIMENTAL", "0") != "1",
+                    reason="experimental tcgen05 attention variant (pd_attn_tc2.cu): set PHENDIFF_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mode", ["mmatc2_fp16", "mmatc2_bf16"])
+@pytest.mark.parametrize("shape", [(1, 256, 128), (1, 1024, 64), (3, 1024, 512)])
+def test_attention_experimental_tc2(build_lib, mode, shape):
+    """Same bars as test_attention's tcgen05 modes, for the alternate-tile variant (green on a B200 at the end of round 1); not part
+    of the default matrix until its speed has been measured."""
+    n, s, c = shape
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(n, s, 3 * c, generator=g) * 1.5
+    got, ref, bf = _attention_case(build_lib, mode, qkv, n, s, c)
+    err = (got - ref).abs().max().item()
+    tol = 1.2e-2 if mode.endswith("fp16") else 3e-2
+    assert err <= tol, f"attention {mode} {shape}: {err:.3e}"

@@ -7,7 +7,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build_${tag}.log
 t0=$SECONDS
 timeout 200 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short > gpurun_out/pytest_gpu_${tag}.log 2>&1
 echo "pytest exit=$? after $((SECONDS - t0)) s"; tail -8 gpurun_out/pytest_gpu_${tag}.log
-for v in ${VARIANTS:-v3:6 tc:2 tc:3 tc:4 v3:6}; do
+for v in ${VARIANTS:-v3:6 tc:4 tc2:4 tc2:3 v3:6}; do
   k="${v%%:*}"; pp="${v##*:}"
   PHENDIFF_B200_ATTN_KERNEL=$k PHENDIFF_B200_ATTN_POLYPAIRS=$pp timeout 120 python bench.py --batch 64 --num-inference-steps 6 --steps 2 --warmup 3 \
       --no-cpu-baseline --e2e-steps 1 --dump-ops gpurun_out/ops_${tag}_${k}_$pp.md > gpurun_out/bench_${tag}_${k}_$pp.json 2> gpurun_out/bench_${tag}_${k}_$pp.err
