@@ -121,7 +121,26 @@ __device__ __forceinline__ void atc_exp32_nosub(const uint32_t (&s)[32], uint32_
     }
 }
 
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// 16 scores (already s - m) -> 8 packed pairs; PP of the 8 pairs go to the polynomial
 template <typename T, int PP>
+__device__ __forceinline__ void atc_exp16_nosub(const uint32_t (&s)[16], uint32_t (&p)[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float x0 = __uint_as_float(s[2 * r]), x1 = __uint_as_float(s[2 * r + 1]);
+        const bool poly = ((r * PP) & 7) < PP && PP > 0;
+        p[r] = poly ? ex2_pair_poly<T>(x0, x1) : pack2<T>(ex2(x0), ex2(x1));
+    }
+}
+
+// PIPE (PHENDIFF_B200_ATTN_TC2_PIPE=1, untested at the end of round 1): the 64 columns of a tile are walked in four 16-column
+// chunks with the TMEM load of chunk k + 1 in flight under the exponentials of chunk k (two 16-register buffers instead of one
+// of 32) — long-scoreboard waits on tcgen05.ld led the stall list of pd_attn_tc.cu (profiles/r3_attention_notes.md).
+template <typename T, int PP, bool PIPE>
 __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc2_kernel(const T* __restrict__ qkv, int S, int C, float qmul,
                                                                       T* __restrict__ out, uint8_t* __restrict__ flags) {
     extern __shared__ uint8_t atc_smem_raw[];
@@ -312,6 +331,29 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc2_kernel(const T* 
                     tmem_st_wait();                         // the store above has consumed p before it is rewritten
                     atc_exp32<T, PP>(s, m, p);
                     tmem_st_32x32b_x16(ts, p);
+                } else if (PIPE) {
+                    // chunk k = keys 16 k .. 16 k + 15 = S columns 16 k ..; its P (8 columns) goes where the PV product reads the
+                    // A operand of 16-key slice k: column 32 (k >> 1) + 8 (k & 1) — always inside columns already consumed
+                    uint32_t sa[16], sb[16], pq[8];
+                    tmem_ld_32x32b_x16b(ts, sa);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x16b(ts + 16u, sb);
+                    atc_exp16_nosub<T, PP>(sa, pq);
+                    tmem_st_32x32b_x8(ts, pq);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x16b(ts + 32u, sa);
+                    tmem_st_wait();
+                    atc_exp16_nosub<T, PP>(sb, pq);
+                    tmem_st_32x32b_x8(ts + 8u, pq);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x16b(ts + 48u, sb);
+                    tmem_st_wait();
+                    atc_exp16_nosub<T, PP>(sa, pq);
+                    tmem_st_32x32b_x8(ts + 32u, pq);
+                    tmem_ld_wait();
+                    tmem_st_wait();
+                    atc_exp16_nosub<T, PP>(sb, pq);
+                    tmem_st_32x32b_x8(ts + 40u, pq);
                 } else {
 #pragma unroll 1
                     for (uint32_t h = 0; h < 64u; h += 32u) {
@@ -347,22 +389,25 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc2_kernel(const T* 
 }
 
 
-template <typename T, int PP>
+template <typename T, int PP, bool PIPE>
 static int launch_tc2(const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, cudaStream_t s) {
     const size_t smem = attention_tc_smem_bytes(S);
     static size_t attr = 0;
     if (smem > attr) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<T, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<T, PP, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     dim3 grid(C / 8, N);
-    attention_tc2_kernel<T, PP><<<grid, ATC_THREADS, smem, s>>>((const T*)qkv, S, C, qmul, (T*)out, flags);
+    attention_tc2_kernel<T, PP, PIPE><<<grid, ATC_THREADS, smem, s>>>((const T*)qkv, S, C, qmul, (T*)out, flags);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_attention_tc2(int dt, const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, int poly_pairs, cudaStream_t s) {
-#define PD_ATC(PP) PD_DISPATCH_HALF(dt, T, { return launch_tc2<T, PP>(qkv, N, S, C, qmul, out, flags, s); })
+    const char* pe = getenv("PHENDIFF_B200_ATTN_TC2_PIPE");   // read per call: experimental knob, tests toggle it in-process
+    const bool pipe = pe && pe[0] == '1';
+#define PD_ATC(PP) PD_DISPATCH_HALF(dt, T, { return pipe ? launch_tc2<T, PP, true>(qkv, N, S, C, qmul, out, flags, s) \
+                                                          : launch_tc2<T, PP, false>(qkv, N, S, C, qmul, out, flags, s); })
     switch (poly_pairs) {
         case 0: PD_ATC(0); break;
         case 2: PD_ATC(2); break;

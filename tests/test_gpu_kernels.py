@@ -544,11 +544,13 @@ def test_add_noise_velocity_cfg_denorm(build_lib):
 
 @pytest.mark.skipif(os.environ.get("PHENDIFF_B200_EXPERIMENTAL", "0") != "1",
                     reason="experimental tcgen05 attention variant (pd_attn_tc2.cu): set PHENDIFF_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("pipe", ["0", "1"])
 @pytest.mark.parametrize("mode", ["mmatc2_fp16", "mmatc2_bf16"])
 @pytest.mark.parametrize("shape", [(1, 256, 128), (1, 1024, 64), (3, 1024, 512)])
-def test_attention_experimental_tc2(build_lib, mode, shape):
-    """Same bars as test_attention's tcgen05 modes, for the alternate-tile variant (green on a B200 at the end of round 1); not part
-    of the default matrix until its speed has been measured."""
+def test_attention_experimental_tc2(build_lib, monkeypatch, mode, shape, pipe):
+    """Same bars as test_attention's tcgen05 modes, for the alternate-tile variant (pipe "0": green on a B200 at the end of round 1;
+    pipe "1" was written after the last GPU call); not part of the default matrix until its speed has been measured."""
+    monkeypatch.setenv("PHENDIFF_B200_ATTN_TC2_PIPE", pipe)   # "1": chunk-pipelined TMEM loads (never run on a GPU yet)
     n, s, c = shape
     g = torch.Generator().manual_seed(5)
     qkv = torch.randn(n, s, 3 * c, generator=g) * 1.5
