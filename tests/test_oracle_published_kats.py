@@ -174,3 +174,17 @@ def test_ddim_pipeline_fast_test_whole_unet():
     assert out.shape == (1, 32, 32, 3)
     got = out[0, -3:, -3:, -1].flatten()
     assert np.abs(got - np.array(DDIM_FAST_TEST_SLICE)).max() < 1e-4, got.tolist()   # diffusers' own tolerance: 1e-3
+
+
+# ---- tests/schedulers/test_scheduler_ddim.py: test_variance, test_steps_offset -------------------------------------------
+
+def test_ddim_scheduler_variance_and_steps_offset():
+    """The eta > 0 variance term (`ConditionalDDIMPipeline.__call__` exposes `eta`, pipeline_conditionial_ddim.py:146) and the
+    `steps_offset` timestep grid, against the constants of diffusers' test_variance / test_steps_offset."""
+    cfg = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=True)
+    sched = OracleDDIMScheduler(**cfg)
+    for t, prev, expected in ((0, 0, 0.0), (420, 400, 0.14771), (980, 960, 0.32460), (487, 486, 0.00979), (999, 998, 0.02)):
+        assert abs(float(sched._get_variance(t, prev)) - expected) < 1e-5, (t, prev)
+    sched = OracleDDIMScheduler(**dict(cfg, steps_offset=1))
+    sched.set_timesteps(5)
+    assert torch.equal(sched.timesteps, torch.LongTensor([801, 601, 401, 201, 1]))
