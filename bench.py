@@ -62,7 +62,7 @@ def parse():
     p.add_argument("--scheduler", default="3k_steps_clipping_rescaling")
     p.add_argument("--precision", default=os.environ.get("PHENDIFF_B200_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     p.add_argument("--microbatch", type=int, default=0)
-    p.add_argument("--e2e-steps", type=int, default=1)
+    p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--dump-ops", default="", help="write the per-op device-time table (sampled forwards) to this markdown file")
     p.add_argument("--cpu-sample-images", type=int, default=12)   # ~12 s of 16-thread CPU work on the GPU box (4 images took 4.2 s)
@@ -159,7 +159,38 @@ def cpu_sample(args, pipe=None, images=None, steps=None):
     return {"value": images / full, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{images} images x ({steps}+{steps}) DDIM steps at {args.size}x{args.size} fp32 on the CPU oracle "
                       f"({dt:.1f} s), extrapolated linearly to ({args.num_inference_steps}+{args.num_inference_steps}) steps",
-            "seconds": dt}
+            "seconds": dt, "cpu": cpu_model()}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_config0(args):
+    """BASELINE.json configs[0] MEASURED end to end (no extrapolation): the reference's CPU-runnable case — the same denoiser
+    at 64x64, batch 4, 10 + 10 DDIM steps — through the CPU oracle on this box's host cores."""
+    import copy
+
+    import torch
+    from oracle import oracle_ddib
+
+    a = copy.copy(args)
+    a.size = 64
+    torch.set_num_threads(os.cpu_count() or 1)
+    pipe = oracle_pipe(a)
+    x, src, tgt = make_inputs(4, 64, 0)
+    oracle_ddib(pipe, x[:1], src[:1], tgt[:1], 1, return_raw=True)
+    t0 = time.perf_counter()
+    oracle_ddib(pipe, x, src, tgt, 10, return_raw=True)
+    dt = time.perf_counter() - t0
+    return {"config": f"{args.denoiser} @64x64, batch 4, 10+10 DDIM steps (BASELINE.json configs[0]), measured whole",
+            "seconds": dt, "images_per_s": 4 / dt, "cores": torch.get_num_threads(), "cpu": cpu_model()}
 
 
 def run_reference(args):
@@ -329,6 +360,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_sample(args)
+                line["cpu_baseline"]["config0_measured"] = cpu_config0(args)
             except Exception as ex:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)

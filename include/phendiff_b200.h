@@ -166,8 +166,8 @@ int pd_test_conv(int32_t use_tc, int32_t dtype, int32_t n, int32_t h, int32_t w,
                  void* out, pd_stream_t stream);
 /* extended form: impl 0 = SIMT, 1 = tcgen05 per-tap kernel, 2 = tcgen05 halo kernel.  upsample: nearest-2x + 3x3 conv run as
  * four sub-pixel phase convs (impl 2).  mode 1: conv_out epilogue (cout <= 16) writing NCHW fp32 model_out and / or updating
- * x_t in place with `step`.  stats_out (N, cout/stats_cw, 2), zero on entry, receives the GroupNorm chunk statistics
- * (sum, sum of squares over H*W of every stats_cw-channel chunk) of the stored output.  addvec_row (N) int32 or NULL. */
+ * x_t in place with `step`.  stats_out (N, cout/stats_cw, 2) fp64, zero on entry, receives the GroupNorm chunk
+ * statistics (sum, sum of squares over H*W of every stats_cw-channel chunk) of the stored output.  addvec_row (N) int32 or NULL. */
 typedef struct pd_test_conv_args {
     int32_t impl, dtype, n, h, w, c1, c2, cout, ksize, stride, pad, upsample, mode, stats_cw, csc1, csc2;
     const void *x1, *x2;
@@ -178,7 +178,7 @@ typedef struct pd_test_conv_args {
     const float* sc_w;
     float out_scale;
     void* out;
-    float* stats_out;
+    double* stats_out;
     float* model_out;
     float* x_t;
     const pd_step_coeffs_t* step;
@@ -190,7 +190,7 @@ int pd_test_conv_ex(const pd_test_conv_args_t* args, pd_stream_t stream);
 int pd_test_gn_conv(int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout, int32_t groups, float eps,
                     const void* x1, const void* x2, const float* gamma, const float* beta, const float* weight, const float* bias,
                     const float* addvec, const void* residual, const void* sc1, const void* sc2, int32_t csc1, int32_t csc2,
-                    const float* sc_w, float out_scale, void* out, float* stats_out, pd_stream_t stream);
+                    const float* sc_w, float out_scale, void* out, double* stats_out, pd_stream_t stream);
 /* GroupNorm(+SiLU) over NHWC, two concatenated sources */
 int pd_test_groupnorm(int32_t dtype, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                       int32_t do_silu, const void* x1, const void* x2, const float* gamma, const float* beta,

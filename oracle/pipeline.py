@@ -49,7 +49,7 @@ class OraclePipeline:
     def __call__(self, class_labels, class_emb=None, w=None, generator=None, eta=0.0,
                  num_inference_steps=DEFAULT_NUM_INFERENCE_STEPS, use_clipped_model_output=None,
                  output_type="numpy", return_dict=True, start_image=None, add_forward_noise_to_image=True,
-                 frac_diffusion_skipped=None, guidance_eqn="imagen", return_raw=False):
+                 frac_diffusion_skipped=None, guidance_eqn="imagen", return_raw=False, trace=None):
         self.check_inputs(class_labels, class_emb, w, generator, frac_diffusion_skipped, start_image)
         if num_inference_steps is None:
             num_inference_steps = DEFAULT_NUM_INFERENCE_STEPS
@@ -87,6 +87,8 @@ class OraclePipeline:
                     raise ValueError(f"Unknown guidance equation '{guidance_eqn}'; should be 'imagen' or 'CFG'")
             else:
                 guided = cond
+            if trace is not None:   # (t, x_t, model output) per step, for teacher-forced per-step comparisons
+                trace.append((int(t), image.clone(), guided.clone()))
             image = self.scheduler.step(guided, t, image, eta=eta, use_clipped_model_output=use_clipped_model_output,
                                         generator=generator).prev_sample
         if return_raw:
@@ -114,10 +116,10 @@ def oracle_inversion(pipe, input_images, class_labels, num_inference_steps, vari
 
 @torch.no_grad()
 def oracle_ddib(pipe, clean_images, orig_class_labels, target_class_labels, num_inference_steps,
-                variant="0.18.2", return_raw=False):
+                variant="0.18.2", return_raw=False, trace_inv=None, trace_gen=None):
     # utils_Img2Img.py:566-612 (ConditionalDDIMPipeline branch)
-    inverted = oracle_inversion(pipe, clean_images, orig_class_labels, num_inference_steps, variant)
+    inverted = oracle_inversion(pipe, clean_images, orig_class_labels, num_inference_steps, variant, trace=trace_inv)
     out = pipe(class_labels=target_class_labels, w=0, num_inference_steps=num_inference_steps,
                start_image=inverted, add_forward_noise_to_image=False, frac_diffusion_skipped=0,
-               return_raw=return_raw)
+               return_raw=return_raw, trace=trace_gen)
     return out if return_raw else out.images

@@ -105,7 +105,7 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
         if len(block_out_channels) > _lib.PD_MAX_BLOCKS:
             raise NotImplementedError("too many blocks")
 
-        self._precision = (precision or os.environ.get("PHENDIFF_B200_PRECISION", "bf16")).lower()
+        self._precision = (precision or os.environ.get("PHENDIFF_B200_PRECISION", "fp16")).lower()
         if self._precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
         self._max_microbatch = int(max_microbatch if max_microbatch is not None else os.environ.get("PHENDIFF_B200_MICROBATCH", 0))
@@ -115,6 +115,8 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
         self._handle = None
         self._handle_device = None
         self._synced_version = None
+        self._synced_fingerprint = None
+        self._dirty_epoch = 0
         self._plan_key = None
         self._workspace = None
         self._build_parameter_tree()
@@ -255,6 +257,7 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
                 pass
         d["_handle"] = None
         d["_synced_version"] = None
+        d["_synced_fingerprint"] = None
         d["_plan_key"] = None
         d["_workspace"] = None
 
@@ -290,7 +293,46 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
         return cc
 
     def _weights_version(self):
-        return tuple(p._version for p in self.parameters()) + (str(self.device),)
+        """Cheap key of the parameter state: autograd version counter + storage address of every parameter.  It catches
+        in-place optimiser steps, `load_state_dict`, `.to()` / `_apply` and re-assigned `.data`; it does NOT see a write
+        through `param.data.copy_()` (what diffusers' `EMAModel.copy_to / restore` do, utils_training.py:674-676): those
+        are caught by `weights_fingerprint()` on the whole-path entry points, or announced with `mark_dirty()`."""
+        return tuple((p._version, p.data_ptr()) for p in self.parameters()) + (str(self.device), self._dirty_epoch)
+
+    def mark_dirty(self):
+        """Tell the model its parameters were changed out of band (e.g. `p.data.copy_(...)`): the library-owned,
+        re-laid-out device copy is rebuilt on the next call."""
+        self._dirty_epoch += 1
+        return self
+
+    def sync_weights(self):
+        """Force the re-upload of the parameters into the library's buffers now."""
+        self.mark_dirty()
+        self._ensure_handle()
+        return self
+
+    @torch.no_grad()
+    def weights_fingerprint(self) -> float:
+        """Position-weighted sum of the parameters' L1 norms, in fp64 (one tiny device reduction + ONE host read).  The
+        whole-path entry points (`_ddib`, `_inversion`, the fused pipeline loop: seconds of device work per call) compare it
+        with the value taken at the last upload, so an EMA `copy_to` right before sampling is never silently ignored; the
+        per-op `forward` stays free of host synchronisation and relies on `_weights_version()` / `mark_dirty()`."""
+        ps = [p.detach() for p in self.parameters()]
+        norms = torch.stack(torch._foreach_norm(ps, 1)).double()
+        w = torch.arange(1, len(ps) + 1, dtype=torch.float64, device=norms.device)
+        return float((norms * w).sum().item())
+
+    def check_weights(self):
+        """Re-upload the parameters if their fingerprint moved since the last upload (whole-path entry points call this)."""
+        if self._handle is not None and self._synced_fingerprint is not None \
+                and self._synced_version == self._weights_version() and self.weights_fingerprint() != self._synced_fingerprint:
+            self.mark_dirty()
+        return self
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.__dict__["_dirty_epoch"] = self.__dict__.get("_dirty_epoch", 0) + 1
+        return out
 
     def _ensure_handle(self):
         dev = self.device
@@ -320,6 +362,7 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
                     _lib.check(L.pd_unet_load_weight(self._handle, name.encode(), _lib.ptr(t), arr, len(shape)))
                 _lib.check(L.pd_unet_finalize(self._handle, _lib.current_stream()))
                 self._synced_version = ver
+                self._synced_fingerprint = self.weights_fingerprint()
                 self._plan_key = None
         return self._handle
 
@@ -389,6 +432,7 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
             if own is not None and v.numel() == own.numel() and v.shape != own.shape:
                 v = v.reshape(own.shape)  # deprecated attention blocks stored 1x1-conv shaped linears
             fixed[k] = v
+        self._dirty_epoch += 1   # `assign=True` resets version counters; never trust them across a load
         return super().load_state_dict(fixed, strict=strict, **kw)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -419,8 +463,10 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
         # 1. time (cond_unet_2d.py:276-287): scalar / 0-dim / 1-D -> (B,) on the device
         if not torch.is_tensor(timestep):
             ts = torch.full((B,), float(timestep), dtype=torch.float32, device=dev)
+        elif timestep.dim() == 0 and not timestep.is_cuda:
+            ts = torch.full((B,), float(timestep.item()), dtype=torch.float32, device=dev)   # CPU scalar (scheduler.timesteps): no device sync
         elif timestep.dim() == 0:
-            ts = torch.full((B,), float(timestep.item()), dtype=torch.float32, device=dev)
+            ts = timestep.to(device=dev, dtype=torch.float32).expand(B).contiguous()          # device scalar: stays on the device
         else:
             ts = (timestep.to(dev).to(torch.float32) * torch.ones(B, dtype=torch.float32, device=dev)).contiguous()
 

@@ -434,17 +434,17 @@ struct Rec {
         if (dry) return;
         m->ops.push_back(Op{op, cls, flops, nlaunch, name});
     }
-    // chunk-statistics slot of a tensor: (mb, C/cw, 2) fp32 inside the per-forward zeroed statistics region
+    // chunk-statistics slot of a tensor: (mb, C/cw, 2) fp64 inside the per-forward zeroed statistics region
     void stats_alloc(Tensor* t) {
         t->stats_off = stats_bump;
-        stats_bump += (((size_t)mb * (t->C / m->stats_cw) * 2 * sizeof(float)) + 255) & ~(size_t)255;
+        stats_bump += (((size_t)mb * (t->C / m->stats_cw) * 2 * sizeof(double)) + 255) & ~(size_t)255;
     }
-    float* stats_ptr(const Tensor* t) const { return (float*)((uint8_t*)raw(m->stats_off) + t->stats_off); }
+    double* stats_ptr(const Tensor* t) const { return (double*)((uint8_t*)raw(m->stats_off) + t->stats_off); }
     // standalone producer of chunk statistics (SIMT-produced tensors, shapes whose epilogue cannot emit them)
     void stats_kernel(Tensor* t) {
         stats_alloc(t);
         if (dry) return;
-        const void* x = ptr(t); float* st = stats_ptr(t);
+        const void* x = ptr(t); double* st = stats_ptr(t);
         const int N = mb, HW = t->H * t->W, C = t->C, cw = m->stats_cw, dt = m->dt;
         push([=](const Ctx&, cudaStream_t s) { return launch_gn_chunk_stats(dt, x, N, HW, C, cw, st, s); }, 1, CLS_GN);
     }
@@ -659,7 +659,7 @@ struct Rec {
             M->tail_emb_off = M->arena.alloc((size_t)mb * M->D * sizeof(float));
         }
         if (!dry) {
-            float* stats = (float*)raw(M->stats_off);
+            void* stats = raw(M->stats_off);
             const size_t sb = M->stats_bytes;
             EmbedArgs ea{};
             ea.w1 = M->te_w1->dev; ea.b1 = M->te_b1->dev; ea.w2 = M->te_w2->dev; ea.b2 = M->te_b2->dev;
@@ -856,6 +856,14 @@ static void clear_plan(pd_unet* m) {
     m->prof_every = 0;
     m->bound = false;
     m->tc_layers = m->simt_layers = 0;
+}
+
+// a handle is bound to the device that was current at pd_unet_create: its weights, plans and tensor maps live there
+static int check_device(const pd_unet* m) {
+    int dev = -1;
+    PD_CHECK_CUDA(cudaGetDevice(&dev));
+    PD_REQUIRE(dev == m->device, "the current CUDA device is not the one this handle was created on");
+    return 0;
 }
 
 static int run_program(pd_unet* m, const Ctx& c, cudaStream_t s) {
@@ -1088,6 +1096,7 @@ int pd_unet_forward(pd_unet_t* m, const float* sample, const float* timesteps, c
     PD_REQUIRE(m->bound, "pd_unet_plan + pd_unet_bind_workspace must be called first");
     PD_REQUIRE(!(class_labels && class_emb), "Cannot specify both class_labels and class_emb");
     PD_REQUIRE(!(m->cls && !class_labels && !class_emb), "either class_labels or class_emb should be provided when doing class conditioning");
+    { int rc = check_device(m); if (rc) return rc; }
     const size_t per_in = (size_t)m->cfg.in_channels * m->H * m->W, per_out = (size_t)m->cfg.out_channels * m->H * m->W;
     cudaStream_t s = (cudaStream_t)stream;
     for (int i = 0; i < m->B; i += m->mb) {
@@ -1157,6 +1166,7 @@ int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const in
     PD_REQUIRE(!m->cls || ((n_inv == 0 || src_labels) && (n_gen == 0 || tgt_labels)), "class-conditioned model needs source labels for inversion steps and target labels for generation steps");
     const size_t per = (size_t)m->cfg.in_channels * m->H * m->W;
     cudaStream_t s = (cudaStream_t)stream;
+    { int rc = check_device(m); if (rc) return rc; }
     for (int i = 0; i < m->B; i += m->mb) {
         const int n = std::min(m->mb, m->B - i);
         float* xi = x + (size_t)i * per;
@@ -1330,7 +1340,7 @@ int pd_test_conv_ex(const pd_test_conv_args_t* a, pd_stream_t stream) {
 int pd_test_gn_conv(int32_t dt, int32_t n, int32_t h, int32_t w, int32_t c1, int32_t c2, int32_t cout, int32_t groups, float eps,
                     const void* x1, const void* x2, const float* gamma, const float* beta, const float* weight, const float* bias,
                     const float* addvec, const void* residual, const void* sc1, const void* sc2, int32_t csc1, int32_t csc2,
-                    const float* sc_w, float out_scale, void* out, float* stats_out, pd_stream_t stream) {
+                    const float* sc_w, float out_scale, void* out, double* stats_out, pd_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     PD_REQUIRE(dt == DT_BF16 || dt == DT_F16, "fused GroupNorm convolution takes bf16 / fp16 activations");
     PD_REQUIRE(x1 && gamma && beta && weight && out, "null argument");
@@ -1340,13 +1350,13 @@ int pd_test_gn_conv(int32_t dt, int32_t n, int32_t h, int32_t w, int32_t c1, int
     while (cw > 1 && ((ct / groups) % cw != 0 || c1 % cw != 0)) cw >>= 1;
     const int ktot = 9 * ct + csc1 + csc2;
     const size_t n1 = (size_t)n * (c1 / cw) * 2, n2 = (size_t)n * (c2 / cw) * 2;
-    float* stats = nullptr;
+    double* stats = nullptr;
     float2* coef = nullptr;
     void* wm = nullptr;
-    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (n1 + n2 + 2) * sizeof(float)));
+    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (n1 + n2 + 2) * sizeof(double)));
     PD_CHECK_CUDA(cudaMalloc((void**)&coef, (size_t)n * ct * sizeof(float2)));
     PD_CHECK_CUDA(cudaMalloc(&wm, (size_t)cout * ktot * 2));
-    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (n1 + n2 + 2) * sizeof(float), s));
+    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (n1 + n2 + 2) * sizeof(double), s));
     PD_CHECK_CUDA(cudaMemsetAsync(wm, 0, (size_t)cout * ktot * 2, s));
     GNArgs ga{};
     ga.C1 = c1; ga.C2 = c2; ga.N = n; ga.HW = hw; ga.groups = groups; ga.eps = eps; ga.gamma = gamma; ga.beta = beta; ga.silu = 1;
@@ -1391,10 +1401,10 @@ int pd_test_groupnorm(int32_t dt, int32_t n, int32_t hw, int32_t c1, int32_t c2,
     PD_REQUIRE(groups > 0 && (c1 + c2) % groups == 0, "channels not divisible by groups");
     int cw = 4;
     while (cw > 1 && (((c1 + c2) / groups) % cw != 0 || c1 % cw != 0)) cw >>= 1;
-    float* stats = nullptr;
+    double* stats = nullptr;
     const size_t n1 = (size_t)n * (c1 / cw) * 2, n2 = (size_t)n * (c2 / cw) * 2;
-    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (n1 + n2 + 2) * sizeof(float)));
-    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (n1 + n2 + 2) * sizeof(float), s));
+    PD_CHECK_CUDA(cudaMalloc((void**)&stats, (n1 + n2 + 2) * sizeof(double)));
+    PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, (n1 + n2 + 2) * sizeof(double), s));
     GNArgs ga{};
     ga.x1 = x1; ga.x2 = x2; ga.C1 = c1; ga.C2 = c2; ga.N = n; ga.HW = hw; ga.groups = groups; ga.eps = eps; ga.gamma = gamma;
     ga.beta = beta; ga.silu = do_silu; ga.stats1 = stats; ga.stats2 = c2 ? stats + n1 : nullptr; ga.stats_cw = cw; ga.out = out;

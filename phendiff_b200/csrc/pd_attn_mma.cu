@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(AH_WARPS * 32, AH_MIN_CTAS) attention_head_ker
 template <typename T, uint32_t MASK>
 static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* out, dim3 grid, size_t smem, cudaStream_t s,
                        const uint8_t* redo = nullptr) {
-    static size_t attr = 0;
+    static size_t attr_dev[PD_MAX_DEVICES] = {0};
+    size_t& attr = attr_dev[pd_cur_dev()];
     if (smem > 48 * 1024 && smem > attr) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(attention_head_kernel<T, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
@@ -439,8 +440,10 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
     if (var == 2 || smem > 200 * 1024) return launch_attention_chunked(dt, qkv, N, S, C, d, AH_SL / qfold, out, s);
     if ((var == 4 || var == 5) && S % 128 == 0 && attention_tc_smem_bytes(S) <= 110 * 1024) {
         // flags: one byte per (image, head, 128-query tile, warp); grow-only scratch owned by the library
-        static uint8_t* flags = nullptr;
-        static size_t flags_cap = 0;
+        static uint8_t* flags_dev[PD_MAX_DEVICES] = {nullptr};
+        static size_t flags_cap_dev[PD_MAX_DEVICES] = {0};
+        uint8_t*& flags = flags_dev[pd_cur_dev()];
+        size_t& flags_cap = flags_cap_dev[pd_cur_dev()];
         const size_t need = (size_t)N * (C / 8) * (S >> 7) * 4;
         if (need > flags_cap) {
             if (flags) PD_CHECK_CUDA(cudaFree(flags));

@@ -350,7 +350,8 @@ size_t attention_tc_smem_bytes(int S) { return (size_t)((S + 511) >> 9) * 32768 
 template <typename T, int PP>
 static int launch_tc(const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, cudaStream_t s) {
     const size_t smem = attention_tc_smem_bytes(S);
-    static size_t attr = 0;
+    static size_t attr_dev[PD_MAX_DEVICES] = {0};
+    size_t& attr = attr_dev[pd_cur_dev()];
     if (smem > attr) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<T, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;

@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) attention_tc2_kernel(const T* 
 template <typename T, int PP, bool PIPE>
 static int launch_tc2(const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, cudaStream_t s) {
     const size_t smem = attention_tc_smem_bytes(S);
-    static size_t attr = 0;
+    static size_t attr_dev[PD_MAX_DEVICES] = {0};
+    size_t& attr = attr_dev[pd_cur_dev()];
     if (smem > attr) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<T, PP, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;

@@ -35,6 +35,11 @@ void set_error(const std::string& msg);
         }                                                                                        \
     } while (0)
 
+// Library-owned scratch and one-time function attributes are PER DEVICE (a process may drive several GPUs, e.g.
+// `pipe.to('cuda:1')`): index small static tables with this.
+constexpr int PD_MAX_DEVICES = 64;
+inline int pd_cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < PD_MAX_DEVICES) ? d : 0; }
+
 typedef __nv_bfloat16 bf16;
 typedef __half f16;
 // activation storage types: 0 = fp32 (validation mode), 1 = bf16, 2 = fp16 (both on the tensor-core path)

@@ -658,7 +658,8 @@ void conv_halo_plan_destroy(ConvHaloPlan* p) { delete p; }
 
 template <int BLOCK_N, typename T, int MODE, int CW, int MT, bool GN>
 static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t s) {
-    static size_t attr_smem = 0;
+    static size_t attr_smem_dev[PD_MAX_DEVICES] = {0};
+    size_t& attr_smem = attr_smem_dev[pd_cur_dev()];
     if (pl->smem > attr_smem) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)pl->smem));

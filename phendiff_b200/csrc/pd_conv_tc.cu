@@ -346,7 +346,8 @@ void conv_tap_plan_destroy(ConvTapPlan* p) { delete p; }
 
 template <int BLOCK_N, typename T>
 static int launch_tc(const ConvTapPlan* pl, cudaStream_t s) {
-    static bool attr_set = false;
+    static bool attr_set_dev[PD_MAX_DEVICES] = {false};
+    bool& attr_set = attr_set_dev[pd_cur_dev()];
     if (!attr_set) {
         PD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)TcCfg<BLOCK_N>::SMEM));

@@ -35,15 +35,17 @@ struct GNArgs {
     float eps;
     const float *gamma, *beta;        // (C1+C2)
     int silu;
-    // per-tensor "chunk statistics": (N, C/4, 2) fp32 = sum and sum of squares over H*W of every 4-channel chunk.
+    // per-tensor "chunk statistics": (N, C/4, 2) fp64 = sum and sum of squares over H*W of every 4-channel chunk
+    // (fp32 partial sums over <= 128 elements inside a warp / thread, accumulated across warps and finalised in fp64:
+    // a single-pass fp32 E[x^2] - E[x]^2 cancels catastrophically when |mean| >> std).
     // Written by the producing conv's epilogue (tensor-core path) or by launch_gn_chunk_stats; the chunk
     // width cw (4, 2 or 1; model-wide) divides every group width, so any GroupNorm over any concat is finalised from them.
     int stats_cw;
-    const float* stats1; const float* stats2;
+    const double* stats1; const double* stats2;
     void* out;                        // (N,HW,C1+C2)
 };
 // standalone producer of chunk statistics for one NHWC tensor (stats zero on entry)
-int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, float* stats, cudaStream_t s);
+int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, double* stats, cudaStream_t s);
 int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s);
 // GroupNorm as (scale, shift) per (image, channel) for a consumer that normalises its own input tiles (x1/x2/out/silu unused)
 int launch_gn_coef(const GNArgs& a, float2* coef, cudaStream_t s);
@@ -169,7 +171,7 @@ struct ConvTcDesc {
     const void* residual;             // (N,Ho,Wo,Cout) or null
     float out_scale;
     void* out;                        // (N,Ho,Wo,Cout)
-    float* stats_out;                 // (N, Cout/stats_cw, 2) chunk statistics of the stored output (atomic adds); or null
+    double* stats_out;                // (N, Cout/stats_cw, 2) fp64 chunk statistics of the stored output (atomic adds); or null
     int stats_cw;                     // 4 or 2
     int mode;                         // TC_MODE_STD, or TC_MODE_DDIM: conv_out (Cout <= 16, wmat rows padded to 16) whose
                                       // epilogue writes NCHW fp32 model output and/or updates x_t in place

@@ -54,13 +54,14 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
     }
 }
 
-static float* g_freqs = nullptr;   // per-process table, (<= 4096 entries); rebuilt when (C0, shift) change
-static int g_freqs_c0 = -1;
-static float g_freqs_shift = 0.f;
+struct FreqTable { float* dev = nullptr; int c0 = -1; float shift = 0.f; };
+static FreqTable g_freq_tables[PD_MAX_DEVICES];   // per device, (<= 4096 entries); rebuilt when (C0, shift) change
 
 int launch_embed(const EmbedArgs& a, cudaStream_t s) {
     const int half = a.C0 / 2;
-    if (g_freqs == nullptr || g_freqs_c0 != a.C0 || g_freqs_shift != a.shift) {
+    FreqTable& ft = g_freq_tables[pd_cur_dev()];
+    float*& g_freqs = ft.dev;
+    if (g_freqs == nullptr || ft.c0 != a.C0 || ft.shift != a.shift) {
         PD_REQUIRE(half <= 4096, "time embedding too wide");
         if (!g_freqs) PD_CHECK_CUDA(cudaMalloc(&g_freqs, 4096 * sizeof(float)));
         std::vector<float> f(half);
@@ -71,8 +72,8 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
         }
         PD_CHECK_CUDA(cudaMemcpyAsync(g_freqs, f.data(), half * sizeof(float), cudaMemcpyHostToDevice, s));
         PD_CHECK_CUDA(cudaStreamSynchronize(s));  // f is a local; one-time cost at first use
-        g_freqs_c0 = a.C0;
-        g_freqs_shift = a.shift;
+        ft.c0 = a.C0;
+        ft.shift = a.shift;
     }
     PD_REQUIRE(a.row_idx != nullptr, "embed: row index buffer missing");
     PD_REQUIRE(!a.dedupe || (a.labels && a.class_table && !a.class_emb && !a.timesteps && a.ncls > 0), "embed: dedupe needs labels and one scalar timestep");
@@ -117,7 +118,7 @@ int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat,
 // chunk statistics (N, C/cw, 2): sum and sum of squares over H*W of every cw-channel chunk (cw = 4, 2 or 1)
 template <typename T>
 __global__ void __launch_bounds__(256) gn_chunk_stats_kernel(const T* __restrict__ x, int HW, int C, int cw, int rows_per_block,
-                                                              float* __restrict__ stats) {
+                                                              double* __restrict__ stats) {
     const int ncv = C / 8;
     const int n = blockIdx.y;
     const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
@@ -133,16 +134,17 @@ __global__ void __launch_bounds__(256) gn_chunk_stats_kernel(const T* __restrict
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
     }
-    float* dst = stats + ((size_t)n * (C / cw) + (cv * 8) / cw) * 2;
+    // fp32 partials cover <= 16 rows per thread; everything beyond that is accumulated in fp64
+    double* dst = stats + ((size_t)n * (C / cw) + (cv * 8) / cw) * 2;
     if (cw == 4) {
-        atomicAdd(dst + 0, (s[0] + s[1]) + (s[2] + s[3])); atomicAdd(dst + 1, (q[0] + q[1]) + (q[2] + q[3]));
-        atomicAdd(dst + 2, (s[4] + s[5]) + (s[6] + s[7])); atomicAdd(dst + 3, (q[4] + q[5]) + (q[6] + q[7]));
+        atomicAdd(dst + 0, (double)s[0] + s[1] + s[2] + s[3]); atomicAdd(dst + 1, (double)q[0] + q[1] + q[2] + q[3]);
+        atomicAdd(dst + 2, (double)s[4] + s[5] + s[6] + s[7]); atomicAdd(dst + 3, (double)q[4] + q[5] + q[6] + q[7]);
     } else if (cw == 2) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, s[2 * j] + s[2 * j + 1]); atomicAdd(dst + 2 * j + 1, q[2 * j] + q[2 * j + 1]); }
+        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, (double)s[2 * j] + s[2 * j + 1]); atomicAdd(dst + 2 * j + 1, (double)q[2 * j] + q[2 * j + 1]); }
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, s[j]); atomicAdd(dst + 2 * j + 1, q[j]); }
+        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, (double)s[j]); atomicAdd(dst + 2 * j + 1, (double)q[j]); }
     }
 }
 
@@ -153,7 +155,7 @@ static int gn_block(int C) {
     return ncv * rpp;
 }
 
-int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, float* stats, cudaStream_t s) {
+int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, double* stats, cudaStream_t s) {
     PD_REQUIRE(C % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
     PD_REQUIRE(cw == 4 || cw == 2 || cw == 1, "statistics chunk width must be 4, 2 or 1");
     const int block = gn_block(C);
@@ -203,17 +205,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_bl
 #pragma unroll
         for (int u = 0; u < 4; ++u) pre[u] = ld_raw8(src + (size_t)(r + u * rstep) * pitch);
     }
-    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    const double inv_cnt = 1.0 / ((double)cpg * (double)a.HW);
     for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-        float sum = 0.f, sq = 0.f;
+        double sum = 0.0, sq = 0.0;
         for (int cc = g * cpg; cc < (g + 1) * cpg; cc += cw) {
-            const float* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
-                                          : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
+            const double* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
+                                           : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
             sum += st[0]; sq += st[1];
         }
-        const float mean = sum * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        s_mean[g] = mean;
+        const double mean = sum * inv_cnt;
+        const float var = (float)fmax(sq * inv_cnt - mean * mean, 0.0);   // the subtraction that cancels is done in fp64
+        s_mean[g] = (float)mean;
         s_rstd[g] = kPrecise ? 1.0f / sqrtf(var + a.eps) : rsqrtf(var + a.eps);
     }
     __syncthreads();
@@ -299,17 +301,17 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(GNArgs a, float2* coef) {
     float* s_rstd = sm + a.groups;
     const int C = a.C1 + a.C2, n = blockIdx.x;
     const int cpg = C / a.groups, cw = a.stats_cw;
-    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    const double inv_cnt = 1.0 / ((double)cpg * (double)a.HW);
     for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-        float sum = 0.f, sq = 0.f;
+        double sum = 0.0, sq = 0.0;
         for (int cc = g * cpg; cc < (g + 1) * cpg; cc += cw) {
-            const float* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
-                                          : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
+            const double* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
+                                           : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
             sum += st[0]; sq += st[1];
         }
-        const float mean = sum * inv_cnt;
-        const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        s_mean[g] = mean;
+        const double mean = sum * inv_cnt;
+        const float var = (float)fmax(sq * inv_cnt - mean * mean, 0.0);   // the subtraction that cancels is done in fp64
+        s_mean[g] = (float)mean;
         s_rstd[g] = rsqrtf(var + a.eps);
     }
     __syncthreads();

@@ -22,7 +22,7 @@ struct TcEpi {
     const void* residual;       // NHWC, same geometry as out, or null
     float out_scale;
     void* out;                  // NHWC 16-bit
-    float* stats;               // (N, Cout/stats_cw, 2) or null
+    double* stats;              // (N, Cout/stats_cw, 2) fp64 or null
     int stats_cw;               // channels per statistics chunk: 4 or 2
     int Cout;
     // TC_MODE_DDIM
@@ -160,11 +160,11 @@ __device__ __forceinline__ void tc_epilogue_chunk32(const TcEpi& e, const uint32
         const float tot = warp_transpose_reduce<64 / CW>(sv, lane);
         if ((lane & 1) == 0) {
             const int idx = lane >> 1;   // 0..7: sum of chunk idx, 8..15: sum of squares of chunk idx-8
-            atomicAdd(e.stats + ((size_t)img * (e.Cout >> 2) + (col0 >> 2) + (idx & 7)) * 2 + (idx >> 3), tot);
+            atomicAdd(e.stats + ((size_t)img * (e.Cout >> 2) + (col0 >> 2) + (idx & 7)) * 2 + (idx >> 3), (double)tot);
         }
     } else if (st2) {
         const float tot = warp_transpose_reduce<64 / CW>(sv, lane);
-        atomicAdd(e.stats + ((size_t)img * (e.Cout >> 1) + (col0 >> 1) + (lane & 15)) * 2 + (lane >> 4), tot);
+        atomicAdd(e.stats + ((size_t)img * (e.Cout >> 1) + (col0 >> 1) + (lane & 15)) * 2 + (lane >> 4), (double)tot);
     }
 }
 

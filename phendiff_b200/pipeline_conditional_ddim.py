@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .cond_unet_2d import CustomCondUNet2DModel
-from .schedulers import DDIMScheduler
+from .schedulers import DDIMScheduler, randn_tensor
 
 DEFAULT_NUM_INFERENCE_STEPS = 50
 
@@ -161,9 +161,7 @@ class ConditionalDDIMPipeline:
         if start_image is not None:
             image = start_image.to(device=device, dtype=torch.float32)
         else:
-            gdev = generator.device if isinstance(generator, torch.Generator) else device
-            image = torch.randn(image_shape, generator=generator if not isinstance(generator, list) else None,
-                                device=gdev, dtype=torch.float32).to(device)
+            image = randn_tensor(image_shape, generator, device, torch.float32)
 
         self.scheduler.set_timesteps(num_inference_steps)
         if frac_diffusion_skipped is not None:
@@ -173,9 +171,7 @@ class ConditionalDDIMPipeline:
             timesteps = self.scheduler.timesteps
 
         if add_forward_noise_to_image:
-            gdev = generator.device if isinstance(generator, torch.Generator) else device
-            noise = torch.randn(image.shape, generator=generator if not isinstance(generator, list) else None,
-                                device=gdev, dtype=image.dtype).to(device)
+            noise = randn_tensor(image.shape, generator, device, image.dtype)
             image = self.scheduler.add_noise(image, noise, timesteps[0].repeat(batch_size))
 
         do_classifier_free_guidance = (
@@ -191,8 +187,9 @@ class ConditionalDDIMPipeline:
         if class_emb is not None:
             class_emb = class_emb.to(device)
 
-        fused_ok = (self.fused and not do_classifier_free_guidance and eta == 0.0 and class_emb is None
-                    and self.unet.class_embedding is not None and len(timesteps) > 0)
+        self.unet.check_weights()   # an out-of-band `param.data.copy_` (EMA copy_to) must not sample from stale weights
+        fused_ok = (self.fused_route_ok() and not do_classifier_free_guidance and eta == 0.0 and class_emb is None
+                    and len(timesteps) > 0)
         if fused_ok:
             image = self._fused_generate(image, class_labels, timesteps, use_clipped_model_output)
         else:
@@ -225,6 +222,11 @@ class ConditionalDDIMPipeline:
         return ImagePipelineOutput(images=image)
 
     # -- helpers -----------------------------------------------------------------------------------------------------
+    def fused_route_ok(self) -> bool:
+        """Whether the whole-path C entry point may replace the per-step loop for this model: it feeds x_t to conv_in as
+        is (no `center_input_sample` rescale, cond_unet_2d.py:271-273) and indexes the class table by label."""
+        return bool(self.fused and self.unet.class_embedding is not None and not self.unet.config.center_input_sample)
+
     def postprocess(self, image: torch.Tensor) -> np.ndarray:
         """(image / 2 + 0.5).clamp(0, 1) -> cpu -> NHWC numpy (pipeline:349-350), as one kernel + one D2H copy."""
         B, Cc, H, W = image.shape
@@ -239,6 +241,7 @@ class ConditionalDDIMPipeline:
         B, _, H, W = x.shape
         dev = x.device
         with torch.cuda.device(dev):
+            self.unet.check_weights()   # an out-of-band `param.data.copy_` (EMA copy_to) must not sample from stale weights
             h = self.unet._ensure_plan(B, H, W)
             arr = (_lib.StepCoeffs * len(steps))(*steps)
             src = src_labels.to(device=dev, dtype=torch.int64).contiguous() if src_labels is not None else None

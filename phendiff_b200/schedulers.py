@@ -21,6 +21,20 @@ from . import _lib
 from .config import ConfigMixin
 
 
+def randn_tensor(shape, generator, device, dtype=torch.float32):
+    """diffusers.utils.randn_tensor semantics: one generator draws the whole batch on the generator's own device; a LIST
+    of generators draws sample i from generator i (shape (1, ...) each), so a per-sample seed reproduces that sample
+    whatever the batch composition."""
+    shape = tuple(shape)
+    if isinstance(generator, (list, tuple)):
+        if len(generator) != shape[0]:
+            raise ValueError(f"generator list of length {len(generator)} for a batch of {shape[0]}")
+        parts = [torch.randn((1,) + shape[1:], generator=g, device=g.device, dtype=dtype).to(device) for g in generator]
+        return torch.cat(parts, dim=0)
+    gdev = generator.device if isinstance(generator, torch.Generator) else device
+    return torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
+
+
 @dataclass
 class DDIMSchedulerOutput:
     prev_sample: torch.Tensor
@@ -177,8 +191,7 @@ class DDIMScheduler(_SchedulerBase):
                 raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either `generator` or `variance_noise` stays `None`.")
             noise = variance_noise
             if noise is None:
-                gdev = generator.device if generator is not None and not isinstance(generator, list) else model_output.device
-                noise = torch.randn(model_output.shape, generator=generator, device=gdev, dtype=model_output.dtype).to(model_output.device)
+                noise = randn_tensor(model_output.shape, generator, model_output.device, model_output.dtype)
         prev, x0 = self._run_step(co, model_output, sample, noise)
         if not return_dict:
             return (prev,)

@@ -43,10 +43,11 @@ def _inversion(pipe: ConditionalDDIMPipeline, input_images: Tensor, class_labels
     """Real images + source class -> Gaussian latents (the input is not modified: it is cloned, :773)."""
     gauss = _to_device(pipe, input_images, torch.float32).contiguous().clone()
     labels = _to_device(pipe, class_labels, torch.int64)
-    if pipe.fused and pipe.unet.class_embedding is not None:
+    if pipe.fused_route_ok():
         _, steps = _inversion_steps(pipe, num_inference_steps)
         return pipe._run_fused(gauss, labels, None, steps, len(steps), 0)
     inv, _ = _inversion_steps(pipe, num_inference_steps)
+    pipe.unet.check_weights()
     for t in inv.timesteps:
         model_output = pipe.unet(gauss, t, labels).sample
         gauss = inv.step(model_output, t, gauss).prev_sample
@@ -73,7 +74,7 @@ def _ddib(pipe: ConditionalDDIMPipeline, clean_images: Tensor, orig_class_labels
     """Same contract as the reference: returns the list of PIL images `pipe(...).images` would return."""
     if not isinstance(pipe, ConditionalDDIMPipeline):
         raise NotImplementedError("only the pixel-space ConditionalDDIMPipeline path is implemented (SURVEY §8)")
-    if pipe.fused and pipe.unet.class_embedding is not None:
+    if pipe.fused_route_ok():
         x = ddib_transfer(pipe, clean_images, orig_class_labels, target_class_labels, num_inference_steps)
         return pipe.numpy_to_pil(pipe.postprocess(x))
     inverted_gauss = _inversion(pipe, clean_images, orig_class_labels, num_inference_steps, process_idx)

@@ -255,3 +255,48 @@ def test_cfg_lookup_reads_attribute_and_dict_configs():
         assert _cfg_lookup(node, "guidance_scale") == 2.5 and _cfg_lookup(node, "frac_diffusion_skipped") == 0.5
     with pytest.raises((AttributeError, KeyError)):
         _cfg_lookup(a, "class_transfer_method", "ddib")
+
+
+def test_weight_state_tracking_sees_out_of_band_writes():
+    """Round-1 advisor finding: `p.data.copy_()` (diffusers EMAModel.copy_to / restore, utils_training.py:674-676) does not
+    move the autograd version counter.  The cheap key must see everything else; the fingerprint must see this."""
+    import torch
+
+    from phendiff_b200 import CustomCondUNet2DModel
+    from phendiff_b200.reference_configs import DENOISER_CONFIGS
+
+    m = CustomCondUNet2DModel.from_config(dict(DENOISER_CONFIGS["super_small"], sample_size=32))
+    k0, f0 = m._weights_version(), m.weights_fingerprint()
+    p = m.conv_in.weight
+    p.data.copy_(p.data * 1.01)                       # out of band: version key blind, fingerprint not
+    assert m._weights_version() == k0
+    assert m.weights_fingerprint() != f0
+    m.mark_dirty()
+    assert m._weights_version() != k0
+    k1 = m._weights_version()
+    with torch.no_grad():
+        p.mul_(1.01)                                  # in-place op through the parameter: version counter moves
+    assert m._weights_version() != k1
+    k2 = m._weights_version()
+    m.load_state_dict(m.state_dict())                 # load_state_dict always invalidates
+    assert m._weights_version() != k2
+    k3 = m._weights_version()
+    m.double().float()                                # _apply (to / cuda / dtype casts) invalidates
+    assert m._weights_version() != k3
+    k4 = m._weights_version()
+    p.data = p.data.clone()                           # re-assigned storage: data_ptr moves
+    assert m._weights_version() != k4
+
+
+def test_randn_tensor_generator_list_is_per_sample():
+    import torch
+
+    from phendiff_b200.schedulers import randn_tensor
+
+    gens = [torch.Generator().manual_seed(s) for s in (5, 6, 7)]
+    a = randn_tensor((3, 2, 4, 4), gens, torch.device("cpu"))
+    b = randn_tensor((1, 2, 4, 4), [torch.Generator().manual_seed(6)], torch.device("cpu"))
+    assert torch.equal(a[1:2], b)                     # sample i depends on generator i only (diffusers randn_tensor)
+    import pytest
+    with pytest.raises(ValueError):
+        randn_tensor((2, 2, 4, 4), gens, torch.device("cpu"))

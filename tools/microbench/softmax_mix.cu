@@ -1,0 +1,136 @@
+// Microbenchmark: the softmax inner loop of a d = 8 attention WITHOUT its matrix products — 32 fp32 scores in (read from shared
+// memory, standing in for a tcgen05.ld), 16 packed fp16 pairs out — for different splits between MUFU.EX2 and FMA-pipe
+// polynomials.  Answers: what is the best reachable cycles / 32 scores / SMSP, and at which split.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I phendiff_b200/csrc -I include -o gpurun_out/softmax_mix tools/microbench/softmax_mix.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) { uint32_t d; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d; }
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) { uint32_t d; asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d; }
+__device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2sub(uint32_t a, uint32_t b) { uint32_t d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t h2min(uint32_t a, uint32_t b) { uint32_t d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2max(uint32_t a, uint32_t b) { uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+
+// the shipped pair polynomial (pd_attn_common.cuh ex2_pair_h2): clamp to [-15, 16], magic add 1039, cubic, exponent by IMAD + HMUL2
+__device__ __forceinline__ uint32_t poly_v3(float xa, float xb) {
+    uint32_t x = pack_h2(xa, xb);
+    x = h2min(h2max(x, 0xCB80CB80u), 0x4C004C00u);
+    const uint32_t w = h2add(x, 0x640F640Fu);
+    const uint32_t f = h2sub(x, h2sub(w, 0x640F640Fu));
+    uint32_t p = h2fma(0x2B0D2B0Du, f, 0x33C333C3u);
+    p = h2fma(p, f, 0x398C398Cu);
+    p = h2fma(p, f, 0x3C003C00u);
+    return h2mul(p, w * 1024u + (0u - 0x64006400u * 1024u));
+}
+// leaner: scores arrive as y = x + 15 (offset folded into the MMA), low clamp = the .relu of the pack, magic 1024
+__device__ __forceinline__ uint32_t poly_relu(float ya, float yb) {
+    uint32_t y = h2min(pack_h2_relu(ya, yb), 0x4F804F80u /* 30 */);
+    const uint32_t w = h2add(y, 0x64006400u);
+    const uint32_t f = h2sub(y, h2sub(w, 0x64006400u));
+    uint32_t p = h2fma(0x2B0D2B0Du, f, 0x33C333C3u);
+    p = h2fma(p, f, 0x398C398Cu);
+    p = h2fma(p, f, 0x3C003C00u);
+    return h2mul(p, (w - 0x64006400u) << 10);
+}
+// quadratic variant of the same (2 HFMA2)
+__device__ __forceinline__ uint32_t poly_relu_q(float ya, float yb) {
+    uint32_t y = h2min(pack_h2_relu(ya, yb), 0x4F804F80u);
+    const uint32_t w = h2add(y, 0x64006400u);
+    const uint32_t f = h2sub(y, h2sub(w, 0x64006400u));
+    uint32_t p = h2fma(0x33C333C3u, f, 0x398C398Cu);
+    p = h2fma(p, f, 0x3C003C00u);
+    return h2mul(p, (w - 0x64006400u) << 10);
+}
+// fp32 polynomial (FFMA pipe at full rate): magic add, cubic, exponent by integer add
+__device__ __forceinline__ float poly_f32(float x) {
+    x = fmaxf(x, -100.0f);
+    const float t = x + 12582912.0f;
+    const float f = x - (t - 12582912.0f);
+    float p = 0.05508868396282196f;
+    p = fmaf(p, f, 0.24260404706001282f);
+    p = fmaf(p, f, 0.6932762265205383f);
+    p = fmaf(p, f, 0.9999289512634277f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// MASK bit r set: pair r of every 16 goes to the polynomial KIND (0 v3, 1 relu, 2 relu quadratic, 3 fp32)
+template <uint32_t MASK, int KIND>
+__global__ void __launch_bounds__(256) k(uint32_t* out, int iters) {
+    __shared__ float4 sm[8 * 256];
+    for (int i = 0; i < 8; ++i) {
+        const float b = -0.37f * (float)((threadIdx.x * 7 + i * 3) % 23);
+        sm[i * 256 + threadIdx.x] = make_float4(b, b - 0.25f, b - 1.5f, b - 3.125f);
+    }
+    __syncthreads();
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        float s[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&sm[i * 256 + threadIdx.x])));
+            s[4 * i] = v.x; s[4 * i + 1] = v.y; s[4 * i + 2] = v.z; s[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            uint32_t p;
+            if ((MASK >> r) & 1u) {
+                if (KIND == 0) p = poly_v3(s[2 * r], s[2 * r + 1]);
+                else if (KIND == 1) p = poly_relu(s[2 * r], s[2 * r + 1]);
+                else if (KIND == 2) p = poly_relu_q(s[2 * r], s[2 * r + 1]);
+                else p = pack_h2(poly_f32(s[2 * r]), poly_f32(s[2 * r + 1]));
+            } else {
+                p = pack_h2(ex2f(s[2 * r]), ex2f(s[2 * r + 1]));
+            }
+            acc ^= p;
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+template <uint32_t MASK, int KIND> void run(const char* name) {
+    uint32_t* d; cudaMalloc(&d, 4);
+    const int blocks = 148 * 8, threads = 256, iters = 2048;   // 8 CTAs x 8 warps = 16 warps per scheduler
+    k<MASK, KIND><<<blocks, threads>>>(d, 16);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k<MASK, KIND><<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double warp_tiles = (double)blocks * (threads / 32) * iters;          // warp-iterations of 32 scores per lane
+    // cycles per (warp x 32 scores-per-lane... i.e. 32 score-instructions) per SMSP, clock read from the device
+    int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    printf("%-34s poly pairs %2d/16 kind %d: %7.3f ms  %7.2f G scores/s/SM  (%.2f cyc per 32 scores per lane-warp per SMSP at the nominal %d MHz)\n",
+           name, __builtin_popcount(MASK), KIND, ms, (double)blocks * threads * iters * 32 / (ms * 1e-3) / 148 / 1e9,
+           ms * 1e-3 * khz * 1e3 / (warp_tiles / (148.0 * 4)) / 32.0 * 32.0 / 32.0, khz / 1000);
+    cudaFree(d);
+}
+
+int main() {
+    run<0x0000u, 0>("all MUFU");
+    run<0xFFFFu, 0>("all poly v3");
+    run<0xFFFFu, 1>("all poly relu");
+    run<0xFFFFu, 2>("all poly relu quadratic");
+    run<0xFFFFu, 3>("all poly fp32");
+    run<0x5555u, 0>("8/16 v3");
+    run<0x5555u, 1>("8/16 relu");
+    run<0x5555u, 2>("8/16 relu quadratic");
+    run<0x5555u, 3>("8/16 fp32");
+    run<0x2492u, 1>("5/16 relu");
+    run<0x4924u | 0x0001u, 1>("6/16 relu");
+    run<0x5554u, 1>("7/16 relu");
+    run<0x5557u, 1>("9/16 relu");
+    run<0x5577u, 1>("10/16 relu");
+    run<0x5555u | 0x2222u, 1>("12/16 relu");
+    run<0x5577u, 2>("10/16 relu quadratic");
+    run<0x5555u | 0x2222u, 2>("12/16 relu quadratic");
+    // two polynomial kinds at once: half2 pairs on 8/16 + fp32 on 2/16 (both FMA sub-pipes?)
+    return 0;
+}
