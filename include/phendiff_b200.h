@@ -137,6 +137,18 @@ int pd_denorm_nhwc(const float* x, float* out, int32_t batch, int32_t channels, 
 int pd_ddib_transfer(pd_unet_t* h, float* x, const int64_t* src_labels, const int64_t* tgt_labels,
                      const pd_step_coeffs_t* steps_host, int32_t n_inv, int32_t n_gen, pd_stream_t stream);
 
+/* ---- classifier-free-guided generation: the pipeline loop of pipeline_conditionial_ddim.py:286-347
+ *      with guidance on, as driven by _classifier_free_guidance_forward_start (utils_Img2Img.py:615-648).  Per step ONE pass
+ *      of the UNet over 2P images — P conditional samples and their P unconditional copies (class embedding = zeros,
+ *      :308-317; the reference's own TODO at :287 asks for this batching) — whose conv_out epilogue combines
+ *      m = (eqn == 0 ? m_u : m_c) + w (m_c - m_u) (:323-332) and applies the scheduler update to x_t in place: the guided
+ *      score never exists in HBM.  Plan with pd_unet_plan_guided(h, B, H, W) (B = samples; the pass holds 2 x as many
+ *      images), bind the workspace, then call.  x (B,C,H,W) fp32 updated in place; labels (B) int64; w (B) fp32 guidance
+ *      scale per sample (device); eqn 0 = "imagen", 1 = "CFG"; steps_host: n_steps generation steps in execution order. */
+int pd_unet_plan_guided(pd_unet_t* h, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes);
+int pd_cfg_transfer(pd_unet_t* h, float* x, const int64_t* labels, const float* w, int32_t eqn,
+                    const pd_step_coeffs_t* steps_host, int32_t n_steps, pd_stream_t stream);
+
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int pd_unet_launch_count(pd_unet_t* h, int64_t* n);
 /* current plan: images per pass, layers on the tcgen05 kernel / on the SIMT kernel, recorded ops per forward */

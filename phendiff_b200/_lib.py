@@ -65,6 +65,8 @@ _SIGNATURES = {
     "pd_cfg_combine": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int64, _P]),
     "pd_denorm_nhwc": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "pd_ddib_transfer": (C.c_int, [_P, _P, _P, _P, C.POINTER(StepCoeffs), C.c_int32, C.c_int32, _P]),
+    "pd_unet_plan_guided": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "pd_cfg_transfer": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(StepCoeffs), C.c_int32, _P]),
     "pd_unet_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "pd_unet_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pd_unet_profile_begin": (C.c_int, [_P, C.c_int32, C.c_int32]),

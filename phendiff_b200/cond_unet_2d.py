@@ -366,13 +366,15 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
                 self._plan_key = None
         return self._handle
 
-    def _ensure_plan(self, B: int, H: int, W: int):
+    def _ensure_plan(self, B: int, H: int, W: int, guided: bool = False):
+        """Static buffer plan + workspace for B samples of H x W.  guided: plan for the classifier-free-guidance pass
+        (2B images per step: every sample once with its class row, once with the unconditional row; `pd_cfg_transfer`)."""
         h = self._ensure_handle()
-        key = (B, H, W)
+        key = (B, H, W, bool(guided))
         if self._plan_key != key:
             L = _lib.lib()
             nbytes = C.c_size_t()
-            _lib.check(L.pd_unet_plan(h, B, H, W, C.byref(nbytes)))
+            _lib.check((L.pd_unet_plan_guided if guided else L.pd_unet_plan)(h, B, H, W, C.byref(nbytes)))
             ws = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
             off = (-ws.data_ptr()) % 1024
             _lib.check(L.pd_unet_bind_workspace(h, C.c_void_p(ws.data_ptr() + off), nbytes.value))

@@ -115,6 +115,11 @@ struct Ctx {   // per-call inputs of the recorded program
     float* model_out = nullptr;        // (mb, Cout, H, W) or null
     float* x_update = nullptr;         // x_t updated in place by the fused conv_out epilogue, or null
     const pd_step_coeffs_t* step = nullptr;
+    // classifier-free guidance in one pass: the mb images are P = cfg_pairs conditional samples followed by their P
+    // unconditional copies (x holds P images; image P + i reads x[i] and the embedding row without class embedding)
+    int cfg_pairs = 0;
+    const float* cfg_w = nullptr;      // (P) guidance scale per sample
+    int cfg_eqn = 0;                   // 0 "imagen", 1 "CFG"
 };
 
 typedef std::function<int(const Ctx&, cudaStream_t)> OpFn;
@@ -156,6 +161,7 @@ struct pd_unet {
     std::vector<void*> owned;   // derived device buffers
     // plan
     int B = 0, H = 0, W = 0, mb = 0;
+    bool pairs = false;         // plan made by pd_unet_plan_guided: B = 2 x samples, mb even
     int tail = 0;               // images in the last micro-batch when the batch is ragged (B % mb), else 0
     size_t tail_x_off = 0, tail_out_off = 0, tail_t_off = 0, tail_lab_off = 0, tail_emb_off = 0;   // padded scratch copies of the tail
     size_t ws_bytes = 0;
@@ -164,7 +170,7 @@ struct pd_unet {
     std::vector<ConvTcPlan*> tc_plans;
     std::vector<std::unique_ptr<Tensor>> tensors;
     bool bound = false;
-    size_t stats_off = 0, stats_bytes = 0, emb_off = 0, temb_off = 0;
+    size_t stats_off = 0, stats_bytes = 0, emb_off = 0, temb_off = 0, cfg_u_off = 0;
     int64_t launches = 0;
     int tc_layers = 0, simt_layers = 0;
     // sampled per-op device timing (bench.py's roofline): every `prof_every`-th program run is bracketed with events
@@ -643,12 +649,15 @@ struct Rec {
         pd_unet* M = m;
         const pd_unet_config_t& c = M->cfg;
         const int H = M->H, W = M->W, C0 = c.block_out_channels[0];
-        const int rows_max = std::max(mb, c.num_class_embeds);
+        const int rows_max = std::max(mb, c.num_class_embeds + 1);   // + the unconditional row of the guidance pass
         // fixed small buffers: statistics region (zeroed once per forward), embedding rows, projected table, row index
         M->stats_off = M->arena.alloc(std::max<size_t>(M->stats_bytes, 1024));
         M->emb_off = M->arena.alloc((size_t)rows_max * M->D * sizeof(float));
         M->temb_off = M->arena.alloc((size_t)rows_max * M->J * sizeof(float));
         M->rowidx_off = M->arena.alloc((size_t)mb * sizeof(int32_t));
+        // unconditional model output of the guidance pass (P = mb / 2 samples, NCHW fp32): written by conv_out's first launch,
+        // read by the epilogue of its second
+        M->cfg_u_off = M->arena.alloc((size_t)std::max(1, mb / 2) * c.out_channels * H * W * sizeof(float));
         if (M->tail) {
             // ragged batch: the last micro-batch runs on scratch copies of its inputs, padded to mb images with its first image
             const size_t hw = (size_t)H * W;
@@ -673,6 +682,7 @@ struct Rec {
                 if (sb) { PD_CHECK_CUDA(cudaMemsetAsync(stats, 0, sb, s)); }
                 EmbedArgs e = ea;
                 e.timesteps = cx.timesteps; e.t_scalar = cx.t_scalar; e.labels = cx.labels; e.class_emb = cx.class_emb;
+                e.cfg_pairs = cx.cfg_pairs;
                 // one scalar timestep + integer labels (the DDIB path): only ncls distinct embedding rows exist
                 e.dedupe = (!cx.timesteps && cx.labels && !cx.class_emb && e.class_table && e.ncls > 0 && e.ncls <= e.B) ? 1 : 0;
                 int r = launch_embed(e, s);
@@ -695,7 +705,7 @@ struct Rec {
             if (!dry) {
                 void* o = ptr(col);
                 const int N = mb, Cin = c.in_channels, dt = M->dt;
-                push([=](const Ctx& cx, cudaStream_t s) { return launch_im2col_in(dt, cx.x, N, Cin, H, W, o, s); }, 1, CLS_CONV_IN);
+                push([=](const Ctx& cx, cudaStream_t s) { return launch_im2col_in(dt, cx.x, N, Cin, H, W, o, s, cx.cfg_pairs); }, 1, CLS_CONV_IN);
             }
             ConvL l1; l1.cin = 64; l1.cout = C0; l1.k = 1; l1.stride = 1; l1.pad = 0;
             ConvOpt oi;
@@ -708,7 +718,7 @@ struct Rec {
                 void* o = ptr(x);
                 const float* w = M->w_in; const float* b = M->conv_in.b->dev;
                 const int N = mb, Cin = c.in_channels, dt = M->dt;
-                push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s); }, 1, CLS_CONV_IN,
+                push([=](const Ctx& cx, cudaStream_t s) { return launch_conv_in(dt, cx.x, w, b, N, Cin, H, W, C0, o, s, cx.cfg_pairs); }, 1, CLS_CONV_IN,
                      2.0 * N * H * W * 9.0 * Cin * C0);
             }
             stats_kernel(x);
@@ -809,8 +819,21 @@ struct Rec {
                 if (r) return r;
                 M->tc_plans.push_back(pl);
                 M->tc_layers += 1;
-                push([pl](const Ctx& cx, cudaStream_t s) {
+                float* cfg_u = (float*)raw(M->cfg_u_off);
+                push([pl, cfg_u, M](const Ctx& cx, cudaStream_t s) {
                     ConvTcLaunch ex{cx.model_out, cx.x_update, cx.step};
+                    if (cx.cfg_pairs > 0) {
+                        // guidance pass: (1) the unconditional half writes its plain output, (2) the conditional half combines
+                        // m = base + w (m_c - m_u) in its epilogue and applies the scheduler update to x_t — the guided score
+                        // never exists in HBM
+                        ConvTcLaunch un{cfg_u, nullptr, nullptr};
+                        un.img_begin = cx.cfg_pairs; un.img_count = cx.cfg_pairs;
+                        int r = conv_tc_launch(pl, s, &un);
+                        if (r) return r;
+                        M->launches += 1;
+                        ex.img_begin = 0; ex.img_count = cx.cfg_pairs;
+                        ex.cfg = CfgEpi{cfg_u, cx.cfg_w, cx.cfg_eqn};
+                    }
                     return conv_tc_launch(pl, s, &ex);
                 }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels, out_gn ? "gn+conv_out+ddim" : "conv_out+ddim");
             }
@@ -819,9 +842,19 @@ struct Rec {
             oa.act = ptr(xn); oa.w = M->w_out; oa.bias = M->conv_out.b->dev; oa.N = mb; oa.H = H; oa.W = W; oa.Cin = C0;
             oa.Cout = c.out_channels;
             const int dt = M->dt;
+            float* cfg_u = (float*)raw(M->cfg_u_off);
             push([=](const Ctx& cx, cudaStream_t s) {
                 ConvOutArgs a = oa;
                 a.model_out = cx.model_out; a.x = cx.x_update; a.step = cx.step;
+                if (cx.cfg_pairs > 0) {   // guidance pass, as on the tensor-core path: unconditional half first, then combine + update
+                    ConvOutArgs un = oa;
+                    un.model_out = cfg_u; un.img_begin = cx.cfg_pairs; un.img_count = cx.cfg_pairs;
+                    int r = launch_conv_out(dt, un, s);
+                    if (r) return r;
+                    M->launches += 1;
+                    a.img_begin = 0; a.img_count = cx.cfg_pairs;
+                    a.cfg = CfgEpi{cfg_u, cx.cfg_w, cx.cfg_eqn};
+                }
                 return launch_conv_out(dt, a, s);
             }, 1, CLS_CONV_OUT, 2.0 * mb * H * W * 9.0 * C0 * c.out_channels);
         }
@@ -1037,7 +1070,18 @@ int pd_unet_time_embed_dim(pd_unet_t* m, int32_t* dim) {
     return 0;
 }
 
+static int plan_impl(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes, bool pairs);
+
 int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes) {
+    return plan_impl(m, batch, height, width, workspace_bytes, false);
+}
+
+int pd_unet_plan_guided(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes) {
+    PD_REQUIRE(batch > 0, "bad shape");
+    return plan_impl(m, 2 * batch, height, width, workspace_bytes, true);
+}
+
+static int plan_impl(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes, bool pairs) {
     PD_REQUIRE(m && workspace_bytes, "null argument");
     PD_REQUIRE(m->finalized, "pd_unet_finalize must be called before planning");
     PD_REQUIRE(batch > 0 && height > 0 && width > 0, "bad shape");
@@ -1048,13 +1092,16 @@ int pd_unet_plan(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, siz
     int cap = m->cfg.max_microbatch > 0 ? m->cfg.max_microbatch : 64;   // 64 images: >= 6.9 waves of 148 CTAs at every UNet level
     const int lim = std::min(cap, batch);
     int mb = 1;
-    for (int d = 1; d <= lim; ++d) if (batch % d == 0) mb = d;
-    if (mb * 2 < lim) {
+    // guided plans (pairs): a pass holds P conditional samples and their P unconditional copies, so the micro-batch is even
+    for (int d = 1; d <= lim; ++d) if (batch % d == 0 && (!pairs || d % 2 == 0)) mb = d;
+    if (mb * 2 < lim || (pairs && mb % 2)) {
         // no divisor of the batch within a factor 2 of the cap (prime batches: 1): even micro-batches and a padded ragged tail
         const int k = (batch + lim - 1) / lim;
         mb = (batch + k - 1) / k;
+        if (pairs && mb % 2) ++mb;
     }
     m->mb = mb;
+    m->pairs = pairs;
     m->tail = batch % mb;
     // dry pass 1 sizes the statistics region, dry pass 2 gives the arena peak with that region in place
     m->stats_bytes = 0;
@@ -1094,6 +1141,7 @@ int pd_unet_forward(pd_unet_t* m, const float* sample, const float* timesteps, c
                     const float* class_emb, float* out, pd_stream_t stream) {
     PD_REQUIRE(m && sample && timesteps && out, "null argument");
     PD_REQUIRE(m->bound, "pd_unet_plan + pd_unet_bind_workspace must be called first");
+    PD_REQUIRE(!m->pairs, "the current plan is a guided plan (pd_unet_plan_guided): re-plan with pd_unet_plan");
     PD_REQUIRE(!(class_labels && class_emb), "Cannot specify both class_labels and class_emb");
     PD_REQUIRE(!(m->cls && !class_labels && !class_emb), "either class_labels or class_emb should be provided when doing class conditioning");
     { int rc = check_device(m); if (rc) return rc; }
@@ -1162,6 +1210,7 @@ int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const in
                      const pd_step_coeffs_t* steps_host, int32_t n_inv, int32_t n_gen, pd_stream_t stream) {
     PD_REQUIRE(m && x && steps_host, "null argument");
     PD_REQUIRE(m->bound, "pd_unet_plan + pd_unet_bind_workspace must be called first");
+    PD_REQUIRE(!m->pairs, "the current plan is a guided plan (pd_unet_plan_guided): re-plan with pd_unet_plan");
     PD_REQUIRE(m->cfg.in_channels == m->cfg.out_channels, "in/out channels must match for sampling");
     PD_REQUIRE(!m->cls || ((n_inv == 0 || src_labels) && (n_gen == 0 || tgt_labels)), "class-conditioned model needs source labels for inversion steps and target labels for generation steps");
     const size_t per = (size_t)m->cfg.in_channels * m->H * m->W;
@@ -1194,6 +1243,51 @@ int pd_ddib_transfer(pd_unet_t* m, float* x, const int64_t* src_labels, const in
             if (rc) return rc;
         }
         if (n < m->mb)
+            PD_CHECK_CUDA(cudaMemcpyAsync(x + (size_t)i * per, xi, per * sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+int pd_cfg_transfer(pd_unet_t* m, float* x, const int64_t* labels, const float* w, int32_t eqn,
+                    const pd_step_coeffs_t* steps_host, int32_t n_steps, pd_stream_t stream) {
+    PD_REQUIRE(m && x && labels && w && steps_host, "null argument");
+    PD_REQUIRE(m->bound && m->pairs, "pd_unet_plan_guided + pd_unet_bind_workspace must be called first");
+    PD_REQUIRE(m->cls, "classifier-free guidance needs a class-conditioned model");
+    PD_REQUIRE(m->cfg.in_channels == m->cfg.out_channels, "in/out channels must match for sampling");
+    PD_REQUIRE(eqn == 0 || eqn == 1, "Unknown guidance equation; should be 'imagen' (0) or 'CFG' (1)");
+    { int rc = check_device(m); if (rc) return rc; }
+    const size_t per = (size_t)m->cfg.in_channels * m->H * m->W;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = m->mb / 2, samples = m->B / 2;
+    for (int i = 0; i < samples; i += P) {
+        const int n = std::min(P, samples - i);
+        float* xi = x + (size_t)i * per;
+        const int64_t* lab_i = labels + i;
+        const float* w_i = w + i;
+        if (n < P) {   // ragged tail: the trajectory runs on padded scratch copies, the n real samples are copied back
+            uint8_t* base = m->arena.base;
+            int rc = copy_padded(base + m->tail_x_off, xi, per * sizeof(float), n, P, s);
+            if (rc) return rc;
+            if ((rc = copy_padded(base + m->tail_lab_off, lab_i, sizeof(int64_t), n, P, s))) return rc;
+            if ((rc = copy_padded(base + m->tail_t_off, w_i, sizeof(float), n, P, s))) return rc;
+            xi = (float*)(base + m->tail_x_off);
+            lab_i = (const int64_t*)(base + m->tail_lab_off);
+            w_i = (const float*)(base + m->tail_t_off);
+        }
+        for (int sidx = 0; sidx < n_steps; ++sidx) {
+            Ctx c;
+            c.x = xi;
+            c.timesteps = nullptr;
+            c.t_scalar = steps_host[sidx].timestep;
+            c.labels = lab_i;
+            c.model_out = nullptr;
+            c.x_update = xi;
+            c.step = &steps_host[sidx];
+            c.cfg_pairs = P; c.cfg_w = w_i; c.cfg_eqn = eqn;
+            int rc = run_program(m, c, s);
+            if (rc) return rc;
+        }
+        if (n < P)
             PD_CHECK_CUDA(cudaMemcpyAsync(x + (size_t)i * per, xi, per * sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
     }
     return 0;

@@ -416,6 +416,7 @@ static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* o
 int attention_mma_launches(int S) {
     const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
     const bool tc = e && e[0] == 't' && e[1] == 'c';
+    if (tc && e[2] == '3') return (S % 128 == 0 && (size_t)S * 32 <= 200 * 1024 && attention_tc3_supported(S, 8)) ? 2 : 1;
     return (tc && S % 128 == 0 && (size_t)S * 32 <= 200 * 1024 && attention_tc_smem_bytes(S) <= 110 * 1024) ? 2 : 1;
 }
 
@@ -431,14 +432,16 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
         // "v2": chunked warp-level kernel (any S)
         const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
         // "tc2": experimental second tcgen05 kernel (pd_attn_tc2.cu: softmax warpgroups on alternate tiles), unmeasured at the end of round 1
-        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : ((e && e[0] == 't' && e[1] == 'c') ? (e[2] == '2' ? 5 : 4) : 3);
+        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : ((e && e[0] == 't' && e[1] == 'c') ? (e[2] == '3' ? 6 : (e[2] == '2' ? 5 : 4)) : 3);
         const char* pe = getenv("PHENDIFF_B200_ATTN_POLYPAIRS");   // score pairs per 16 (v3) / per 8 (tc) on the FMA/ALU pipes
         polyv = pe ? atoi(pe) : -1;
     }
     const size_t smem = (size_t)S * 32;
     const int var = force_variant ? force_variant : variant;
     if (var == 2 || smem > 200 * 1024) return launch_attention_chunked(dt, qkv, N, S, C, d, AH_SL / qfold, out, s);
-    if ((var == 4 || var == 5) && S % 128 == 0 && attention_tc_smem_bytes(S) <= 110 * 1024) {
+    // tc3 stages q by TMA exactly as it lies in memory: it needs the finalize-time fold (qfold == AH_SL); raw q takes the v3 kernel
+    const bool tc3 = var == 6 && S % 128 == 0 && attention_tc3_supported(S, C) && fabsf(AH_SL / qfold - 1.0f) < 1e-6f;
+    if (tc3 || ((var == 4 || var == 5) && S % 128 == 0 && attention_tc_smem_bytes(S) <= 110 * 1024)) {
         // flags: one byte per (image, head, 128-query tile, warp); grow-only scratch owned by the library
         static uint8_t* flags_dev[PD_MAX_DEVICES] = {nullptr};
         static size_t flags_cap_dev[PD_MAX_DEVICES] = {0};
@@ -451,8 +454,9 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
             flags_cap = need;
         }
         const int tc_pp = polyv < 0 ? (dt == DT_F16 ? 4 : 2) : polyv;
-        int rc = var == 5 ? launch_attention_tc2(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s)
-                          : launch_attention_tc(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s);
+        int rc = tc3 ? launch_attention_tc3(dt, qkv, N, S, C, out, flags, tc_pp, s)
+                 : (var == 5 ? launch_attention_tc2(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s)
+                             : launch_attention_tc(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s));
         if (rc) return rc;
         dim3 grid(1, C / 8, N);
         PD_DISPATCH_HALF(dt, T, (launch_head<T, 0x0000u>(qkv, N, S, C, AH_SL / qfold, out, grid, smem, s, flags)));

@@ -55,6 +55,7 @@ struct HaloParams {
     const float2* gn_coef;         // GN variant: (N, C) (scale, shift) of the fused GroupNorm, SiLU follows; else null
     int H, W;                      // input extent (halo mask of the GN variant)
     int gn_tanh;                   // SiLU of the GN variant through tanh.approx (1 MUFU / element) instead of ex2 + rcp
+    int tile_begin, tile_end;      // tile range of this launch (default: 0 .. m_tiles * phases * n_tiles)
     TcEpi epi;
 };
 
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.m_tiles * p.phases * p.n_tiles;
+    const int total_tiles = p.tile_end;   // [tile_begin, tile_end): all tiles, or the image range of a conv_out launch
     const int tiles_per_img = p.tilesW * p.tilesH;
 
     // GN variant: 512 threads start at 128 registers each; every role branch opens with the setmaxnreg of its warpgroup
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
             // ===================== TMA producer, weight tiles (B ring) =====================
             int sb = 0;
             uint32_t phb = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = p.tile_begin + blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles;
                 const int phase = (tile / p.n_tiles) % p.phases;
                 const int brow = phase * p.b_rows_per_phase + n_tile * BLOCK_N;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
             // tile was needed, which left no room for the GN variant's in-place transform).
             int sa = 0;
             uint32_t pha = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = p.tile_begin + blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int t2 = tile / p.n_tiles;
                 const int phase = t2 % p.phases, m_tile = t2 / p.phases;
                 const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = p.tile_begin + blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int as = iter & 1;
                 const uint32_t aphase = (iter >> 1) & 1;
                 mbar_wait_addr(bar_tempty + as * 8, aphase ^ 1);
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
         const int hh = row >> 3, ww = row & 7;
         uint8_t* buf = smEpi + ew * 4096;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = p.tile_begin + blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int n_tile = tile % p.n_tiles;
             const int t2 = tile / p.n_tiles;
             const int phase = t2 % p.phases, m_tile = t2 / p.phases;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(GN ? HALO_THREADS_GN : HALO_THREADS, 1) conv_h
         uint32_t pha = 0;
         // the coefficient table is written by the kernel this grid may have overtaken (programmatic dependent launch, see launch_halo)
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = p.tile_begin + blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int t2 = tile / p.n_tiles;
             const int m_tile = t2 / p.phases;
             const int img = m_tile / tiles_per_img, rem = m_tile - img * tiles_per_img;
@@ -649,7 +650,8 @@ int conv_halo_plan_create(const ConvTcDesc& d, ConvHaloPlan** out) {
         }
         if (rc) { delete pl; return rc; }
     }
-    pl->grid = std::min(p.m_tiles * p.phases * p.n_tiles, tc_num_sms());
+    p.tile_begin = 0; p.tile_end = p.m_tiles * p.phases * p.n_tiles;
+    pl->grid = std::min(p.tile_end, tc_num_sms());
     *out = pl;
     return 0;
 }
@@ -672,7 +674,7 @@ static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t
         // only the transform warps wait (griddepcontrol.wait) before they read the table.  PHENDIFF_B200_PDL=0 disables.
         static const int pdl = [] { const char* e = getenv("PHENDIFF_B200_PDL"); return e ? atoi(e) : 1; }();
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(HALO_THREADS_GN); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+        cfg.gridDim = dim3(std::min(pl->grid, p.tile_end - p.tile_begin)); cfg.blockDim = dim3(HALO_THREADS_GN); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -680,7 +682,7 @@ static int launch_halo(const ConvHaloPlan* pl, const HaloParams& p, cudaStream_t
         PD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN>, p));
         return 0;
     }
-    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN><<<pl->grid, HALO_THREADS, pl->smem, s>>>(p);
+    conv_halo_kernel<BLOCK_N, T, MODE, CW, MT, GN><<<std::min(pl->grid, p.tile_end - p.tile_begin), HALO_THREADS, pl->smem, s>>>(p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -700,6 +702,16 @@ int conv_halo_launch(const ConvHaloPlan* pl, cudaStream_t s, const ConvTcLaunch*
         HaloParams p = pl->p;
         p.epi.model_out = extra->model_out;
         p.epi.x_t = extra->x_t;
+        p.epi.cfg = extra->cfg;
+        if (extra->img_count > 0) {
+            // conv_out tiles are (image, tile-in-image) with one N tile and one phase: an image range is a tile range
+            const int per_img = p.tilesW * p.tilesH;
+            PD_REQUIRE(p.n_tiles == 1 && p.phases == 1 && extra->img_begin >= 0 && (extra->img_begin + extra->img_count) * per_img <= p.tile_end,
+                       "conv_out image range outside the plan");
+            p.tile_begin = extra->img_begin * per_img;
+            p.tile_end = (extra->img_begin + extra->img_count) * per_img;
+            p.epi.img_off = extra->img_begin;
+        }
         if (extra->x_t) {
             PD_REQUIRE(extra->step != nullptr, "x_t update needs step coefficients");
             PD_REQUIRE(extra->step->sigma == 0.f, "fused conv_out update requires eta == 0");

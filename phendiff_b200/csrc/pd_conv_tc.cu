@@ -224,7 +224,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int tc_encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box) {
+                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
     PFN_encodeTiled enc = get_encode();
     PD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t gd[5], gs[4];
@@ -232,7 +232,7 @@ int tc_encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uin
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = 1; }
     for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
     CUresult r = enc(tm, dt == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bd, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));

@@ -21,8 +21,20 @@ struct EmbedArgs {
     // distinct rows exist.  dedupe != 0: rows = ncls, row_idx[b] = labels[b]; else rows = B, row_idx[b] = b.
     int dedupe;
     int32_t* row_idx;             // (B) out: row of emb_act / of the projected table used by image b
+    // classifier-free guidance in ONE pass (pipeline_conditionial_ddim.py:308-317): cfg_pairs = P > 0 (needs dedupe):
+    // the pass holds 2P images, image P + i is the UNCONDITIONAL copy of image i (class embedding = zeros): one extra row
+    // `ncls` without class embedding, row_idx[i] = labels[i] for i < P and ncls for i >= P.
+    int cfg_pairs;
 };
-inline int embed_rows(const EmbedArgs& a) { return a.dedupe ? a.ncls : a.B; }
+inline int embed_rows(const EmbedArgs& a) { return a.dedupe ? a.ncls + (a.cfg_pairs > 0 ? 1 : 0) : a.B; }
+
+// guidance combine applied by a conv_out epilogue to its conditional output m_c before the scheduler update
+// (pipeline_conditionial_ddim.py:323-332): m = (eqn == 0 ? u : m_c) + w[img] * (m_c - u), u = uncond[(img, c, hw)]
+struct CfgEpi {
+    const float* uncond;          // (P, Cout, H, W) fp32 unconditional model output, or null: no guidance
+    const float* w;               // (P) guidance scale per image
+    int eqn;                      // 0 "imagen", 1 "CFG"
+};
 int launch_embed(const EmbedArgs& a, cudaStream_t s);
 // all ResnetBlock2D.time_emb_proj at once: out(B,J) = emb_act(B,D) @ wcat(J,D)^T + bcat(J)
 int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat, int B, int D, int J, float* out,
@@ -66,8 +78,9 @@ struct ConvArgs {
 int launch_conv_simt(int dt, const ConvArgs& a, cudaStream_t s);
 
 // conv_in: NCHW fp32 sample -> NHWC activations (cond_unet_2d.py:313)
+// n_src: image n reads x[n % n_src] (the 2P-image guidance pass feeds every sample twice); 0 = N
 int launch_conv_in(int dt, const float* x, const float* w /*(9*Cin,Cout)*/, const float* bias, int N, int Cin, int H,
-                   int W, int Cout, void* out, cudaStream_t s);
+                   int W, int Cout, void* out, cudaStream_t s, int n_src = 0);
 // conv_out (+ optional fused DDIM update): NHWC activations -> NCHW fp32 (cond_unet_2d.py:348, A.5)
 struct ConvOutArgs {
     const void* act;                  // (N,H,W,Cin) = SiLU(GN(sample))
@@ -77,13 +90,17 @@ struct ConvOutArgs {
     float* model_out;                 // (N,Cout,H,W) or null
     float* x;                         // (N,Cout,H,W) updated in place when `step` != null
     const pd_step_coeffs_t* step;     // host pointer (copied by value into the launch) or null
+    // image range [img_begin, img_begin + img_count) of `act` handled by this launch (img_count 0: all N); model_out / x /
+    // cfg are indexed by (image - img_begin)
+    int img_begin, img_count;
+    CfgEpi cfg;
 };
 int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s);
 
 int launch_upsample2x(int dt, const void* x, int N, int H, int W, int C, void* out, cudaStream_t s);
 // conv_in on the tensor cores: gather the 3x3 neighbourhood of the NCHW fp32 sample into (N,H,W,64) 16-bit rows
 // (k = tap*Cin + ci, zero padded), which a 1x1 tcgen05 GEMM with the (Cout, 64) re-laid-out weights consumes
-int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void* out, cudaStream_t s);
+int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void* out, cudaStream_t s, int n_src = 0);
 
 // ---- attention core: softmax(q k^T / sqrt(d)) v on packed qkv (N,S,3C) ------------------------------------------
 int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
@@ -91,7 +108,8 @@ int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, i
 // bf16 / fp16 tensor-core path.  qfold = the factor already folded into q by the caller: 1 for raw q, PD_ATTN_QFOLD when
 // the q rows of the fused qkv weight were pre-multiplied at finalize (scores then leave the MMA in log2 units)
 constexpr float PD_ATTN_QFOLD = 0.35355339059327373f * 1.4426950408889634f;   // log2(e) / sqrt(8)
-// force_variant: 0 = PHENDIFF_B200_ATTN_KERNEL / default, 2 = chunked warp-level, 3 = head-resident warp-level, 4 = tcgen05
+// force_variant: 0 = PHENDIFF_B200_ATTN_KERNEL / default, 2 = chunked warp-level, 3 = head-resident warp-level, 4 / 5 / 6 = tcgen05
+// kernels tc / tc2 / tc3
 int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, float qfold, void* out, cudaStream_t s,
                          int force_variant = 0);
 // tcgen05 / TMEM kernel (pd_attn_tc.cu): q is multiplied by qmul while staging; flags[(n, head, 128-query tile, warp)] = 1 where
@@ -103,6 +121,11 @@ int launch_attention_tc(int dt, const void* qkv, int N, int S, int C, float qmul
 // experimental variant (pd_attn_tc2.cu): same contract
 int launch_attention_tc2(int dt, const void* qkv, int N, int S, int C, float qmul, void* out, uint8_t* flags, int poly_pairs,
                         cudaStream_t s);
+
+// third tcgen05 design (pd_attn_tc3.cu): persistent, TMA-staged, three independent softmax warpgroup streams.  q must carry the
+// finalize-time fold (scores in log2 units); same flags contract as the other two
+bool attention_tc3_supported(int S, int C);
+int launch_attention_tc3(int dt, const void* qkv, int N, int S, int C, void* out, uint8_t* flags, int poly_pairs, cudaStream_t s);
 
 // ---- scheduler / pipeline elementwise ---------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -180,6 +203,8 @@ struct ConvTcLaunch {                 // per-launch values of a TC_MODE_DDIM pla
     float* model_out;                 // (N,Cout,Ho,Wo) fp32 or null
     float* x_t;                       // (N,Cout,Ho,Wo) fp32 updated in place, or null
     const pd_step_coeffs_t* step;     // host pointer, copied by value; required when x_t != null
+    int img_begin = 0, img_count = 0; // image range of the plan's N handled by this launch (0: all); outputs indexed from img_begin
+    CfgEpi cfg = {nullptr, nullptr, 0};
 };
 bool conv_tc_supported(const ConvTcDesc& d, std::string* why);      // per-tap kernel (v1)
 bool conv_halo_supported(const ConvTcDesc& d, std::string* why);    // halo kernel (v2)

@@ -22,7 +22,11 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
     // dedupe: block b computes the row of class b at the (single) timestep; else the row of image b
     const float t = a.timesteps ? a.timesteps[a.dedupe ? 0 : b] : a.t_scalar;
     if (b == 0 && blockIdx.y == 0) {
-        for (int i = tid; i < a.B; i += blockDim.x) a.row_idx[i] = a.dedupe ? (int32_t)a.labels[i] : i;
+        for (int i = tid; i < a.B; i += blockDim.x) {
+            int32_t r = i;
+            if (a.dedupe) r = (a.cfg_pairs > 0 && i >= a.cfg_pairs) ? a.ncls : (int32_t)a.labels[i];   // row ncls: unconditional
+            a.row_idx[i] = r;
+        }
     }
     const int half = a.C0 / 2;
     for (int k = tid; k < half; k += blockDim.x) {
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
         acc = warp_sum(acc);
         if (lane == 0) {
             float e = acc + a.b2[j];
-            if (a.dedupe) e += a.class_table[(size_t)b * a.D + j];
+            if (a.dedupe) e += (b < a.ncls) ? a.class_table[(size_t)b * a.D + j] : 0.f;   // row ncls = class_emb of zeros (guidance pass)
             else if (a.class_emb) e += a.class_emb[(size_t)b * a.D + j];
             else if (a.labels) e += a.class_table[(size_t)a.labels[b] * a.D + j];
             a.emb_act[(size_t)b * a.D + j] = silu<true>(e);
@@ -77,6 +81,7 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
     }
     PD_REQUIRE(a.row_idx != nullptr, "embed: row index buffer missing");
     PD_REQUIRE(!a.dedupe || (a.labels && a.class_table && !a.class_emb && !a.timesteps && a.ncls > 0), "embed: dedupe needs labels and one scalar timestep");
+    PD_REQUIRE(a.cfg_pairs == 0 || (a.dedupe && 2 * a.cfg_pairs == a.B), "embed: the guidance pass needs labels, one scalar timestep and 2P images");
     size_t smem = (size_t)(a.C0 + a.D) * sizeof(float);
     embed_kernel<<<dim3(embed_rows(a), (a.D + 63) / 64), 256, smem, s>>>(a, g_freqs);
     PD_CHECK_CUDA(cudaGetLastError());
@@ -125,26 +130,41 @@ __global__ void __launch_bounds__(256) gn_chunk_stats_kernel(const T* __restrict
     const int row_begin = blockIdx.x * rows_per_block;
     const int row_end = min(row_begin + rows_per_block, HW);
     const T* src = x + (size_t)n * HW * C + cv * 8;
-    float s[8], q[8];
+    // shifted sums: the first row this thread sees is its pivot, so the fp32 partials hold deviations (size ~ std), not values
+    // (size ~ mean); they are turned back into plain sum / sum of squares in fp64: sum v = n p + s, sum v^2 = q + 2 p s + n p^2
+    float s[8], q[8], pv[8];
+    int cnt = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; pv[i] = 0.f; }
     for (int r = row_begin + r0; r < row_end; r += rstep) {
         float v[8];
         load8(src + (size_t)r * C, v);
+        if (cnt == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+            for (int i = 0; i < 8; ++i) pv[i] = v[i];
+        }
+        ++cnt;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - pv[i]; s[i] += d; q[i] += d * d; }
     }
-    // fp32 partials cover <= 16 rows per thread; everything beyond that is accumulated in fp64
+    if (cnt == 0) return;
+    double S[8], Q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double pd_ = (double)pv[i], nn = (double)cnt;
+        S[i] = nn * pd_ + (double)s[i];
+        Q[i] = (double)q[i] + 2.0 * pd_ * (double)s[i] + nn * pd_ * pd_;
+    }
     double* dst = stats + ((size_t)n * (C / cw) + (cv * 8) / cw) * 2;
     if (cw == 4) {
-        atomicAdd(dst + 0, (double)s[0] + s[1] + s[2] + s[3]); atomicAdd(dst + 1, (double)q[0] + q[1] + q[2] + q[3]);
-        atomicAdd(dst + 2, (double)s[4] + s[5] + s[6] + s[7]); atomicAdd(dst + 3, (double)q[4] + q[5] + q[6] + q[7]);
+        atomicAdd(dst + 0, (S[0] + S[1]) + (S[2] + S[3])); atomicAdd(dst + 1, (Q[0] + Q[1]) + (Q[2] + Q[3]));
+        atomicAdd(dst + 2, (S[4] + S[5]) + (S[6] + S[7])); atomicAdd(dst + 3, (Q[4] + Q[5]) + (Q[6] + Q[7]));
     } else if (cw == 2) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, (double)s[2 * j] + s[2 * j + 1]); atomicAdd(dst + 2 * j + 1, (double)q[2 * j] + q[2 * j + 1]); }
+        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, S[2 * j] + S[2 * j + 1]); atomicAdd(dst + 2 * j + 1, Q[2 * j] + Q[2 * j + 1]); }
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, (double)s[j]); atomicAdd(dst + 2 * j + 1, (double)q[j]); }
+        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, S[j]); atomicAdd(dst + 2 * j + 1, Q[j]); }
     }
 }
 
@@ -431,7 +451,7 @@ int launch_conv_simt(int dt, const ConvArgs& a, cudaStream_t s) {
 template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, int N, int Cin, int H, int W,
-                                                       int Cout, T* __restrict__ out) {
+                                                       int Cout, T* __restrict__ out, int n_src) {
     extern __shared__ float sw[];  // (9*Cin, Cout) + bias
     const int K = 9 * Cin;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
@@ -445,13 +465,14 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     const int n = p / HW;
     const int hw = p - (size_t)n * HW;
     const int h = hw / W, ww = hw - h * W;
+    const int ns = n % n_src;   // source image (the guidance pass reads every sample twice)
     // gather the 9*Cin input values once (Cin <= 4 supported in registers)
     float in[36];
     for (int tap = 0; tap < 9; ++tap) {
         int ih = h + tap / 3 - 1, iw = ww + tap % 3 - 1;
         bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
         for (int ci = 0; ci < Cin; ++ci)
-            in[tap * Cin + ci] = ok ? x[((size_t)n * Cin + ci) * HW + (size_t)ih * W + iw] : 0.f;
+            in[tap * Cin + ci] = ok ? x[((size_t)ns * Cin + ci) * HW + (size_t)ih * W + iw] : 0.f;
     }
     for (int cg = warp; cg * 16 < Cout; cg += nwarp) {
         float acc[16];
@@ -474,7 +495,8 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 }
 
 int launch_conv_in(int dt, const float* x, const float* w, const float* bias, int N, int Cin, int H, int W, int Cout,
-                   void* out, cudaStream_t s) {
+                   void* out, cudaStream_t s, int n_src) {
+    if (n_src <= 0) n_src = N;
     PD_REQUIRE(Cin <= 4 && Cout % 16 == 0, "conv_in supports in_channels <= 4 and block_out_channels[0] % 16 == 0");
     size_t smem = ((size_t)9 * Cin * Cout + Cout) * sizeof(float);
     PD_REQUIRE(smem <= 200 * 1024, "conv_in weights do not fit shared memory");
@@ -482,7 +504,7 @@ int launch_conv_in(int dt, const float* x, const float* w, const float* bias, in
     int grid = (int)((total + 31) / 32);
     PD_DISPATCH_DT(dt, T, {
         PD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_in_kernel<T><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (T*)out);
+        conv_in_kernel<T><<<grid, 256, smem, s>>>(x, w, bias, N, Cin, H, W, Cout, (T*)out, n_src);
     });
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -548,12 +570,13 @@ __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_co
             float4 w4 = *reinterpret_cast<const float4*>(a.w + ((size_t)tap * a.Cin + lane * CPL + j) * 4);
             wr[tap][j][0] = w4.x; wr[tap][j][1] = w4.y; wr[tap][j][2] = w4.z;
         }
-    const size_t HW = (size_t)a.H * a.W, total = (size_t)a.N * HW;
-    const size_t nruns = (total + 31) / 32;
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t first = (size_t)a.img_begin * HW, total = first + (size_t)(a.img_count > 0 ? a.img_count : a.N) * HW;
+    const size_t nruns = (total - first + 31) / 32;
     for (size_t run = gwarp; run < nruns; run += nwarps) {
         float keep[3] = {0.f, 0.f, 0.f};
         for (int i = 0; i < 32; ++i) {
-            const size_t p = run * 32 + i;
+            const size_t p = first + run * 32 + i;
             if (p >= total) break;
             const int n = p / HW;
             const int hw = p - (size_t)n * HW;
@@ -582,15 +605,20 @@ __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_co
                 if (lane == i) keep[co] = v;
             }
         }
-        const size_t p = run * 32 + lane;
+        const size_t p = first + run * 32 + lane;
         if (p < total) {
             const int n = p / HW;
             const size_t hw = p - (size_t)n * HW;
+            const int no = n - a.img_begin;   // outputs are indexed from the first image of the launch
 #pragma unroll
             for (int co = 0; co < 3; ++co) {
                 if (co >= a.Cout) break;
-                const float m = keep[co] + a.bias[co];
-                const size_t idx = ((size_t)n * a.Cout + co) * HW + hw;
+                float m = keep[co] + a.bias[co];
+                const size_t idx = ((size_t)no * a.Cout + co) * HW + hw;
+                if (a.cfg.uncond) {
+                    const float u = a.cfg.uncond[idx];
+                    m = (a.cfg.eqn == 0 ? u : m) + a.cfg.w[no] * (m - u);
+                }
                 if (a.model_out) a.model_out[idx] = m;
                 if (has_step) a.x[idx] = ddim_update(st, a.x[idx], m, 0.f, nullptr);
             }
@@ -606,7 +634,8 @@ int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s) {
     pd_step_coeffs_t st{};
     int has = 0;
     if (a.step) { st = *a.step; has = 1; PD_REQUIRE(st.sigma == 0.f, "fused conv_out update requires eta == 0"); }
-    size_t total = (size_t)a.N * a.H * a.W;
+    PD_REQUIRE(a.img_begin >= 0 && a.img_begin + a.img_count <= a.N, "conv_out image range outside the tensor");
+    size_t total = (size_t)(a.img_count > 0 ? a.img_count : a.N) * a.H * a.W;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 8);
     if (grid < 1) grid = 1;
     PD_DISPATCH_DT(dt, T, {
@@ -654,12 +683,12 @@ int launch_upsample2x(int dt, const void* x, int N, int H, int W, int C, void* o
 // conv_in on the tensor cores: im2col of the NCHW fp32 sample into (N,H,W,64) 16-bit rows, k = tap*Cin + ci (zero padded)
 // =====================================================================================================================
 template <typename T, int CIN>
-__global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict__ x, int N, int H, int W, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict__ x, int N, int H, int W, T* __restrict__ out, int n_src) {
     const size_t HW = (size_t)H * W, total = (size_t)N * HW;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total) return;
-    const int n = p / HW;
-    const int hw = p - (size_t)n * HW;
+    const int n = (int)(p / HW) % n_src;   // source image (the guidance pass reads every sample twice)
+    const int hw = p % HW;
     const int h = hw / W, w = hw - h * W;
     float v[64];
 #pragma unroll
@@ -677,16 +706,17 @@ __global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict_
     for (int j = 0; j < 8; ++j) store8(o + j * 8, v + j * 8);
 }
 
-int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void* out, cudaStream_t s) {
+int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void* out, cudaStream_t s, int n_src) {
     PD_REQUIRE(Cin >= 1 && Cin <= 4, "im2col conv_in supports 1..4 input channels");
+    if (n_src <= 0) n_src = N;
     const size_t total = (size_t)N * H * W;
     const int grid = (int)((total + 255) / 256);
     PD_DISPATCH_HALF(dt, T, {
         switch (Cin) {
-            case 1: im2col_in_kernel<T, 1><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
-            case 2: im2col_in_kernel<T, 2><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
-            case 3: im2col_in_kernel<T, 3><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
-            default: im2col_in_kernel<T, 4><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out); break;
+            case 1: im2col_in_kernel<T, 1><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out, n_src); break;
+            case 2: im2col_in_kernel<T, 2><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out, n_src); break;
+            case 3: im2col_in_kernel<T, 3><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out, n_src); break;
+            default: im2col_in_kernel<T, 4><<<grid, 256, 0, s>>>(x, N, H, W, (T*)out, n_src); break;
         }
     });
     PD_CHECK_CUDA(cudaGetLastError());

@@ -31,6 +31,8 @@ struct TcEpi {
     pd_step_coeffs_t step;
     int c_valid;                // real output channels (<= 16)
     int plane;                  // Ho*Wo
+    int img_off;                // first image of this launch: model_out / x_t / cfg are indexed by (img - img_off)
+    CfgEpi cfg;                 // classifier-free guidance combine ahead of the scheduler update, or uncond == null
 };
 
 // K-major SWIZZLE_128B operand descriptor (PTX "matrix descriptor"): start address >> 4, LBO unused for swizzled
@@ -173,17 +175,26 @@ __device__ __forceinline__ void tc_epilogue_ddim(const TcEpi& e, const uint32_t 
     // all x_t loads are issued before the first store: the compiler cannot prove that a store to x_t[.., c, ..] does not feed
     // the load of channel c + 1, and would otherwise serialise three global round trips per pixel (ncu r1r: conv_out spent
     // 9 k cycles per tile at 6 % tensor activity, long-scoreboard bound)
-    float xv[16];
-    const size_t base = (size_t)img * e.c_valid * e.plane + hw;
+    float xv[16], uv[16];
+    const size_t base = (size_t)(img - e.img_off) * e.c_valid * e.plane + hw;
     if (e.x_t) {
 #pragma unroll
         for (int c = 0; c < 16; ++c)
             if (c < e.c_valid) xv[c] = e.x_t[base + (size_t)c * e.plane];
     }
+    const bool guided = e.cfg.uncond != nullptr;
+    float gw = 0.f;
+    if (guided) {
+        gw = __ldg(e.cfg.w + (img - e.img_off));
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c < e.c_valid) uv[c] = e.cfg.uncond[base + (size_t)c * e.plane];
+    }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
         if (c < e.c_valid) {
-            const float m = __uint_as_float(r[c]) + (e.bias ? __ldg(e.bias + c) : 0.f);
+            float m = __uint_as_float(r[c]) + (e.bias ? __ldg(e.bias + c) : 0.f);
+            if (guided) m = (e.cfg.eqn == 0 ? uv[c] : m) + gw * (m - uv[c]);
             const size_t idx = base + (size_t)c * e.plane;
             if (e.model_out) e.model_out[idx] = m;
             if (e.x_t) e.x_t[idx] = ddim_update(e.step, xv[c], m, 0.f, nullptr);
@@ -193,7 +204,7 @@ __device__ __forceinline__ void tc_epilogue_ddim(const TcEpi& e, const uint32_t 
 
 // ---- host-side helpers shared by both kernels ---------------------------------------------------------------------
 int tc_encode_map(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+                  const uint32_t* box, bool swizzle128 = true);
 int tc_num_sms();
 
 enum { TC_KIND_TAP = 0, TC_KIND_HALO = 1 };

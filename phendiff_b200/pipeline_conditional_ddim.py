@@ -190,8 +190,18 @@ class ConditionalDDIMPipeline:
         self.unet.check_weights()   # an out-of-band `param.data.copy_` (EMA copy_to) must not sample from stale weights
         fused_ok = (self.fused_route_ok() and not do_classifier_free_guidance and eta == 0.0 and class_emb is None
                     and len(timesteps) > 0)
+        fused_cfg_ok = (self.fused_route_ok() and do_classifier_free_guidance and eta == 0.0 and class_emb is None
+                        and class_labels is not None and len(timesteps) > 0)
         if fused_ok:
             image = self._fused_generate(image, class_labels, timesteps, use_clipped_model_output)
+        elif fused_cfg_ok:
+            # one pass over 2B images per step (conditional + unconditional copies), the guidance combine and
+            # the scheduler update in the conv_out epilogue (`pd_cfg_transfer`)
+            if isinstance(w, torch.Tensor):
+                w_dev = w.to(device=device, dtype=torch.float32).contiguous()
+            else:
+                w_dev = torch.full((batch_size,), float(w), dtype=torch.float32, device=device)
+            image = self._fused_guided_generate(image, class_labels, w_dev, guidance_eqn, timesteps, use_clipped_model_output)
         else:
             if do_classifier_free_guidance:
                 if isinstance(w, torch.Tensor):
@@ -248,6 +258,19 @@ class ConditionalDDIMPipeline:
             tgt = tgt_labels.to(device=dev, dtype=torch.int64).contiguous() if tgt_labels is not None else None
             _lib.check(_lib.lib().pd_ddib_transfer(h, _lib.ptr(x), _lib.ptr(src), _lib.ptr(tgt), arr, n_inv, n_gen,
                                                    _lib.current_stream()))
+        return x
+
+    def _fused_guided_generate(self, image, class_labels, w_dev, guidance_eqn, timesteps, use_clipped_model_output):
+        x = image.to(torch.float32).contiguous().clone()
+        steps = [self.scheduler.step_coeffs(t, 0.0, use_clipped_model_output) for t in timesteps]
+        B, _, H, W = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            h = self.unet._ensure_plan(B, H, W, guided=True)
+            arr = (_lib.StepCoeffs * len(steps))(*steps)
+            labels = class_labels.to(device=dev, dtype=torch.int64).contiguous()
+            _lib.check(_lib.lib().pd_cfg_transfer(h, _lib.ptr(x), _lib.ptr(labels), _lib.ptr(w_dev),
+                                                  0 if guidance_eqn == "imagen" else 1, arr, len(steps), _lib.current_stream()))
         return x
 
     def _fused_generate(self, image, class_labels, timesteps, use_clipped_model_output):

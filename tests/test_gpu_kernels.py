@@ -446,12 +446,13 @@ def _attention_case(build_lib, mode, qkv, n, s, c):
     ref = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(8), -1) @ v
     ref = ref.transpose(1, 2).reshape(n, s, c).float()
     out = torch.empty(n, s, c, dtype=dt, device="cuda")
-    use = {"simt": 0, "mmaraw": 1, "mma": 2, "mmav2": 3, "mmav3": 4, "mmatc": 5, "mmatc2": 6}[kind]
+    use = {"simt": 0, "mmaraw": 1, "mma": 2, "mmav2": 3, "mmav3": 4, "mmatc": 5, "mmatc2": 6, "mmatc3": 7}[kind]
     build_lib.check(L.pd_test_attention(use, bf, n, s, c, 8, _p(qkv.to(dt).cuda()), _p(out), None))
     return out.float().cpu(), ref, bf
 
 
-@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "mma_bf16", "mma_fp16", "mmaraw_fp16", "mmav2_fp16", "mmav3_bf16", "mmav3_fp16", "mmatc_fp16", "mmatc_bf16"])
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "mma_bf16", "mma_fp16", "mmaraw_fp16", "mmav2_fp16", "mmav3_bf16", "mmav3_fp16", "mmatc_fp16", "mmatc_bf16",
+                                  "mmatc3_fp16", "mmatc3_bf16"])
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 256, 128), (1, 1024, 64), (3, 1024, 512)])
 def test_attention(build_lib, mode, shape):
     n, s, c = shape
@@ -462,7 +463,7 @@ def test_attention(build_lib, mode, shape):
     tol = {0: 1e-4, 1: 3e-2, 2: 4e-3}[bf]
     if mode.startswith("mmaraw"):
         tol = 1.2e-2   # q * log2(e)/sqrt(8) is rounded to fp16 a second time inside the kernel
-    if mode in ("mma_fp16", "mmav3_fp16", "mmatc_fp16"):
+    if mode in ("mma_fp16", "mmav3_fp16", "mmatc_fp16", "mmatc3_fp16"):
         # This input is a stress case: scores have a standard deviation of 3.2 (log2 units), so a row's maximum over 1024 keys
         # sits ~5 above the maximum of its first 64 keys.  The head-resident kernels fix the row max after key block 0; the
         # first dominant key met later is exponentiated at x ~ +5, where the packed-half polynomial's input (x rounded to
@@ -472,7 +473,7 @@ def test_attention(build_lib, mode, shape):
     assert err <= tol, f"attention {mode} {shape}: {err:.3e}"
 
 
-@pytest.mark.parametrize("mode", ["mma_bf16", "mma_fp16", "mmav2_fp16", "mmatc_fp16"])
+@pytest.mark.parametrize("mode", ["mma_bf16", "mma_fp16", "mmav2_fp16", "mmatc_fp16", "mmatc3_fp16", "mmatc3_bf16"])
 def test_attention_model_scale(build_lib, mode):
     """Scores at the scale the UNet produces (|q.k| / sqrt(8) of order 1): every kernel must sit at the rounding of P."""
     n, s, c = 2, 1024, 128
@@ -484,7 +485,7 @@ def test_attention_model_scale(build_lib, mode):
     assert err <= tol, f"attention {mode} model scale: {err:.3e}"
 
 
-@pytest.mark.parametrize("mode", ["mma_bf16", "mma_fp16", "mmatc_fp16", "mmatc_bf16"])
+@pytest.mark.parametrize("mode", ["mma_bf16", "mma_fp16", "mmatc_fp16", "mmatc_bf16", "mmatc3_fp16", "mmatc3_bf16"])
 @pytest.mark.parametrize("s", [256, 1024, 4096])
 def test_attention_stale_max_fallback(build_lib, mode, s):
     """The head-resident kernel fixes each row's max after key block 0.  A late key whose score exceeds that max by more

@@ -35,7 +35,7 @@ def test_san_conv_halo_upsample_and_stats(build_lib):
     assert (r["got"] - r["ref"]).abs().max().item() <= 2e-3 * max(1.0, r["ref"].abs().max().item())
 
 
-@pytest.mark.parametrize("mode", ["mma_fp16", "mmav3_bf16", "mmatc_fp16", "simt_fp32"])
+@pytest.mark.parametrize("mode", ["mma_fp16", "mmav3_bf16", "mmatc_fp16", "mmatc3_fp16", "simt_fp32"])
 def test_san_attention(build_lib, mode):
     n, s, c = 1, 256, 64
     g = torch.Generator().manual_seed(5)

@@ -234,3 +234,29 @@ def test_classifier_free_guidance_forward_start_dropin(build_lib):
                generator=torch.Generator().manual_seed(9), output_type="numpy").images
     err = float(abs(ref - got).max())
     assert err <= 1e-3, f"forward-noised CFG route vs oracle: {err:.3e}"
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16", 2e-2)])
+def test_fused_guided_route_matches_per_op_route(build_lib, precision, tol):
+    """`pd_cfg_transfer` (one pass over 2B images per step, guidance combine + scheduler update in the
+    conv_out epilogue) against the per-op route (two forwards of B + pd_cfg_combine + pd_ddim_step), same weights and inputs.
+    Batch 5 with a micro-batch cap of 8 plans passes of 3 sample pairs with a ragged, padded last pass of 2.
+    fp32 validation mode pins the LOGIC (identical arithmetic, 6e-6 measured); in fp16 the two routes differ by rounding noise
+    only (GroupNorm statistics are summed with atomics), which guidance amplifies by (1 + 2 w) per step: 7e-3 measured at w = 3."""
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler
+
+    _, model = make_pair("super_small", 32, precision, max_microbatch=8)
+    x, labels = synth_images(5, 32)
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(_sched("3k_steps_clipping_rescaling")))
+    for eqn, w in (("imagen", 2.5), ("CFG", torch.tensor([0.5, 1.0, 1.5, 2.0, 3.0]))):
+        outs = []
+        for fused in (True, False):
+            pipe.fused = fused
+            outs.append(pipe(labels, w=w, num_inference_steps=6, start_image=x.cuda(), add_forward_noise_to_image=False,
+                             frac_diffusion_skipped=0.5, guidance_eqn=eqn, output_type="numpy").images)
+            if fused:
+                info = model.plan_info()
+                assert info["microbatch"] == 6, info      # 3 pairs per pass
+        err = float(abs(outs[0] - outs[1]).max())
+        print(f"[guided {precision} {eqn}] fused vs per-op max abs diff {err:.3e}")
+        assert err <= tol, f"{eqn}: {err:.3e}"
