@@ -416,7 +416,7 @@ static int launch_head(const void* qkv, int N, int S, int C, float qmul, void* o
 int attention_mma_launches(int S) {
     const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
     const bool tc = e && e[0] == 't' && e[1] == 'c';
-    if (tc && e[2] == '3') return (S % 128 == 0 && (size_t)S * 32 <= 200 * 1024 && attention_tc3_supported(S, 8)) ? 2 : 1;
+    if (!e || (tc && e[2] == '3')) return (S % 128 == 0 && (size_t)S * 32 <= 200 * 1024 && attention_tc3_supported(S, 8)) ? 2 : 1;
     return (tc && S % 128 == 0 && (size_t)S * 32 <= 200 * 1024 && attention_tc_smem_bytes(S) <= 110 * 1024) ? 2 : 1;
 }
 
@@ -427,12 +427,11 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
     PD_REQUIRE(S % 64 == 0 && C % 8 == 0, "attention_mma needs S % 64 == 0");
     static int variant = -1, polyv = -1;
     if (variant < 0) {
-        // "v3" (default): warp-level head-resident kernel; "tc": tcgen05 / TMEM kernel + repair pass (functional, 1.3x slower
-        // than v3 in round 1: its two softmax warpgroups starve on three S buffers, profiles/r1o_attention_tc.md);
-        // "v2": chunked warp-level kernel (any S)
         const char* e = getenv("PHENDIFF_B200_ATTN_KERNEL");
-        // "tc2": experimental second tcgen05 kernel (pd_attn_tc2.cu: softmax warpgroups on alternate tiles), unmeasured at the end of round 1
-        variant = (e && e[0] == 'v' && e[1] == '2') ? 2 : ((e && e[0] == 't' && e[1] == 'c') ? (e[2] == '3' ? 6 : (e[2] == '2' ? 5 : 4)) : 3);
+        // default "tc3" (pd_attn_tc3.cu: persistent tcgen05 / TMEM / TMA kernel, three independent softmax streams; shapes it does
+        // not take — S < 384, S not a multiple of 128, raw q — fall through to "v3"); "v3": warp-level head-resident mma.sync kernel;
+        // "tc" / "tc2": the first two tcgen05 kernels; "v2": chunked warp-level kernel (any S)
+        variant = !e ? 6 : ((e[0] == 'v' && e[1] == '2') ? 2 : ((e[0] == 't' && e[1] == 'c') ? (e[2] == '3' ? 6 : (e[2] == '2' ? 5 : 4)) : 3));
         const char* pe = getenv("PHENDIFF_B200_ATTN_POLYPAIRS");   // score pairs per 16 (v3) / per 8 (tc) on the FMA/ALU pipes
         polyv = pe ? atoi(pe) : -1;
     }
@@ -453,7 +452,7 @@ int launch_attention_mma(int dt, const void* qkv, int N, int S, int C, int d, fl
             PD_CHECK_CUDA(cudaMalloc(&flags, need));
             flags_cap = need;
         }
-        const int tc_pp = polyv < 0 ? (dt == DT_F16 ? 4 : 2) : polyv;
+        const int tc_pp = polyv < 0 ? (dt == DT_F16 ? 4 : 2) : polyv;   // fp16: half of the exponent pairs on the packed-half polynomial
         int rc = tc3 ? launch_attention_tc3(dt, qkv, N, S, C, out, flags, tc_pp, s)
                  : (var == 5 ? launch_attention_tc2(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s)
                              : launch_attention_tc(dt, qkv, N, S, C, AH_SL / qfold, out, flags, tc_pp, s));

@@ -38,7 +38,7 @@
 namespace pd {
 
 constexpr int A3_NWG = 3;                          // softmax warpgroups = independent query-tile streams
-constexpr int A3_THREADS = 128 + 128 * A3_NWG;     // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
+__host__ __device__ constexpr int a3_threads(int sp) { return 128 + 128 * A3_NWG * sp; }   // warps 0-3: TMA producer + one MMA issuer per stream
 constexpr int A3_TMEM_COLS = 512;
 constexpr int A3_WG_COLS = 160;                    // S0 [0,64) | S1 [64,128) | O0 [128,144) | O1 [144,160)
 constexpr int A3_KT = 64;                          // keys per S tile
@@ -49,6 +49,7 @@ struct A3Params {
     void* out;
     uint8_t* flags;
     int swap_k, swap_mn;   // probe knobs: exchange the LBO / SBO roles of the K-major / MN-major descriptors
+    int nws;               // active streams (diagnosis knob PHENDIFF_B200_ATTN_TC3_STREAMS; default A3_NWG)
 };
 
 __device__ __forceinline__ void a3_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -76,19 +77,51 @@ __device__ __forceinline__ void a3_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// spinning — a spinning softmax warp takes issue slots from the two other streams' warps on its scheduler (the r4d capture had
+// 2.5 try_wait executions per wait and the spin loop among the top-sampled instructions)
+__device__ __forceinline__ bool a3_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 // bounded wait (a protocol bug must trap, not hang the box); the 64-bit clock is read once per 64 polls
 __device__ __forceinline__ void a3_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (a3_try_wait_hint(bar, parity, 2000u)) return;
     const long long t0 = clock64();
     for (;;) {
 #pragma unroll 1
         for (int k = 0; k < 64; ++k)
-            if (mbar_try_wait(bar, parity)) return;
+            if (a3_try_wait_hint(bar, parity, 2000u)) return;
         if (clock64() - t0 > 4000000000LL) {
             printf("phendiff_b200: attention_tc3 mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
+}
+
+// the same for a whole warp whose lanes all need the barrier: ONE lane polls (a 32-lane SYNCS.PHASECHK costs ~270 cycles even on
+// a completed barrier, r4h trace), the others park at the convergence barrier
+__device__ __forceinline__ void a3_wait_warp(uint64_t* bar, uint32_t parity) {
+    if (elect_one()) {
+        // non-blocking probes first: try_wait is a potentially-blocking instruction (r4h trace: ~300 cycles on an already completed
+        // phase when issued right behind a tcgen05.commit)
+        bool ok = mbar_test(bar, parity);
+#pragma unroll 1
+        for (int k = 0; k < 4096 && !ok; ++k) ok = mbar_test(bar, parity);
+        if (!ok) a3_wait(bar, parity);
+    }
+    __syncwarp();
+}
+
+// bare spin on a 32-bit shared barrier address (issuer warps only: the softmax warps keep the bounded waits, so a protocol bug
+// still traps the grid instead of hanging it)
+__device__ __forceinline__ void a3_spin(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tA3_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra A3_DONE;\n\tbra A3_WAIT;\n\tA3_DONE:\n\t}\n"
+        ::"r"(bar), "r"(parity) : "memory");
 }
 
 // no-swizzle ("interleave") shared-memory matrix descriptor: start >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 | version 1
@@ -112,13 +145,18 @@ __device__ __forceinline__ void a3_exp32(const uint32_t (&s)[32], float sub, uin
     for (int r = 0; r < 16; ++r) {
         float x0 = __uint_as_float(s[2 * r]), x1 = __uint_as_float(s[2 * r + 1]);
         if (SUB) { x0 -= sub; x1 -= sub; }
+        if (PP == 9) { p[r] = pack2<T>(fmaf(fabsf(x0), 1e-4f, 1e-3f), fmaf(fabsf(x1), 1e-4f, 1e-3f)); continue; }   // diagnosis only (PHENDIFF_B200_ATTN_POLYPAIRS=9): no exponentials, wrong results
         const bool poly = PP > 0 && ((r * PP) & 7) < PP;
         p[r] = poly ? ex2_pair_poly<T>(x0, x1) : pack2<T>(ex2(x0), ex2(x1));
     }
 }
 
-template <typename T, int PP>
-__global__ void __launch_bounds__(A3_THREADS, 1) attention_tc3_kernel(const __grid_constant__ A3Params p) {
+// SP = softmax warps per TMEM lane quarter of a stream: 1 = a thread owns a query row and all 64 columns of a tile; 2 = two
+// threads (in two warpgroups) own a row and 32 columns each — twice the warps per scheduler (6 instead of 3) for latency cover,
+// half the registers per thread, one extra exchange of the row max per query tile.
+template <typename T, int PP, int SP>
+__global__ void __launch_bounds__(a3_threads(SP), 1) attention_tc3_kernel(const __grid_constant__ A3Params p) {
+    constexpr int A3_THREADS = a3_threads(SP);
     extern __shared__ uint8_t a3_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a3_smem_raw) + 127) & ~(uintptr_t)127);
     const int S = p.S, C = p.C;
@@ -137,16 +175,24 @@ __global__ void __launch_bounds__(A3_THREADS, 1) attention_tc3_kernel(const __gr
     uint64_t* oread = bars + 22;               // [3][2] softmax -> MMA: O slot read
     uint64_t* qmready = bars + 28;             // [3]    softmax -> MMA: -m written into the Q augmentation
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+    float* sm_xmax = reinterpret_cast<float*>(bars + 32);   // [3 streams][2 halves][128 rows]: row max exchange (SP == 2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nqt = S >> 7, ntl = S / A3_KT;
+#ifdef A3_TRACE
+    __shared__ long long tr_soft[40][5];    // stream 0, warp 4 lane 0: after sfull wait / after loads / after exps / after st wait / after arrive
+    __shared__ long long tr_iss[40][4];     // issuer of stream 0: after pready wait / after PV issue / after S issue
+    __shared__ long long tr_w[40][4][2];    // stream 0, warps 4..7 lane 0: sfull wake / pready arrive
+    __shared__ long long tr_mma[40][6];     // issuer of stream 0: clock after each PV MMA, after the commits
+#endif
     const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_T = my_items * nqt;        // query tiles of this CTA, in order (item-major)
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&qkv_full[i], 1); mbar_init(&qkv_empty[i], (uint32_t)nqt); }
-        for (int i = 0; i < A3_NWG * 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pready[i], 128); mbar_init(&ofull[i], 1); mbar_init(&oread[i], 128); }
-        for (int i = 0; i < A3_NWG; ++i) mbar_init(&qmready[i], 128);
+        for (int i = 0; i < A3_NWG * 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pready[i], 4 * SP); mbar_init(&ofull[i], 1); mbar_init(&oread[i], 4); }
+        for (int i = 0; i < A3_NWG; ++i) mbar_init(&qmready[i], 4);   // ONE arrival per warp (after __syncwarp): 128 per-thread arrivals on
+                                                                       // one barrier serialise in the SYNCS unit (~350 cycles per step, r4 trace)
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) prefetch_tmap(&p.tm);
@@ -183,86 +229,147 @@ __global__ void __launch_bounds__(A3_THREADS, 1) attention_tc3_kernel(const __gr
             }
         }
     } else if (warp < 4) {
-        if (lane == 0 && warp - 1 < A3_NWG) {
-            // ===================== MMA issuers: one thread per stream (warps 1, 2, 3) =====================
-            // A single thread multiplexing the three streams was the bottleneck of the first cut (r4b: ~1450 cycles of scalar
-            // work per tile step, 2.8 ms per launch): every stream now has its own issuer with plain blocking waits, and
-            // everything a step needs is a 32-bit add away — descriptors are kept as (high word, low word) with running
-            // updates, tile coordinates advance without divisions.
-            const int g = warp - 1;
+        // ===================== MMA issuers: one WARP per stream (warps 1, 2, 3) =====================
+        // History (cycle traces, profiles/r4_attention_tc3.md): a single thread multiplexing the three streams spent ~1450
+        // cycles of scalar work per tile step (2.8 ms per launch); one issuer THREAD per stream still ~1400 (inside an
+        // `if (lane == 0)` region ptxas treats every tcgen05 operand as divergent and wraps each UTCHMMA / UTCBAR in an
+        // ELECT + 4 x R2UR.BROADCAST loop); a whole warp with bounded, watchdogged waits ~1000 (300 SASS instructions and a
+        // dozen branches per step).  This version is written for instruction count: the WHOLE warp runs warp-uniform code
+        // (stream index from a shuffle so that ptxas can prove it), the inner loop over key tiles is unrolled by two so that
+        // buffer indices and barrier addresses are constants, descriptors are running 32-bit words, waits are bare try_wait
+        // spins (the softmax warps keep the bounded waits: a protocol bug still traps instead of hanging).
+        const int g = __shfl_sync(0xffffffffu, warp, 0) - 1;
+        const int nTg = (g >= 0 && g < p.nws && total_T > g) ? (total_T - g + p.nws - 1) / p.nws : 0;
+        if (nTg > 0) {
             constexpr uint32_t idS = a3_idesc<T, A3_KT, false>(), idPV = a3_idesc<T, 16, true>();
             constexpr uint32_t HI_K = (128u >> 4) | (1u << 14);          // K-major operands: SBO = 128 B, descriptor version 1
             const uint32_t sm0 = smem_u32(smem), kaug = smem_u32(sm_kaug), vaug = smem_u32(sm_vaug), zaug = smem_u32(sm_zero);
             const uint32_t qaug = smem_u32(sm_qaug) + (uint32_t)g * 2048u;
             const uint32_t tS = tmem_base + (uint32_t)(g * A3_WG_COLS), tO = tS + 128u;
-            const int nTg = total_T > g ? (total_T - g + A3_NWG - 1) / A3_NWG : 0;
+            const uint32_t bar_sfull = smem_u32(&sfull[g * 2]), bar_pready = smem_u32(&pready[g * 2]);
+            const uint32_t bar_ofull = smem_u32(&ofull[g * 2]), bar_oread = smem_u32(&oread[g * 2]);
+            const uint32_t bar_qm = smem_u32(&qmready[g]), bar_full = smem_u32(qkv_full), bar_empty = smem_u32(qkv_empty);
             auto lo_k = [](uint32_t start, uint32_t aug) { return ((start & 0x3FFFFu) >> 4) | ((((aug - start) >> 4) & 0x3FFFu) << 16); };
-            // S-issue cursor: query tile kS = (item itS, tile qtS), key tile jS, step sS.  PV cursor likewise.
-            int itS = 0, qtS = g, kS = 0, jS = 0, sS = 0;
-            while (qtS >= nqt) { qtS -= nqt; ++itS; }
-            int itP = itS, qtP = qtS, kP = 0, jP = 0;
-            int items_seen = 0;                                           // items whose Q/K/V this thread has waited for
-            uint32_t b_lo = 0;                                            // K' descriptor low word of key tile jS
-            auto issue_S = [&]() {
-                if (itS == items_seen) {                                  // first touch of this item by this stream (nqt >= 3: every
-                    a3_wait(&qkv_full[itS & 1], (uint32_t)(itS >> 1) & 1u);   // stream has tiles in every item, in order)
-                    ++items_seen;
+            // one S tile: S[buf] = Q' K'^T (fresh accumulator), then its completion is committed to sfull[buf]
+            auto mma_S = [&](int buf, uint32_t a_lo, uint32_t b_lo) {
+                if (elect_one()) {
+                    umma_f16kind(tS + (uint32_t)(buf * 64), desc64(HI_K, a_lo), desc64(HI_K, b_lo), idS, 0u);
+                    umma_commit_addr(bar_sfull + buf * 8);
                 }
-                if (jS == 1) a3_wait(&qmready[g], (uint32_t)kS & 1u);     // -m of this query tile is in the Q augmentation
-                tc_fence_after();
-                const uint32_t stage0 = sm0 + (uint32_t)(itS & 1) * stage_bytes;
-                const uint32_t qs = stage0 + (uint32_t)qtS * 2048u;
-                if (jS == 0) b_lo = lo_k(stage0 + opb, kaug);
-                const uint32_t a_lo = lo_k(qs, jS == 0 ? zaug : qaug);
-                const int buf = sS & 1;
-                umma_f16kind(tS + (uint32_t)(buf * 64), desc64(HI_K, a_lo), desc64(HI_K, b_lo), idS, 0u);
-                umma_commit(&sfull[g * 2 + buf]);
-                b_lo += 64u - (64u << 16);                                // next key tile: start + 1024 B, LBO - 1024 B
-                ++sS;
-                if (++jS == ntl) { jS = 0; ++kS; qtS += A3_NWG; while (qtS >= nqt) { qtS -= nqt; ++itS; } }
+                __syncwarp();
             };
-            if (nTg > 0) issue_S();                                        // S(0); S(1) follows the first PV (it needs the row max)
-            const int total_steps = nTg * ntl;
-            for (int s = 0; s < total_steps; ++s) {
-                const int buf = s & 1;
-                if (s == 0 && total_steps > 1) issue_S();                  // step 1 goes out as soon as qmready(0) fires
-                a3_wait(&pready[g * 2 + buf], (uint32_t)(s >> 1) & 1u);
-                if (jP == 0 && kP >= 2) a3_wait(&oread[g * 2 + (kP & 1)], (uint32_t)((kP >> 1) - 1) & 1u);
-                tc_fence_after();
-                // PV product: O (+)= P V'.  MN-major B: LBO = 128 B between 8-key groups, SBO = distance to the ones block
-                const uint32_t vs = sm0 + (uint32_t)(itP & 1) * stage_bytes + 2u * opb + (uint32_t)jP * (A3_KT * 16u);
-                uint32_t v_lo = ((vs & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
-                uint32_t v_hi = (((vaug - vs) >> 4) & 0x3FFFu) | (1u << 14);
-                const uint32_t d = tO + (uint32_t)(16 * (kP & 1));
-                const uint32_t a0 = tS + (uint32_t)(buf * 64);
+            // one PV product: O (+)= P[buf] V'(64 keys) as four K = 16 MMAs; MN-major B: LBO = 128 B between 8-key groups, SBO =
+            // distance to the ones block (running: + 256 B start, - 256 B SBO per 16 keys)
+            auto mma_PV = [&](int buf, uint32_t d, uint32_t v_lo, uint32_t v_hi, bool first, bool last, uint32_t ob, uint32_t eb) {
+                if (elect_one()) {
+                    const uint32_t a0 = tS + (uint32_t)(buf * 64);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    a3_mma_ts(d, a0 + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)), desc64(v_hi, v_lo), idPV, (jP | kk) ? 1u : 0u);
-                    v_lo += 16u; v_hi -= 16u;                              // next 16 keys: start + 256 B, SBO - 256 B
+                    for (int kk = 0; kk < 4; ++kk)
+                        a3_mma_ts(d, a0 + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)), desc64(v_hi - 16u * kk, v_lo + 16u * kk), idPV, (!first || kk) ? 1u : 0u);
+                    if (last) { umma_commit_addr(ob); umma_commit_addr(eb); }
                 }
-                if (jP == ntl - 1) {
-                    umma_commit(&ofull[g * 2 + (kP & 1)]);
-                    umma_commit(&qkv_empty[itP & 1]);                      // this query tile no longer reads the head's Q / K / V
-                    jP = 0; ++kP; qtP += A3_NWG;
-                    while (qtP >= nqt) { qtP -= nqt; ++itP; }
-                } else {
-                    ++jP;
+                __syncwarp();
+            };
+            int it = 0, qt = g, items_seen = 0;
+            while (qt >= nqt) { qt -= nqt; ++it; }
+            // S tile 0 of the first query tile (zero augmentation: needs only the head's Q / K / V)
+            a3_spin(bar_full + (it & 1) * 8, (uint32_t)(it >> 1) & 1u);
+            items_seen = it + 1;
+            tc_fence_after();
+            uint32_t stage0 = sm0 + (uint32_t)(it & 1) * stage_bytes;
+            uint32_t qs = stage0 + (uint32_t)qt * 2048u;
+            mma_S(0, lo_k(qs, zaug), lo_k(stage0 + opb, kaug));
+            for (int k = 0; k < nTg; ++k) {
+                // this query tile: item `it` (stage it & 1), tile qt; S(k, 0) is in flight or done in buffer 0 (ntl is even)
+                const uint32_t a_aug = lo_k(qs, qaug);
+                uint32_t b_lo = lo_k(stage0 + opb + A3_KT * 16u, kaug);                 // K' of key tile 1
+                const uint32_t vs0 = stage0 + 2u * opb;
+                uint32_t v_lo = ((vs0 & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+                uint32_t v_hi = (((vaug - vs0) >> 4) & 0x3FFFu) | (1u << 14);
+                const uint32_t d = tO + (uint32_t)(16 * (k & 1));
+                const uint32_t ob = bar_ofull + (k & 1) * 8, eb = bar_empty + (it & 1) * 8;
+                // next query tile of this stream (its S tile 0 is issued two steps before this one ends)
+                int it_n = it, qt_n = qt + p.nws;
+                while (qt_n >= nqt) { qt_n -= nqt; ++it_n; }
+                const bool has_next = k + 1 < nTg;
+                const uint32_t stage_n = sm0 + (uint32_t)(it_n & 1) * stage_bytes;
+                const uint32_t qs_n = stage_n + (uint32_t)qt_n * 2048u;
+                // S(k, 1) needs -m of this query tile
+                a3_spin(bar_qm, (uint32_t)k & 1u);
+                tc_fence_after();
+                mma_S(1, a_aug, b_lo);
+                b_lo += 64u - (64u << 16);
+                if (k >= 2) a3_spin(bar_oread + (k & 1) * 8, (uint32_t)((k >> 1) - 1) & 1u);   // O slot of query tile k - 2 has been read
+                const uint32_t par0 = (uint32_t)(k * (ntl >> 1)) & 1u;                  // parity of buffer use (k ntl / 2 + j / 2)
+#pragma unroll 1
+                for (int j = 0; j < ntl; j += 2) {
+                    const uint32_t par = (par0 + (uint32_t)(j >> 1)) & 1u;
+                    // ---- even step j: buffer 0 ----
+#ifdef A3_TRACE
+                    const int sT = k * ntl + j;
+                    const bool trI = blockIdx.x == 0 && g == 0 && lane == 0 && sT >= 20 && sT < 60;
+                    if (trI) tr_iss[sT - 20][3] = clock64();
+#endif
+                    a3_spin(bar_pready, par);
+#ifdef A3_TRACE
+                    if (trI) tr_iss[sT - 20][0] = clock64();
+#endif
+                    tc_fence_after();
+                    mma_PV(0, d, v_lo, v_hi, j == 0, false, ob, eb);
+#ifdef A3_TRACE
+                    if (trI) tr_iss[sT - 20][1] = clock64();
+#endif
+                    v_lo += 64u; v_hi -= 64u;
+                    if (j + 2 < ntl) {
+                        mma_S(0, a_aug, b_lo);                                          // S(k, j + 2)
+                        b_lo += 64u - (64u << 16);
+                    } else if (has_next) {
+                        if (it_n == items_seen) {                                       // first touch of the next item by this stream
+                            a3_spin(bar_full + (it_n & 1) * 8, (uint32_t)(it_n >> 1) & 1u);
+                            ++items_seen;
+                            tc_fence_after();
+                        }
+                        mma_S(0, lo_k(qs_n, zaug), lo_k(stage_n + opb, kaug));          // S(k + 1, 0)
+                    }
+#ifdef A3_TRACE
+                    if (trI) tr_iss[sT - 20][2] = clock64();
+                    if (trI) tr_iss[sT + 1 - 20][3] = clock64();
+#endif
+                    // ---- odd step j + 1: buffer 1 ----
+                    a3_spin(bar_pready + 8, par);
+#ifdef A3_TRACE
+                    if (trI) tr_iss[sT + 1 - 20][0] = clock64();
+#endif
+                    tc_fence_after();
+                    mma_PV(1, d, v_lo, v_hi, false, j + 2 >= ntl, ob, eb);
+                    v_lo += 64u; v_hi -= 64u;
+#ifdef A3_TRACE
+                    if (trI) tr_iss[sT + 1 - 20][1] = clock64();
+#endif
+                    if (j + 3 < ntl) {
+                        mma_S(1, a_aug, b_lo);                                          // S(k, j + 3)
+                        b_lo += 64u - (64u << 16);
+                    }
+#ifdef A3_TRACE
+                    if (trI) tr_iss[sT + 1 - 20][2] = clock64();
+#endif
                 }
-                // the S buffer of step s is free again (tcgen05 ops of one thread execute in issue order): S of step s + 2
-                if (sS < total_steps) issue_S();
+                it = it_n; qt = qt_n; stage0 = stage_n; qs = qs_n;
             }
         }
 
     } else if (warp >= 4) {
-        // ===================== softmax: warpgroup g = one stream of query tiles, thread = one query row =====================
-        const int g = (warp - 4) >> 2, wq = warp & 3;             // TMEM lanes 32 wq .. 32 wq + 31 are this warp's
+        // ===================== softmax: stream g = SP warpgroups; thread = one query row x (64 / SP) columns of every tile =====================
+        const int sw = warp - 4;
+        const int g = sw / (4 * SP), half = (sw >> 2) % SP, wq = warp & 3;   // TMEM lanes 32 wq .. 32 wq + 31 are this warp's
         const int row = wq * 32 + lane;
+        constexpr int NC = 64 / SP;                                           // columns of a tile per thread
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * A3_WG_COLS);
         uint8_t* my_qaug = sm_qaug + g * 2048 + row * 16;
         T* out = reinterpret_cast<T*>(p.out);
-        const int nTg = total_T > g ? (total_T - g + A3_NWG - 1) / A3_NWG : 0;
+        const int nTg = (g < p.nws && total_T > g) ? (total_T - g + p.nws - 1) / p.nws : 0;
         auto finish_qtile = [&](int k) {
-            const int Tq = g + A3_NWG * k, it = Tq / nqt, qt = Tq - it * nqt;
+            const int Tq = g + p.nws * k, it = Tq / nqt, qt = Tq - it * nqt;
             const int item = (int)blockIdx.x + it * (int)gridDim.x;
             const int n = item / p.heads, head = item - n * p.heads;
             a3_wait(&ofull[g * 2 + (k & 1)], (uint32_t)(k >> 1) & 1u);
@@ -271,7 +378,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) attention_tc3_kernel(const __gr
             a3_ld_x16(lane_base + (uint32_t)(128 + 16 * (k & 1)), o);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&oread[g * 2 + (k & 1)]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&oread[g * 2 + (k & 1)]);
             const float l = __uint_as_float(o[8]);
             bool bad = !(fabsf(l) <= 3.0e38f) || !(l > 0.f);
             float v[8];
@@ -293,71 +401,127 @@ __global__ void __launch_bounds__(A3_THREADS, 1) attention_tc3_kernel(const __gr
                 const int buf = s & 1;
                 a3_wait(&sfull[g * 2 + buf], (uint32_t)(s >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t ts = lane_base + (uint32_t)(buf * 64);
-                uint32_t s0[32], s1[32], p0[16], p1[16];
+#ifdef A3_TRACE
+                const bool trc = blockIdx.x == 0 && warp == 4 && lane == 0 && s >= 20 && s < 60;
+                if (trc) tr_soft[s - 20][0] = clock64();
+                const bool trw = blockIdx.x == 0 && g == 0 && lane == 0 && s >= 20 && s < 60;
+                if (trw) tr_w[s - 20][wq][0] = clock64();
+#endif
+                const uint32_t ts = lane_base + (uint32_t)(buf * 64 + half * NC);
+                uint32_t s0[32], p0[16];
                 tmem_ld_32x32b_x32(ts, s0);
                 tmem_ld_wait();
-                tmem_ld_32x32b_x32(ts + 32u, s1);                   // in flight under the first half's exponentials
-                if (j == 0) {
-                    // exact row max of key tile 0 -> Q augmentation (every later S tile of this query tile arrives as s - m);
-                    // this tile subtracts in registers
-                    tmem_ld_wait();
-                    float mx = __uint_as_float(s0[0]);
+                if (SP == 1) {
+                    uint32_t s1[32], p1[16];
+                    tmem_ld_32x32b_x32(ts + 32u, s1);               // in flight under the first half's exponentials
+                    if (j == 0) {
+                        // exact row max of key tile 0 -> Q augmentation (every later S tile of this query tile arrives as s - m);
+                        // this tile subtracts in registers
+                        tmem_ld_wait();
+                        float mx = __uint_as_float(s0[0]);
 #pragma unroll
-                    for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s0[c]));
+                        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s0[c]));
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s1[c]));
-                    m = mx;
-                    const T mh = from_f<T>(-m);
-                    const T ml = from_f<T>(-m - to_f(mh));
-                    *reinterpret_cast<uint4*>(my_qaug) = make_uint4(a3_pack_raw<T>(mh, ml), 0u, 0u, 0u);
-                    fence_proxy_async();
-                    mbar_arrive(&qmready[g]);
-                    a3_exp32<T, PP, true>(s0, m, p0);
-                    a3_st_x16(ts, p0);
-                    a3_exp32<T, PP, true>(s1, m, p1);
-                    a3_st_x16(ts + 32u, p1);
+                        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s1[c]));
+                        m = mx;
+                        const T mh = from_f<T>(-m);
+                        const T ml = from_f<T>(-m - to_f(mh));
+                        *reinterpret_cast<uint4*>(my_qaug) = make_uint4(a3_pack_raw<T>(mh, ml), 0u, 0u, 0u);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&qmready[g]);
+                        a3_exp32<T, PP, true>(s0, m, p0);
+                        a3_st_x16(ts, p0);
+                        a3_exp32<T, PP, true>(s1, m, p1);
+                        a3_st_x16(ts + 32u, p1);
+                    } else {
+                        a3_exp32<T, PP, false>(s0, 0.f, p0);
+                        a3_st_x16(ts, p0);                          // P of keys 0..31 lands on the first 16 of their own S columns
+                        tmem_ld_wait();
+#ifdef A3_TRACE
+                        if (trc) tr_soft[s - 20][1] = clock64();
+#endif
+                        a3_exp32<T, PP, false>(s1, 0.f, p1);
+                        a3_st_x16(ts + 32u, p1);
+#ifdef A3_TRACE
+                        if (trc) tr_soft[s - 20][2] = clock64();
+#endif
+                    }
                 } else {
-                    a3_exp32<T, PP, false>(s0, 0.f, p0);
-                    a3_st_x16(ts, p0);                              // P of keys 0..31 lands on the first 16 of their own S columns
-                    tmem_ld_wait();
-                    a3_exp32<T, PP, false>(s1, 0.f, p1);
-                    a3_st_x16(ts + 32u, p1);
+                    if (j == 0) {
+                        float mx = __uint_as_float(s0[0]);
+#pragma unroll
+                        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(s0[c]));
+                        // the other 32 columns of this row belong to the thread `row` of the stream's other warpgroup
+                        sm_xmax[(g * 2 + half) * 128 + row] = mx;
+                        asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128 * SP) : "memory");
+                        m = fmaxf(mx, sm_xmax[(g * 2 + (half ^ 1)) * 128 + row]);
+                        if (half == 0) {
+                            const T mh = from_f<T>(-m);
+                            const T ml = from_f<T>(-m - to_f(mh));
+                            *reinterpret_cast<uint4*>(my_qaug) = make_uint4(a3_pack_raw<T>(mh, ml), 0u, 0u, 0u);
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&qmready[g]);
+                        }
+                        a3_exp32<T, PP, true>(s0, m, p0);
+                    } else {
+                        a3_exp32<T, PP, false>(s0, 0.f, p0);
+                    }
+                    a3_st_x16(ts, p0);                              // P of this thread's 32 keys lands on the first 16 of their own S columns
                 }
                 a3_st_wait();
+#ifdef A3_TRACE
+                if (trc) tr_soft[s - 20][3] = clock64();
+#endif
                 tc_fence_before();
-                mbar_arrive(&pready[g * 2 + buf]);
-                // O of the PREVIOUS query tile of this stream: its last PV product was issued when this warpgroup handed over the
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pready[g * 2 + buf]);
+#ifdef A3_TRACE
+                if (trc) tr_soft[s - 20][4] = clock64();
+                if (trw) tr_w[s - 20][wq][1] = clock64();
+#endif
+                // O of the PREVIOUS query tile of this stream: its last PV product was issued when this stream handed over the
                 // last P, a whole tile ago
-                if (j == 0 && k >= 1) finish_qtile(k - 1);
+                if (j == 0 && k >= 1 && half == 0) finish_qtile(k - 1);
             }
         }
-        if (nTg > 0) finish_qtile(nTg - 1);
+        if (nTg > 0 && half == 0) finish_qtile(nTg - 1);
     }
     tc_fence_before();
     __syncthreads();
+#ifdef A3_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < 40; ++i) {
+            printf("step %2d soft(w4..7): wake %lld %lld %lld %lld arrive %lld %lld %lld %lld || iss: top %lld spin-done %lld (+%lld) PV-done +%lld S-done +%lld\n", 20 + i,
+                   tr_w[i][0][0] - tr_soft[0][0], tr_w[i][1][0] - tr_soft[0][0], tr_w[i][2][0] - tr_soft[0][0], tr_w[i][3][0] - tr_soft[0][0],
+                   tr_w[i][0][1] - tr_soft[0][0], tr_w[i][1][1] - tr_soft[0][0], tr_w[i][2][1] - tr_soft[0][0], tr_w[i][3][1] - tr_soft[0][0],
+                   tr_iss[i][3] - tr_soft[0][0], tr_iss[i][0] - tr_soft[0][0], tr_iss[i][0] - tr_iss[i][3], tr_iss[i][1] - tr_iss[i][0], tr_iss[i][2] - tr_iss[i][1]);
+        }
+    }
+#endif
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, A3_TMEM_COLS);
     }
 }
 
-size_t attention_tc3_smem_bytes(int S) { return (size_t)2 * 3 * S * 16 + 1024 + 256 + 2048 + A3_NWG * 2048 + 32 * 8 + 16 + 128; }
+size_t attention_tc3_smem_bytes(int S) { return (size_t)2 * 3 * S * 16 + 1024 + 256 + 2048 + A3_NWG * 2048 + 32 * 8 + A3_NWG * 2 * 128 * 4 + 128; }
 
 bool attention_tc3_supported(int S, int C) {
     // >= 3 query tiles per head: every stream then has work in every head, which the head-ring barrier parities rely on
     return S % 128 == 0 && S >= 128 * A3_NWG && C % 8 == 0 && attention_tc3_smem_bytes(S) <= 227 * 1024;
 }
 
-template <typename T, int PP>
+template <typename T, int PP, int SP>
 static int launch_tc3(const A3Params& p, size_t smem, int grid, cudaStream_t s) {
     static size_t attr_dev[PD_MAX_DEVICES] = {0};
     size_t& attr = attr_dev[pd_cur_dev()];
     if (smem > attr) {
-        PD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<T, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<T, PP, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    attention_tc3_kernel<T, PP><<<grid, A3_THREADS, smem, s>>>(p);
+    attention_tc3_kernel<T, PP, SP><<<grid, a3_threads(SP), smem, s>>>(p);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -374,6 +538,8 @@ int launch_attention_tc3(int dt, const void* qkv, int N, int S, int C, void* out
         const char* e = getenv("PHENDIFF_B200_ATTN_TC3_SWAP");   // probe knob: bit 0 swaps LBO / SBO of the K-major descriptors, bit 1 of the MN-major one
         const int sw = e ? atoi(e) : 0;
         p.swap_k = sw & 1; p.swap_mn = (sw >> 1) & 1;
+        const char* ns = getenv("PHENDIFF_B200_ATTN_TC3_STREAMS");
+        p.nws = ns ? std::min(A3_NWG, std::max(1, atoi(ns))) : A3_NWG;
     }
     const uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)S, (uint64_t)N};
     const uint64_t strides[2] = {(uint64_t)3 * C * 2, (uint64_t)S * 3 * C * 2};
@@ -382,12 +548,15 @@ int launch_attention_tc3(int dt, const void* qkv, int N, int S, int C, void* out
     if (rc) return rc;
     const size_t smem = attention_tc3_smem_bytes(S);
     const int grid = std::min(p.items, tc_num_sms());
-#define PD_A3(PP) PD_DISPATCH_HALF(dt, T, { return launch_tc3<T, PP>(p, smem, grid, s); })
+    static const int split = [] { const char* e = getenv("PHENDIFF_B200_ATTN_TC3_SPLIT"); return e ? atoi(e) : 2; }();
+#define PD_A3(PP) PD_DISPATCH_HALF(dt, T, { return split == 1 ? launch_tc3<T, PP, 1>(p, smem, grid, s) : launch_tc3<T, PP, 2>(p, smem, grid, s); })
     switch (poly_pairs) {
         case 0: PD_A3(0); break;
         case 2: PD_A3(2); break;
         case 3: PD_A3(3); break;
         case 5: PD_A3(5); break;
+        case 8: PD_A3(8); break;
+        case 9: PD_A3(9); break;
         default: PD_A3(4); break;
     }
 #undef PD_A3
