@@ -371,8 +371,9 @@ def run_ours(args):
 
 def run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local):
     """Secondary workload (reference utils_Img2Img.py:615-648 with the example config's guidance_scale 2.5 /
-    frac_diffusion_skipped 0.5): forward-noise the images to the middle of the trajectory, then per kept step one conditional
-    and one unconditional UNet forward, the guidance combine and the DDIM update, through the per-op route of the C ABI.
+    frac_diffusion_skipped 0.5): forward-noise the images to the middle of the trajectory, then per kept step ONE pass of the UNet
+    over 2B images (conditional samples + their unconditional copies) whose conv_out epilogue applies the guidance combine and
+    the DDIM update (`pd_cfg_transfer`).
     Both figures go through the drop-in call and end in PIL images; `value` starts from device-resident images and is timed
     with CUDA events, `e2e` starts from pinned host images and is timed on the host clock."""
     import torch
@@ -412,8 +413,9 @@ def run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local
     assert len(imgs) == args.batch
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    # UNet kernels (counted by the library) + per call: add_noise, denorm, and per kept step the guidance combine and the DDIM update
-    launches = unet.launch_count() - l0 + args.steps * (2 + 2 * kept)
+    # UNet kernels (counted by the library: the guidance combine and the scheduler update live in conv_out's epilogue on the fused
+    # route, `pd_cfg_transfer`) + per call: add_noise, denorm
+    launches = unet.launch_count() - l0 + args.steps * 2
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

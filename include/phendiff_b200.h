@@ -46,7 +46,7 @@ typedef struct pd_unet_config {
     int32_t down_attn[PD_MAX_BLOCKS]; /* 1: AttnDownBlock2D, 0: DownBlock2D */
     int32_t up_attn[PD_MAX_BLOCKS];   /* 1: AttnUpBlock2D,   0: UpBlock2D   */
     int32_t layers_per_block;
-    int32_t attention_head_dim;
+    int32_t attention_head_dim; /* <= 0: the JSON's null = ONE head of dim C (cond_unet_2d.py:176-178) */
     int32_t norm_num_groups;
     float norm_eps;
     int32_t num_class_embeds; /* 0: no class embedding table */

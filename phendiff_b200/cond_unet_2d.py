@@ -94,8 +94,6 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
             raise NotImplementedError("class_embed_type 'timestep'/'identity' are not used by any shipped config and are not implemented")
         if act_fn != "silu" or resnet_time_scale_shift != "default":
             raise NotImplementedError("only act_fn='silu' and resnet_time_scale_shift='default' are implemented")
-        if attention_head_dim is None:
-            raise NotImplementedError("attention_head_dim=None (single-head attention) is not implemented")
         for t in down_block_types:
             if t not in ("DownBlock2D", "AttnDownBlock2D"):
                 raise NotImplementedError(f"down block type {t} is not implemented")
@@ -277,7 +275,7 @@ class CustomCondUNet2DModel(nn.Module, ConfigMixin):
             cc.down_attn[i] = int(c.down_block_types[i] == "AttnDownBlock2D")
             cc.up_attn[i] = int(c.up_block_types[i] == "AttnUpBlock2D")
         cc.layers_per_block = c.layers_per_block
-        cc.attention_head_dim = c.attention_head_dim
+        cc.attention_head_dim = c.attention_head_dim or 0   # None: one head of dim C (cond_unet_2d.py:176-178)
         cc.norm_num_groups = c.norm_num_groups
         cc.norm_eps = c.norm_eps
         cc.num_class_embeds = c.num_class_embeds or 0

@@ -684,7 +684,9 @@ struct Rec {
                 e.timesteps = cx.timesteps; e.t_scalar = cx.t_scalar; e.labels = cx.labels; e.class_emb = cx.class_emb;
                 e.cfg_pairs = cx.cfg_pairs;
                 // one scalar timestep + integer labels (the DDIB path): only ncls distinct embedding rows exist
-                e.dedupe = (!cx.timesteps && cx.labels && !cx.class_emb && e.class_table && e.ncls > 0 && e.ncls <= e.B) ? 1 : 0;
+                // (or, for an unconditional model, exactly one)
+                e.dedupe = (!cx.timesteps && !cx.class_emb && ((cx.labels && e.class_table && e.ncls > 0 && e.ncls <= e.B) || !e.class_table)) ? 1 : 0;
+                if (!e.class_table) e.ncls = 0;
                 int r = launch_embed(e, s);
                 if (r) return r;
                 return launch_temb_proj(e.emb_act, wcat, bcat, embed_rows(e), D, J, temb, s);

@@ -26,7 +26,8 @@ struct EmbedArgs {
     // `ncls` without class embedding, row_idx[i] = labels[i] for i < P and ncls for i >= P.
     int cfg_pairs;
 };
-inline int embed_rows(const EmbedArgs& a) { return a.dedupe ? a.ncls + (a.cfg_pairs > 0 ? 1 : 0) : a.B; }
+// (an unconditional model — no class table, ncls = 0 — has ONE row under dedupe: every image reads row 0)
+inline int embed_rows(const EmbedArgs& a) { return a.dedupe ? a.ncls + ((a.cfg_pairs > 0 || a.ncls == 0) ? 1 : 0) : a.B; }
 
 // guidance combine applied by a conv_out epilogue to its conditional output m_c before the scheduler update
 // (pipeline_conditionial_ddim.py:323-332): m = (eqn == 0 ? u : m_c) + w[img] * (m_c - u), u = uncond[(img, c, hw)]
@@ -105,6 +106,8 @@ int launch_im2col_in(int dt, const float* x, int N, int Cin, int H, int W, void*
 // ---- attention core: softmax(q k^T / sqrt(d)) v on packed qkv (N,S,3C) ------------------------------------------
 int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out,
                           cudaStream_t s);
+// any head dimension (attention_head_dim: null -> one head of dim C); launch_attention_simt forwards d != 8 here
+int launch_attention_generic(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s);
 // bf16 / fp16 tensor-core path.  qfold = the factor already folded into q by the caller: 1 for raw q, PD_ATTN_QFOLD when
 // the q rows of the fused qkv weight were pre-multiplied at finalize (scores then leave the MMA in log2 units)
 constexpr float PD_ATTN_QFOLD = 0.35355339059327373f * 1.4426950408889634f;   // log2(e) / sqrt(8)

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
     if (b == 0 && blockIdx.y == 0) {
         for (int i = tid; i < a.B; i += blockDim.x) {
             int32_t r = i;
-            if (a.dedupe) r = (a.cfg_pairs > 0 && i >= a.cfg_pairs) ? a.ncls : (int32_t)a.labels[i];   // row ncls: unconditional
+            if (a.dedupe) r = (a.ncls == 0 || (a.cfg_pairs > 0 && i >= a.cfg_pairs)) ? a.ncls : (int32_t)a.labels[i];   // row ncls: unconditional
             a.row_idx[i] = r;
         }
     }
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a, const float* __
             float e = acc + a.b2[j];
             if (a.dedupe) e += (b < a.ncls) ? a.class_table[(size_t)b * a.D + j] : 0.f;   // row ncls = class_emb of zeros (guidance pass)
             else if (a.class_emb) e += a.class_emb[(size_t)b * a.D + j];
-            else if (a.labels) e += a.class_table[(size_t)a.labels[b] * a.D + j];
+            else if (a.labels && a.class_table) e += a.class_table[(size_t)a.labels[b] * a.D + j];
             a.emb_act[(size_t)b * a.D + j] = silu<true>(e);
         }
     }
@@ -80,7 +80,7 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
         ft.shift = a.shift;
     }
     PD_REQUIRE(a.row_idx != nullptr, "embed: row index buffer missing");
-    PD_REQUIRE(!a.dedupe || (a.labels && a.class_table && !a.class_emb && !a.timesteps && a.ncls > 0), "embed: dedupe needs labels and one scalar timestep");
+    PD_REQUIRE(!a.dedupe || (!a.class_emb && !a.timesteps && (a.ncls == 0 || (a.labels && a.class_table))), "embed: dedupe needs one scalar timestep and, for class-conditioned models, labels");
     PD_REQUIRE(a.cfg_pairs == 0 || (a.dedupe && 2 * a.cfg_pairs == a.B), "embed: the guidance pass needs labels, one scalar timestep and 2P images");
     size_t smem = (size_t)(a.C0 + a.D) * sizeof(float);
     embed_kernel<<<dim3(embed_rows(a), (a.D + 63) / 64), 256, smem, s>>>(a, g_freqs);
@@ -807,8 +807,88 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const T* __restrict
     }
 }
 
+// Any head dimension (attention_head_dim: null = ONE head of dim C, cond_unet_2d.py:176-178,192-194,222-224; the shipped
+// orig_google_ddpm_model_denoiser.json): a warp owns two queries, its lanes split the head dimension (element e of a row lives in
+// lane e % 32), a score is a 32-lane shuffle reduction, softmax is online (running max and sum per query), fp32 throughout.
+// K and V rows are read straight from L2 (one coalesced row per key): these layers are 0.1 % of the FLOPs of the models that
+// use them, so the kernel is written for generality, not for the roofline.
+template <typename T, bool kPrecise, int DPL>
+__global__ void __launch_bounds__(256) attention_generic_kernel(const T* __restrict__ qkv, int S, int C, int d, float scale,
+                                                                 T* __restrict__ out) {
+    const int n = blockIdx.z, head = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = (blockIdx.x * 8 + warp) * 2;
+    if (q0 >= S) return;
+    const bool two = q0 + 1 < S;
+    const size_t rowp = (size_t)3 * C;
+    const T* base = qkv + (size_t)n * S * rowp + (size_t)head * d;
+    float qa[DPL], qb[DPL], oa[DPL], ob[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+        const int e = lane + 32 * i;
+        qa[i] = e < d ? to_f(base[(size_t)q0 * rowp + e]) * scale : 0.f;
+        qb[i] = (e < d && two) ? to_f(base[(size_t)(q0 + 1) * rowp + e]) * scale : 0.f;
+        oa[i] = 0.f; ob[i] = 0.f;
+    }
+    float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
+    for (int k = 0; k < S; ++k) {
+        const T* kr = base + (size_t)k * rowp + C;
+        const T* vr = kr + C;
+        float sa = 0.f, sb = 0.f, vv[DPL];
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+            const int e = lane + 32 * i;
+            const float kv = e < d ? to_f(kr[e]) : 0.f;
+            vv[i] = e < d ? to_f(vr[e]) : 0.f;
+            sa = fmaf(qa[i], kv, sa);
+            sb = fmaf(qb[i], kv, sb);
+        }
+        sa = warp_sum(sa); sb = warp_sum(sb);
+        const float na = fmaxf(ma, sa), nb = fmaxf(mb, sb);
+        const float ca = kPrecise ? expf(ma - na) : __expf(ma - na), cb = kPrecise ? expf(mb - nb) : __expf(mb - nb);
+        const float pa = kPrecise ? expf(sa - na) : __expf(sa - na), pb = kPrecise ? expf(sb - nb) : __expf(sb - nb);
+        la = la * ca + pa; lb = lb * cb + pb;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) { oa[i] = fmaf(oa[i], ca, pa * vv[i]); ob[i] = fmaf(ob[i], cb, pb * vv[i]); }
+        ma = na; mb = nb;
+    }
+    const float ia = 1.0f / la, ib = 1.0f / lb;
+    T* o = out + ((size_t)n * S + q0) * C + (size_t)head * d;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+        const int e = lane + 32 * i;
+        if (e < d) {
+            o[e] = from_f<T>(oa[i] * ia);
+            if (two) o[C + e] = from_f<T>(ob[i] * ib);
+        }
+    }
+}
+
+template <typename T, int DPL>
+static void launch_attn_generic_t(bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+    dim3 grid((S + 15) / 16, C / d, N);
+    const float scale = 1.0f / sqrtf((float)d);
+    if (precise) attention_generic_kernel<T, true, DPL><<<grid, 256, 0, s>>>((const T*)qkv, S, C, d, scale, (T*)out);
+    else attention_generic_kernel<T, false, DPL><<<grid, 256, 0, s>>>((const T*)qkv, S, C, d, scale, (T*)out);
+}
+
+int launch_attention_generic(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
+    PD_REQUIRE(d > 0 && C % d == 0, "attention channels must be a multiple of the head dimension");
+    PD_REQUIRE(d <= 1024, "attention head dimension above 1024 is not implemented");
+    PD_DISPATCH_DT(dt, T, {
+        if (d <= 32) launch_attn_generic_t<T, 1>(precise, qkv, N, S, C, d, out, s);
+        else if (d <= 64) launch_attn_generic_t<T, 2>(precise, qkv, N, S, C, d, out, s);
+        else if (d <= 128) launch_attn_generic_t<T, 4>(precise, qkv, N, S, C, d, out, s);
+        else if (d <= 256) launch_attn_generic_t<T, 8>(precise, qkv, N, S, C, d, out, s);
+        else if (d <= 512) launch_attn_generic_t<T, 16>(precise, qkv, N, S, C, d, out, s);
+        else launch_attn_generic_t<T, 32>(precise, qkv, N, S, C, d, out, s);
+    });
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_attention_simt(int dt, bool precise, const void* qkv, int N, int S, int C, int d, void* out, cudaStream_t s) {
-    PD_REQUIRE(d == 8, "attention kernels implement attention_head_dim == 8 (the shipped configs)");
+    if (d != 8) return launch_attention_generic(dt, precise, qkv, N, S, C, d, out, s);
     PD_REQUIRE(C % 8 == 0, "attention channels must be a multiple of 8");
     dim3 grid((S + 127) / 128, C / d, N);
     if (precise) PD_DISPATCH_DT(dt, T, (attention_simt_kernel<T, true><<<grid, 128, 0, s>>>((const T*)qkv, S, C, (T*)out)));

@@ -235,7 +235,7 @@ class ConditionalDDIMPipeline:
     def fused_route_ok(self) -> bool:
         """Whether the whole-path C entry point may replace the per-step loop for this model: it feeds x_t to conv_in as
         is (no `center_input_sample` rescale, cond_unet_2d.py:271-273) and indexes the class table by label."""
-        return bool(self.fused and self.unet.class_embedding is not None and not self.unet.config.center_input_sample)
+        return bool(self.fused and not self.unet.config.center_input_sample)
 
     def postprocess(self, image: torch.Tensor) -> np.ndarray:
         """(image / 2 + 0.5).clamp(0, 1) -> cpu -> NHWC numpy (pipeline:349-350), as one kernel + one D2H copy."""

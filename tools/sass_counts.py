@@ -25,7 +25,7 @@ def main():
             cur = re.sub(r"\(.*", "", cur).replace("void pd::", "").replace("pd::", "")
             counts.setdefault(cur, collections.Counter())
             continue
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
+        m = re.search(r"/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
         if m and cur:
             op = m.group(1)
             for k in MNEMONICS:
