@@ -29,6 +29,7 @@ extern "C" {
 #endif
 
 typedef struct pd_unet pd_unet_t;
+typedef struct pd_train pd_train_t;
 typedef void* pd_stream_t; /* cudaStream_t */
 
 enum { PD_PREC_FP32 = 0, PD_PREC_BF16 = 1, PD_PREC_FP16 = 2 };
@@ -148,6 +149,33 @@ int pd_ddib_transfer(pd_unet_t* h, float* x, const int64_t* src_labels, const in
 int pd_unet_plan_guided(pd_unet_t* h, int32_t batch, int32_t height, int32_t width, size_t* workspace_bytes);
 int pd_cfg_transfer(pd_unet_t* h, float* x, const int64_t* labels, const float* w, int32_t eqn,
                     const pd_step_coeffs_t* steps_host, int32_t n_steps, pd_stream_t stream);
+
+/* ---- training step (BASELINE.json configs[3]): the inner step of perform_training_epoch for the DDIM model type
+ *      (src/utils_training.py:244-456).  The caller (Python mirror phendiff_b200/training.py) samples noise and timesteps, forms the
+ *      noisy images with DDIMScheduler.add_noise and the regression target by prediction type (:415-433: noise / clean images /
+ *      velocity; per-sample SNR weights for "sample"); this entry point runs forward + backward of the UNet and ACCUMULATES
+ *      the gradients of mean_b,chw( weight[b] * (model_out - target)^2 ).  Parameters and gradients are flat fp32 vectors in
+ *      parameter-table order (pd_unet_param_info; PyTorch layouts), owned by the caller: offsets from pd_train_param_offset.
+ *      labels NULL = the unconditional pass of classifier-free-guidance training (class_emb = zeros, :508-516).
+ *      fp32 path: every operator of the backward pass as a CUDA-core kernel (validated against torch.autograd on the oracle). */
+int pd_train_create(pd_unet_t* h, int32_t batch, int32_t height, int32_t width, pd_train_t** out);
+int pd_train_destroy(pd_train_t* t);
+int pd_train_num_params_flat(pd_train_t* t, int64_t* numel);
+int pd_train_param_offset(pd_train_t* t, int32_t idx, int64_t* offset);
+int pd_train_workspace_bytes(pd_train_t* t, size_t* bytes);
+int pd_train_bind(pd_train_t* t, void* workspace, size_t bytes);   /* 256-byte aligned, caller-owned */
+/* noisy, target, model_out (optional): (B,C,H,W) fp32; timesteps (B) fp32; labels (B) int64 or NULL; sample_weight (B) fp32 or NULL;
+ * loss_out: one fp32 on the device */
+int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const float* noisy, const float* timesteps,
+                       const int64_t* labels, const float* target, const float* sample_weight, float* loss_out, float* model_out,
+                       pd_stream_t stream);
+int pd_train_launch_count(pd_train_t* t, int64_t* n);
+/* accelerator.clip_grad_norm_(params, max_grad_norm) (utils_training.py:439; <= 0: no clipping) + torch.optim.AdamW.step
+ * (train.py:279-285; `step` counts from 1) + diffusers EMAModel.step with the given decay (utils_training.py:224-241; ema NULL:
+ * none) over flat fp32 vectors, in place.  scratch: one fp32 on the device; grad_norm_out (optional): the pre-clip global norm. */
+int pd_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float ema_decay, float* scratch,
+                  float* grad_norm_out, pd_stream_t stream);
 
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int pd_unet_launch_count(pd_unet_t* h, int64_t* n);

@@ -67,6 +67,16 @@ _SIGNATURES = {
     "pd_ddib_transfer": (C.c_int, [_P, _P, _P, _P, C.POINTER(StepCoeffs), C.c_int32, C.c_int32, _P]),
     "pd_unet_plan_guided": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "pd_cfg_transfer": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(StepCoeffs), C.c_int32, _P]),
+    "pd_train_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "pd_train_destroy": (C.c_int, [_P]),
+    "pd_train_num_params_flat": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "pd_train_param_offset": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64)]),
+    "pd_train_workspace_bytes": (C.c_int, [_P, C.POINTER(C.c_size_t)]),
+    "pd_train_bind": (C.c_int, [_P, _P, C.c_size_t]),
+    "pd_train_step_grad": (C.c_int, [_P] * 11),
+    "pd_train_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "pd_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                 C.c_float, C.c_float, _P, _P, _P]),
     "pd_unet_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "pd_unet_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pd_unet_profile_begin": (C.c_int, [_P, C.c_int32, C.c_int32]),

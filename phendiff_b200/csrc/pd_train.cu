@@ -1,0 +1,505 @@
+// phendiff_b200 — the training step behind the C ABI: forward + backward of the conditional UNet for one batch
+// and the loss of the reference's `_diffusion_and_backward` (src/utils_training.py:374-456), gradient clipping, AdamW and EMA
+// (train.py:279-285, utils_training.py:224-241, :439).
+//
+// fp32 path (this file + pd_train_kernels.cu): NHWC fp32 activations, every forward tensor kept (bump allocation, no reuse), a
+// tape of backward closures played in reverse — the graph walk mirrors CustomCondUNet2DModel.forward (cond_unet_2d.py:244-362)
+// exactly as the inference recorder in pd_api.cu does.  Parameters and gradients are FLAT fp32 vectors in parameter-table
+// order (diffusers checkpoint naming, PyTorch layouts: OIHW convolutions, (out, in) linears), owned by the caller: the Python
+// side views them as the module's parameters / .grad, hands the gradient vector to NCCL as one buffer, and the optimiser kernel
+// updates the vector in place.  Gradients are ACCUMULATED (+=): the caller zeroes them (optimizer.zero_grad()).
+#include "pd_model.h"
+#include "pd_train.h"
+
+namespace pd {
+
+struct TT {   // an NHWC fp32 activation and its gradient
+    float* d = nullptr;
+    float* g = nullptr;
+    int C = 0, H = 0, W = 0;
+    double* stats = nullptr;   // GroupNorm chunk statistics (computed on first use)
+};
+
+}  // namespace pd
+
+using namespace pd;
+
+struct pd_train {
+    pd_unet* m = nullptr;
+    int B = 0, H = 0, W = 0;
+    std::map<const Param*, size_t> poff;
+    std::vector<size_t> poff_by_index;
+    size_t nflat = 0;
+    size_t act_bytes = 0, aux_bytes = 0, ws_bytes = 0;
+    uint8_t* ws = nullptr;
+    // per step
+    bool dry = true;
+    size_t act_bump = 0, aux_bump = 0;
+    std::vector<std::function<int(cudaStream_t)>> tape;
+    std::vector<std::unique_ptr<TT>> tts;
+    const float* P = nullptr;
+    float* G = nullptr;
+    cudaStream_t s = nullptr;
+    int rc = 0;
+    int64_t launches = 0;
+};
+
+namespace pd {
+
+struct Walk {
+    pd_train* t;
+    pd_unet* m;
+    int B;
+
+    const float* p(const Param* q) const { return t->P ? t->P + t->poff.at(q) : nullptr; }
+    float* gr(const Param* q) const { return t->G ? t->G + t->poff.at(q) : nullptr; }
+    bool dry() const { return t->dry; }
+    cudaStream_t s() const { return t->s; }
+    void run(int rc) { if (rc && !t->rc) t->rc = rc; }
+    void cu(cudaError_t e) { if (e != cudaSuccess && !t->rc) { set_error(std::string("training step: ") + cudaGetErrorString(e)); t->rc = 2; } }
+    void count(int n = 1) { t->launches += n; }
+    template <typename F> void bwd(F f) { if (!dry()) t->tape.push_back(f); }
+
+    // activations: data in [0, act_bytes), gradients mirrored at + act_bytes; aux buffers (no gradient mirror) behind both
+    TT* act(int C, int H, int W) {
+        auto tt = std::make_unique<TT>();
+        tt->C = C; tt->H = H; tt->W = W;
+        const size_t bytes = (((size_t)B * H * W * C * sizeof(float)) + 255) & ~(size_t)255;
+        if (!dry()) {
+            tt->d = (float*)(t->ws + t->act_bump);
+            tt->g = (float*)(t->ws + t->act_bytes + t->act_bump);
+        }
+        t->act_bump += bytes;
+        TT* r = tt.get();
+        t->tts.push_back(std::move(tt));
+        return r;
+    }
+    void* aux(size_t bytes, bool zero = false) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        void* r = dry() ? nullptr : (void*)(t->ws + 2 * t->act_bytes + t->aux_bump);
+        t->aux_bump += bytes;
+        if (r && zero) cu(cudaMemsetAsync(r, 0, bytes, s()));
+        return r;
+    }
+
+    double* stats_of(TT* x) {
+        if (!x->stats) {
+            x->stats = (double*)aux((size_t)B * (x->C / m->stats_cw) * 2 * sizeof(double), true);
+            if (!dry()) {
+                run(launch_gn_chunk_stats(DT_F32, x->d, B, x->H * x->W, x->C, m->stats_cw, x->stats, s()));
+                count();
+            } else {
+                x->stats = reinterpret_cast<double*>(uintptr_t(8));   // dry pass: remember that the slot exists
+            }
+        }
+        return x->stats;
+    }
+
+    // y = act(GroupNorm(concat(a, b)))
+    TT* gn(const GNL& g, TT* a, TT* b, bool silu) {
+        const int C = a->C + (b ? b->C : 0), HW = a->H * a->W;
+        TT* o = act(C, a->H, a->W);
+        double* st1 = stats_of(a);
+        double* st2 = b ? stats_of(b) : nullptr;
+        float* gsum = (float*)aux((size_t)B * m->cfg.norm_num_groups * 2 * sizeof(float));
+        if (dry()) return o;
+        GNArgs ga{};
+        ga.x1 = a->d; ga.x2 = b ? b->d : nullptr; ga.C1 = a->C; ga.C2 = b ? b->C : 0; ga.N = B; ga.HW = HW; ga.groups = m->cfg.norm_num_groups;
+        ga.eps = m->cfg.norm_eps; ga.gamma = p(g.g); ga.beta = p(g.b); ga.silu = silu; ga.stats_cw = m->stats_cw; ga.stats1 = st1; ga.stats2 = st2;
+        ga.out = o->d;
+        run(launch_gn_apply(DT_F32, true, ga, s()));
+        count();
+        GNBwdArgs ba{};
+        ba.x1 = a->d; ba.x2 = b ? b->d : nullptr; ba.dx1 = a->g; ba.dx2 = b ? b->g : nullptr; ba.dy = o->g; ba.C1 = a->C; ba.C2 = b ? b->C : 0;
+        ba.N = B; ba.HW = HW; ba.groups = m->cfg.norm_num_groups; ba.silu = silu; ba.stats_cw = m->stats_cw; ba.eps = m->cfg.norm_eps; ba.scale = 1.f;
+        ba.gamma = p(g.g); ba.beta = p(g.b); ba.dgamma = gr(g.g); ba.dbeta = gr(g.b); ba.stats1 = st1; ba.stats2 = st2; ba.gsum = gsum;
+        pd_train* tr = t;
+        bwd([ba, tr](cudaStream_t st) { tr->launches += 2; return launch_gn_bwd(ba, st); });
+        return o;
+    }
+
+    // out = (conv(concat(a, b)) + bias + addvec[n] + residual) * out_scale; d_addvec (B, Cout) receives the per-image column sums
+    TT* conv(const Param* w, const Param* bias, int cout, int k, int stride, int pad, TT* a, TT* b, const float* addvec, float* d_addvec,
+             TT* residual, float out_scale) {
+        const int Ct = a->C + (b ? b->C : 0);
+        const int Ho = stride == 2 ? a->H / 2 : a->H, Wo = stride == 2 ? a->W / 2 : a->W;
+        TT* o = act(cout, Ho, Wo);
+        const int kk = k * k;
+        float* w_fwd = (float*)aux((size_t)kk * Ct * cout * sizeof(float));
+        float* wd1 = stride == 1 ? (float*)aux((size_t)kk * cout * a->C * sizeof(float)) : nullptr;
+        float* wd2 = (stride == 1 && b) ? (float*)aux((size_t)kk * cout * b->C * sizeof(float)) : nullptr;
+        if (dry()) return o;
+        if ((size_t)cout * Ct * kk != w->numel) { set_error("internal: training conv shape mismatch for " + w->name); run(1); return o; }
+        run(launch_relayout_simt(p(w), cout, Ct, k, w_fwd, s()));
+        ConvArgs ca{};
+        ca.x1 = a->d; ca.x2 = b ? b->d : nullptr; ca.C1 = a->C; ca.C2 = b ? b->C : 0; ca.N = B; ca.H = a->H; ca.W = a->W; ca.Cout = cout;
+        ca.ksize = k; ca.stride = stride; ca.pad = pad; ca.Ho = Ho; ca.Wo = Wo; ca.w = w_fwd; ca.bias = bias ? p(bias) : nullptr;
+        ca.addvec = addvec; ca.addvec_stride = cout; ca.residual = residual ? residual->d : nullptr; ca.out_scale = out_scale; ca.out = o->d;
+        run(launch_conv_simt(DT_F32, ca, s()));
+        count(2);
+        const float* pw = p(w);
+        float* gw = gr(w);
+        float* gb = bias ? gr(bias) : nullptr;
+        const int Bn = B;
+        pd_train* tr = t;
+        const TT A = *a, Bt = b ? *b : TT(), O = *o, R = residual ? *residual : TT();
+        const bool hasB = b != nullptr, hasR = residual != nullptr;
+        bwd([=](cudaStream_t st) {
+            int rc = 0;
+            const size_t on = (size_t)Bn * O.H * O.W * O.C;
+            // everything below is the gradient of the pre-scale sum
+            if (out_scale != 1.0f && (rc = launch_add_inplace(O.g, O.g, out_scale - 1.0f, on, st))) return rc;
+            const int M = Bn * O.H * O.W;
+            if (gb && (rc = launch_colsum(O.g, M, O.C, M, 1.f, gb, st))) return rc;
+            if (d_addvec && (rc = launch_colsum(O.g, M, O.C, O.H * O.W, 1.f, d_addvec, st))) return rc;   // per image: (B, Cout)
+            if (hasR && R.g && (rc = launch_add_inplace(R.g, O.g, 1.0f, on, st))) return rc;
+            WgradArgs wa{};
+            wa.x1 = A.d; wa.x2 = hasB ? Bt.d : nullptr; wa.C1 = A.C; wa.C2 = hasB ? Bt.C : 0; wa.N = Bn; wa.H = A.H; wa.W = A.W; wa.Cout = O.C;
+            wa.ksize = k; wa.stride = stride; wa.pad = pad; wa.Ho = O.H; wa.Wo = O.W; wa.dy = O.g; wa.dw = gw; wa.scale = 1.f;
+            if ((rc = launch_conv_wgrad(wa, st))) return rc;
+            tr->launches += 4;
+            if (stride == 1) {
+                const TT* srcs[2] = {&A, hasB ? &Bt : nullptr};
+                float* wds[2] = {wd1, wd2};
+                int i0 = 0;
+                for (int q = 0; q < 2; ++q) {
+                    if (!srcs[q]) continue;
+                    if (srcs[q]->g) {
+                        if ((rc = launch_relayout_dgrad(pw, O.C, A.C + (hasB ? Bt.C : 0), k, i0, srcs[q]->C, wds[q], st))) return rc;
+                        ConvArgs da{};
+                        da.x1 = O.g; da.C1 = O.C; da.N = Bn; da.H = O.H; da.W = O.W; da.Cout = srcs[q]->C; da.ksize = k; da.stride = 1;
+                        da.pad = k - 1 - pad; da.Ho = O.H; da.Wo = O.W; da.w = wds[q]; da.residual = srcs[q]->g; da.out_scale = 1.f; da.out = srcs[q]->g;
+                        if ((rc = launch_conv_simt(DT_F32, da, st))) return rc;
+                        tr->launches += 2;
+                    }
+                    i0 += srcs[q]->C;
+                }
+            } else if (A.g) {
+                if ((rc = launch_conv_dgrad_gather(O.g, O.C, pw, Bn, A.H, A.W, A.C, O.H, O.W, O.C, pad, stride, A.g, st))) return rc;
+                tr->launches += 1;
+            }
+            return 0;
+        });
+        return o;
+    }
+
+    // ---- time + class embedding (cond_unet_2d.py:289-309) and the per-resnet projections ----
+    struct Emb { float *act = nullptr, *dact = nullptr; };
+    Emb embedding(const float* timesteps, const int64_t* labels) {
+        const int C0 = m->cfg.block_out_channels[0], D = m->D;
+        float* e0 = (float*)aux((size_t)B * C0 * sizeof(float));
+        float* pre1 = (float*)aux((size_t)B * D * sizeof(float));
+        float* h1 = (float*)aux((size_t)B * D * sizeof(float));
+        float* emb = (float*)aux((size_t)B * D * sizeof(float));
+        Emb e;
+        e.act = (float*)aux((size_t)B * D * sizeof(float));
+        e.dact = (float*)aux((size_t)B * D * sizeof(float), true);
+        float* demb = (float*)aux((size_t)B * D * sizeof(float));
+        float* dh1 = (float*)aux((size_t)B * D * sizeof(float));
+        float* dpre1 = (float*)aux((size_t)B * D * sizeof(float));
+        if (dry()) return e;
+        const float *w1 = p(m->te_w1), *b1 = p(m->te_b1), *w2 = p(m->te_w2), *b2 = p(m->te_b2);
+        const float* table = (m->cls && labels) ? p(m->cls) : nullptr;
+        run(launch_sinusoid(timesteps, B, C0, m->cfg.flip_sin_to_cos, m->cfg.freq_shift, e0, s()));
+        run(launch_sgemm(0, 1, B, D, C0, 1.f, e0, C0, w1, C0, pre1, D, 0, s()));
+        run(launch_bias_silu_fwd(pre1, b1, nullptr, nullptr, B, D, h1, s()));
+        run(launch_sgemm(0, 1, B, D, D, 1.f, h1, D, w2, D, emb, D, 0, s()));
+        run(launch_bias_silu_fwd(emb, b2, table, labels, B, D, e.act, s()));
+        count(5);
+        float *gw1 = gr(m->te_w1), *gb1 = gr(m->te_b1), *gw2 = gr(m->te_w2), *gb2 = gr(m->te_b2);
+        float* gcls = table ? gr(m->cls) : nullptr;
+        const int Bn = B;
+        float* dact = e.dact;
+        pd_train* tr = t;
+        bwd([=](cudaStream_t st) {
+            int rc = 0;
+            if ((rc = launch_silu_bwd(emb, dact, (size_t)Bn * D, demb, st))) return rc;
+            if (gcls && (rc = launch_scatter_rows(demb, labels, Bn, D, 1.f, gcls, st))) return rc;
+            if ((rc = launch_colsum(demb, Bn, D, Bn, 1.f, gb2, st))) return rc;
+            if ((rc = launch_sgemm(1, 0, D, D, Bn, 1.f, demb, D, h1, D, gw2, D, 1, st))) return rc;       // dW2 += demb^T h1
+            if ((rc = launch_sgemm(0, 0, Bn, D, D, 1.f, demb, D, w2, D, dh1, D, 0, st))) return rc;        // dh1 = demb W2
+            if ((rc = launch_silu_bwd(pre1, dh1, (size_t)Bn * D, dpre1, st))) return rc;
+            if ((rc = launch_colsum(dpre1, Bn, D, Bn, 1.f, gb1, st))) return rc;
+            if ((rc = launch_sgemm(1, 0, D, C0, Bn, 1.f, dpre1, D, e0, C0, gw1, C0, 1, st))) return rc;   // dW1 += dpre1^T e0
+            tr->launches += 8;
+            return 0;
+        });
+        return e;
+    }
+    // temb_r (B, cout) = act W_r^T + b_r; returns the table and its gradient table (filled by the conv that adds it)
+    void temb_proj(const ResL& R, const Emb& e, float** temb, float** dtemb) {
+        const int D = m->D, co = R.cout;
+        *temb = (float*)aux((size_t)B * co * sizeof(float));
+        *dtemb = (float*)aux((size_t)B * co * sizeof(float), true);
+        if (dry()) return;
+        const float *tw = p(R.tw), *tb = p(R.tb);
+        run(launch_sgemm(0, 1, B, co, D, 1.f, e.act, D, tw, D, *temb, co, 0, s()));
+        run(launch_add_bias_rows(*temb, tb, B, co, s()));
+        count(2);
+        float *gtw = gr(R.tw), *gtb = gr(R.tb), *dt = *dtemb, *dact = e.dact;
+        const float* actp = e.act;
+        const int Bn = B;
+        pd_train* tr = t;
+        bwd([=](cudaStream_t st) {
+            int rc = 0;
+            if ((rc = launch_colsum(dt, Bn, co, Bn, 1.f, gtb, st))) return rc;
+            if ((rc = launch_sgemm(1, 0, co, D, Bn, 1.f, dt, co, actp, D, gtw, D, 1, st))) return rc;     // dW_r += dtemb^T act
+            if ((rc = launch_sgemm(0, 0, Bn, D, co, 1.f, dt, co, tw, D, dact, D, 1, st))) return rc;      // dact += dtemb W_r
+            tr->launches += 3;
+            return 0;
+        });
+    }
+
+    // ResnetBlock2D on concat(a, b)
+    TT* resnet(const ResL& R, TT* a, TT* b, float* temb, float* dtemb) {
+        TT* hn = gn(R.n1, a, b, true);
+        TT* h1 = conv(R.c1.w, R.c1.b, R.cout, 3, 1, 1, hn, nullptr, temb, dtemb, nullptr, 1.f);
+        TT* h1n = gn(R.n2, h1, nullptr, true);
+        TT* res = a;
+        if (R.has_sc) res = conv(R.sc.w, R.sc.b, R.cout, 1, 1, 0, a, b, nullptr, nullptr, nullptr, 1.f);
+        return conv(R.c2.w, R.c2.b, R.cout, 3, 1, 1, h1n, nullptr, nullptr, nullptr, res, 1.0f / R.scale);
+    }
+
+    // Attention, head_dim 8
+    TT* attention(const AttnL& A, TT* x) {
+        const int C = A.C, S = x->H * x->W;
+        TT* xn = gn(A.gn, x, nullptr, false);
+        TT* q = conv(A.qw, A.qb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+        TT* k = conv(A.kw, A.kb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+        TT* v = conv(A.vw, A.vb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+        TT* o = act(C, x->H, x->W);
+        float* lse = (float*)aux((size_t)B * (C / 8) * S * sizeof(float));
+        float* delta = (float*)aux((size_t)B * (C / 8) * S * sizeof(float));
+        if (!dry()) {
+            run(launch_attn8_fwd(q->d, k->d, v->d, C, B, S, C, o->d, lse, s()));
+            count();
+            const TT Q = *q, K = *k, V = *v, O = *o;
+            const int Bn = B;
+            pd_train* tr = t;
+            bwd([=](cudaStream_t st) {
+                tr->launches += 2;
+                return launch_attn8_bwd(Q.d, K.d, V.d, C, O.d, O.g, lse, Bn, S, C, Q.g, K.g, V.g, delta, st);
+            });
+        }
+        return conv(A.ow, A.ob, C, 1, 1, 0, o, nullptr, nullptr, nullptr, x, 1.0f / A.rescale);
+    }
+
+    TT* upsample(TT* x) {
+        TT* o = act(x->C, 2 * x->H, 2 * x->W);
+        if (dry()) return o;
+        run(launch_upsample2x(DT_F32, x->d, B, x->H, x->W, x->C, o->d, s()));
+        count();
+        const TT X = *x, O = *o;
+        const int Bn = B;
+        pd_train* tr = t;
+        bwd([=](cudaStream_t st) { tr->launches += 1; return launch_upsample2x_bwd(O.g, Bn, X.H, X.W, X.C, X.g, st); });
+        return o;
+    }
+
+    // whole forward; returns the NCHW fp32 model output (aux) and registers every backward closure
+    float* forward(const float* noisy, const float* timesteps, const int64_t* labels, float** dm_out) {
+        const pd_unet_config_t& c = m->cfg;
+        const int H = t->H, W = t->W, C0 = c.block_out_channels[0], Cin = c.in_channels, Cout = c.out_channels;
+        Emb e = embedding(timesteps, labels);
+        std::vector<std::pair<float*, float*>> tembs;   // per resnet in graph order
+        auto all_res = [&](auto&& f) {
+            for (auto& d : m->down) for (auto& r : d.res) f(r);
+            f(m->mid_r0); f(m->mid_r1);
+            for (auto& u : m->up) for (auto& r : u.res) f(r);
+        };
+        std::map<const ResL*, std::pair<float*, float*>> temb_of;
+        all_res([&](const ResL& r) { float *a = nullptr, *b = nullptr; temb_proj(r, e, &a, &b); temb_of[&r] = {a, b}; });
+        // conv_in (cond_unet_2d.py:313): NCHW fp32 -> NHWC
+        TT* x = act(C0, H, W);
+        float* w_in = (float*)aux((size_t)9 * Cin * C0 * sizeof(float));
+        float* xin = (float*)aux((size_t)B * H * W * 4 * sizeof(float));
+        if (!dry()) {
+            run(launch_relayout_simt(p(m->conv_in.w), C0, Cin, 3, w_in, s()));
+            run(launch_conv_in(DT_F32, noisy, w_in, p(m->conv_in.b), B, Cin, H, W, C0, x->d, s()));
+            run(launch_nchw_to_nhwc_pad(noisy, B, Cin, H * W, 4, xin, s()));
+            count(3);
+            const TT X = *x;
+            float *gw = gr(m->conv_in.w), *gb = gr(m->conv_in.b);
+            const int Bn = B;
+            pd_train* tr = t;
+            bwd([=](cudaStream_t st) {
+                int rc = launch_colsum(X.g, Bn * H * W, C0, Bn * H * W, 1.f, gb, st);
+                if (rc) return rc;
+                WgradArgs wa{};
+                wa.x1 = xin; wa.C1 = 4; wa.N = Bn; wa.H = H; wa.W = W; wa.Cout = C0; wa.ksize = 3; wa.stride = 1; wa.pad = 1; wa.Ho = H; wa.Wo = W;
+                wa.dy = X.g; wa.dw = gw; wa.scale = 1.f; wa.Iw = Cin;
+                tr->launches += 2;
+                return launch_conv_wgrad(wa, st);
+            });
+        }
+        std::vector<TT*> skips{x};
+        for (auto& d : m->down) {
+            for (size_t j = 0; j < d.res.size(); ++j) {
+                auto tp = temb_of[&d.res[j]];
+                x = resnet(d.res[j], x, nullptr, tp.first, tp.second);
+                if (d.has_attn) x = attention(d.attn[j], x);
+                skips.push_back(x);
+            }
+            if (d.has_down) {
+                x = conv(d.down.w, d.down.b, d.down.cout, 3, 2, c.downsample_padding, x, nullptr, nullptr, nullptr, nullptr, 1.f);
+                skips.push_back(x);
+            }
+        }
+        { auto tp = temb_of[&m->mid_r0]; x = resnet(m->mid_r0, x, nullptr, tp.first, tp.second); }
+        if (m->mid_has_attn) x = attention(m->mid_attn, x);
+        { auto tp = temb_of[&m->mid_r1]; x = resnet(m->mid_r1, x, nullptr, tp.first, tp.second); }
+        for (auto& u : m->up) {
+            for (size_t j = 0; j < u.res.size(); ++j) {
+                TT* sk = skips.back(); skips.pop_back();
+                auto tp = temb_of[&u.res[j]];
+                x = resnet(u.res[j], x, sk, tp.first, tp.second);
+                if (u.has_attn) x = attention(u.attn[j], x);
+            }
+            if (u.has_up) {
+                TT* big = upsample(x);
+                x = conv(u.up.w, u.up.b, u.up.cout, 3, 1, 1, big, nullptr, nullptr, nullptr, nullptr, 1.f);
+            }
+        }
+        // conv_norm_out + SiLU + conv_out (cond_unet_2d.py:346-348) -> NCHW fp32
+        TT* xn = gn(m->norm_out, x, nullptr, true);
+        float* w_out = (float*)aux((size_t)9 * C0 * 4 * sizeof(float));
+        float* mo = (float*)aux((size_t)B * Cout * H * W * sizeof(float));
+        float* dm = (float*)aux((size_t)B * Cout * H * W * sizeof(float));
+        float* dy4 = (float*)aux((size_t)B * H * W * 4 * sizeof(float));
+        *dm_out = dm;
+        if (!dry()) {
+            run(launch_relayout_convout(p(m->conv_out.w), Cout, C0, w_out, s()));
+            ConvOutArgs oa{};
+            oa.act = xn->d; oa.w = w_out; oa.bias = p(m->conv_out.b); oa.N = B; oa.H = H; oa.W = W; oa.Cin = C0; oa.Cout = Cout; oa.model_out = mo;
+            run(launch_conv_out(DT_F32, oa, s()));
+            count(2);
+            const TT XN = *xn;
+            float *gw = gr(m->conv_out.w), *gb = gr(m->conv_out.b);
+            const float* pw = p(m->conv_out.w);
+            const int Bn = B;
+            pd_train* tr = t;
+            bwd([=](cudaStream_t st) {
+                int rc = launch_nchw_to_nhwc_pad(dm, Bn, Cout, H * W, 4, dy4, st);
+                if (rc) return rc;
+                if ((rc = launch_colsum(dy4, Bn * H * W, 4, Bn * H * W, 1.f, gb, st, Cout))) return rc;
+                WgradArgs wa{};
+                wa.x1 = XN.d; wa.C1 = C0; wa.N = Bn; wa.H = H; wa.W = W; wa.Cout = Cout; wa.ksize = 3; wa.stride = 1; wa.pad = 1; wa.Ho = H; wa.Wo = W;
+                wa.dy = dy4; wa.dy_pitch = 4; wa.dw = gw; wa.scale = 1.f;
+                if ((rc = launch_conv_wgrad(wa, st))) return rc;
+                tr->launches += 4;
+                return launch_conv_dgrad_gather(dy4, 4, pw, Bn, H, W, C0, H, W, Cout, 1, 1, XN.g, st);
+            });
+        }
+        return mo;
+    }
+};
+
+static int walk(pd_train* t, bool dry, const float* noisy, const float* timesteps, const int64_t* labels, float** mo, float** dm) {
+    t->dry = dry;
+    t->act_bump = t->aux_bump = 0;
+    t->tape.clear();
+    t->tts.clear();
+    t->rc = 0;
+    Walk w{t, t->m, t->B};
+    *mo = w.forward(noisy, timesteps, labels, dm);
+    return t->rc;
+}
+
+}  // namespace pd
+
+extern "C" {
+
+int pd_train_create(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, pd_train_t** out) {
+    PD_REQUIRE(m && out, "null argument");
+    PD_REQUIRE(batch > 0 && height > 0 && width > 0, "bad shape");
+    const int ds = 1 << (m->cfg.n_blocks - 1);
+    PD_REQUIRE(height % ds == 0 && width % ds == 0, "sample size must be a multiple of 2^(n_blocks-1)");
+    PD_REQUIRE(m->cfg.attention_head_dim == 8, "the training step implements attention_head_dim == 8 (the shipped trainable configs)");
+    PD_REQUIRE(m->cfg.in_channels <= 4 && m->cfg.out_channels <= 3, "the training step supports in_channels <= 4 and out_channels <= 3");
+    for (int i = 0; i < m->cfg.n_blocks; ++i) PD_REQUIRE(m->cfg.block_out_channels[i] % 32 == 0, "block_out_channels must be multiples of 32");
+    pd_train* t = new pd_train();
+    t->m = m; t->B = batch; t->H = height; t->W = width;
+    size_t off = 0;
+    for (auto& p : m->params) { t->poff[p.get()] = off; t->poff_by_index.push_back(off); off += p->numel; }
+    t->nflat = off;
+    float *mo, *dm;
+    int rc = walk(t, true, nullptr, nullptr, nullptr, &mo, &dm);
+    if (rc) { delete t; return rc; }
+    t->act_bytes = t->act_bump;
+    t->aux_bytes = t->aux_bump;
+    t->ws_bytes = 2 * t->act_bytes + t->aux_bytes + 1024;
+    *out = t;
+    return 0;
+}
+
+int pd_train_destroy(pd_train_t* t) {
+    delete t;
+    return 0;
+}
+
+int pd_train_num_params_flat(pd_train_t* t, int64_t* numel) {
+    PD_REQUIRE(t && numel, "null argument");
+    *numel = (int64_t)t->nflat;
+    return 0;
+}
+
+int pd_train_param_offset(pd_train_t* t, int32_t idx, int64_t* offset) {
+    PD_REQUIRE(t && offset && idx >= 0 && idx < (int)t->poff_by_index.size(), "parameter index out of range");
+    *offset = (int64_t)t->poff_by_index[idx];
+    return 0;
+}
+
+int pd_train_workspace_bytes(pd_train_t* t, size_t* bytes) {
+    PD_REQUIRE(t && bytes, "null argument");
+    *bytes = t->ws_bytes;
+    return 0;
+}
+
+int pd_train_bind(pd_train_t* t, void* workspace, size_t bytes) {
+    PD_REQUIRE(t && workspace, "null argument");
+    PD_REQUIRE(bytes >= t->ws_bytes, "workspace too small");
+    PD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    t->ws = (uint8_t*)workspace;
+    return 0;
+}
+
+int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const float* noisy, const float* timesteps, const int64_t* labels,
+                       const float* target, const float* sample_weight, float* loss_out, float* model_out, pd_stream_t stream) {
+    PD_REQUIRE(t && params && grads && noisy && timesteps && target && loss_out, "null argument");
+    PD_REQUIRE(t->ws, "pd_train_bind must be called first");
+    int dev = -1;
+    PD_CHECK_CUDA(cudaGetDevice(&dev));
+    PD_REQUIRE(dev == t->m->device, "the current CUDA device is not the one this handle was created on");
+    cudaStream_t s = (cudaStream_t)stream;
+    t->P = params; t->G = grads; t->s = s;
+    // gradients of the activations start at zero (every backward operator accumulates)
+    PD_CHECK_CUDA(cudaMemsetAsync(t->ws + t->act_bytes, 0, t->act_bytes, s));
+    float *mo = nullptr, *dm = nullptr;
+    int rc = walk(t, false, noisy, timesteps, labels, &mo, &dm);
+    if (rc) return rc;
+    PD_REQUIRE(t->act_bump <= t->act_bytes && t->aux_bump <= t->aux_bytes, "internal: training workspace plan mismatch");
+    const size_t per = (size_t)t->m->cfg.out_channels * t->H * t->W;
+    if ((rc = launch_mse_loss(mo, target, sample_weight, t->B, per, loss_out, dm, s))) return rc;
+    if (model_out) PD_CHECK_CUDA(cudaMemcpyAsync(model_out, mo, (size_t)t->B * per * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (auto it = t->tape.rbegin(); it != t->tape.rend(); ++it)
+        if ((rc = (*it)(s))) return rc;
+    t->tape.clear();
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pd_train_launch_count(pd_train_t* t, int64_t* n) {
+    PD_REQUIRE(t && n, "null argument");
+    *n = t->launches;
+    return 0;
+}
+
+int pd_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float ema_decay, float* scratch,
+                  float* grad_norm_out, pd_stream_t stream) {
+    PD_REQUIRE(params && grads && exp_avg && exp_avg_sq && scratch && n > 0 && step >= 1, "bad argument");
+    return launch_adamw(params, grads, exp_avg, exp_avg_sq, ema, (size_t)n, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm, ema_decay,
+                        scratch, grad_norm_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

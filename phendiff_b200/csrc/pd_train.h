@@ -1,0 +1,56 @@
+// phendiff_b200 — launch interface of the training-step kernels (pd_train_kernels.cu), used by the driver in pd_train.cu.
+#pragma once
+#include "pd_common.cuh"
+
+namespace pd {
+
+struct WgradArgs {
+    const float *x1, *x2;     // NHWC fp32 sources of the conv input (channel concat), x2 may be null
+    int C1, C2, N, H, W, Cout, ksize, stride, pad, Ho, Wo;
+    const float* dy;          // (N, Ho, Wo, Cout)
+    float* dw;                // OIHW (Cout, C1 + C2, k, k), accumulated
+    float scale;
+    int Iw;                   // I dimension of dw (input channels >= Iw are padding and skipped); 0: C1 + C2
+    int dy_pitch;             // row pitch of dy in floats; 0: Cout
+    int chunk;                // pixels per CTA (set by the launcher)
+};
+int launch_conv_wgrad(const WgradArgs& a, cudaStream_t s);
+int launch_relayout_dgrad(const float* w, int O, int I, int k, int i0, int Isub, float* out, cudaStream_t s);
+int launch_colsum(const float* dy, int M, int C, int rows_per_seg, float scale, float* out, cudaStream_t s, int Cvalid = 0);
+int launch_add_bias_rows(float* x, const float* bias, int B, int D, cudaStream_t s);
+int launch_conv_dgrad_gather(const float* dy, int dy_pitch, const float* w, int N, int H, int W, int C, int Ho, int Wo, int Cout, int pad,
+                             int stride, float* dx, cudaStream_t s);
+int launch_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx, cudaStream_t s);
+
+struct GNBwdArgs {
+    const float *x1, *x2;     // GroupNorm input (concat), NHWC fp32
+    float *dx1, *dx2;         // accumulated
+    const float* dy;          // (N, HW, C1 + C2) gradient w.r.t. the (activated) output
+    int C1, C2, N, HW, groups, silu, stats_cw;
+    float eps, scale;
+    const float *gamma, *beta;
+    float *dgamma, *dbeta;    // accumulated
+    const double *stats1, *stats2;   // chunk statistics of the inputs (forward)
+    float* gsum;              // scratch (N, groups, 2)
+};
+int launch_gn_bwd(const GNBwdArgs& a, cudaStream_t s);
+
+// q, k, v: (N, S, pitch)-strided rows with the head's 8 values at head * 8 (packed qkv: pitch 3C, k = q + C, v = q + 2C)
+int launch_attn8_fwd(const float* q, const float* k, const float* v, int pitch, int N, int S, int C, float* out, float* lse, cudaStream_t s);
+int launch_attn8_bwd(const float* q, const float* k, const float* v, int pitch, const float* o, const float* dout, const float* lse, int N,
+                     int S, int C, float* dq, float* dk, float* dv, float* delta, cudaStream_t s);
+
+// C[M, N] (+)= alpha * op(A) op(B); ta: A is stored (K, M); tb: B is stored (N, K)
+int launch_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                 int accumulate, cudaStream_t s);
+int launch_sinusoid(const float* t, int B, int C0, int flip, float shift, float* out, cudaStream_t s);
+int launch_bias_silu_fwd(float* pre, const float* bias, const float* table, const int64_t* labels, int B, int D, float* act, cudaStream_t s);
+int launch_silu_bwd(const float* pre, const float* dact, size_t total, float* dpre, cudaStream_t s);
+int launch_scatter_rows(const float* d, const int64_t* labels, int B, int D, float scale, float* table_grad, cudaStream_t s);
+int launch_nchw_to_nhwc_pad(const float* x, int N, int C, int HW, int Cp, float* out, cudaStream_t s);
+int launch_add_inplace(float* y, const float* x, float alpha, size_t n, cudaStream_t s);
+int launch_mse_loss(const float* m, const float* target, const float* weight, int B, size_t per, float* loss, float* dm, cudaStream_t s);
+int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float b1, float b2, float eps, float wd,
+                 int step, float max_norm, float ema_decay, float* scratch_sumsq, float* norm_out, cudaStream_t s);
+
+}  // namespace pd

@@ -1,0 +1,609 @@
+// phendiff_b200 — kernels of the TRAINING step (reference src/utils_training.py:244-456: noise / timestep
+// sampling, `_diffusion_and_backward`, loss by prediction type :415-433, clip_grad_norm_(1.0) :439, AdamW train.py:279-285, EMA
+// utils_training.py:224-241).  This file is the fp32 path of the backward pass: every backward operator of the UNet graph as a
+// CUDA-core kernel over NHWC fp32 activations, checked against torch.autograd on the oracle (tests/test_gpu_training.py).  It
+// plays the role the SIMT kernels play for inference: the validation mode the tensor-core backward is compared against.
+//   conv wgrad    dW[co, ci, r, s] += sum_pixels dY[p, co] * X[p @ (r, s), ci]        (split over pixel chunks, atomics)
+//   conv dgrad    stride 1: the forward SIMT conv on tap-flipped, transposed weights; stride 2: gather kernel below
+//   bias / time-embedding grads: column sums of dY per tensor / per image
+//   GroupNorm (+SiLU) backward, softmax attention backward (head_dim 8, probabilities recomputed from the saved log-sum-exp),
+//   nearest-upsample backward, small dense GEMMs of the embedding MLP, the weighted-MSE loss and its gradient,
+//   global-norm clip + AdamW + EMA over flat parameter vectors.
+#include "pd_kernels.h"
+#include "pd_train.h"
+
+namespace pd {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight re-layouts for the backward convolutions
+// ---------------------------------------------------------------------------------------------------------------------
+// OIHW (O, I, k, k) -> dgrad weights (k*k*O, Isub) for input channels [i0, i0 + Isub): row = tap' * O + o with tap' the FLIPPED
+// tap (k*k - 1 - tap), so that the stride-1 forward kernel computes dX = conv(dY, W^T flipped)
+__global__ void relayout_dgrad_kernel(const float* __restrict__ w, int O, int I, int k, int i0, int Isub, float* __restrict__ out) {
+    const int kk = k * k;
+    const size_t total = (size_t)kk * O * Isub;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = idx % Isub;
+        const size_t r = idx / Isub;
+        const int o = r % O, tapf = r / O;
+        const int tap = kk - 1 - tapf;
+        out[idx] = w[((size_t)o * I + i0 + i) * kk + tap];
+    }
+}
+int launch_relayout_dgrad(const float* w, int O, int I, int k, int i0, int Isub, float* out, cudaStream_t s) {
+    const size_t total = (size_t)k * k * O * Isub;
+    relayout_dgrad_kernel<<<(int)std::min<size_t>((total + 255) / 256, 4096), 256, 0, s>>>(w, O, I, k, i0, Isub, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// conv wgrad: 64 (ci) x 64 (co) tile of one tap per CTA over a chunk of output pixels, K = pixels, fp32 atomics into OIHW
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ __align__(16) float Xs[BK][BM + 4];   // [pixel][ci]
+    __shared__ __align__(16) float Gs[BK][BN + 4];   // [pixel][co]
+    const int tid = threadIdx.x;
+    const int Ct = a.C1 + a.C2, kk = a.ksize * a.ksize;
+    const int citiles = (Ct + BM - 1) / BM;
+    const int tap = blockIdx.x / citiles, ci0 = (blockIdx.x - tap * citiles) * BM;
+    const int co0 = blockIdx.y * BN;
+    const int r = tap / a.ksize, sx = tap - r * a.ksize;
+    const int M = a.N * a.Ho * a.Wo;
+    const int m_begin = blockIdx.z * a.chunk, m_end = min(m_begin + a.chunk, M);
+    // load roles: pixel row lp (0..15), 4 consecutive channels at lc
+    const int lp = tid >> 4, lc = (tid & 15) * 4;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int m0 = m_begin; m0 < m_end; m0 += BK) {
+        const int m = m0 + lp;
+        float xv[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < m_end) {
+            const int img = m / (a.Ho * a.Wo), rem = m - img * a.Ho * a.Wo, ho = rem / a.Wo, wo = rem - ho * a.Wo;
+            const int ih = ho * a.stride - a.pad + r, iw = wo * a.stride - a.pad + sx;
+            if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
+                const size_t pix = ((size_t)img * a.H + ih) * a.W + iw;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ci = ci0 + lc + i;
+                    if (ci < a.C1) xv[i] = a.x1[pix * a.C1 + ci];
+                    else if (ci < Ct) xv[i] = a.x2[pix * a.C2 + (ci - a.C1)];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (co0 + lc + i < a.Cout) gv[i] = a.dy[(size_t)m * a.dy_pitch + co0 + lc + i];
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&Xs[lp][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        *reinterpret_cast<float4*>(&Gs[lp][lc]) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 xf = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+            const float4 gf = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
+            const float xx[4] = {xf.x, xf.y, xf.z, xf.w}, gg[4] = {gf.x, gf.y, gf.z, gf.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xx[i], gg[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ci = ci0 + ty * 4 + i;
+        if (ci >= a.Iw) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + tx * 4 + j;
+            if (co < a.Cout) atomicAdd(a.dw + ((size_t)co * a.Iw + ci) * kk + tap, acc[i][j] * a.scale);
+        }
+    }
+}
+int launch_conv_wgrad(const WgradArgs& a_, cudaStream_t s) {
+    WgradArgs a = a_;
+    const int Ct = a.C1 + a.C2, M = a.N * a.Ho * a.Wo;
+    if (a.Iw <= 0) a.Iw = Ct;
+    if (a.dy_pitch <= 0) a.dy_pitch = a.Cout;
+    PD_REQUIRE(a.C1 % 4 == 0 && Ct % 4 == 0, "conv_wgrad needs channel counts that are multiples of 4");
+    const int tiles = ((Ct + 63) / 64) * a.ksize * a.ksize * ((a.Cout + 63) / 64);
+    int split = std::max(1, std::min((M + 255) / 256, (148 * 6 + tiles - 1) / tiles));
+    a.chunk = (((M + split - 1) / split) + 15) / 16 * 16;
+    split = (M + a.chunk - 1) / a.chunk;
+    dim3 grid(((Ct + 63) / 64) * a.ksize * a.ksize, (a.Cout + 63) / 64, split);
+    conv_wgrad_kernel<<<grid, 256, 0, s>>>(a);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// column sums of dY (M rows x C): per tensor (rows_per_seg = M) or per image (rows_per_seg = H*W) -> out[seg, c] += scale * sum
+// (C = row pitch of dy; only the first Cvalid columns are summed: conv_out's gradient rows are padded from 3 to 4 channels)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int M, int C, int Cvalid, int rows_per_seg,
+                                                      int rows_per_block, float scale, float* __restrict__ out) {
+    const int seg = blockIdx.y;
+    const int r0 = seg * rows_per_seg + blockIdx.x * rows_per_block;
+    const int r1 = min(min(r0 + rows_per_block, (seg + 1) * rows_per_seg), M);
+    for (int c = threadIdx.x; c < Cvalid; c += blockDim.x) {
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) acc += dy[(size_t)r * C + c];
+        atomicAdd(out + (size_t)seg * Cvalid + c, acc * scale);
+    }
+}
+int launch_colsum(const float* dy, int M, int C, int rows_per_seg, float scale, float* out, cudaStream_t s, int Cvalid) {
+    if (Cvalid <= 0) Cvalid = C;
+    const int segs = M / rows_per_seg;
+    const int rpb = std::max(16, std::min(rows_per_seg, 256));
+    dim3 grid((rows_per_seg + rpb - 1) / rpb, segs);
+    colsum_kernel<<<grid, 256, 0, s>>>(dy, M, C, Cvalid, rows_per_seg, rpb, scale, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// gather dgrad for the shapes the GEMM-style path does not take (stride-2 Downsample2D, conv_out's 3 output channels):
+// dX[n, ih, iw, ci] += sum_{taps with (ih + pad - r) divisible by stride, co} dY[n, oh, ow, co] W[co, ci, r, s]
+// one warp per input pixel, lanes over ci (weights OIHW through L1 / L2: three layers per model, validation path)
+__global__ void __launch_bounds__(256) conv_dgrad_gather_kernel(const float* __restrict__ dy, int dy_pitch, const float* __restrict__ w, int N,
+                                                                 int H, int W, int C, int Ho, int Wo, int Cout, int pad, int stride,
+                                                                 float* __restrict__ dx) {
+    const int lane = threadIdx.x & 31;
+    const size_t pixel = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pixel >= (size_t)N * H * W) return;
+    const int n = pixel / ((size_t)H * W), rem = pixel - (size_t)n * H * W, ih = rem / W, iw = rem - ih * W;
+    for (int ci = lane; ci < C; ci += 32) {
+        float acc = 0.f;
+        for (int r = 0; r < 3; ++r) {
+            const int t = ih + pad - r;
+            if (t < 0 || (t % stride)) continue;
+            const int oh = t / stride;
+            if (oh >= Ho) continue;
+            for (int sx = 0; sx < 3; ++sx) {
+                const int u = iw + pad - sx;
+                if (u < 0 || (u % stride)) continue;
+                const int ow = u / stride;
+                if (ow >= Wo) continue;
+                const float* g = dy + (((size_t)n * Ho + oh) * Wo + ow) * dy_pitch;
+                const float* wp = w + (size_t)ci * 9 + r * 3 + sx;
+                for (int co = 0; co < Cout; ++co) acc = fmaf(g[co], wp[(size_t)co * C * 9], acc);
+            }
+        }
+        dx[pixel * C + ci] += acc;
+    }
+}
+int launch_conv_dgrad_gather(const float* dy, int dy_pitch, const float* w, int N, int H, int W, int C, int Ho, int Wo, int Cout, int pad,
+                             int stride, float* dx, cudaStream_t s) {
+    const size_t pixels = (size_t)N * H * W;
+    conv_dgrad_gather_kernel<<<(int)((pixels + 7) / 8), 256, 0, s>>>(dy, dy_pitch, w, N, H, W, C, Ho, Wo, Cout, pad, stride, dx);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// nearest 2x upsample backward: dx[n, h, w, c] += sum of the 2x2 block of dy
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C, float* __restrict__ dx) {
+    const size_t total = (size_t)N * H * W * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % C;
+        size_t p = i / C;
+        const int w = p % W; p /= W;
+        const int h = p % H;
+        const int n = p / H;
+        const float* b = dy + (((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
+        dx[i] += b[0] + b[C] + b[(size_t)2 * W * C] + b[(size_t)2 * W * C + C];
+    }
+}
+int launch_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx, cudaStream_t s) {
+    const size_t total = (size_t)N * H * W * C;
+    upsample2x_bwd_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, s>>>(dy, N, H, W, C, dx);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) backward over concat(x1, x2).  y = act(z), z = xhat * gamma + beta, xhat = (x - mean) * rstd.
+//   pass 1 (reduce): dz = dy * act'(z); dbeta_c += sum dz; dgamma_c += sum dz xhat; s1[n,g] += gamma_c dz; s2[n,g] += gamma_c dz xhat
+//   pass 2 (apply):  dx += rstd * (gamma dz - (s1 + xhat s2) / count)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_grad(float z) {
+    const float sg = 1.0f / (1.0f + expf(-z));
+    return sg * (1.0f + z * (1.0f - sg));
+}
+__device__ __forceinline__ void gn_mean_rstd(const GNBwdArgs& a, int n, int g, float* mean, float* rstd) {
+    const int C = a.C1 + a.C2, cpg = C / a.groups, cw = a.stats_cw;
+    double sum = 0.0, sq = 0.0;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; cc += cw) {
+        const double* st = (cc < a.C1) ? a.stats1 + ((size_t)n * (a.C1 / cw) + cc / cw) * 2
+                                       : a.stats2 + ((size_t)n * (a.C2 / cw) + (cc - a.C1) / cw) * 2;
+        sum += st[0]; sq += st[1];
+    }
+    const double inv = 1.0 / ((double)cpg * a.HW), mu = sum * inv;
+    *mean = (float)mu;
+    *rstd = 1.0f / sqrtf((float)fmax(sq * inv - mu * mu, 0.0) + a.eps);
+}
+template <int PASS>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(GNBwdArgs a, int rows_per_block) {
+    extern __shared__ float sm[];   // mean[groups], rstd[groups], (pass 2) s1[groups], s2[groups]
+    const int C = a.C1 + a.C2, cpg = C / a.groups;
+    const int n = blockIdx.y;
+    float* s_mean = sm;
+    float* s_rstd = sm + a.groups;
+    float* s_s1 = sm + 2 * a.groups;
+    float* s_s2 = sm + 3 * a.groups;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        gn_mean_rstd(a, n, g, &s_mean[g], &s_rstd[g]);
+        if (PASS == 2) { s_s1[g] = a.gsum[((size_t)n * a.groups + g) * 2]; s_s2[g] = a.gsum[((size_t)n * a.groups + g) * 2 + 1]; }
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, a.HW);
+    const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float mu = s_mean[g], rs = s_rstd[g], ga = a.gamma[c], be = a.beta[c];
+        const float* x;
+        float* dx;
+        int pitch, co;
+        if (c < a.C1) { x = a.x1; dx = a.dx1; pitch = a.C1; co = c; } else { x = a.x2; dx = a.dx2; pitch = a.C2; co = c - a.C1; }
+        const size_t base = (size_t)n * a.HW;
+        float sa = 0.f, sb = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const float xh = (x[(base + r) * pitch + co] - mu) * rs;
+            float dz = a.dy[(base + r) * C + c];
+            if (a.silu) dz *= silu_grad(fmaf(xh, ga, be));
+            if (PASS == 1) { sa += dz; sb += dz * xh; }
+            else dx[(base + r) * pitch + co] += rs * (ga * dz - (s_s1[g] + xh * s_s2[g]) * inv_cnt);
+        }
+        if (PASS == 1) {
+            atomicAdd(a.dbeta + c, sa * a.scale);
+            atomicAdd(a.dgamma + c, sb * a.scale);
+            atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2, ga * sa);
+            atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2 + 1, ga * sb);
+        }
+    }
+}
+int launch_gn_bwd(const GNBwdArgs& a, cudaStream_t s) {
+    const int C = a.C1 + a.C2;
+    PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
+    PD_CHECK_CUDA(cudaMemsetAsync(a.gsum, 0, (size_t)a.N * a.groups * 2 * sizeof(float), s));
+    const int rpb = std::max(8, std::min(a.HW, 64));
+    dim3 grid((a.HW + rpb - 1) / rpb, a.N);
+    const size_t smem = (size_t)4 * a.groups * sizeof(float);
+    gn_bwd_kernel<1><<<grid, 256, smem, s>>>(a, rpb);
+    gn_bwd_kernel<2><<<grid, 256, smem, s>>>(a, rpb);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// attention, head_dim 8: forward that also stores the log-sum-exp of every query row, and the backward that recomputes P from it
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr float kAttnScale8 = 0.35355339059327373f;   // 1 / sqrt(8)
+__global__ void __launch_bounds__(128) attn8_fwd_kernel(const float* __restrict__ qp, const float* __restrict__ kp,
+                                                         const float* __restrict__ vp, int pitch, int S, int C, float* __restrict__ out,
+                                                         float* __restrict__ lse) {
+    constexpr int D = 8, TK = 128;
+    __shared__ float Ks[TK][D], Vs[TK][D];
+    const int n = blockIdx.z, head = blockIdx.y, qi = blockIdx.x * 128 + threadIdx.x;
+    const size_t rowp = (size_t)pitch, off = (size_t)n * S * rowp + head * D;
+    const float *qb = qp + off, *kb = kp + off, *vb = vp + off;
+    float q[D], o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { q[i] = qi < S ? qb[(size_t)qi * rowp + i] * kAttnScale8 : 0.f; o[i] = 0.f; }
+    float mx = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < S; k0 += TK) {
+        __syncthreads();
+        const int kj = k0 + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            Ks[threadIdx.x][i] = kj < S ? kb[(size_t)kj * rowp + i] : 0.f;
+            Vs[threadIdx.x][i] = kj < S ? vb[(size_t)kj * rowp + i] : 0.f;
+        }
+        __syncthreads();
+        const int kmax = min(TK, S - k0);
+        for (int j = 0; j < kmax; ++j) {
+            float sc = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) sc = fmaf(q[i], Ks[j][i], sc);
+            const float nm = fmaxf(mx, sc), corr = expf(mx - nm), p = expf(sc - nm);
+            l = l * corr + p;
+#pragma unroll
+            for (int i = 0; i < D; ++i) o[i] = fmaf(o[i], corr, p * Vs[j][i]);
+            mx = nm;
+        }
+    }
+    if (qi < S) {
+        const float inv = 1.0f / l;
+        float* op = out + ((size_t)n * S + qi) * C + head * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) op[i] = o[i] * inv;
+        lse[((size_t)n * (C / D) + head) * S + qi] = mx + logf(l);
+    }
+}
+// dq: thread per query, keys staged; dk / dv: thread per key, queries staged.  delta[q] = sum_d dO[q, d] O[q, d].
+__global__ void __launch_bounds__(128) attn8_bwd_q_kernel(const float* __restrict__ qp, const float* __restrict__ kp,
+                                                           const float* __restrict__ vp, int pitch, const float* __restrict__ o,
+                                                           const float* __restrict__ dout, const float* __restrict__ lse, int S, int C,
+                                                           float* __restrict__ dq_out, float* __restrict__ delta) {
+    constexpr int D = 8, TK = 128;
+    __shared__ float Ks[TK][D], Vs[TK][D];
+    const int n = blockIdx.z, head = blockIdx.y, qi = blockIdx.x * 128 + threadIdx.x;
+    const size_t rowp = (size_t)pitch, off = (size_t)n * S * rowp + head * D;
+    const float *qb = qp + off, *kb = kp + off, *vb = vp + off;
+    float q[D], dq[D], g[D];
+    float dl = 0.f, L = 0.f;
+    if (qi < S) {
+        const size_t orow = ((size_t)n * S + qi) * C + head * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { q[i] = qb[(size_t)qi * rowp + i] * kAttnScale8; g[i] = dout[orow + i]; dl = fmaf(g[i], o[orow + i], dl); }
+        L = lse[((size_t)n * (C / D) + head) * S + qi];
+        delta[((size_t)n * (C / D) + head) * S + qi] = dl;
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) { q[i] = 0.f; g[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) dq[i] = 0.f;
+    for (int k0 = 0; k0 < S; k0 += TK) {
+        __syncthreads();
+        const int kj = k0 + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            Ks[threadIdx.x][i] = kj < S ? kb[(size_t)kj * rowp + i] : 0.f;
+            Vs[threadIdx.x][i] = kj < S ? vb[(size_t)kj * rowp + i] : 0.f;
+        }
+        __syncthreads();
+        const int kmax = min(TK, S - k0);
+        for (int j = 0; j < kmax; ++j) {
+            float sc = 0.f, dp = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { sc = fmaf(q[i], Ks[j][i], sc); dp = fmaf(g[i], Vs[j][i], dp); }
+            const float ds = expf(sc - L) * (dp - dl);
+#pragma unroll
+            for (int i = 0; i < D; ++i) dq[i] = fmaf(ds, Ks[j][i], dq[i]);
+        }
+    }
+    if (qi < S) {
+        float* dp = dq_out + off + (size_t)qi * rowp;
+#pragma unroll
+        for (int i = 0; i < D; ++i) dp[i] += dq[i] * kAttnScale8;
+    }
+}
+__global__ void __launch_bounds__(128) attn8_bwd_kv_kernel(const float* __restrict__ qp, const float* __restrict__ kp,
+                                                            const float* __restrict__ vp, int pitch, const float* __restrict__ dout,
+                                                            const float* __restrict__ lse, const float* __restrict__ delta, int S, int C,
+                                                            float* __restrict__ dk_out, float* __restrict__ dv_out) {
+    constexpr int D = 8, TQ = 128;
+    __shared__ float Qs[TQ][D], Gs[TQ][D], Ls[TQ], Ds[TQ];
+    const int n = blockIdx.z, head = blockIdx.y, kj = blockIdx.x * 128 + threadIdx.x;
+    const size_t rowp = (size_t)pitch, off = (size_t)n * S * rowp + head * D;
+    const float *qb = qp + off, *kb = kp + off, *vb = vp + off;
+    float k[D], v[D], dk[D], dv[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        k[i] = kj < S ? kb[(size_t)kj * rowp + i] : 0.f;
+        v[i] = kj < S ? vb[(size_t)kj * rowp + i] : 0.f;
+        dk[i] = 0.f; dv[i] = 0.f;
+    }
+    for (int q0 = 0; q0 < S; q0 += TQ) {
+        __syncthreads();
+        const int qi = q0 + threadIdx.x;
+        const size_t orow = ((size_t)n * S + qi) * C + head * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            Qs[threadIdx.x][i] = qi < S ? qb[(size_t)qi * rowp + i] * kAttnScale8 : 0.f;
+            Gs[threadIdx.x][i] = qi < S ? dout[orow + i] : 0.f;
+        }
+        Ls[threadIdx.x] = qi < S ? lse[((size_t)n * (C / D) + head) * S + qi] : INFINITY;   // exp(s - inf) = 0 for padding queries
+        Ds[threadIdx.x] = qi < S ? delta[((size_t)n * (C / D) + head) * S + qi] : 0.f;
+        __syncthreads();
+        const int qmax = min(TQ, S - q0);
+        for (int j = 0; j < qmax; ++j) {
+            float sc = 0.f, dp = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { sc = fmaf(Qs[j][i], k[i], sc); dp = fmaf(Gs[j][i], v[i], dp); }
+            const float p = expf(sc - Ls[j]), ds = p * (dp - Ds[j]);
+#pragma unroll
+            for (int i = 0; i < D; ++i) { dv[i] = fmaf(p, Gs[j][i], dv[i]); dk[i] = fmaf(ds, Qs[j][i], dk[i]); }   // Qs carries 1/sqrt(d)
+        }
+    }
+    if (kj < S) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) { dk_out[off + (size_t)kj * rowp + i] += dk[i]; dv_out[off + (size_t)kj * rowp + i] += dv[i]; }
+    }
+}
+int launch_attn8_fwd(const float* q, const float* k, const float* v, int pitch, int N, int S, int C, float* out, float* lse, cudaStream_t s) {
+    PD_REQUIRE(C % 8 == 0, "attention channels must be a multiple of 8");
+    attn8_fwd_kernel<<<dim3((S + 127) / 128, C / 8, N), 128, 0, s>>>(q, k, v, pitch, S, C, out, lse);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_attn8_bwd(const float* q, const float* k, const float* v, int pitch, const float* o, const float* dout, const float* lse, int N,
+                     int S, int C, float* dq, float* dk, float* dv, float* delta, cudaStream_t s) {
+    dim3 grid((S + 127) / 128, C / 8, N);
+    attn8_bwd_q_kernel<<<grid, 128, 0, s>>>(q, k, v, pitch, o, dout, lse, S, C, dq, delta);
+    attn8_bwd_kv_kernel<<<grid, 128, 0, s>>>(q, k, v, pitch, dout, lse, delta, S, C, dk, dv);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small dense GEMMs of the embedding MLP (rows = batch): C[M, N] (+)= alpha * op(A)[M, K] op(B)[K, N]; one thread per output
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void sgemm_kernel(int ta, int tb, int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                             const float* __restrict__ B, int ldb, float* __restrict__ Cm, int ldc, int accumulate) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (n >= N || m >= M) return;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float av = ta ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+        const float bv = tb ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+        acc = fmaf(av, bv, acc);
+    }
+    float* c = Cm + (size_t)m * ldc + n;
+    *c = (accumulate ? *c : 0.f) + alpha * acc;
+}
+int launch_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                 int accumulate, cudaStream_t s) {
+    sgemm_kernel<<<dim3((N + 127) / 128, M), 128, 0, s>>>(ta, tb, M, N, K, alpha, A, lda, B, ldb, C, ldc, accumulate);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// elementwise helpers of the embedding path
+__global__ void sinusoid_kernel(const float* __restrict__ t, int B, int C0, int flip, float shift, float* __restrict__ out) {
+    const int b = blockIdx.x, half = C0 / 2;
+    for (int k = threadIdx.x; k < half; k += blockDim.x) {
+        const float f = expf((-9.210340371976184f * (float)k) / ((float)half - shift));
+        const float arg = t[b] * f, sn = sinf(arg), cs = cosf(arg);
+        if (flip) { out[(size_t)b * C0 + k] = cs; out[(size_t)b * C0 + half + k] = sn; }
+        else { out[(size_t)b * C0 + k] = sn; out[(size_t)b * C0 + half + k] = cs; }
+    }
+}
+// y = silu(x + bias [+ table[label]]) with the pre-activation kept; backward: dpre = dy * silu'(pre)
+__global__ void bias_silu_fwd_kernel(float* __restrict__ pre, const float* __restrict__ bias, const float* __restrict__ table,
+                                     const int64_t* __restrict__ labels, int B, int D, float* __restrict__ act) {
+    const size_t total = (size_t)B * D;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i / D, j = i - (size_t)b * D;
+        float v = pre[i] + bias[j];
+        if (table && labels) v += table[(size_t)labels[b] * D + j];
+        pre[i] = v;
+        act[i] = v / (1.0f + expf(-v));
+    }
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dact, size_t total, float* __restrict__ dpre) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        dpre[i] = dact[i] * silu_grad(pre[i]);
+}
+// table_grad[labels[b], :] += scale * d[b, :]
+__global__ void scatter_rows_kernel(const float* __restrict__ d, const int64_t* __restrict__ labels, int B, int D, float scale,
+                                    float* __restrict__ table_grad) {
+    const size_t total = (size_t)B * D;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i / D, j = i - (size_t)b * D;
+        atomicAdd(table_grad + (size_t)labels[b] * D + j, d[i] * scale);
+    }
+}
+// x[b, j] += bias[j]
+__global__ void add_bias_rows_kernel(float* __restrict__ x, const float* __restrict__ bias, int B, int D) {
+    const size_t total = (size_t)B * D;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) x[i] += bias[i % D];
+}
+int launch_add_bias_rows(float* x, const float* bias, int B, int D, cudaStream_t s) {
+    add_bias_rows_kernel<<<std::min((B * D + 255) / 256, 1024), 256, 0, s>>>(x, bias, B, D);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_sinusoid(const float* t, int B, int C0, int flip, float shift, float* out, cudaStream_t s) {
+    sinusoid_kernel<<<B, 128, 0, s>>>(t, B, C0, flip, shift, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_bias_silu_fwd(float* pre, const float* bias, const float* table, const int64_t* labels, int B, int D, float* act, cudaStream_t s) {
+    bias_silu_fwd_kernel<<<std::min((B * D + 255) / 256, 1024), 256, 0, s>>>(pre, bias, table, labels, B, D, act);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_silu_bwd(const float* pre, const float* dact, size_t total, float* dpre, cudaStream_t s) {
+    silu_bwd_kernel<<<(int)std::min<size_t>((total + 255) / 256, 1024), 256, 0, s>>>(pre, dact, total, dpre);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_scatter_rows(const float* d, const int64_t* labels, int B, int D, float scale, float* table_grad, cudaStream_t s) {
+    scatter_rows_kernel<<<std::min((B * D + 255) / 256, 1024), 256, 0, s>>>(d, labels, B, D, scale, table_grad);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// NCHW fp32 (N, C, HW) -> NHWC fp32 (N, HW, Cp) zero-padded to Cp channels (the loss gradient entering conv_out's backward)
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int N, int C, int HW, int Cp, float* __restrict__ out) {
+    const size_t total = (size_t)N * HW * Cp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % Cp;
+        const size_t p = i / Cp;
+        const int hw = p % HW, n = p / HW;
+        out[i] = c < C ? x[((size_t)n * C + c) * HW + hw] : 0.f;
+    }
+}
+int launch_nchw_to_nhwc_pad(const float* x, int N, int C, int HW, int Cp, float* out, cudaStream_t s) {
+    const size_t total = (size_t)N * HW * Cp;
+    nchw_to_nhwc_pad_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, s>>>(x, N, C, HW, Cp, out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+// y += x (elementwise)
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(alpha, x[i], y[i]);
+}
+int launch_add_inplace(float* y, const float* x, float alpha, size_t n, cudaStream_t s) {
+    add_inplace_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, s>>>(y, x, alpha, n);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// loss of utils_training.py:415-433 in one form: mean over all elements of weight[b] * (m - target)^2 (epsilon: target = noise,
+// weight = 1; v_prediction: target = velocity; sample: target = clean images, weight = alpha_t / (1 - alpha_t)), and its gradient
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ m, const float* __restrict__ target,
+                                                        const float* __restrict__ weight, int B, size_t per, float* __restrict__ loss,
+                                                        float* __restrict__ dm) {
+    const size_t total = (size_t)B * per;
+    const float inv = 1.0f / (float)total;
+    float acc = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float w = weight ? weight[i / per] : 1.0f, d = m[i] - target[i];
+        acc = fmaf(w * d, d, acc);
+        dm[i] = 2.0f * w * d * inv;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc * inv);
+}
+int launch_mse_loss(const float* m, const float* target, const float* weight, int B, size_t per, float* loss, float* dm, cudaStream_t s) {
+    PD_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+    mse_loss_kernel<<<(int)std::min<size_t>(((size_t)B * per + 255) / 256, 148 * 8), 256, 0, s>>>(m, target, weight, B, per, loss, dm);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// clip_grad_norm_(max_norm) + AdamW (torch.optim.AdamW semantics, decoupled weight decay) + EMA over flat fp32 vectors
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+    float acc = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc = fmaf(g[i], g[i], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ v, float* __restrict__ ema, size_t n, float lr, float b1, float b2,
+                                                     float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
+                                                     const float* __restrict__ sumsq, float ema_decay, float* __restrict__ norm_out) {
+    const float norm = sqrtf(*sumsq);
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    const float coef = max_norm > 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * (1.0f - lr * wd);
+        const float mi = b1 * m[i] + (1.0f - b1) * gi, vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        p[i] = pi;
+        if (ema) ema[i] -= (1.0f - ema_decay) * (ema[i] - pi);   // diffusers EMAModel.step: s -= (1 - decay) (s - p)
+    }
+}
+int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float b1, float b2, float eps, float wd,
+                 int step, float max_norm, float ema_decay, float* scratch_sumsq, float* norm_out, cudaStream_t s) {
+    PD_CHECK_CUDA(cudaMemsetAsync(scratch_sumsq, 0, sizeof(float), s));
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    sumsq_kernel<<<grid, 256, 0, s>>>(g, n, scratch_sumsq);
+    const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+    adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, ema, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), max_norm, scratch_sumsq, ema_decay, norm_out);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pd

@@ -1,0 +1,194 @@
+"""Training step against torch.autograd on the oracle.
+
+The oracle UNet is plain PyTorch, so `loss.backward()` on it IS the reference's `accelerator.backward(loss)` for this model
+(src/utils_training.py:436).  Every parameter gradient of the CUDA path (`pd_train_step_grad`) is compared with autograd's, for
+the three losses of utils_training.py:415-433 and for the unconditional pass of classifier-free-guidance training (:508-516);
+clip + AdamW + EMA (`pd_adamw_step`) against `torch.nn.utils.clip_grad_norm_` + `torch.optim.AdamW` + the EMAModel recurrence.
+Tolerances are fp32 round-off of two different summation orders: 2e-3 of each gradient's own max (most land below 1e-4)."""
+import math
+
+import pytest
+import torch
+
+from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+from tests.util import make_pair, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_loss(oracle, sched, clean, labels, noise, timesteps, ptype, uncond):
+    import torch.nn.functional as F
+
+    noisy = sched.add_noise(clean, noise, timesteps)
+    if uncond:
+        out = oracle(noisy, timesteps, class_labels=None, class_emb=torch.zeros(clean.shape[0], oracle.time_embed_dim, device=clean.device)).sample
+    else:
+        out = oracle(noisy, timesteps, class_labels=labels).sample
+    if ptype == "epsilon":
+        return F.mse_loss(out, noise), out
+    if ptype == "sample":
+        a = sched.alphas_cumprod.to(clean.device)[timesteps].view(-1, 1, 1, 1)
+        return ((a / (1 - a)) * F.mse_loss(out, clean, reduction="none")).mean(), out
+    vel = sched.get_velocity(clean, noise, timesteps)
+    return F.mse_loss(out, vel), out
+
+
+def _setup(denoiser, size, B, sched_name, seed=0):
+    from oracle import OracleDDIMScheduler
+    from phendiff_b200 import DDIMScheduler
+    from phendiff_b200.training import DenoiserTrainer
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, model = make_pair(denoiser, size, "fp32", seed=seed)
+    oracle = oracle.cuda().train()
+    for p in oracle.parameters():
+        p.requires_grad_(True)
+    cfg = dict(SCHEDULER_CONFIGS["1k_epsilon_pred" if sched_name == "sample" else sched_name])
+    if sched_name == "sample":
+        cfg["prediction_type"] = "sample"
+    osched = OracleDDIMScheduler.from_config(cfg)
+    sched = DDIMScheduler.from_config(cfg)
+    return oracle, model, osched, sched, DenoiserTrainer
+
+
+def _inputs(B, size, seed=5):
+    x, labels = synth_images(B, size, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    noise = torch.randn(x.shape, generator=g)
+    timesteps = torch.randint(0, 1000, (B,), generator=g)
+    return x.cuda(), labels.cuda(), noise.cuda(), timesteps.cuda()
+
+
+def _compare_grads(oracle, trainer, tol=2e-3):
+    ref = {n: p.grad for n, p in oracle.named_parameters()}
+    worst = (0.0, None)
+    for name, g in trainer.named_gradients():
+        r = ref[name]
+        if r is None:                         # parameter unused in this pass (class table in the unconditional pass)
+            assert g.abs().max().item() == 0.0, name
+            continue
+        scale = max(r.abs().max().item(), 1e-6)
+        err = (g - r).abs().max().item() / scale
+        if err > worst[0]:
+            worst = (err, name)
+        assert err <= tol, f"{name}: max|dg| / max|g| = {err:.3e} (max|g| = {scale:.3e})"
+    return worst
+
+
+@pytest.mark.parametrize("sched_name,uncond", [("1k_epsilon_pred", False), ("1k_epsilon_pred", True),
+                                               ("3k_steps_clipping_rescaling", False), ("sample", False)])
+def test_gradients_match_autograd(sched_name, uncond):
+    B, size = 3, 32
+    oracle, model, osched, sched, Trainer = _setup("super_small", size, B, sched_name)
+    ptype = sched.config.prediction_type
+    x, labels, noise, timesteps = _inputs(B, size)
+    if sched_name == "sample":
+        timesteps = timesteps.clamp(min=50)          # SNR weights explode at t -> 0; keep the comparison well scaled
+    loss_ref, out_ref = _oracle_loss(oracle, osched, x, labels, noise, timesteps, ptype, uncond)
+    loss_ref.backward()
+    trainer = Trainer(model, sched, B, size)
+    loss, out = trainer.diffusion_and_backward(x, labels, noise=noise, timesteps=timesteps, do_unconditional_pass=uncond,
+                                               return_model_output=True)
+    assert (out - out_ref).abs().max().item() <= 2e-4 * max(1.0, out_ref.abs().max().item())
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item()) + 1e-7
+    worst = _compare_grads(oracle, trainer)
+    print(f"{sched_name} uncond={uncond}: loss {loss.item():.6f} vs {loss_ref.item():.6f}; worst gradient {worst[1]} {worst[0]:.2e}")
+    if uncond:
+        g = dict(trainer.named_gradients())["class_embedding.weight"]
+        assert g.abs().max().item() == 0.0
+
+
+def test_gradients_small_denoiser_64():
+    """The trainable config the reference ships for 128^2 data (small_denoiser: three attention levels), at 64^2."""
+    B, size = 2, 64
+    oracle, model, osched, sched, Trainer = _setup("small_denoiser_config", size, B, "1k_epsilon_pred")
+    x, labels, noise, timesteps = _inputs(B, size, seed=9)
+    loss_ref, _ = _oracle_loss(oracle, osched, x, labels, noise, timesteps, "epsilon", False)
+    loss_ref.backward()
+    trainer = Trainer(model, sched, B, size)
+    loss = trainer.diffusion_and_backward(x, labels, noise=noise, timesteps=timesteps)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    worst = _compare_grads(oracle, trainer)
+    print(f"small_denoiser 64^2: worst gradient {worst[1]} {worst[0]:.2e}")
+
+
+def test_gradients_accumulate():
+    B, size = 2, 32
+    oracle, model, osched, sched, Trainer = _setup("super_small", size, B, "1k_epsilon_pred")
+    x, labels, noise, timesteps = _inputs(B, size)
+    trainer = Trainer(model, sched, B, size)
+    trainer.diffusion_and_backward(x, labels, noise=noise, timesteps=timesteps)
+    g1 = trainer.grads.clone()
+    trainer.diffusion_and_backward(x, labels, noise=noise, timesteps=timesteps)
+    assert torch.allclose(trainer.grads, 2 * g1, rtol=1e-5, atol=1e-8)
+    trainer.zero_grad()
+    assert trainer.grads.abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("max_norm,use_ema", [(1.0, True), (0.0, False), (1e-3, True)])
+def test_clip_adamw_ema_matches_torch(max_norm, use_ema):
+    from phendiff_b200 import _lib
+    from phendiff_b200.training import ema_decay_at
+
+    torch.manual_seed(3)
+    n = 100_003
+    p0 = torch.randn(n, device="cuda")
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ema = p.clone() if use_ema else None
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, eps=1e-8)
+    ref_ema = p0.clone()
+    scratch, norm = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    for step in range(1, 6):
+        g = torch.randn(n, device="cuda") * (0.1 * step)
+        ref.grad = g.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([ref], max_norm) if max_norm > 0 else g.norm()
+        opt.step()
+        decay = ema_decay_at(step, max_decay=0.9999, inv_gamma=1.0, power=0.75)
+        ref_ema.sub_((1 - decay) * (ref_ema - ref.data))
+        _lib.check(_lib.lib().pd_adamw_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.ptr(ema), n, 3e-3, 0.95, 0.999, 1e-8,
+                                           1e-2, step, max_norm, decay, _lib.ptr(scratch), _lib.ptr(norm), _lib.current_stream()))
+        assert abs(norm.item() - ref_norm.item()) <= 1e-5 * ref_norm.item()
+        assert (p - ref.data).abs().max().item() <= 2e-6, step
+        if use_ema:
+            assert (ema - ref_ema).abs().max().item() <= 2e-6, step
+
+
+def test_ema_decay_schedule():
+    from phendiff_b200.training import ema_decay_at
+
+    assert ema_decay_at(1) == 0.0
+    assert math.isclose(ema_decay_at(2, inv_gamma=1.0, power=0.75), 1 - 2 ** -0.75)
+    assert ema_decay_at(10 ** 9) == 0.9999
+    assert math.isclose(ema_decay_at(5, use_ema_warmup=False), 5 / 14)
+
+
+def test_training_reduces_loss_and_inference_sees_new_weights():
+    """A few optimizer steps on one fixed batch: the loss goes down, the module's parameters (views of the flat vector) move, and
+    the inference route re-reads them."""
+    B, size = 4, 32
+    oracle, model, osched, sched, Trainer = _setup("super_small", size, B, "1k_epsilon_pred")
+    x, labels, noise, timesteps = _inputs(B, size, seed=11)
+    trainer = Trainer(model, sched, B, size, learning_rate=2e-3, use_ema=True)
+    w0 = model.conv_in.weight.detach().clone()
+    t0 = torch.full((B,), 500, device="cuda")
+    before = model(x, t0, class_labels=labels).sample.clone()
+    losses = [trainer.step(x, labels, noise=noise, timesteps=timesteps, do_unconditional_pass=False).item() for _ in range(12)]
+    assert losses[-1] < 0.7 * losses[0], losses
+    assert trainer.global_step == 12 and trainer.grads.abs().max().item() == 0.0
+    assert (model.conv_in.weight - w0).abs().max().item() > 0
+    after = model(x, t0, class_labels=labels).sample
+    assert (after - before).abs().max().item() > 1e-4
+    # parity of the updated weights with the same 12 steps of torch on the oracle
+    opt = torch.optim.AdamW(oracle.parameters(), lr=2e-3, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8)
+    for _ in range(12):
+        loss_ref, _ = _oracle_loss(oracle, osched, x, labels, noise, timesteps, "epsilon", False)
+        opt.zero_grad()
+        loss_ref.backward()
+        torch.nn.utils.clip_grad_norm_(oracle.parameters(), 1.0)
+        opt.step()
+    assert abs(loss_ref.item() - losses[-1]) <= 0.05 * abs(loss_ref.item()), (loss_ref.item(), losses[-1])
+    ema = trainer.ema_state()
+    assert ema is not None and (ema["conv_in.weight"] - model.conv_in.weight).abs().max().item() > 0
