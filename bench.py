@@ -51,8 +51,9 @@ def parse():
     p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="ddib", choices=["ddib", "cfg"],
-                   help="ddib (default, the BASELINE.json metric) or cfg: SURVEY §8 row f1, classifier-free-guidance forward start")
+    p.add_argument("--workload", default="ddib", choices=["ddib", "cfg", "train"],
+                   help="ddib (default, the BASELINE.json metric); cfg: SURVEY §8 row f1, classifier-free-guidance forward start; "
+                        "train: SURVEY §8 row f2, one training step (BASELINE.json configs[3]; default --batch 64 there)")
     p.add_argument("--guidance-scale", type=float, default=2.5)
     p.add_argument("--frac-diffusion-skipped", type=float, default=0.5)
     p.add_argument("--batch", type=int, default=256, help="images per GPU per step")
@@ -264,6 +265,8 @@ def run_ours(args):
 
     if args.workload == "cfg":
         return run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local)
+    if args.workload == "train":
+        return run_train(args, pipe, unet, x_host, x_dev, src, src_d, dev, rank, world, local)
 
     def step():
         out = ddib_transfer(pipe, x_dev, src_d, tgt_d, n)
@@ -449,6 +452,94 @@ def run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local
             tf = value / world * 2 * kept * gf / 1e3
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf / pk["tflops"],
                                 "traffic": None, "kernel": "whole path (2 x kept UNet forwards per image, SURVEY §8d algorithmic FLOPs)",
+                                "peak_source": pk["src"] + " sustained bf16 cuBLAS"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_train(args, pipe, unet, x_host, x_dev, labels, labels_d, dev, rank, world, local):
+    """SURVEY §8 row f2 / BASELINE.json configs[3]: one iteration of the reference's training loop body
+    (utils_training.py:244-456 + :552-556) through `phendiff_b200.training.DenoiserTrainer.step`: noise / timestep sampling,
+    add_noise, forward + backward of the UNet, NCCL all-reduce of the flat gradient vector (N > 1), clip 1.0 + AdamW + EMA.
+    The backward pass computes in fp32 on CUDA cores (the validated path; tensor-core dgrad / wgrad is the next stage), so
+    `dtype` says fp32 whatever --precision asks for."""
+    import torch
+    import torch.distributed as dist
+
+    from phendiff_b200.training import DenoiserTrainer
+
+    trainer = DenoiserTrainer(unet, pipe.scheduler, args.batch, args.size, learning_rate=1e-4, use_ema=True)
+    total = args.batch * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x):
+        noise = torch.randn(x_dev.shape, device=dev, generator=g)
+        ts = torch.randint(0, pipe.scheduler.config.num_train_timesteps, (args.batch,), device=dev, generator=g)
+        return trainer.step(x, labels_d, noise=noise, timesteps=ts, do_unconditional_pass=False)
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    sync()
+    l0 = trainer.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        loss = step(x_dev)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = trainer.launch_count() - l0 + args.steps * 4      # + add_noise, adamw (memset + sumsq + update)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total * args.steps / (ms / 1000.0)
+    # end to end: pinned host images -> device every step, loss read back on the host every step
+    sync()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, args.e2e_steps)
+    for _ in range(e2e_steps):
+        lv = step(x_host.to(dev, non_blocking=True)).item()
+    sync()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        gf = GFLOP_PER_IMAGE_FORWARD.get((args.denoiser, args.size))
+        line = {"metric": f"images/sec, training step {args.size}x{args.size} (forward + backward + gradient all-reduce + clip + AdamW + EMA)",
+                "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": f"CondUNet2D {args.denoiser} {args.size}x{args.size} RGB, 2 classes, training step, batch "
+                                       f"{args.batch}/GPU (BASELINE.json configs[3]; SURVEY §8 row f2), scheduler {args.scheduler}",
+                           "global_batch": total, "parallelism": f"data-parallel x{world}, one all-reduce of the flat fp32 gradient vector"
+                                                                 f" ({trainer.numel * 4 / 1e6:.1f} MB)",
+                           "parameters": trainer.numel, "workspace_gb": trainer.workspace_bytes / 1e9,
+                           "l2": "activations (GBs) exceed the 126 MB L2; a 256 MB buffer is also rewritten between timed steps",
+                           "final_loss": float(loss.item()), "last_e2e_loss": lv},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": total * e2e_steps / float(t_e2e.item()), "unit": "images/s",
+                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                        "api": "phendiff_b200.training.DenoiserTrainer.step(pinned_host_images.to(dev), labels) -> loss.item()"}}
+        if gf:
+            tf = value / world * 3 * gf / 1e3     # forward + dgrad + wgrad = 3 x the forward's algorithmic FLOPs
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf / pk["tflops"],
+                                "traffic": None, "kernel": "whole step (3 x forward algorithmic FLOPs per image; fp32 CUDA-core kernels, "
+                                                           "reported against the bf16 tensor peak the next stage targets)",
                                 "peak_source": pk["src"] + " sustained bf16 cuBLAS"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -10,6 +10,7 @@
 #   cpu0                  MEASURED CPU baseline of BASELINE config[0] (64x64, batch 4, 10+10 steps) on the box's host cores
 #   bench[:<args>]        bench.py (default workload) -> bench_<tag>.json + per-op table
 #   cfg                   bench.py --workload cfg
+#   train[:<args>]        bench.py --workload train (one training step, batch 64/GPU);  trainlaunches[:batch]: its ncu launch list by kernel
 #   strong                strong-scaling line: total batch 256 over --gpus N ranks is not applicable at N=1; runs --batch 32 (the per-GPU share of 8)
 #   launches              ncu launch list of one forward window;  dram: ncu DRAM bytes per launch
 #   ncu:<regex>[:<env>]   one ncu --set full capture of kernels matching <regex> (optionally with ENV=VAL,... set)
@@ -65,6 +66,11 @@ PY
       kill $SMI; tail -c 3000 gpurun_out/bench_${tag}.json;;
     cfg)
       python bench.py --workload cfg --steps 2 --warmup 3 > gpurun_out/bench_cfg_${tag}.json 2> gpurun_out/bench_cfg_${tag}.err; echo "cfg exit=$?"; tail -c 1500 gpurun_out/bench_cfg_${tag}.json;;
+    train)
+      timeout 600 python bench.py --workload train --batch 64 --steps 3 --warmup 3 $arg > gpurun_out/bench_train_${tag}.json 2> gpurun_out/bench_train_${tag}.err; echo "train exit=$?"; tail -c 1800 gpurun_out/bench_train_${tag}.json; tail -3 gpurun_out/bench_train_${tag}.err;;
+    trainlaunches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_${tag}.csv \
+          python bench.py --workload train --batch ${arg:-16} --steps 1 --warmup 1 --e2e-steps 0 > gpurun_out/ncu_launches_train_${tag}.log 2>&1; echo "trainlaunches exit=$?";;   # then here: python tools/summarize_profile.py train_<tag>
     strong)
       python bench.py --batch 32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_strong32_${tag}.json 2> gpurun_out/bench_strong32_${tag}.err; echo "strong exit=$?"; tail -c 1200 gpurun_out/bench_strong32_${tag}.json;;
     launches)
