@@ -54,6 +54,8 @@ def parse():
     p.add_argument("--workload", default="ddib", choices=["ddib", "cfg", "train"],
                    help="ddib (default, the BASELINE.json metric); cfg: SURVEY §8 row f1, classifier-free-guidance forward start; "
                         "train: SURVEY §8 row f2, one training step (BASELINE.json configs[3]; default --batch 64 there)")
+    p.add_argument("--train-precision", default="bf16", choices=["bf16", "no"],
+                   help="train workload: accelerate-style mixed precision (bf16 tensor-core convolutions) or the fp32 validation path")
     p.add_argument("--guidance-scale", type=float, default=2.5)
     p.add_argument("--frac-diffusion-skipped", type=float, default=0.5)
     p.add_argument("--batch", type=int, default=256, help="images per GPU per step")
@@ -470,7 +472,7 @@ def run_train(args, pipe, unet, x_host, x_dev, labels, labels_d, dev, rank, worl
 
     from phendiff_b200.training import DenoiserTrainer
 
-    trainer = DenoiserTrainer(unet, pipe.scheduler, args.batch, args.size, learning_rate=1e-4, use_ema=True)
+    trainer = DenoiserTrainer(unet, pipe.scheduler, args.batch, args.size, learning_rate=1e-4, use_ema=True, mixed_precision=args.train_precision)
     total = args.batch * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
@@ -523,12 +525,13 @@ def run_train(args, pipe, unet, x_host, x_dev, labels, labels_d, dev, rank, worl
         line = {"metric": f"images/sec, training step {args.size}x{args.size} (forward + backward + gradient all-reduce + clip + AdamW + EMA)",
                 "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32", "data": "synthetic",
+                "dtype": "bf16" if args.train_precision == "bf16" else "fp32", "data": "synthetic",
                 "config": {"workload": f"CondUNet2D {args.denoiser} {args.size}x{args.size} RGB, 2 classes, training step, batch "
                                        f"{args.batch}/GPU (BASELINE.json configs[3]; SURVEY §8 row f2), scheduler {args.scheduler}",
                            "global_batch": total, "parallelism": f"data-parallel x{world}, one all-reduce of the flat fp32 gradient vector"
                                                                  f" ({trainer.numel * 4 / 1e6:.1f} MB)",
                            "parameters": trainer.numel, "workspace_gb": trainer.workspace_bytes / 1e9,
+                           "mixed_precision": args.train_precision, "tensor_core_layers_since_start": trainer.tensor_core_counts(),
                            "l2": "activations (GBs) exceed the 126 MB L2; a 256 MB buffer is also rewritten between timed steps",
                            "final_loss": float(loss.item()), "last_e2e_loss": lv},
                 "clocks": clocks, "gpu_launches": launches,
@@ -538,8 +541,7 @@ def run_train(args, pipe, unet, x_host, x_dev, labels, labels_d, dev, rank, worl
         if gf:
             tf = value / world * 3 * gf / 1e3     # forward + dgrad + wgrad = 3 x the forward's algorithmic FLOPs
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf / pk["tflops"],
-                                "traffic": None, "kernel": "whole step (3 x forward algorithmic FLOPs per image; fp32 CUDA-core kernels, "
-                                                           "reported against the bf16 tensor peak the next stage targets)",
+                                "traffic": None, "kernel": "whole step (3 x forward algorithmic FLOPs per image: forward + dgrad + wgrad)",
                                 "peak_source": pk["src"] + " sustained bf16 cuBLAS"}
         print(json.dumps(line), flush=True)
     if world > 1:

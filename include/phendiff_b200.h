@@ -160,6 +160,13 @@ int pd_cfg_transfer(pd_unet_t* h, float* x, const int64_t* labels, const float* 
  *      fp32 path: every operator of the backward pass as a CUDA-core kernel (validated against torch.autograd on the oracle). */
 int pd_train_create(pd_unet_t* h, int32_t batch, int32_t height, int32_t width, pd_train_t** out);
 int pd_train_destroy(pd_train_t* t);
+/* precision 0 (default): fp32 on CUDA cores, the validation path.  1: "bf16" mixed precision as accelerate runs the reference
+ * (mixed_precision="bf16", train.py:57-61): convolutions (forward, dgrad, wgrad) take bf16 operands on the tcgen05 kernels with fp32
+ * accumulation for every shape those kernels support, everything else (GroupNorm, attention, embeddings, loss, optimizer, master
+ * weights, gradients) stays fp32.  Changes the workspace plan: call before pd_train_workspace_bytes / pd_train_bind. */
+int pd_train_set_precision(pd_train_t* t, int32_t precision);
+/* convolution forward passes / weight gradients that took the tensor-core path since creation */
+int pd_train_tc_counts(pd_train_t* t, int64_t* convs, int64_t* wgrads);
 int pd_train_num_params_flat(pd_train_t* t, int64_t* numel);
 int pd_train_param_offset(pd_train_t* t, int32_t idx, int64_t* offset);
 int pd_train_workspace_bytes(pd_train_t* t, size_t* bytes);

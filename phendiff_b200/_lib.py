@@ -69,6 +69,8 @@ _SIGNATURES = {
     "pd_cfg_transfer": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(StepCoeffs), C.c_int32, _P]),
     "pd_train_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "pd_train_destroy": (C.c_int, [_P]),
+    "pd_train_set_precision": (C.c_int, [_P, C.c_int32]),
+    "pd_train_tc_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pd_train_num_params_flat": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "pd_train_param_offset": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64)]),
     "pd_train_workspace_bytes": (C.c_int, [_P, C.POINTER(C.c_size_t)]),

@@ -18,6 +18,7 @@ struct TT {   // an NHWC fp32 activation and its gradient
     float* g = nullptr;
     int C = 0, H = 0, W = 0;
     double* stats = nullptr;   // GroupNorm chunk statistics (computed on first use)
+    void* h = nullptr;         // 16-bit copy feeding the tensor-core convolutions (mixed-precision mode; made on first use)
 };
 
 }  // namespace pd
@@ -42,6 +43,43 @@ struct pd_train {
     cudaStream_t s = nullptr;
     int rc = 0;
     int64_t launches = 0;
+    // mixed precision (pd_train_set_precision): 16-bit operands for the convolutions on the tcgen05 kernels, everything else fp32
+    int dt = DT_F32;
+    unsigned tc_mask = 7;          // 1 forward, 2 dgrad, 4 wgrad (PHENDIFF_B200_TRAIN_TC)
+    size_t scr_max = 0, wstage_max = 0;          // shared scratch: two 16-bit activation-sized buffers + the wgrad staging tile
+    struct ConvSlot { ConvTcDesc d; ConvTcPlan* pl = nullptr; };
+    struct WgSlot { WgradTcDesc d; WgradTcPlan* pl = nullptr; };
+    std::vector<ConvSlot> conv_plans;
+    std::vector<WgSlot> wg_plans;
+    size_t conv_cursor = 0, wg_cursor = 0;
+    int tc_convs = 0, tc_wgrads = 0;
+    void* scr_a() const { return ws + 2 * act_bytes + aux_bytes - 2 * scr_max - wstage_max; }
+    void* scr_b() const { return ws + 2 * act_bytes + aux_bytes - scr_max - wstage_max; }
+    float* wstage() const { return (float*)(ws + 2 * act_bytes + aux_bytes - wstage_max); }
+    ConvTcPlan* conv_plan(size_t idx, const ConvTcDesc& d, int* rc_out) {
+        if (idx >= conv_plans.size()) conv_plans.resize(idx + 1);
+        ConvSlot& sl = conv_plans[idx];
+        if (sl.pl && memcmp(&sl.d, &d, sizeof(d)) == 0) return sl.pl;
+        if (sl.pl) { conv_tc_plan_destroy(sl.pl); sl.pl = nullptr; }
+        int r = conv_tc_plan_create(d, &sl.pl);
+        if (r) { *rc_out = r; return nullptr; }
+        sl.d = d;
+        return sl.pl;
+    }
+    WgradTcPlan* wg_plan(size_t idx, const WgradTcDesc& d, int* rc_out) {
+        if (idx >= wg_plans.size()) wg_plans.resize(idx + 1);
+        WgSlot& sl = wg_plans[idx];
+        if (sl.pl && memcmp(&sl.d, &d, sizeof(d)) == 0) return sl.pl;
+        if (sl.pl) { wgrad_tc_plan_destroy(sl.pl); sl.pl = nullptr; }
+        int r = wgrad_tc_plan_create(d, &sl.pl);
+        if (r) { *rc_out = r; return nullptr; }
+        sl.d = d;
+        return sl.pl;
+    }
+    ~pd_train() {
+        for (auto& c : conv_plans) if (c.pl) conv_tc_plan_destroy(c.pl);
+        for (auto& w : wg_plans) if (w.pl) wgrad_tc_plan_destroy(w.pl);
+    }
 };
 
 namespace pd {
@@ -95,6 +133,18 @@ struct Walk {
         return x->stats;
     }
 
+    // 16-bit copy of an activation (made once, on first use by a tensor-core convolution)
+    void* half_of(TT* x) {
+        if (!x->h) {
+            const size_t n = (size_t)B * x->H * x->W * x->C;
+            x->h = aux(n * 2);
+            if (!dry()) { run(launch_f2h(t->dt, x->d, x->h, n, s())); count(); }
+            else x->h = reinterpret_cast<void*>(uintptr_t(8));
+        }
+        return x->h;
+    }
+    void need_scratch(size_t bytes) { bytes = (bytes + 255) & ~(size_t)255; if (bytes > t->scr_max) t->scr_max = bytes; }
+
     // y = act(GroupNorm(concat(a, b)))
     TT* gn(const GNL& g, TT* a, TT* b, bool silu) {
         const int C = a->C + (b ? b->C : 0), HW = a->H * a->W;
@@ -125,18 +175,67 @@ struct Walk {
         const int Ho = stride == 2 ? a->H / 2 : a->H, Wo = stride == 2 ? a->W / 2 : a->W;
         TT* o = act(cout, Ho, Wo);
         const int kk = k * k;
-        float* w_fwd = (float*)aux((size_t)kk * Ct * cout * sizeof(float));
-        float* wd1 = stride == 1 ? (float*)aux((size_t)kk * cout * a->C * sizeof(float)) : nullptr;
-        float* wd2 = (stride == 1 && b) ? (float*)aux((size_t)kk * cout * b->C * sizeof(float)) : nullptr;
+        // which pieces of this layer run on the tensor cores (mixed-precision mode, shapes the tcgen05 kernels take)
+        bool tc_fwd = false, tc_dg[2] = {false, false}, tc_wg = false;
+        if (t->dt != DT_F32) {
+            ConvTcDesc d{};
+            d.dt = t->dt; d.C = Ct; d.C2 = b ? b->C : 0; d.N = B; d.H = a->H; d.W = a->W; d.ksize = k; d.stride = stride; d.pad = pad; d.Ho = Ho; d.Wo = Wo;
+            d.Cout = cout; d.mode = TC_MODE_STD; d.stats_cw = m->stats_cw;
+            tc_fwd = (t->tc_mask & 1) && (conv_halo_supported(d, nullptr) || (!b && conv_tc_supported(d, nullptr)));
+            if (stride == 1 && pad == k / 2) {
+                const TT* srcs[2] = {a, b};
+                for (int q = 0; q < 2; ++q) {
+                    if (!srcs[q]) continue;
+                    ConvTcDesc g{};
+                    g.dt = t->dt; g.C = cout; g.N = B; g.H = Ho; g.W = Wo; g.ksize = k; g.stride = 1; g.pad = pad; g.Ho = Ho; g.Wo = Wo; g.Cout = srcs[q]->C;
+                    g.mode = TC_MODE_STD; g.stats_cw = m->stats_cw;
+                    tc_dg[q] = (t->tc_mask & 2) && conv_halo_supported(g, nullptr);
+                }
+                WgradTcDesc wd{};
+                wd.dt = t->dt; wd.C1 = a->C; wd.C2 = b ? b->C : 0; wd.N = B; wd.H = a->H; wd.W = a->W; wd.Cout = cout; wd.ksize = k;
+                tc_wg = (t->tc_mask & 4) && wgrad_tc_supported(wd, nullptr);
+            }
+        }
+        const bool any_dg_simt = stride == 1 && ((!tc_dg[0]) || (b && !tc_dg[1]));
+        float* w_fwd = tc_fwd ? nullptr : (float*)aux((size_t)kk * Ct * cout * sizeof(float));
+        float* wd1 = (stride == 1 && !tc_dg[0]) ? (float*)aux((size_t)kk * cout * a->C * sizeof(float)) : nullptr;
+        float* wd2 = (stride == 1 && b && !tc_dg[1]) ? (float*)aux((size_t)kk * cout * b->C * sizeof(float)) : nullptr;
+        (void)any_dg_simt;
+        void* w16 = tc_fwd ? aux((size_t)kk * Ct * cout * 2) : nullptr;
+        void* wd16[2] = {tc_dg[0] ? aux((size_t)kk * cout * a->C * 2) : nullptr, (b && tc_dg[1]) ? aux((size_t)kk * cout * b->C * 2) : nullptr};
+        void* a16 = (tc_fwd || tc_wg) ? half_of(a) : nullptr;
+        void* b16 = (b && (tc_fwd || tc_wg)) ? half_of(b) : nullptr;
+        if (tc_fwd || tc_dg[0] || tc_dg[1] || tc_wg) {
+            need_scratch((size_t)B * Ho * Wo * cout * 2);
+            need_scratch((size_t)B * a->H * a->W * std::max(a->C, b ? b->C : 0) * 2);
+        }
+        if (tc_wg && (size_t)kk * cout * Ct * sizeof(float) > t->wstage_max) t->wstage_max = (((size_t)kk * cout * Ct * sizeof(float)) + 255) & ~(size_t)255;
+        const size_t fwd_idx = t->conv_cursor, dg_idx = t->conv_cursor + 1, wg_idx = t->wg_cursor;
+        t->conv_cursor += 3; t->wg_cursor += 1;
         if (dry()) return o;
         if ((size_t)cout * Ct * kk != w->numel) { set_error("internal: training conv shape mismatch for " + w->name); run(1); return o; }
-        run(launch_relayout_simt(p(w), cout, Ct, k, w_fwd, s()));
-        ConvArgs ca{};
-        ca.x1 = a->d; ca.x2 = b ? b->d : nullptr; ca.C1 = a->C; ca.C2 = b ? b->C : 0; ca.N = B; ca.H = a->H; ca.W = a->W; ca.Cout = cout;
-        ca.ksize = k; ca.stride = stride; ca.pad = pad; ca.Ho = Ho; ca.Wo = Wo; ca.w = w_fwd; ca.bias = bias ? p(bias) : nullptr;
-        ca.addvec = addvec; ca.addvec_stride = cout; ca.residual = residual ? residual->d : nullptr; ca.out_scale = out_scale; ca.out = o->d;
-        run(launch_conv_simt(DT_F32, ca, s()));
-        count(2);
+        if (tc_fwd) {
+            run(launch_relayout_tc(t->dt, p(w), cout, Ct, k, w16, kk * Ct, 0, s()));
+            ConvTcDesc d{};
+            d.dt = t->dt; d.x = a16; d.C = Ct; d.x2 = b ? b16 : nullptr; d.C2 = b ? b->C : 0; d.N = B; d.H = a->H; d.W = a->W; d.ksize = k; d.stride = stride;
+            d.pad = pad; d.Ho = Ho; d.Wo = Wo; d.Cout = cout; d.wmat = w16; d.bias = bias ? p(bias) : nullptr; d.out_scale = 1.f; d.out = t->scr_a();
+            d.mode = TC_MODE_STD; d.stats_cw = m->stats_cw;
+            int prc = 0;
+            ConvTcPlan* pl = t->conv_plan(fwd_idx, d, &prc);
+            if (!pl) { run(prc); return o; }
+            run(conv_tc_launch(pl, s()));
+            run(launch_h2f_epilogue(t->dt, t->scr_a(), addvec, residual ? residual->d : nullptr, out_scale, o->d, B, Ho * Wo, cout, s()));
+            count(3);
+            t->tc_convs++;
+        } else {
+            run(launch_relayout_simt(p(w), cout, Ct, k, w_fwd, s()));
+            ConvArgs ca{};
+            ca.x1 = a->d; ca.x2 = b ? b->d : nullptr; ca.C1 = a->C; ca.C2 = b ? b->C : 0; ca.N = B; ca.H = a->H; ca.W = a->W; ca.Cout = cout;
+            ca.ksize = k; ca.stride = stride; ca.pad = pad; ca.Ho = Ho; ca.Wo = Wo; ca.w = w_fwd; ca.bias = bias ? p(bias) : nullptr;
+            ca.addvec = addvec; ca.addvec_stride = cout; ca.residual = residual ? residual->d : nullptr; ca.out_scale = out_scale; ca.out = o->d;
+            run(launch_conv_simt(DT_F32, ca, s()));
+            count(2);
+        }
         const float* pw = p(w);
         float* gw = gr(w);
         float* gb = bias ? gr(bias) : nullptr;
@@ -144,6 +243,9 @@ struct Walk {
         pd_train* tr = t;
         const TT A = *a, Bt = b ? *b : TT(), O = *o, R = residual ? *residual : TT();
         const bool hasB = b != nullptr, hasR = residual != nullptr;
+        const bool tc_dg0 = tc_dg[0], tc_dg1 = tc_dg[1];
+        void* const wd16_0 = wd16[0];
+        void* const wd16_1 = wd16[1];
         bwd([=](cudaStream_t st) {
             int rc = 0;
             const size_t on = (size_t)Bn * O.H * O.W * O.C;
@@ -153,18 +255,51 @@ struct Walk {
             if (gb && (rc = launch_colsum(O.g, M, O.C, M, 1.f, gb, st))) return rc;
             if (d_addvec && (rc = launch_colsum(O.g, M, O.C, O.H * O.W, 1.f, d_addvec, st))) return rc;   // per image: (B, Cout)
             if (hasR && R.g && (rc = launch_add_inplace(R.g, O.g, 1.0f, on, st))) return rc;
-            WgradArgs wa{};
-            wa.x1 = A.d; wa.x2 = hasB ? Bt.d : nullptr; wa.C1 = A.C; wa.C2 = hasB ? Bt.C : 0; wa.N = Bn; wa.H = A.H; wa.W = A.W; wa.Cout = O.C;
-            wa.ksize = k; wa.stride = stride; wa.pad = pad; wa.Ho = O.H; wa.Wo = O.W; wa.dy = O.g; wa.dw = gw; wa.scale = 1.f;
-            if ((rc = launch_conv_wgrad(wa, st))) return rc;
-            tr->launches += 4;
+            const int dt = tr->dt;
+            if (tc_wg || tc_dg0 || tc_dg1) {
+                if ((rc = launch_f2h(dt, O.g, tr->scr_a(), on, st))) return rc;
+                tr->launches += 1;
+            }
+            if (tc_wg) {
+                const size_t wbytes = (size_t)kk * O.C * Ct * sizeof(float);
+                PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, wbytes, st));
+                WgradTcDesc wd{};
+                wd.dt = dt; wd.x1 = A.h; wd.x2 = hasB ? Bt.h : nullptr; wd.C1 = A.C; wd.C2 = hasB ? Bt.C : 0; wd.N = Bn; wd.H = A.H; wd.W = A.W;
+                wd.Cout = O.C; wd.ksize = k; wd.dy = tr->scr_a(); wd.stage = tr->wstage();
+                WgradTcPlan* wp = tr->wg_plan(wg_idx, wd, &rc);
+                if (!wp) return rc;
+                if ((rc = wgrad_tc_launch(wp, st))) return rc;
+                if ((rc = launch_wgrad_unstage(tr->wstage(), O.C, Ct, kk, gw, st))) return rc;
+                tr->launches += 3;
+                tr->tc_wgrads++;
+            } else {
+                WgradArgs wa{};
+                wa.x1 = A.d; wa.x2 = hasB ? Bt.d : nullptr; wa.C1 = A.C; wa.C2 = hasB ? Bt.C : 0; wa.N = Bn; wa.H = A.H; wa.W = A.W; wa.Cout = O.C;
+                wa.ksize = k; wa.stride = stride; wa.pad = pad; wa.Ho = O.H; wa.Wo = O.W; wa.dy = O.g; wa.dw = gw; wa.scale = 1.f;
+                if ((rc = launch_conv_wgrad(wa, st))) return rc;
+                tr->launches += 1;
+            }
+            tr->launches += 3;
             if (stride == 1) {
                 const TT* srcs[2] = {&A, hasB ? &Bt : nullptr};
                 float* wds[2] = {wd1, wd2};
+                const bool tcd[2] = {tc_dg0, tc_dg1};
+                void* const wd16s[2] = {wd16_0, wd16_1};
                 int i0 = 0;
                 for (int q = 0; q < 2; ++q) {
                     if (!srcs[q]) continue;
-                    if (srcs[q]->g) {
+                    if (srcs[q]->g && tcd[q]) {
+                        // dX = conv(dY, W^T flipped) on the halo kernel, 16-bit result accumulated into the fp32 gradient
+                        if ((rc = launch_relayout_tc_dgrad(dt, pw, O.C, Ct, k, i0, srcs[q]->C, wd16s[q], st))) return rc;
+                        ConvTcDesc g{};
+                        g.dt = dt; g.x = tr->scr_a(); g.C = O.C; g.N = Bn; g.H = O.H; g.W = O.W; g.ksize = k; g.stride = 1; g.pad = pad; g.Ho = O.H; g.Wo = O.W;
+                        g.Cout = srcs[q]->C; g.wmat = wd16s[q]; g.out_scale = 1.f; g.out = tr->scr_b(); g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
+                        ConvTcPlan* gp = tr->conv_plan(dg_idx + q, g, &rc);
+                        if (!gp) return rc;
+                        if ((rc = conv_tc_launch(gp, st))) return rc;
+                        if ((rc = launch_h2f_accumulate(dt, tr->scr_b(), srcs[q]->g, (size_t)Bn * O.H * O.W * srcs[q]->C, st))) return rc;
+                        tr->launches += 3;
+                    } else if (srcs[q]->g) {
                         if ((rc = launch_relayout_dgrad(pw, O.C, A.C + (hasB ? Bt.C : 0), k, i0, srcs[q]->C, wds[q], st))) return rc;
                         ConvArgs da{};
                         da.x1 = O.g; da.C1 = O.C; da.N = Bn; da.H = O.H; da.W = O.W; da.Cout = srcs[q]->C; da.ksize = k; da.stride = 1;
@@ -397,6 +532,8 @@ struct Walk {
 static int walk(pd_train* t, bool dry, const float* noisy, const float* timesteps, const int64_t* labels, float** mo, float** dm) {
     t->dry = dry;
     t->act_bump = t->aux_bump = 0;
+    t->conv_cursor = t->wg_cursor = 0;
+    if (dry) { t->scr_max = 0; t->wstage_max = 0; }
     t->tape.clear();
     t->tts.clear();
     t->rc = 0;
@@ -426,9 +563,30 @@ int pd_train_create(pd_unet_t* m, int32_t batch, int32_t height, int32_t width, 
     int rc = walk(t, true, nullptr, nullptr, nullptr, &mo, &dm);
     if (rc) { delete t; return rc; }
     t->act_bytes = t->act_bump;
-    t->aux_bytes = t->aux_bump;
+    t->aux_bytes = t->aux_bump + 2 * t->scr_max + t->wstage_max;
     t->ws_bytes = 2 * t->act_bytes + t->aux_bytes + 1024;
+    if (const char* e = getenv("PHENDIFF_B200_TRAIN_TC")) t->tc_mask = (unsigned)atoi(e);
     *out = t;
+    return 0;
+}
+
+int pd_train_set_precision(pd_train_t* t, int32_t precision) {
+    PD_REQUIRE(t, "null argument");
+    PD_REQUIRE(precision == 0 || precision == 1, "precision: 0 = fp32 (validation path), 1 = bf16 tensor-core convolutions");
+    t->dt = precision == 1 ? DT_BF16 : DT_F32;
+    t->ws = nullptr;   // the workspace plan changes: bind again
+    float *mo, *dm;
+    int rc = walk(t, true, nullptr, nullptr, nullptr, &mo, &dm);
+    if (rc) return rc;
+    t->act_bytes = t->act_bump;
+    t->aux_bytes = t->aux_bump + 2 * t->scr_max + t->wstage_max;
+    t->ws_bytes = 2 * t->act_bytes + t->aux_bytes + 1024;
+    return 0;
+}
+
+int pd_train_tc_counts(pd_train_t* t, int64_t* convs, int64_t* wgrads) {
+    PD_REQUIRE(t && convs && wgrads, "null argument");
+    *convs = t->tc_convs; *wgrads = t->tc_wgrads;
     return 0;
 }
 
@@ -477,7 +635,7 @@ int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const f
     float *mo = nullptr, *dm = nullptr;
     int rc = walk(t, false, noisy, timesteps, labels, &mo, &dm);
     if (rc) return rc;
-    PD_REQUIRE(t->act_bump <= t->act_bytes && t->aux_bump <= t->aux_bytes, "internal: training workspace plan mismatch");
+    PD_REQUIRE(t->act_bump <= t->act_bytes && t->aux_bump + 2 * t->scr_max + t->wstage_max <= t->aux_bytes, "internal: training workspace plan mismatch");
     const size_t per = (size_t)t->m->cfg.out_channels * t->H * t->W;
     if ((rc = launch_mse_loss(mo, target, sample_weight, t->B, per, loss_out, dm, s))) return rc;
     if (model_out) PD_CHECK_CUDA(cudaMemcpyAsync(model_out, mo, (size_t)t->B * per * sizeof(float), cudaMemcpyDeviceToDevice, s));

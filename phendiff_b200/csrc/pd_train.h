@@ -1,6 +1,7 @@
 // phendiff_b200 — launch interface of the training-step kernels (pd_train_kernels.cu), used by the driver in pd_train.cu.
 #pragma once
 #include "pd_common.cuh"
+#include <string>
 
 namespace pd {
 
@@ -52,5 +53,28 @@ int launch_add_inplace(float* y, const float* x, float alpha, size_t n, cudaStre
 int launch_mse_loss(const float* m, const float* target, const float* weight, int B, size_t per, float* loss, float* dm, cudaStream_t s);
 int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float b1, float b2, float eps, float wd,
                  int step, float max_norm, float ema_decay, float* scratch_sumsq, float* norm_out, cudaStream_t s);
+
+// ---- mixed-precision path (bf16 tensor-core convolutions; pd_train_wgrad_tc.cu) -------------------------------------------------
+int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s);
+int launch_f2h(int dt, const float* x, void* out, size_t n, cudaStream_t s);
+int launch_h2f_epilogue(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
+                        cudaStream_t s);
+int launch_h2f_accumulate(int dt, const void* y16, float* out, size_t n, cudaStream_t s);
+int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s);
+
+// tcgen05 weight gradient of a stride-1 'same' convolution (k = 1 or 3): stage[tap][co][ci] += sum_pixels dY[p, co] * X[p @ tap, ci],
+// K = pixels.  x1 / x2: the NHWC 16-bit sources of the conv input (channel concat), dy: (N, H, W, Cout) 16-bit.
+struct WgradTcDesc {
+    int dt;
+    const void *x1, *x2;
+    int C1, C2, N, H, W, Cout, ksize;
+    const void* dy;
+    float* stage;          // (k*k, Cout, C1 + C2) fp32, accumulated with vector reductions (zeroed by the caller)
+};
+struct WgradTcPlan;
+bool wgrad_tc_supported(const WgradTcDesc& d, std::string* why);
+int wgrad_tc_plan_create(const WgradTcDesc& d, WgradTcPlan** out);
+void wgrad_tc_plan_destroy(WgradTcPlan* p);
+int wgrad_tc_launch(const WgradTcPlan* p, cudaStream_t s);
 
 }  // namespace pd

@@ -606,4 +606,113 @@ int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// mixed-precision (bf16 tensor-core) path: casts between the fp32 activations / gradients and the 16-bit conv operands
+// ---------------------------------------------------------------------------------------------------------------------
+// OIHW (O, I, k, k) fp32 -> 16-bit dgrad GEMM weights (Isub, k*k*O) for input channels [i0, i0 + Isub): K index = tap' * O + o with
+// tap' the FLIPPED tap, so that the stride-1 tensor-core conv computes dX = conv(dY, W^T flipped)
+template <typename T>
+__global__ void relayout_tc_dgrad_kernel(const float* __restrict__ w, int O, int I, int k, int i0, int Isub, T* __restrict__ out) {
+    const int kk = k * k;
+    const size_t total = (size_t)Isub * kk * O;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = idx % O;
+        const size_t r = idx / O;
+        const int tapf = r % kk, i = r / kk;
+        out[idx] = from_f<T>(w[((size_t)o * I + i0 + i) * kk + (kk - 1 - tapf)]);
+    }
+}
+int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s) {
+    const size_t total = (size_t)k * k * O * Isub;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
+    PD_DISPATCH_HALF(dt, T, (relayout_tc_dgrad_kernel<T><<<grid, 256, 0, s>>>(w, O, I, k, i0, Isub, (T*)out)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T> struct alignas(16) Half8 { T v[8]; };
+
+// out16 = T(x) (n a multiple of 8)
+template <typename T>
+__global__ void __launch_bounds__(256) f2h_kernel(const float4* __restrict__ x, Half8<T>* __restrict__ out, size_t n8) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = x[2 * i], b = x[2 * i + 1];
+        Half8<T> h;
+        h.v[0] = from_f<T>(a.x); h.v[1] = from_f<T>(a.y); h.v[2] = from_f<T>(a.z); h.v[3] = from_f<T>(a.w);
+        h.v[4] = from_f<T>(b.x); h.v[5] = from_f<T>(b.y); h.v[6] = from_f<T>(b.z); h.v[7] = from_f<T>(b.w);
+        out[i] = h;
+    }
+}
+int launch_f2h(int dt, const float* x, void* out, size_t n, cudaStream_t s) {
+    PD_REQUIRE(n % 8 == 0, "f2h: element count must be a multiple of 8");
+    const int grid = (int)std::min<size_t>((n / 8 + 255) / 256, 148 * 16);
+    PD_DISPATCH_HALF(dt, T, (f2h_kernel<T><<<grid, 256, 0, s>>>((const float4*)x, (Half8<T>*)out, n / 8)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// forward epilogue of a tensor-core conv: out = (float(y16) + addvec[img] + residual) * scale      (rows of C channels, HW rows per image)
+// ACC: out += float(y16) (gradient accumulation of a tensor-core dgrad)
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(256) h2f_kernel(const Half8<T>* __restrict__ y, const float* __restrict__ addvec, const float4* __restrict__ residual,
+                                                  float scale, float4* __restrict__ out, size_t n8, int C8, size_t per_img8) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const Half8<T> h = y[i];
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = to_f(h.v[j]);
+        if (ACC) {
+            const float4 a = out[2 * i], b = out[2 * i + 1];
+            out[2 * i] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
+            out[2 * i + 1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
+        } else {
+            if (addvec) {
+                const float* av = addvec + (i / per_img8) * (size_t)(C8 * 8) + (i % C8) * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += av[j];
+            }
+            if (residual) {
+                const float4 a = residual[2 * i], b = residual[2 * i + 1];
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            }
+            out[2 * i] = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+            out[2 * i + 1] = make_float4(v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale);
+        }
+    }
+}
+int launch_h2f_epilogue(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
+                        cudaStream_t s) {
+    PD_REQUIRE(C % 8 == 0, "h2f: channel count must be a multiple of 8");
+    const size_t n8 = (size_t)B * HW * C / 8;
+    const int grid = (int)std::min<size_t>((n8 + 255) / 256, 148 * 16);
+    PD_DISPATCH_HALF(dt, T, (h2f_kernel<T, false><<<grid, 256, 0, s>>>((const Half8<T>*)y16, addvec, (const float4*)residual, scale, (float4*)out,
+                                                                        n8, C / 8, (size_t)HW * C / 8)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_h2f_accumulate(int dt, const void* y16, float* out, size_t n, cudaStream_t s) {
+    PD_REQUIRE(n % 8 == 0, "h2f: element count must be a multiple of 8");
+    const int grid = (int)std::min<size_t>((n / 8 + 255) / 256, 148 * 16);
+    PD_DISPATCH_HALF(dt, T, (h2f_kernel<T, true><<<grid, 256, 0, s>>>((const Half8<T>*)y16, nullptr, nullptr, 1.f, (float4*)out, n / 8, 1, 1)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// dW (O, I, k, k) += stage (k*k, O, I): the tensor-core wgrad accumulates into a [tap][co][ci] staging buffer (coalesced vector
+// reductions); this folds it into the OIHW gradient
+__global__ void wgrad_unstage_kernel(const float* __restrict__ stage, int O, int I, int kk, float* __restrict__ dw) {
+    const size_t total = (size_t)O * I * kk;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int tap = idx % kk;
+        const size_t oi = idx / kk;
+        dw[idx] += stage[(size_t)tap * O * I + oi];
+    }
+}
+int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s) {
+    const size_t total = (size_t)O * I * kk;
+    wgrad_unstage_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, s>>>(stage, O, I, kk, dw);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace pd

@@ -69,7 +69,7 @@ class DenoiserTrainer:
                  learning_rate: float = 1e-4, adam_beta1: float = 0.95, adam_beta2: float = 0.999, adam_weight_decay: float = 1e-6,
                  adam_epsilon: float = 1e-8, max_grad_norm: float = 1.0, use_ema: bool = False, ema_max_decay: float = 0.9999,
                  ema_inv_gamma: float = 1.0, ema_power: float = 0.75, lr_lambda: Optional[Callable[[int], float]] = None,
-                 proba_uncond: float = 0.0):
+                 proba_uncond: float = 0.0, mixed_precision: str = "no"):
         self.model = denoiser_model
         self.noise_scheduler = noise_scheduler
         self.batch_size, self.resolution = int(batch_size), int(resolution)
@@ -90,6 +90,11 @@ class DenoiserTrainer:
             t = C.c_void_p()
             _lib.check(L.pd_train_create(h, self.batch_size, self.resolution, self.resolution, C.byref(t)))
             self._t, self._h = t, h
+            if mixed_precision not in ("no", "bf16"):
+                raise ValueError(f"mixed_precision must be 'no' or 'bf16' (accelerate's names), not {mixed_precision!r}")
+            self.mixed_precision = mixed_precision
+            if mixed_precision == "bf16":
+                _lib.check(L.pd_train_set_precision(t, 1))
             n = C.c_int64()
             _lib.check(L.pd_train_num_params_flat(t, C.byref(n)))
             self.numel = n.value
@@ -140,6 +145,11 @@ class DenoiserTrainer:
 
     def zero_grad(self):
         self.grads.zero_()
+
+    def tensor_core_counts(self) -> dict:
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().pd_train_tc_counts(self._t, C.byref(a), C.byref(b)))
+        return {"conv_forward": a.value, "conv_wgrad": b.value}
 
     def launch_count(self) -> int:
         n = C.c_int64()
