@@ -45,7 +45,7 @@ struct pd_train {
     int64_t launches = 0;
     // mixed precision (pd_train_set_precision): 16-bit operands for the convolutions on the tcgen05 kernels, everything else fp32
     int dt = DT_F32;
-    unsigned tc_mask = 7;          // 1 forward, 2 dgrad, 4 wgrad (PHENDIFF_B200_TRAIN_TC)
+    unsigned tc_mask = 15;         // 1 conv forward, 2 dgrad, 4 wgrad, 8 attention (PHENDIFF_B200_TRAIN_TC)
     size_t scr_max = 0, wstage_max = 0;          // shared scratch: two 16-bit activation-sized buffers + the wgrad staging tile
     struct ConvSlot { ConvTcDesc d; ConvTcPlan* pl = nullptr; };
     struct WgSlot { WgradTcDesc d; WgradTcPlan* pl = nullptr; };
@@ -176,7 +176,7 @@ struct Walk {
         TT* o = act(cout, Ho, Wo);
         const int kk = k * k;
         // which pieces of this layer run on the tensor cores (mixed-precision mode, shapes the tcgen05 kernels take)
-        bool tc_fwd = false, tc_dg[2] = {false, false}, tc_wg = false;
+        bool tc_fwd = false, tc_dg[2] = {false, false}, tc_wg = false, tc_dg_s2 = false;
         if (t->dt != DT_F32) {
             ConvTcDesc d{};
             d.dt = t->dt; d.C = Ct; d.C2 = b ? b->C : 0; d.N = B; d.H = a->H; d.W = a->W; d.ksize = k; d.stride = stride; d.pad = pad; d.Ho = Ho; d.Wo = Wo;
@@ -194,6 +194,12 @@ struct Walk {
                 WgradTcDesc wd{};
                 wd.dt = t->dt; wd.C1 = a->C; wd.C2 = b ? b->C : 0; wd.N = B; wd.H = a->H; wd.W = a->W; wd.Cout = cout; wd.ksize = k;
                 tc_wg = (t->tc_mask & 4) && wgrad_tc_supported(wd, nullptr);
+            } else if (stride == 2 && k == 3 && pad == 1 && !b && a->H == 2 * Ho && a->W == 2 * Wo) {
+                // stride-2 dgrad = the halo kernel's sub-pixel phase mode on dY (launch_relayout_tc_dgrad_s2)
+                ConvTcDesc g{};
+                g.dt = t->dt; g.C = cout; g.N = B; g.H = Ho; g.W = Wo; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = a->H; g.Wo = a->W; g.Cout = a->C;
+                g.upsample = 1; g.mode = TC_MODE_STD; g.stats_cw = m->stats_cw;
+                tc_dg_s2 = (t->tc_mask & 2) && conv_halo_supported(g, nullptr);
             }
         }
         const bool any_dg_simt = stride == 1 && ((!tc_dg[0]) || (b && !tc_dg[1]));
@@ -202,10 +208,11 @@ struct Walk {
         float* wd2 = (stride == 1 && b && !tc_dg[1]) ? (float*)aux((size_t)kk * cout * b->C * sizeof(float)) : nullptr;
         (void)any_dg_simt;
         void* w16 = tc_fwd ? aux((size_t)kk * Ct * cout * 2) : nullptr;
-        void* wd16[2] = {tc_dg[0] ? aux((size_t)kk * cout * a->C * 2) : nullptr, (b && tc_dg[1]) ? aux((size_t)kk * cout * b->C * 2) : nullptr};
+        void* wd16[2] = {tc_dg[0] ? aux((size_t)kk * cout * a->C * 2) : (tc_dg_s2 ? aux((size_t)16 * cout * a->C * 2) : nullptr),
+                         (b && tc_dg[1]) ? aux((size_t)kk * cout * b->C * 2) : nullptr};
         void* a16 = (tc_fwd || tc_wg) ? half_of(a) : nullptr;
         void* b16 = (b && (tc_fwd || tc_wg)) ? half_of(b) : nullptr;
-        if (tc_fwd || tc_dg[0] || tc_dg[1] || tc_wg) {
+        if (tc_fwd || tc_dg[0] || tc_dg[1] || tc_wg || tc_dg_s2) {
             need_scratch((size_t)B * Ho * Wo * cout * 2);
             need_scratch((size_t)B * a->H * a->W * std::max(a->C, b ? b->C : 0) * 2);
         }
@@ -252,14 +259,16 @@ struct Walk {
             // everything below is the gradient of the pre-scale sum
             if (out_scale != 1.0f && (rc = launch_add_inplace(O.g, O.g, out_scale - 1.0f, on, st))) return rc;
             const int M = Bn * O.H * O.W;
-            if (gb && (rc = launch_colsum(O.g, M, O.C, M, 1.f, gb, st))) return rc;
-            if (d_addvec && (rc = launch_colsum(O.g, M, O.C, O.H * O.W, 1.f, d_addvec, st))) return rc;   // per image: (B, Cout)
-            if (hasR && R.g && (rc = launch_add_inplace(R.g, O.g, 1.0f, on, st))) return rc;
             const int dt = tr->dt;
-            if (tc_wg || tc_dg0 || tc_dg1) {
-                if ((rc = launch_f2h(dt, O.g, tr->scr_a(), on, st))) return rc;
-                tr->launches += 1;
+            const bool need16 = tc_wg || tc_dg0 || tc_dg1 || tc_dg_s2;
+            if (need16 || (O.C % 4 == 0 && O.H * O.W >= 64 && (gb || d_addvec))) {
+                // one pass over dY: bias gradient, per-image sums for the time-embedding projection, and the 16-bit copy
+                if ((rc = launch_colsum_cast(dt == DT_F32 ? DT_BF16 : dt, O.g, Bn, O.H * O.W, O.C, gb, d_addvec, need16 ? tr->scr_a() : nullptr, st))) return rc;
+            } else {
+                if (gb && (rc = launch_colsum(O.g, M, O.C, M, 1.f, gb, st))) return rc;
+                if (d_addvec && (rc = launch_colsum(O.g, M, O.C, O.H * O.W, 1.f, d_addvec, st))) return rc;   // per image: (B, Cout)
             }
+            if (hasR && R.g && (rc = launch_add_inplace(R.g, O.g, 1.0f, on, st))) return rc;
             if (tc_wg) {
                 const size_t wbytes = (size_t)kk * O.C * Ct * sizeof(float);
                 PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, wbytes, st));
@@ -309,6 +318,16 @@ struct Walk {
                     }
                     i0 += srcs[q]->C;
                 }
+            } else if (A.g && tc_dg_s2) {
+                if ((rc = launch_relayout_tc_dgrad_s2(dt, pw, O.C, A.C, wd16_0, st))) return rc;
+                ConvTcDesc g{};
+                g.dt = dt; g.x = tr->scr_a(); g.C = O.C; g.N = Bn; g.H = O.H; g.W = O.W; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = A.H; g.Wo = A.W;
+                g.Cout = A.C; g.upsample = 1; g.wmat = wd16_0; g.out_scale = 1.f; g.out = tr->scr_b(); g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
+                ConvTcPlan* gp = tr->conv_plan(dg_idx, g, &rc);
+                if (!gp) return rc;
+                if ((rc = conv_tc_launch(gp, st))) return rc;
+                if ((rc = launch_h2f_accumulate(dt, tr->scr_b(), A.g, (size_t)Bn * A.H * A.W * A.C, st))) return rc;
+                tr->launches += 3;
             } else if (A.g) {
                 if ((rc = launch_conv_dgrad_gather(O.g, O.C, pw, Bn, A.H, A.W, A.C, O.H, O.W, O.C, pad, stride, A.g, st))) return rc;
                 tr->launches += 1;
@@ -406,14 +425,16 @@ struct Walk {
         float* lse = (float*)aux((size_t)B * (C / 8) * S * sizeof(float));
         float* delta = (float*)aux((size_t)B * (C / 8) * S * sizeof(float));
         if (!dry()) {
-            run(launch_attn8_fwd(q->d, k->d, v->d, C, B, S, C, o->d, lse, s()));
+            const bool mma = t->dt != DT_F32 && (t->tc_mask & 8) && attn8_mma_supported(S, C, C);
+            run(mma ? launch_attn8_mma_fwd(q->d, k->d, v->d, C, B, S, C, o->d, lse, s()) : launch_attn8_fwd(q->d, k->d, v->d, C, B, S, C, o->d, lse, s()));
             count();
             const TT Q = *q, K = *k, V = *v, O = *o;
             const int Bn = B;
             pd_train* tr = t;
             bwd([=](cudaStream_t st) {
                 tr->launches += 2;
-                return launch_attn8_bwd(Q.d, K.d, V.d, C, O.d, O.g, lse, Bn, S, C, Q.g, K.g, V.g, delta, st);
+                return mma ? launch_attn8_mma_bwd(Q.d, K.d, V.d, C, O.d, O.g, lse, Bn, S, C, Q.g, K.g, V.g, delta, st)
+                           : launch_attn8_bwd(Q.d, K.d, V.d, C, O.d, O.g, lse, Bn, S, C, Q.g, K.g, V.g, delta, st);
             });
         }
         return conv(A.ow, A.ob, C, 1, 1, 0, o, nullptr, nullptr, nullptr, x, 1.0f / A.rescale);

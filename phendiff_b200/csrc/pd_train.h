@@ -60,7 +60,17 @@ int launch_f2h(int dt, const float* x, void* out, size_t n, cudaStream_t s);
 int launch_h2f_epilogue(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
                         cudaStream_t s);
 int launch_h2f_accumulate(int dt, const void* y16, float* out, size_t n, cudaStream_t s);
+int launch_relayout_tc_dgrad_s2(int dt, const float* w, int O, int I, void* out, cudaStream_t s);
+// one pass over dY: column sums per tensor (out_all) and / or per image (out_img), optional 16-bit copy (dt: DT_BF16 / DT_F16)
+int launch_colsum_cast(int dt, const float* dy, int B, int rows_per_img, int C, float* out_all, float* out_img, void* out16, cudaStream_t s);
 int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s);
+
+// softmax attention (head_dim 8) on the warp-level tensor cores, bf16 operands staged from the fp32 activations (pd_train_attn_mma.cu);
+// same interface as launch_attn8_fwd / launch_attn8_bwd
+bool attn8_mma_supported(int S, int C, int pitch);
+int launch_attn8_mma_fwd(const float* q, const float* k, const float* v, int pitch, int N, int S, int C, float* out, float* lse, cudaStream_t s);
+int launch_attn8_mma_bwd(const float* q, const float* k, const float* v, int pitch, const float* o, const float* dout, const float* lse, int N,
+                         int S, int C, float* dq, float* dk, float* dv, float* delta, cudaStream_t s);
 
 // tcgen05 weight gradient of a stride-1 'same' convolution (k = 1 or 3): stage[tap][co][ci] += sum_pixels dY[p, co] * X[p @ tap, ci],
 // K = pixels.  x1 / x2: the NHWC 16-bit sources of the conv input (channel concat), dy: (N, H, W, Cout) 16-bit.

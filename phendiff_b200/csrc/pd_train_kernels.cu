@@ -715,4 +715,87 @@ int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cu
     return 0;
 }
 
+// OIHW (O, I, 3, 3) fp32 -> 16-bit phase weights of the stride-2 (padding 1) dgrad, in the layout of the halo kernel's upsample mode:
+// dX(2i + a, 2j + b) = sum_{dr, dc} Wd[(a, b)][(dr, dc)] dY(i - 1 + a + dr, j - 1 + b + dc); out (4*I, 4*O), row = (a*2+b)*I + i,
+// k = (dr*2+dc)*O + o.  Input row 2i + a receives kernel row r through output row (2i + a + 1 - r) / 2: a = 0 -> r = 1 (dr = 1);
+// a = 1 -> r = 2 (dr = 0), r = 0 (dr = 1); the remaining (a, dr) = (0, 0) slot is zero.  Same for columns.
+template <typename T>
+__global__ void relayout_tc_dgrad_s2_kernel(const float* __restrict__ w, int O, int I, T* __restrict__ out) {
+    const size_t total = (size_t)16 * O * I;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = idx % O;
+        size_t q = idx / O;
+        const int tap = q % 4; q /= 4;
+        const int i = q % I;
+        const int ph = q / I;
+        const int a = ph >> 1, b = ph & 1, dr = tap >> 1, dc = tap & 1;
+        const int r = a == 0 ? (dr == 1 ? 1 : -1) : (dr == 0 ? 2 : 0);
+        const int sx = b == 0 ? (dc == 1 ? 1 : -1) : (dc == 0 ? 2 : 0);
+        out[idx] = from_f<T>((r < 0 || sx < 0) ? 0.f : w[((size_t)o * I + i) * 9 + r * 3 + sx]);
+    }
+}
+int launch_relayout_tc_dgrad_s2(int dt, const float* w, int O, int I, void* out, cudaStream_t s) {
+    const size_t total = (size_t)16 * O * I;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
+    PD_DISPATCH_HALF(dt, T, (relayout_tc_dgrad_s2_kernel<T><<<grid, 256, 0, s>>>(w, O, I, (T*)out)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// column sums of dY (M rows x C fp32) in one pass, four columns per thread: out_all[c] += sum over all rows, out_img[n][c] += sum over
+// image n's rows (either may be null), and optionally the 16-bit copy of dY that the tensor-core dgrad / wgrad read (same pass).
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_cast_kernel(const float4* __restrict__ dy, int C4, int rows_per_img, int rows_per_block,
+                                                          float* __restrict__ out_all, float* __restrict__ out_img, T* __restrict__ out16) {
+    __shared__ float4 red[256];
+    const int img = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows_per_img);
+    const int rstep = max(1, 256 / C4);
+    const size_t base = (size_t)img * rows_per_img;
+    for (int cg0 = 0; cg0 < C4; cg0 += 256) {
+        const int cg = cg0 + (C4 >= 256 ? threadIdx.x : threadIdx.x % C4);
+        const int rr = C4 >= 256 ? 0 : threadIdx.x / C4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cg < C4 && rr < rstep) {
+#pragma unroll 4
+            for (int r = r0 + rr; r < r1; r += rstep) {
+                const float4 v = dy[(base + r) * C4 + cg];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                if (out16) {
+                    T* o = out16 + ((base + r) * C4 + cg) * 4;
+                    union { T h[4]; uint2 u; } pk;
+                    pk.h[0] = from_f<T>(v.x); pk.h[1] = from_f<T>(v.y); pk.h[2] = from_f<T>(v.z); pk.h[3] = from_f<T>(v.w);
+                    *reinterpret_cast<uint2*>(o) = pk.u;
+                }
+            }
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        if (rr == 0 && cg < C4) {
+            for (int k = 1; k < rstep; ++k) {
+                const float4 v = red[threadIdx.x + k * C4];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (out_all) {
+                float* o = out_all + cg * 4;
+                atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+            }
+            if (out_img) {
+                float* o = out_img + ((size_t)img * C4 + cg) * 4;
+                atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+            }
+        }
+        __syncthreads();
+    }
+}
+int launch_colsum_cast(int dt, const float* dy, int B, int rows_per_img, int C, float* out_all, float* out_img, void* out16, cudaStream_t s) {
+    PD_REQUIRE(C % 4 == 0, "colsum_cast: channel count must be a multiple of 4");
+    const int rpb = 256;
+    dim3 grid((rows_per_img + rpb - 1) / rpb, B);
+    if (dt == DT_F16) colsum_cast_kernel<f16><<<grid, 256, 0, s>>>((const float4*)dy, C / 4, rows_per_img, rpb, out_all, out_img, (f16*)out16);
+    else colsum_cast_kernel<bf16><<<grid, 256, 0, s>>>((const float4*)dy, C / 4, rows_per_img, rpb, out_all, out_img, (bf16*)out16);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace pd
