@@ -25,6 +25,15 @@ def shard_sizes(total: int, world_size: int) -> List[int]:
     return [shard_range(total, r, world_size)[1] - shard_range(total, r, world_size)[0] for r in range(world_size)]
 
 
+def average_gradients(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Data-parallel gradient averaging of the training step: ONE all-reduce over the flat gradient vector, in
+    place (what DDP does in buckets for the reference, train.py:57-61 through accelerate).  NCCL on the GPU box, gloo in the CPU tests."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / dist.get_world_size(group))
+    return flat
+
+
 def gather_outputs(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
     """All-gather the per-rank outputs (ragged along dim 0) into the full batch, in rank order.
     NCCL over NVLink on the GPU box, gloo in the CPU tests."""

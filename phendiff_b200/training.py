@@ -31,6 +31,7 @@ import torch.distributed as dist
 from . import _lib
 from .cond_unet_2d import CustomCondUNet2DModel
 from .schedulers import DDIMScheduler
+from .sharding import average_gradients
 
 
 def ema_decay_at(optimization_step: int, max_decay: float = 0.9999, min_decay: float = 0.0, update_after_step: int = 0,
@@ -207,9 +208,7 @@ class DenoiserTrainer:
 
     def all_reduce_gradients(self, group=None):
         """Average the flat gradient vector over the data-parallel ranks: one collective (NCCL over NVLink on the GPU box)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
-            self.grads.mul_(1.0 / dist.get_world_size(group))
+        average_gradients(self.grads, group)
 
     def current_lr(self) -> float:
         return self.lr * (self.lr_lambda(self.global_step) if self.lr_lambda is not None else 1.0)

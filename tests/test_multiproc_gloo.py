@@ -59,3 +59,56 @@ def test_sharded_transfer_equals_unsharded_world2(total):
         assert p.exitcode == 0
     assert shape == (total, 3, 16, 16)
     assert err <= 1e-4, f"sharded vs unsharded differ by {err:.3e}"
+
+
+def _train_worker(rank, world, port, q):
+    """Data-parallel training step: each rank computes the gradient of the oracle's loss on ITS half of the batch,
+    `average_gradients` all-reduces the flat vector once; the result must equal the gradient of the loss on the whole batch
+    (mse is a mean over the batch, so the average of the two half-batch gradients is the full-batch gradient)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch.nn.functional as F
+
+        from oracle import OracleCondUNet2D
+        from phendiff_b200.reference_configs import DENOISER_CONFIGS
+        from phendiff_b200.sharding import average_gradients, shard_range
+
+        torch.manual_seed(0)
+        unet = OracleCondUNet2D(**dict(DENOISER_CONFIGS["super_small"], sample_size=16))
+        g = torch.Generator().manual_seed(7)
+        total = 4
+        x = torch.randn(total, 3, 16, 16, generator=g)
+        noise = torch.randn(total, 3, 16, 16, generator=g)
+        t = torch.randint(0, 1000, (total,), generator=g)
+        labels = torch.arange(total) % 2
+
+        def flat_grad(lo, hi):
+            unet.zero_grad()
+            F.mse_loss(unet(x[lo:hi], t[lo:hi], class_labels=labels[lo:hi]).sample, noise[lo:hi]).backward()
+            return torch.cat([p.grad.flatten() for p in unet.parameters()])
+
+        lo, hi = shard_range(total, rank, world)
+        flat = average_gradients(flat_grad(lo, hi))
+        if rank == 0:
+            ref = flat_grad(0, total)
+            q.put(float((flat - ref).abs().max() / ref.abs().max()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_equals_full_batch_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert err <= 1e-5, f"averaged shard gradients differ from the full-batch gradient by {err:.3e}"

@@ -82,7 +82,8 @@ PY
     ncu)
       rx="${arg%%:*}"; envs=""; [[ "$arg" == *:* ]] && envs="${arg#*:}"
       ( for kv in ${envs//,/ }; do export "$kv"; done
-        timeout 300 ncu --set full --clock-control none --import-source on -k regex:$rx -s ${NCU_KSKIP:-6} -c ${NCU_KCOUNT:-2} \
+        base=function; [[ "$rx" == *"<"* ]] && base=demangled     # template arguments in the pattern: match the demangled name
+        timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base $base -k "regex:$rx" -s ${NCU_KSKIP:-6} -c ${NCU_KCOUNT:-2} \
           -o gpurun_out/prof_${rx//[^a-zA-Z0-9_]/_}_${tag} -f $SHORT --num-inference-steps 1 --steps 1 --warmup 1 > gpurun_out/ncu_${rx//[^a-zA-Z0-9_]/_}_${tag}.log 2>&1 )
       echo "ncu $rx exit=$?"; tail -2 gpurun_out/ncu_${rx//[^a-zA-Z0-9_]/_}_${tag}.log;;
     *) echo "unknown stage $stage";;
