@@ -19,6 +19,9 @@ struct TT {   // an NHWC fp32 activation and its gradient
     int C = 0, H = 0, W = 0;
     double* stats = nullptr;   // GroupNorm chunk statistics (computed on first use)
     void* h = nullptr;         // 16-bit copy feeding the tensor-core convolutions (mixed-precision mode; made on first use)
+    bool only16 = false;
+    void* g16 = nullptr;       // 16-bit-only tensors (GroupNorm outputs whose single consumer is a tensor-core conv: d == g == null): the
+                               // gradient the consumer's dgrad writes directly
 };
 
 }  // namespace pd
@@ -45,7 +48,8 @@ struct pd_train {
     int64_t launches = 0;
     // mixed precision (pd_train_set_precision): 16-bit operands for the convolutions on the tcgen05 kernels, everything else fp32
     int dt = DT_F32;
-    unsigned tc_mask = 15;         // 1 conv forward, 2 dgrad, 4 wgrad, 8 attention (PHENDIFF_B200_TRAIN_TC)
+    unsigned tc_mask = 63;         // 1 conv forward, 2 dgrad, 4 wgrad, 8 attention, 16 16-bit-only GroupNorm outputs + fused q/k/v, 32 padded
+                                   // tensor-core GEMMs for conv_in / conv_out gradients (PHENDIFF_B200_TRAIN_TC)
     size_t scr_max = 0, wstage_max = 0;          // shared scratch: two 16-bit activation-sized buffers + the wgrad staging tile
     struct ConvSlot { ConvTcDesc d; ConvTcPlan* pl = nullptr; };
     struct WgSlot { WgradTcDesc d; WgradTcPlan* pl = nullptr; };
@@ -112,6 +116,22 @@ struct Walk {
         t->tts.push_back(std::move(tt));
         return r;
     }
+    // 16-bit-only activation: data and gradient in the same two regions, half the bytes
+    TT* act16(int C, int H, int W) {
+        auto tt = std::make_unique<TT>();
+        tt->C = C; tt->H = H; tt->W = W; tt->only16 = true;
+        const size_t bytes = (((size_t)B * H * W * C * 2) + 255) & ~(size_t)255;
+        if (!dry()) {
+            tt->h = (void*)(t->ws + t->act_bump);
+            tt->g16 = (void*)(t->ws + t->act_bytes + t->act_bump);
+        } else {
+            tt->h = reinterpret_cast<void*>(uintptr_t(8));
+        }
+        t->act_bump += bytes;
+        TT* r = tt.get();
+        t->tts.push_back(std::move(tt));
+        return r;
+    }
     void* aux(size_t bytes, bool zero = false) {
         bytes = (bytes + 255) & ~(size_t)255;
         void* r = dry() ? nullptr : (void*)(t->ws + 2 * t->act_bytes + t->aux_bump);
@@ -145,24 +165,50 @@ struct Walk {
     }
     void need_scratch(size_t bytes) { bytes = (bytes + 255) & ~(size_t)255; if (bytes > t->scr_max) t->scr_max = bytes; }
 
-    // y = act(GroupNorm(concat(a, b)))
-    TT* gn(const GNL& g, TT* a, TT* b, bool silu) {
+    // which pieces of a stride-1 'same' convolution over ONE source of C channels run on the tensor cores
+    struct TcFlags { bool fwd, dgrad, wgrad; bool all() const { return fwd && dgrad && wgrad; } };
+    TcFlags tc_flags(int C, int H, int W, int cout, int k) const {
+        TcFlags f{false, false, false};
+        if (t->dt == DT_F32) return f;
+        ConvTcDesc d{};
+        d.dt = t->dt; d.C = C; d.N = B; d.H = H; d.W = W; d.ksize = k; d.stride = 1; d.pad = k / 2; d.Ho = H; d.Wo = W; d.Cout = cout;
+        d.mode = TC_MODE_STD; d.stats_cw = m->stats_cw;
+        f.fwd = (t->tc_mask & 1) && conv_halo_supported(d, nullptr);
+        ConvTcDesc g = d;
+        g.C = cout; g.Cout = C;
+        f.dgrad = (t->tc_mask & 2) && conv_halo_supported(g, nullptr);
+        WgradTcDesc wd{};
+        wd.dt = t->dt; wd.C1 = C; wd.N = B; wd.H = H; wd.W = W; wd.Cout = cout; wd.ksize = k;
+        f.wgrad = (t->tc_mask & 4) && wgrad_tc_supported(wd, nullptr);
+        return f;
+    }
+
+    // y = act(GroupNorm(concat(a, b))).  to16: the output exists in 16 bits only (its single consumer is a tensor-core convolution
+    // that reads it as an operand and whose dgrad writes the 16-bit gradient this backward reads)
+    TT* gn(const GNL& g, TT* a, TT* b, bool silu, bool to16 = false) {
         const int C = a->C + (b ? b->C : 0), HW = a->H * a->W;
-        TT* o = act(C, a->H, a->W);
+        to16 = to16 && (t->tc_mask & 16) && C % 8 == 0 && a->C % 8 == 0;
+        TT* o = to16 ? act16(C, a->H, a->W) : act(C, a->H, a->W);
         double* st1 = stats_of(a);
         double* st2 = b ? stats_of(b) : nullptr;
         float* gsum = (float*)aux((size_t)B * m->cfg.norm_num_groups * 2 * sizeof(float));
         if (dry()) return o;
-        GNArgs ga{};
-        ga.x1 = a->d; ga.x2 = b ? b->d : nullptr; ga.C1 = a->C; ga.C2 = b ? b->C : 0; ga.N = B; ga.HW = HW; ga.groups = m->cfg.norm_num_groups;
-        ga.eps = m->cfg.norm_eps; ga.gamma = p(g.g); ga.beta = p(g.b); ga.silu = silu; ga.stats_cw = m->stats_cw; ga.stats1 = st1; ga.stats2 = st2;
-        ga.out = o->d;
-        run(launch_gn_apply(DT_F32, true, ga, s()));
-        count();
         GNBwdArgs ba{};
-        ba.x1 = a->d; ba.x2 = b ? b->d : nullptr; ba.dx1 = a->g; ba.dx2 = b ? b->g : nullptr; ba.dy = o->g; ba.C1 = a->C; ba.C2 = b ? b->C : 0;
+        ba.x1 = a->d; ba.x2 = b ? b->d : nullptr; ba.dx1 = a->g; ba.dx2 = b ? b->g : nullptr; ba.C1 = a->C; ba.C2 = b ? b->C : 0;
         ba.N = B; ba.HW = HW; ba.groups = m->cfg.norm_num_groups; ba.silu = silu; ba.stats_cw = m->stats_cw; ba.eps = m->cfg.norm_eps; ba.scale = 1.f;
         ba.gamma = p(g.g); ba.beta = p(g.b); ba.dgamma = gr(g.g); ba.dbeta = gr(g.b); ba.stats1 = st1; ba.stats2 = st2; ba.gsum = gsum;
+        if (to16) {
+            run(launch_gn_apply16(t->dt, ba, o->h, s()));
+            ba.dy = o->g16; ba.dy_dt = t->dt;
+        } else {
+            GNArgs ga{};
+            ga.x1 = a->d; ga.x2 = b ? b->d : nullptr; ga.C1 = a->C; ga.C2 = b ? b->C : 0; ga.N = B; ga.HW = HW; ga.groups = m->cfg.norm_num_groups;
+            ga.eps = m->cfg.norm_eps; ga.gamma = p(g.g); ga.beta = p(g.b); ga.silu = silu; ga.stats_cw = m->stats_cw; ga.stats1 = st1; ga.stats2 = st2;
+            ga.out = o->d;
+            run(launch_gn_apply(DT_F32, true, ga, s()));
+            ba.dy = o->g; ba.dy_dt = DT_F32;
+        }
+        count();
         pd_train* tr = t;
         bwd([ba, tr](cudaStream_t st) { tr->launches += 2; return launch_gn_bwd(ba, st); });
         return o;
@@ -201,6 +247,9 @@ struct Walk {
                 g.upsample = 1; g.mode = TC_MODE_STD; g.stats_cw = m->stats_cw;
                 tc_dg_s2 = (t->tc_mask & 2) && conv_halo_supported(g, nullptr);
             }
+        }
+        if ((a->only16 && !(tc_fwd && tc_dg[0] && tc_wg)) || (b && b->only16)) {
+            set_error("internal: 16-bit-only activation feeding a convolution that is not fully on the tensor-core path"); run(1);
         }
         const bool any_dg_simt = stride == 1 && ((!tc_dg[0]) || (b && !tc_dg[1]));
         float* w_fwd = tc_fwd ? nullptr : (float*)aux((size_t)kk * Ct * cout * sizeof(float));
@@ -297,7 +346,17 @@ struct Walk {
                 int i0 = 0;
                 for (int q = 0; q < 2; ++q) {
                     if (!srcs[q]) continue;
-                    if (srcs[q]->g && tcd[q]) {
+                    if (srcs[q]->g16 && tcd[q]) {
+                        // 16-bit-only source (a GroupNorm output): the dgrad result IS its gradient, no fp32 accumulation pass
+                        if ((rc = launch_relayout_tc_dgrad(dt, pw, O.C, Ct, k, i0, srcs[q]->C, wd16s[q], st))) return rc;
+                        ConvTcDesc g{};
+                        g.dt = dt; g.x = tr->scr_a(); g.C = O.C; g.N = Bn; g.H = O.H; g.W = O.W; g.ksize = k; g.stride = 1; g.pad = pad; g.Ho = O.H; g.Wo = O.W;
+                        g.Cout = srcs[q]->C; g.wmat = wd16s[q]; g.out_scale = 1.f; g.out = srcs[q]->g16; g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
+                        ConvTcPlan* gp = tr->conv_plan(dg_idx + q, g, &rc);
+                        if (!gp) return rc;
+                        if ((rc = conv_tc_launch(gp, st))) return rc;
+                        tr->launches += 2;
+                    } else if (srcs[q]->g && tcd[q]) {
                         // dX = conv(dY, W^T flipped) on the halo kernel, 16-bit result accumulated into the fp32 gradient
                         if ((rc = launch_relayout_tc_dgrad(dt, pw, O.C, Ct, k, i0, srcs[q]->C, wd16s[q], st))) return rc;
                         ConvTcDesc g{};
@@ -406,35 +465,122 @@ struct Walk {
 
     // ResnetBlock2D on concat(a, b)
     TT* resnet(const ResL& R, TT* a, TT* b, float* temb, float* dtemb) {
-        TT* hn = gn(R.n1, a, b, true);
+        const int Cin = a->C + (b ? b->C : 0);
+        TT* hn = gn(R.n1, a, b, true, tc_flags(Cin, a->H, a->W, R.cout, 3).all());
         TT* h1 = conv(R.c1.w, R.c1.b, R.cout, 3, 1, 1, hn, nullptr, temb, dtemb, nullptr, 1.f);
-        TT* h1n = gn(R.n2, h1, nullptr, true);
+        TT* h1n = gn(R.n2, h1, nullptr, true, tc_flags(R.cout, a->H, a->W, R.cout, 3).all());
         TT* res = a;
         if (R.has_sc) res = conv(R.sc.w, R.sc.b, R.cout, 1, 1, 0, a, b, nullptr, nullptr, nullptr, 1.f);
         return conv(R.c2.w, R.c2.b, R.cout, 3, 1, 1, h1n, nullptr, nullptr, nullptr, res, 1.0f / R.scale);
     }
 
+    // q, k, v projections as ONE C -> 3C GEMM on the tensor cores (three parameter tensors, one operand): the GroupNorm output has a single
+    // consumer, so it can live in 16 bits only and its gradient is the one dgrad's output
+    TT* qkv_fused(const AttnL& A, TT* xn) {
+        const int C = A.C, H = xn->H, W = xn->W, HW = H * W, C3 = 3 * C;
+        TT* o = act(C3, H, W);
+        void* w16 = aux((size_t)C3 * C * 2);
+        void* wd16 = aux((size_t)C * C3 * 2);
+        float* bias3 = (float*)aux((size_t)C3 * sizeof(float));
+        float* btmp = (float*)aux((size_t)C3 * sizeof(float));
+        void* x16 = half_of(xn);
+        need_scratch((size_t)B * HW * C3 * 2);
+        if ((size_t)C3 * C * sizeof(float) > t->wstage_max) t->wstage_max = (((size_t)C3 * C * sizeof(float)) + 255) & ~(size_t)255;
+        const size_t fwd_idx = t->conv_cursor, dg_idx = t->conv_cursor + 1, wg_idx = t->wg_cursor;
+        t->conv_cursor += 2; t->wg_cursor += 1;
+        if (dry()) return o;
+        const Param* ws[3] = {A.qw, A.kw, A.vw};
+        const Param* bs[3] = {A.qb, A.kb, A.vb};
+        const int dt = t->dt;
+        for (int j = 0; j < 3; ++j) {
+            run(launch_relayout_tc(dt, p(ws[j]), C, C, 1, (uint8_t*)w16 + (size_t)j * C * C * 2, C, 0, s()));
+            cu(cudaMemcpyAsync(bias3 + j * C, p(bs[j]), C * sizeof(float), cudaMemcpyDeviceToDevice, s()));
+        }
+        ConvTcDesc d{};
+        d.dt = dt; d.x = x16; d.C = C; d.N = B; d.H = H; d.W = W; d.ksize = 1; d.stride = 1; d.pad = 0; d.Ho = H; d.Wo = W; d.Cout = C3; d.wmat = w16;
+        d.bias = bias3; d.out_scale = 1.f; d.out = t->scr_a(); d.mode = TC_MODE_STD; d.stats_cw = m->stats_cw;
+        int prc = 0;
+        ConvTcPlan* pl = t->conv_plan(fwd_idx, d, &prc);
+        if (!pl) { run(prc); return o; }
+        run(conv_tc_launch(pl, s()));
+        run(launch_h2f_epilogue(dt, t->scr_a(), nullptr, nullptr, 1.f, o->d, B, HW, C3, s()));
+        count(8);
+        t->tc_convs++;
+        pd_train* tr = t;
+        const TT X = *xn, O = *o;
+        const int Bn = B;
+        const float* pw[3] = {p(ws[0]), p(ws[1]), p(ws[2])};
+        float* gw[3] = {gr(ws[0]), gr(ws[1]), gr(ws[2])};
+        float* gb[3] = {gr(bs[0]), gr(bs[1]), gr(bs[2])};
+        const float *pw0 = pw[0], *pw1 = pw[1], *pw2 = pw[2];
+        float *gw0 = gw[0], *gw1 = gw[1], *gw2 = gw[2], *gb0 = gb[0], *gb1 = gb[1], *gb2 = gb[2];
+        bwd([=](cudaStream_t st) {
+            int rc = 0;
+            const float* pws[3] = {pw0, pw1, pw2};
+            float* gws[3] = {gw0, gw1, gw2};
+            float* gbs[3] = {gb0, gb1, gb2};
+            PD_CHECK_CUDA(cudaMemsetAsync(btmp, 0, (size_t)C3 * sizeof(float), st));
+            if ((rc = launch_colsum_cast(dt, O.g, Bn, HW, C3, btmp, nullptr, tr->scr_a(), st))) return rc;
+            for (int j = 0; j < 3; ++j)
+                if ((rc = launch_add_inplace(gbs[j], btmp + j * C, 1.0f, (size_t)C, st))) return rc;
+            PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)C3 * C * sizeof(float), st));
+            WgradTcDesc wd{};
+            wd.dt = dt; wd.x1 = X.h; wd.C1 = C; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = C3; wd.ksize = 1; wd.dy = tr->scr_a(); wd.stage = tr->wstage();
+            WgradTcPlan* wp = tr->wg_plan(wg_idx, wd, &rc);
+            if (!wp) return rc;
+            if ((rc = wgrad_tc_launch(wp, st))) return rc;
+            for (int j = 0; j < 3; ++j) {
+                if ((rc = launch_wgrad_unstage(tr->wstage() + (size_t)j * C * C, C, C, 1, gws[j], st))) return rc;
+                if ((rc = launch_relayout_tc_dgrad(dt, pws[j], C, C, 1, 0, C, wd16, st, C3, j * C))) return rc;
+            }
+            ConvTcDesc g{};
+            g.dt = dt; g.x = tr->scr_a(); g.C = C3; g.N = Bn; g.H = H; g.W = W; g.ksize = 1; g.stride = 1; g.pad = 0; g.Ho = H; g.Wo = W; g.Cout = C;
+            g.wmat = wd16; g.out_scale = 1.f; g.out = X.g16 ? X.g16 : tr->scr_b(); g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
+            ConvTcPlan* gp = tr->conv_plan(dg_idx, g, &rc);
+            if (!gp) return rc;
+            if ((rc = conv_tc_launch(gp, st))) return rc;
+            if (!X.g16 && (rc = launch_h2f_accumulate(dt, tr->scr_b(), X.g, (size_t)Bn * HW * C, st))) return rc;
+            tr->launches += 16;
+            tr->tc_wgrads++;
+            return 0;
+        });
+        return o;
+    }
+
     // Attention, head_dim 8
     TT* attention(const AttnL& A, TT* x) {
         const int C = A.C, S = x->H * x->W;
-        TT* xn = gn(A.gn, x, nullptr, false);
-        TT* q = conv(A.qw, A.qb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
-        TT* k = conv(A.kw, A.kb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
-        TT* v = conv(A.vw, A.vb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+        const bool fused = (t->tc_mask & 16) && tc_flags(C, x->H, x->W, 3 * C, 1).all();
+        TT* xn = gn(A.gn, x, nullptr, false, fused);
+        const float *qd, *kd, *vd;
+        float *qg, *kg, *vg;
+        int pitch = C;
+        if (fused) {
+            TT* qkv = qkv_fused(A, xn);
+            need_scratch((size_t)B * S * C * 2);
+            qd = qkv->d; kd = qkv->d ? qkv->d + C : nullptr; vd = qkv->d ? qkv->d + 2 * C : nullptr;
+            qg = qkv->g; kg = qkv->g ? qkv->g + C : nullptr; vg = qkv->g ? qkv->g + 2 * C : nullptr;
+            pitch = 3 * C;
+        } else {
+            TT* q = conv(A.qw, A.qb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+            TT* k = conv(A.kw, A.kb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+            TT* v = conv(A.vw, A.vb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+            qd = q->d; kd = k->d; vd = v->d; qg = q->g; kg = k->g; vg = v->g;
+        }
         TT* o = act(C, x->H, x->W);
         float* lse = (float*)aux((size_t)B * (C / 8) * S * sizeof(float));
         float* delta = (float*)aux((size_t)B * (C / 8) * S * sizeof(float));
         if (!dry()) {
-            const bool mma = t->dt != DT_F32 && (t->tc_mask & 8) && attn8_mma_supported(S, C, C);
-            run(mma ? launch_attn8_mma_fwd(q->d, k->d, v->d, C, B, S, C, o->d, lse, s()) : launch_attn8_fwd(q->d, k->d, v->d, C, B, S, C, o->d, lse, s()));
+            const bool mma = t->dt != DT_F32 && (t->tc_mask & 8) && attn8_mma_supported(S, C, pitch);
+            run(mma ? launch_attn8_mma_fwd(qd, kd, vd, pitch, B, S, C, o->d, lse, s()) : launch_attn8_fwd(qd, kd, vd, pitch, B, S, C, o->d, lse, s()));
             count();
-            const TT Q = *q, K = *k, V = *v, O = *o;
+            const TT O = *o;
             const int Bn = B;
             pd_train* tr = t;
             bwd([=](cudaStream_t st) {
                 tr->launches += 2;
-                return mma ? launch_attn8_mma_bwd(Q.d, K.d, V.d, C, O.d, O.g, lse, Bn, S, C, Q.g, K.g, V.g, delta, st)
-                           : launch_attn8_bwd(Q.d, K.d, V.d, C, O.d, O.g, lse, Bn, S, C, Q.g, K.g, V.g, delta, st);
+                return mma ? launch_attn8_mma_bwd(qd, kd, vd, pitch, O.d, O.g, lse, Bn, S, C, qg, kg, vg, delta, st)
+                           : launch_attn8_bwd(qd, kd, vd, pitch, O.d, O.g, lse, Bn, S, C, qg, kg, vg, delta, st);
             });
         }
         return conv(A.ow, A.ob, C, 1, 1, 0, o, nullptr, nullptr, nullptr, x, 1.0f / A.rescale);
@@ -469,6 +615,29 @@ struct Walk {
         TT* x = act(C0, H, W);
         float* w_in = (float*)aux((size_t)9 * Cin * C0 * sizeof(float));
         float* xin = (float*)aux((size_t)B * H * W * 4 * sizeof(float));
+        // gradients of conv_in / conv_out on the tensor cores: the 3-channel side zero-padded to 128 channels (the wasted MACs are
+        // cheaper than the CUDA-core kernels by an order of magnitude)
+        constexpr int CP = 128;
+        bool tc_in = false, tc_out = false;
+        if (t->dt != DT_F32 && (t->tc_mask & 32) && Cin <= CP && Cout <= CP) {
+            WgradTcDesc wi{};
+            wi.dt = t->dt; wi.C1 = CP; wi.N = B; wi.H = H; wi.W = W; wi.Cout = C0; wi.ksize = 3;
+            tc_in = wgrad_tc_supported(wi, nullptr);
+            WgradTcDesc wo{};
+            wo.dt = t->dt; wo.C1 = C0; wo.N = B; wo.H = H; wo.W = W; wo.Cout = CP; wo.ksize = 3;
+            ConvTcDesc g{};
+            g.dt = t->dt; g.C = CP; g.N = B; g.H = H; g.W = W; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = H; g.Wo = W; g.Cout = C0; g.mode = TC_MODE_STD;
+            g.stats_cw = m->stats_cw;
+            tc_out = wgrad_tc_supported(wo, nullptr) && conv_halo_supported(g, nullptr);
+        }
+        void* pad16 = (tc_in || tc_out) ? aux((size_t)B * H * W * CP * 2) : nullptr;     // padded operand (conv_out: dY, then conv_in: X)
+        void* wd16_out = tc_out ? aux((size_t)C0 * 9 * CP * 2) : nullptr;
+        if (tc_in || tc_out) {
+            need_scratch((size_t)B * H * W * C0 * 2);
+            if ((size_t)9 * CP * C0 * sizeof(float) > t->wstage_max) t->wstage_max = (size_t)9 * CP * C0 * sizeof(float);
+        }
+        const size_t in_wg_idx = t->wg_cursor, out_wg_idx = t->wg_cursor + 1, out_dg_idx = t->conv_cursor;
+        t->wg_cursor += 2; t->conv_cursor += 1;
         if (!dry()) {
             run(launch_relayout_simt(p(m->conv_in.w), C0, Cin, 3, w_in, s()));
             run(launch_conv_in(DT_F32, noisy, w_in, p(m->conv_in.b), B, Cin, H, W, C0, x->d, s()));
@@ -479,7 +648,22 @@ struct Walk {
             const int Bn = B;
             pd_train* tr = t;
             bwd([=](cudaStream_t st) {
-                int rc = launch_colsum(X.g, Bn * H * W, C0, Bn * H * W, 1.f, gb, st);
+                int rc = 0;
+                if (tc_in) {
+                    const int dt = tr->dt;
+                    if ((rc = launch_colsum_cast(dt, X.g, Bn, H * W, C0, gb, nullptr, tr->scr_a(), st))) return rc;
+                    if ((rc = launch_nchw_to_nhwc16_pad(dt, noisy, Bn, Cin, H * W, CP, pad16, st))) return rc;
+                    PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)9 * C0 * CP * sizeof(float), st));
+                    WgradTcDesc wd{};
+                    wd.dt = dt; wd.x1 = pad16; wd.C1 = CP; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = C0; wd.ksize = 3; wd.dy = tr->scr_a(); wd.stage = tr->wstage();
+                    WgradTcPlan* wp = tr->wg_plan(in_wg_idx, wd, &rc);
+                    if (!wp) return rc;
+                    if ((rc = wgrad_tc_launch(wp, st))) return rc;
+                    tr->launches += 5;
+                    tr->tc_wgrads++;
+                    return launch_wgrad_unstage(tr->wstage(), C0, Cin, 9, gw, st, C0, CP);
+                }
+                rc = launch_colsum(X.g, Bn * H * W, C0, Bn * H * W, 1.f, gb, st);
                 if (rc) return rc;
                 WgradArgs wa{};
                 wa.x1 = xin; wa.C1 = 4; wa.N = Bn; wa.H = H; wa.W = W; wa.Cout = C0; wa.ksize = 3; wa.stride = 1; wa.pad = 1; wa.Ho = H; wa.Wo = W;
@@ -523,6 +707,7 @@ struct Walk {
         float* dm = (float*)aux((size_t)B * Cout * H * W * sizeof(float));
         float* dy4 = (float*)aux((size_t)B * H * W * 4 * sizeof(float));
         *dm_out = dm;
+        if (tc_out) half_of(xn);
         if (!dry()) {
             run(launch_relayout_convout(p(m->conv_out.w), Cout, C0, w_out, s()));
             ConvOutArgs oa{};
@@ -538,6 +723,28 @@ struct Walk {
                 int rc = launch_nchw_to_nhwc_pad(dm, Bn, Cout, H * W, 4, dy4, st);
                 if (rc) return rc;
                 if ((rc = launch_colsum(dy4, Bn * H * W, 4, Bn * H * W, 1.f, gb, st, Cout))) return rc;
+                if (tc_out) {
+                    const int dt = tr->dt;
+                    if ((rc = launch_nchw_to_nhwc16_pad(dt, dm, Bn, Cout, H * W, CP, pad16, st))) return rc;
+                    PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)9 * CP * C0 * sizeof(float), st));
+                    WgradTcDesc wd{};
+                    wd.dt = dt; wd.x1 = XN.h; wd.C1 = C0; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = CP; wd.ksize = 3; wd.dy = pad16; wd.stage = tr->wstage();
+                    WgradTcPlan* wp = tr->wg_plan(out_wg_idx, wd, &rc);
+                    if (!wp) return rc;
+                    if ((rc = wgrad_tc_launch(wp, st))) return rc;
+                    if ((rc = launch_wgrad_unstage(tr->wstage(), Cout, C0, 9, gw, st, CP, C0))) return rc;
+                    PD_CHECK_CUDA(cudaMemsetAsync(wd16_out, 0, (size_t)C0 * 9 * CP * 2, st));
+                    if ((rc = launch_relayout_tc_dgrad(dt, pw, Cout, C0, 3, 0, C0, wd16_out, st, 9 * CP, 0, CP))) return rc;
+                    ConvTcDesc g{};
+                    g.dt = dt; g.x = pad16; g.C = CP; g.N = Bn; g.H = H; g.W = W; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = H; g.Wo = W; g.Cout = C0;
+                    g.wmat = wd16_out; g.out_scale = 1.f; g.out = tr->scr_b(); g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
+                    ConvTcPlan* gp = tr->conv_plan(out_dg_idx, g, &rc);
+                    if (!gp) return rc;
+                    if ((rc = conv_tc_launch(gp, st))) return rc;
+                    tr->launches += 9;
+                    tr->tc_wgrads++;
+                    return launch_h2f_accumulate(dt, tr->scr_b(), XN.g, (size_t)Bn * H * W * C0, st);
+                }
                 WgradArgs wa{};
                 wa.x1 = XN.d; wa.C1 = C0; wa.N = Bn; wa.H = H; wa.W = W; wa.Cout = Cout; wa.ksize = 3; wa.stride = 1; wa.pad = 1; wa.Ho = H; wa.Wo = W;
                 wa.dy = dy4; wa.dy_pitch = 4; wa.dw = gw; wa.scale = 1.f;

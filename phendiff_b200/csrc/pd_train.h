@@ -26,15 +26,19 @@ int launch_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx
 struct GNBwdArgs {
     const float *x1, *x2;     // GroupNorm input (concat), NHWC fp32
     float *dx1, *dx2;         // accumulated
-    const float* dy;          // (N, HW, C1 + C2) gradient w.r.t. the (activated) output
+    const void* dy;           // (N, HW, C1 + C2) gradient w.r.t. the (activated) output: fp32, or 16-bit when dy_dt says so
     int C1, C2, N, HW, groups, silu, stats_cw;
     float eps, scale;
     const float *gamma, *beta;
     float *dgamma, *dbeta;    // accumulated
     const double *stats1, *stats2;   // chunk statistics of the inputs (forward)
     float* gsum;              // scratch (N, groups, 2)
+    int dy_dt;                // DT_F32 (0, default) or the 16-bit type `dy` is stored in (written by a tensor-core dgrad)
 };
 int launch_gn_bwd(const GNBwdArgs& a, cudaStream_t s);
+// forward of the mixed-precision path: fp32 sources -> 16-bit output only (uses x1/x2, C1/C2, N, HW, groups, silu, eps, gamma, beta, stats)
+int launch_gn_apply16(int dt, const GNBwdArgs& a, void* out, cudaStream_t s);
+int launch_nchw_to_nhwc16_pad(int dt, const float* x, int N, int C, int HW, int Cp, void* out, cudaStream_t s);
 
 // q, k, v: (N, S, pitch)-strided rows with the head's 8 values at head * 8 (packed qkv: pitch 3C, k = q + C, v = q + 2C)
 int launch_attn8_fwd(const float* q, const float* k, const float* v, int pitch, int N, int S, int C, float* out, float* lse, cudaStream_t s);
@@ -55,7 +59,8 @@ int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_
                  int step, float max_norm, float ema_decay, float* scratch_sumsq, float* norm_out, cudaStream_t s);
 
 // ---- mixed-precision path (bf16 tensor-core convolutions; pd_train_wgrad_tc.cu) -------------------------------------------------
-int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s);
+int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s, int ktot = 0, int koff = 0,
+                             int ostride = 0);
 int launch_f2h(int dt, const float* x, void* out, size_t n, cudaStream_t s);
 int launch_h2f_epilogue(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
                         cudaStream_t s);
@@ -63,7 +68,7 @@ int launch_h2f_accumulate(int dt, const void* y16, float* out, size_t n, cudaStr
 int launch_relayout_tc_dgrad_s2(int dt, const float* w, int O, int I, void* out, cudaStream_t s);
 // one pass over dY: column sums per tensor (out_all) and / or per image (out_img), optional 16-bit copy (dt: DT_BF16 / DT_F16)
 int launch_colsum_cast(int dt, const float* dy, int B, int rows_per_img, int C, float* out_all, float* out_img, void* out16, cudaStream_t s);
-int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s);
+int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s, int Opad = 0, int Ipad = 0);
 
 // softmax attention (head_dim 8) on the warp-level tensor cores, bf16 operands staged from the fp32 activations (pd_train_attn_mma.cu);
 // same interface as launch_attn8_fwd / launch_attn8_bwd

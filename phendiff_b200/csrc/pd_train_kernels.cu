@@ -14,6 +14,8 @@
 
 namespace pd {
 
+template <typename T> struct alignas(16) Half8 { T v[8]; };
+
 // ---------------------------------------------------------------------------------------------------------------------
 // weight re-layouts for the backward convolutions
 // ---------------------------------------------------------------------------------------------------------------------
@@ -223,15 +225,30 @@ __device__ __forceinline__ void gn_mean_rstd(const GNBwdArgs& a, int n, int g, f
     *mean = (float)mu;
     *rstd = 1.0f / sqrtf((float)fmax(sq * inv - mu * mu, 0.0) + a.eps);
 }
-template <int PASS>
+template <typename TD> __device__ __forceinline__ float4 ld_dy4(const TD* p);
+template <> __device__ __forceinline__ float4 ld_dy4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld_dy4<bf16>(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+template <> __device__ __forceinline__ float4 ld_dy4<f16>(const f16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __half2 a = *reinterpret_cast<const __half2*>(&u.x), b = *reinterpret_cast<const __half2*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+// four channels per thread (float4 rows), rows strided over the block; TD = type of dy (fp32, or the 16-bit gradient a tensor-core
+// dgrad wrote directly)
+template <int PASS, typename TD>
 __global__ void __launch_bounds__(256) gn_bwd_kernel(GNBwdArgs a, int rows_per_block) {
-    extern __shared__ float sm[];   // mean[groups], rstd[groups], (pass 2) s1[groups], s2[groups]
-    const int C = a.C1 + a.C2, cpg = C / a.groups;
+    extern __shared__ float sm[];   // mean[groups], rstd[groups], s1[groups], s2[groups], then (pass 1) the reduction buffer
+    const int C = a.C1 + a.C2, cpg = C / a.groups, C4 = C / 4;
     const int n = blockIdx.y;
     float* s_mean = sm;
     float* s_rstd = sm + a.groups;
     float* s_s1 = sm + 2 * a.groups;
     float* s_s2 = sm + 3 * a.groups;
+    float4* red = reinterpret_cast<float4*>(sm + 4 * a.groups);   // [2][256]
     for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
         gn_mean_rstd(a, n, g, &s_mean[g], &s_rstd[g]);
         if (PASS == 2) { s_s1[g] = a.gsum[((size_t)n * a.groups + g) * 2]; s_s2[g] = a.gsum[((size_t)n * a.groups + g) * 2 + 1]; }
@@ -239,39 +256,147 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GNBwdArgs a, int rows_per_b
     __syncthreads();
     const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, a.HW);
     const float inv_cnt = 1.0f / ((float)cpg * (float)a.HW);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float mu = s_mean[g], rs = s_rstd[g], ga = a.gamma[c], be = a.beta[c];
-        const float* x;
-        float* dx;
-        int pitch, co;
-        if (c < a.C1) { x = a.x1; dx = a.dx1; pitch = a.C1; co = c; } else { x = a.x2; dx = a.dx2; pitch = a.C2; co = c - a.C1; }
+    const int rstep = max(1, 256 / C4);
+    const TD* dyp = reinterpret_cast<const TD*>(a.dy);
+    for (int cg0 = 0; cg0 < C4; cg0 += 256) {
+        const int cg = cg0 + (C4 >= 256 ? threadIdx.x : threadIdx.x % C4);
+        const int rr = C4 >= 256 ? 0 : threadIdx.x / C4;
+        const bool worker = cg < C4 && rr < rstep;
+        const int c = cg * 4;
+        float mu[4], rs[4], ga[4], be[4], k1[4], k2[4];
+        const float* x = nullptr;
+        float* dx = nullptr;
+        int pitch = 0, co = 0;
+        if (worker) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g = (c + j) / cpg;
+                mu[j] = s_mean[g]; rs[j] = s_rstd[g]; ga[j] = a.gamma[c + j]; be[j] = a.beta[c + j];
+                k1[j] = PASS == 2 ? s_s1[g] * inv_cnt : 0.f; k2[j] = PASS == 2 ? s_s2[g] * inv_cnt : 0.f;
+            }
+            if (c < a.C1) { x = a.x1; dx = a.dx1; pitch = a.C1; co = c; } else { x = a.x2; dx = a.dx2; pitch = a.C2; co = c - a.C1; }
+        }
         const size_t base = (size_t)n * a.HW;
-        float sa = 0.f, sb = 0.f;
-        for (int r = r0; r < r1; ++r) {
-            const float xh = (x[(base + r) * pitch + co] - mu) * rs;
-            float dz = a.dy[(base + r) * C + c];
-            if (a.silu) dz *= silu_grad(fmaf(xh, ga, be));
-            if (PASS == 1) { sa += dz; sb += dz * xh; }
-            else dx[(base + r) * pitch + co] += rs * (ga * dz - (s_s1[g] + xh * s_s2[g]) * inv_cnt);
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (worker) {
+#pragma unroll 4
+            for (int r = r0 + rr; r < r1; r += rstep) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + (base + r) * pitch + co);
+                const float4 dv = ld_dy4<TD>(dyp + (base + r) * C + c);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                float dz[4] = {dv.x, dv.y, dv.z, dv.w}, xh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    xh[j] = (xs[j] - mu[j]) * rs[j];
+                    if (a.silu) dz[j] *= silu_grad(fmaf(xh[j], ga[j], be[j]));
+                    if (PASS == 1) { sa[j] += dz[j]; sb[j] += dz[j] * xh[j]; }
+                }
+                if (PASS == 2) {
+                    float4* dp = reinterpret_cast<float4*>(dx + (base + r) * pitch + co);
+                    float4 d = *dp;
+                    d.x += rs[0] * (ga[0] * dz[0] - (k1[0] + xh[0] * k2[0]));
+                    d.y += rs[1] * (ga[1] * dz[1] - (k1[1] + xh[1] * k2[1]));
+                    d.z += rs[2] * (ga[2] * dz[2] - (k1[2] + xh[2] * k2[2]));
+                    d.w += rs[3] * (ga[3] * dz[3] - (k1[3] + xh[3] * k2[3]));
+                    *dp = d;
+                }
+            }
         }
         if (PASS == 1) {
-            atomicAdd(a.dbeta + c, sa * a.scale);
-            atomicAdd(a.dgamma + c, sb * a.scale);
-            atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2, ga * sa);
-            atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2 + 1, ga * sb);
+            red[threadIdx.x] = make_float4(sa[0], sa[1], sa[2], sa[3]);
+            red[256 + threadIdx.x] = make_float4(sb[0], sb[1], sb[2], sb[3]);
+            __syncthreads();
+            if (worker && rr == 0) {
+                for (int k = 1; k < rstep; ++k) {
+                    const float4 u = red[threadIdx.x + k * C4], v = red[256 + threadIdx.x + k * C4];
+                    sa[0] += u.x; sa[1] += u.y; sa[2] += u.z; sa[3] += u.w; sb[0] += v.x; sb[1] += v.y; sb[2] += v.z; sb[3] += v.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = (c + j) / cpg;
+                    atomicAdd(a.dbeta + c + j, sa[j] * a.scale);
+                    atomicAdd(a.dgamma + c + j, sb[j] * a.scale);
+                    atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2, ga[j] * sa[j]);
+                    atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2 + 1, ga[j] * sb[j]);
+                }
+            }
+            __syncthreads();
         }
     }
 }
 int launch_gn_bwd(const GNBwdArgs& a, cudaStream_t s) {
     const int C = a.C1 + a.C2;
     PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
+    PD_REQUIRE(C % 4 == 0 && a.C1 % 4 == 0, "GroupNorm backward: channel counts must be multiples of 4");
     PD_CHECK_CUDA(cudaMemsetAsync(a.gsum, 0, (size_t)a.N * a.groups * 2 * sizeof(float), s));
-    const int rpb = std::max(8, std::min(a.HW, 64));
+    const int rpb = std::max(8, std::min(a.HW, 128));
     dim3 grid((a.HW + rpb - 1) / rpb, a.N);
-    const size_t smem = (size_t)4 * a.groups * sizeof(float);
-    gn_bwd_kernel<1><<<grid, 256, smem, s>>>(a, rpb);
-    gn_bwd_kernel<2><<<grid, 256, smem, s>>>(a, rpb);
+    const size_t smem = (size_t)4 * a.groups * sizeof(float) + 2 * 256 * sizeof(float4);
+    if (a.dy_dt == DT_BF16) {
+        gn_bwd_kernel<1, bf16><<<grid, 256, smem, s>>>(a, rpb);
+        gn_bwd_kernel<2, bf16><<<grid, 256, smem, s>>>(a, rpb);
+    } else if (a.dy_dt == DT_F16) {
+        gn_bwd_kernel<1, f16><<<grid, 256, smem, s>>>(a, rpb);
+        gn_bwd_kernel<2, f16><<<grid, 256, smem, s>>>(a, rpb);
+    } else {
+        gn_bwd_kernel<1, float><<<grid, 256, smem, s>>>(a, rpb);
+        gn_bwd_kernel<2, float><<<grid, 256, smem, s>>>(a, rpb);
+    }
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// GroupNorm (+SiLU) forward of the mixed-precision path: fp32 sources (concat) -> 16-bit NHWC output only (the operand of the
+// tensor-core convolution that consumes it; the fp32 copy is never written).  Eight channels per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply16_kernel(GNBwdArgs a, T* __restrict__ out, int rows_per_block) {
+    extern __shared__ float sm[];   // mean[groups], rstd[groups]
+    const int C = a.C1 + a.C2, cpg = C / a.groups, C8 = C / 8;
+    const int n = blockIdx.y;
+    float* s_mean = sm;
+    float* s_rstd = sm + a.groups;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) gn_mean_rstd(a, n, g, &s_mean[g], &s_rstd[g]);
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, a.HW);
+    const int rstep = max(1, 256 / C8);
+    const size_t base = (size_t)n * a.HW;
+    for (int cg0 = 0; cg0 < C8; cg0 += 256) {
+        const int cg = cg0 + (C8 >= 256 ? threadIdx.x : threadIdx.x % C8);
+        const int rr = C8 >= 256 ? 0 : threadIdx.x / C8;
+        if (cg >= C8 || rr >= rstep) continue;
+        const int c = cg * 8;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            sc[j] = s_rstd[g] * a.gamma[c + j];
+            sh[j] = a.beta[c + j] - s_mean[g] * sc[j];
+        }
+        const float* x;
+        int pitch, co;
+        if (c < a.C1) { x = a.x1; pitch = a.C1; co = c; } else { x = a.x2; pitch = a.C2; co = c - a.C1; }
+#pragma unroll 4
+        for (int r = r0 + rr; r < r1; r += rstep) {
+            const float4 u = *reinterpret_cast<const float4*>(x + (base + r) * pitch + co), v = *reinterpret_cast<const float4*>(x + (base + r) * pitch + co + 4);
+            float y[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+            Half8<T> h;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float z = fmaf(y[j], sc[j], sh[j]);
+                if (a.silu) z = z / (1.0f + expf(-z));
+                h.v[j] = from_f<T>(z);
+            }
+            *reinterpret_cast<Half8<T>*>(out + (base + r) * C + c) = h;
+        }
+    }
+}
+int launch_gn_apply16(int dt, const GNBwdArgs& a, void* out, cudaStream_t s) {
+    const int C = a.C1 + a.C2;
+    PD_REQUIRE(C % a.groups == 0 && C % 8 == 0 && a.C1 % 8 == 0, "gn_apply16: channel counts must be multiples of 8");
+    const int rpb = std::max(8, std::min(a.HW, 128));
+    dim3 grid((a.HW + rpb - 1) / rpb, a.N);
+    const size_t smem = (size_t)2 * a.groups * sizeof(float);
+    PD_DISPATCH_HALF(dt, T, (gn_apply16_kernel<T><<<grid, 256, smem, s>>>(a, (T*)out, rpb)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -612,25 +737,29 @@ int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_
 // OIHW (O, I, k, k) fp32 -> 16-bit dgrad GEMM weights (Isub, k*k*O) for input channels [i0, i0 + Isub): K index = tap' * O + o with
 // tap' the FLIPPED tap, so that the stride-1 tensor-core conv computes dX = conv(dY, W^T flipped)
 template <typename T>
-__global__ void relayout_tc_dgrad_kernel(const float* __restrict__ w, int O, int I, int k, int i0, int Isub, T* __restrict__ out) {
+__global__ void relayout_tc_dgrad_kernel(const float* __restrict__ w, int O, int I, int k, int i0, int Isub, T* __restrict__ out, int ktot,
+                                         int koff, int ostride) {
     const int kk = k * k;
     const size_t total = (size_t)Isub * kk * O;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int o = idx % O;
         const size_t r = idx / O;
         const int tapf = r % kk, i = r / kk;
-        out[idx] = from_f<T>(w[((size_t)o * I + i0 + i) * kk + (kk - 1 - tapf)]);
+        out[(size_t)i * ktot + koff + (size_t)tapf * ostride + o] = from_f<T>(w[((size_t)o * I + i0 + i) * kk + (kk - 1 - tapf)]);
     }
 }
-int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s) {
+// ktot / koff: row pitch and column offset of `out` (several weights side by side along K, e.g. the fused q / k / v projection); 0: k*k*O
+// ostride: K distance between taps (output channels zero-padded to ostride, the caller zeroes `out`); 0: O
+int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s, int ktot, int koff, int ostride) {
     const size_t total = (size_t)k * k * O * Isub;
+    if (ostride <= 0) ostride = O;
+    if (ktot <= 0) { ktot = k * k * ostride; koff = 0; }
     const int grid = (int)std::min<size_t>((total + 255) / 256, 4096);
-    PD_DISPATCH_HALF(dt, T, (relayout_tc_dgrad_kernel<T><<<grid, 256, 0, s>>>(w, O, I, k, i0, Isub, (T*)out)));
+    PD_DISPATCH_HALF(dt, T, (relayout_tc_dgrad_kernel<T><<<grid, 256, 0, s>>>(w, O, I, k, i0, Isub, (T*)out, ktot, koff, ostride)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-template <typename T> struct alignas(16) Half8 { T v[8]; };
 
 // out16 = T(x) (n a multiple of 8)
 template <typename T>
@@ -700,17 +829,21 @@ int launch_h2f_accumulate(int dt, const void* y16, float* out, size_t n, cudaStr
 
 // dW (O, I, k, k) += stage (k*k, O, I): the tensor-core wgrad accumulates into a [tap][co][ci] staging buffer (coalesced vector
 // reductions); this folds it into the OIHW gradient
-__global__ void wgrad_unstage_kernel(const float* __restrict__ stage, int O, int I, int kk, float* __restrict__ dw) {
+__global__ void wgrad_unstage_kernel(const float* __restrict__ stage, int O, int I, int kk, float* __restrict__ dw, int Opad, int Ipad) {
     const size_t total = (size_t)O * I * kk;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int tap = idx % kk;
         const size_t oi = idx / kk;
-        dw[idx] += stage[(size_t)tap * O * I + oi];
+        const int i = oi % I, o = oi / I;
+        dw[idx] += stage[((size_t)tap * Opad + o) * Ipad + i];
     }
 }
-int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s) {
+// Opad / Ipad: extents of the staging tile when the GEMM ran on zero-padded channels (conv_in, conv_out); 0: O / I
+int launch_wgrad_unstage(const float* stage, int O, int I, int kk, float* dw, cudaStream_t s, int Opad, int Ipad) {
     const size_t total = (size_t)O * I * kk;
-    wgrad_unstage_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, s>>>(stage, O, I, kk, dw);
+    if (Opad <= 0) Opad = O;
+    if (Ipad <= 0) Ipad = I;
+    wgrad_unstage_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, s>>>(stage, O, I, kk, dw, Opad, Ipad);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -794,6 +927,31 @@ int launch_colsum_cast(int dt, const float* dy, int B, int rows_per_img, int C, 
     dim3 grid((rows_per_img + rpb - 1) / rpb, B);
     if (dt == DT_F16) colsum_cast_kernel<f16><<<grid, 256, 0, s>>>((const float4*)dy, C / 4, rows_per_img, rpb, out_all, out_img, (f16*)out16);
     else colsum_cast_kernel<bf16><<<grid, 256, 0, s>>>((const float4*)dy, C / 4, rows_per_img, rpb, out_all, out_img, (bf16*)out16);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc16_pad_kernel(const float* __restrict__ x, int C, size_t HW, int Cp, T* __restrict__ out, size_t total8) {
+    const int Cp8 = Cp / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+        const int cg = i % Cp8;
+        const size_t pix = i / Cp8;
+        const size_t n = pix / HW, p = pix - n * HW;
+        Half8<T> h;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            h.v[j] = from_f<T>(c < C ? x[(n * C + c) * HW + p] : 0.f);
+        }
+        reinterpret_cast<Half8<T>*>(out)[i] = h;
+    }
+}
+int launch_nchw_to_nhwc16_pad(int dt, const float* x, int N, int C, int HW, int Cp, void* out, cudaStream_t s) {
+    PD_REQUIRE(Cp % 8 == 0 && C <= Cp, "nchw_to_nhwc16_pad: padded channel count must be a multiple of 8");
+    const size_t total8 = (size_t)N * HW * (Cp / 8);
+    const int grid = (int)std::min<size_t>((total8 + 255) / 256, 148 * 16);
+    PD_DISPATCH_HALF(dt, T, (nchw_to_nhwc16_pad_kernel<T><<<grid, 256, 0, s>>>(x, C, (size_t)HW, Cp, (T*)out, total8)));
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
