@@ -177,6 +177,18 @@ int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const f
                        const int64_t* labels, const float* target, const float* sample_weight, float* loss_out, float* model_out,
                        pd_stream_t stream);
 int pd_train_launch_count(pd_train_t* t, int64_t* n);
+
+/* ---- gradient-guided generation: _custom_guided_generation (src/utils_Img2Img.py:701-760).  Per step the reference
+ *      runs the UNet on images.requires_grad_(), takes x0 = scheduler.step(...).pred_original_sample, losses = Lp_loss(x0, input_images, p)
+ *      (:245-270) and torch.autograd.grad(losses, images) (:741).  Here: pd_train_forward keeps the activations, pd_guidance_lp_grad
+ *      turns (x_t, model output, reference images) into the per-image losses and their gradients w.r.t. the model output and (directly)
+ *      w.r.t. x_t, pd_train_backward_input plays the backward pass WITHOUT parameter gradients down to the input of conv_in:
+ *      grad = d_x (direct) + d_input (through the UNet).  All tensors (B,C,H,W) fp32; scratch / losses: B floats on the device. */
+int pd_train_forward(pd_train_t* t, const float* params, const float* x, const float* timesteps, const int64_t* labels, float* model_out,
+                     pd_stream_t stream);
+int pd_train_backward_input(pd_train_t* t, const float* d_model_out, float* d_input, pd_stream_t stream);
+int pd_guidance_lp_grad(const pd_step_coeffs_t* step, const float* x, const float* model_out, const float* ref, int32_t batch, int64_t per,
+                        float p, float* scratch, float* losses, float* d_model_out, float* d_x, pd_stream_t stream);
 /* accelerator.clip_grad_norm_(params, max_grad_norm) (utils_training.py:439; <= 0: no clipping) + torch.optim.AdamW.step
  * (train.py:279-285; `step` counts from 1) + diffusers EMAModel.step with the given decay (utils_training.py:224-241; ema NULL:
  * none) over flat fp32 vectors, in place.  scratch: one fp32 on the device; grad_norm_out (optional): the pre-clip global norm. */

@@ -4,6 +4,7 @@ third-party package's published known-answer tests, tests/test_oracle_published_
 See oracle/unet.py, oracle/schedulers.py, oracle/pipeline.py for the per-function reference citations.
 Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline and --impl reference legs).
 """
-from .pipeline import OraclePipeline, oracle_ddib, oracle_inversion
+from .pipeline import (OraclePipeline, oracle_custom_guided_generation, oracle_ddib, oracle_inversion,
+                       oracle_linear_interp_custom_guidance_inverted_start)
 from .schedulers import OracleDDIMInverseScheduler, OracleDDIMScheduler, rescale_zero_terminal_snr
 from .unet import OracleCondUNet2D

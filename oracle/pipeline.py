@@ -123,3 +123,29 @@ def oracle_ddib(pipe, clean_images, orig_class_labels, target_class_labels, num_
                start_image=inverted, add_forward_noise_to_image=False, frac_diffusion_skipped=0,
                return_raw=return_raw, trace=trace_gen)
     return out if return_raw else out.images
+
+
+def oracle_custom_guided_generation(pipe, input_images, target_class_labels, p, guidance_loss_scale, num_inference_steps, trace=None):
+    # utils_Img2Img.py:701-760 (_custom_guided_generation): per step, gradient of the per-image L_p distance between the predicted
+    # clean image and `input_images` w.r.t. the current images (through the UNet and through the scheduler's x0 formula), a gradient
+    # step on the images, then the scheduler update with the model output computed BEFORE the gradient step
+    images = input_images.clone().detach()
+    pipe.scheduler.set_timesteps(num_inference_steps)
+    for t in pipe.scheduler.timesteps:
+        images = images.detach().requires_grad_()
+        model_output = pipe.unet(images, t, target_class_labels).sample
+        x0 = pipe.scheduler.step(model_output, t, images).pred_original_sample
+        losses = torch.linalg.vector_norm(x0 - input_images, dim=(1, 2, 3), ord=p)          # Lp_loss, utils_Img2Img.py:245-270
+        guidance_grad = torch.autograd.grad([losses[i] for i in range(len(input_images))], images)[0]
+        if trace is not None:
+            trace.append((int(t), images.detach().clone(), model_output.detach().clone(), losses.detach().clone(), guidance_grad.clone()))
+        images = images.detach() - guidance_loss_scale * guidance_grad
+        images = pipe.scheduler.step(model_output.detach(), t, images).prev_sample
+    return images.detach()
+
+
+def oracle_linear_interp_custom_guidance_inverted_start(pipe, clean_images, orig_class_labels, target_class_labels, p, guidance_loss_scale,
+                                                        num_inference_steps, variant="0.18.2"):
+    # utils_Img2Img.py:651-698 (ConditionalDDIMPipeline branch): inversion, then guided generation from (and towards!) the inverted Gaussian
+    inverted = oracle_inversion(pipe, clean_images, orig_class_labels, num_inference_steps, variant)
+    return oracle_custom_guided_generation(pipe, inverted, target_class_labels, p, guidance_loss_scale, num_inference_steps)

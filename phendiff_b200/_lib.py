@@ -77,6 +77,9 @@ _SIGNATURES = {
     "pd_train_bind": (C.c_int, [_P, _P, C.c_size_t]),
     "pd_train_step_grad": (C.c_int, [_P] * 11),
     "pd_train_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "pd_train_forward": (C.c_int, [_P] * 7),
+    "pd_train_backward_input": (C.c_int, [_P] * 4),
+    "pd_guidance_lp_grad": (C.c_int, [C.POINTER(StepCoeffs), _P, _P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P, _P, _P, _P]),
     "pd_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                  C.c_float, C.c_float, _P, _P, _P]),
     "pd_unet_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -57,6 +57,11 @@ struct pd_train {
     std::vector<WgSlot> wg_plans;
     size_t conv_cursor = 0, wg_cursor = 0;
     int tc_convs = 0, tc_wgrads = 0;
+    // input-gradient-only backward (f4, pd_train_forward / pd_train_backward_input): parameter gradients are skipped (G == null)
+    bool param_grads() const { return G != nullptr; }
+    float* d_input = nullptr;      // (B, Cin, H, W) fp32 NCHW, written by conv_in's backward when set
+    float *pending_mo = nullptr, *pending_dm = nullptr;
+    bool forward_pending = false;
     void* scr_a() const { return ws + 2 * act_bytes + aux_bytes - 2 * scr_max - wstage_max; }
     void* scr_b() const { return ws + 2 * act_bytes + aux_bytes - scr_max - wstage_max; }
     float* wstage() const { return (float*)(ws + 2 * act_bytes + aux_bytes - wstage_max); }
@@ -241,6 +246,9 @@ struct Walk {
                 wd.dt = t->dt; wd.C1 = a->C; wd.C2 = b ? b->C : 0; wd.N = B; wd.H = a->H; wd.W = a->W; wd.Cout = cout; wd.ksize = k;
                 tc_wg = (t->tc_mask & 4) && wgrad_tc_supported(wd, nullptr);
             } else if (stride == 2 && k == 3 && pad == 1 && !b && a->H == 2 * Ho && a->W == 2 * Wo) {
+                WgradTcDesc wd{};
+                wd.dt = t->dt; wd.C1 = a->C; wd.N = B; wd.H = a->H; wd.W = a->W; wd.Cout = cout; wd.ksize = 3; wd.stride = 2;
+                tc_wg = (t->tc_mask & 4) && wgrad_tc_supported(wd, nullptr);
                 // stride-2 dgrad = the halo kernel's sub-pixel phase mode on dY (launch_relayout_tc_dgrad_s2)
                 ConvTcDesc g{};
                 g.dt = t->dt; g.C = cout; g.N = B; g.H = Ho; g.W = Wo; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = a->H; g.Wo = a->W; g.Cout = a->C;
@@ -299,7 +307,7 @@ struct Walk {
         pd_train* tr = t;
         const TT A = *a, Bt = b ? *b : TT(), O = *o, R = residual ? *residual : TT();
         const bool hasB = b != nullptr, hasR = residual != nullptr;
-        const bool tc_dg0 = tc_dg[0], tc_dg1 = tc_dg[1];
+        const bool tc_dg0 = tc_dg[0], tc_dg1 = tc_dg[1], tc_wg_plan = tc_wg;
         void* const wd16_0 = wd16[0];
         void* const wd16_1 = wd16[1];
         bwd([=](cudaStream_t st) {
@@ -309,28 +317,30 @@ struct Walk {
             if (out_scale != 1.0f && (rc = launch_add_inplace(O.g, O.g, out_scale - 1.0f, on, st))) return rc;
             const int M = Bn * O.H * O.W;
             const int dt = tr->dt;
-            const bool need16 = tc_wg || tc_dg0 || tc_dg1 || tc_dg_s2;
-            if (need16 || (O.C % 4 == 0 && O.H * O.W >= 64 && (gb || d_addvec))) {
+            const bool need16 = (tc_wg_plan && gw) || tc_dg0 || tc_dg1 || tc_dg_s2;
+            float* dav = tr->param_grads() ? d_addvec : nullptr;     // only feeds parameter gradients (time-embedding MLP)
+            const bool do_tc_wg = tc_wg_plan && gw != nullptr;
+            if (need16 || (O.C % 4 == 0 && O.H * O.W >= 64 && (gb || dav))) {
                 // one pass over dY: bias gradient, per-image sums for the time-embedding projection, and the 16-bit copy
-                if ((rc = launch_colsum_cast(dt == DT_F32 ? DT_BF16 : dt, O.g, Bn, O.H * O.W, O.C, gb, d_addvec, need16 ? tr->scr_a() : nullptr, st))) return rc;
+                if ((rc = launch_colsum_cast(dt == DT_F32 ? DT_BF16 : dt, O.g, Bn, O.H * O.W, O.C, gb, dav, need16 ? tr->scr_a() : nullptr, st))) return rc;
             } else {
                 if (gb && (rc = launch_colsum(O.g, M, O.C, M, 1.f, gb, st))) return rc;
-                if (d_addvec && (rc = launch_colsum(O.g, M, O.C, O.H * O.W, 1.f, d_addvec, st))) return rc;   // per image: (B, Cout)
+                if (dav && (rc = launch_colsum(O.g, M, O.C, O.H * O.W, 1.f, dav, st))) return rc;   // per image: (B, Cout)
             }
             if (hasR && R.g && (rc = launch_add_inplace(R.g, O.g, 1.0f, on, st))) return rc;
-            if (tc_wg) {
+            if (do_tc_wg) {
                 const size_t wbytes = (size_t)kk * O.C * Ct * sizeof(float);
                 PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, wbytes, st));
                 WgradTcDesc wd{};
                 wd.dt = dt; wd.x1 = A.h; wd.x2 = hasB ? Bt.h : nullptr; wd.C1 = A.C; wd.C2 = hasB ? Bt.C : 0; wd.N = Bn; wd.H = A.H; wd.W = A.W;
-                wd.Cout = O.C; wd.ksize = k; wd.dy = tr->scr_a(); wd.stage = tr->wstage();
+                wd.Cout = O.C; wd.ksize = k; wd.dy = tr->scr_a(); wd.stage = tr->wstage(); wd.stride = stride;
                 WgradTcPlan* wp = tr->wg_plan(wg_idx, wd, &rc);
                 if (!wp) return rc;
                 if ((rc = wgrad_tc_launch(wp, st))) return rc;
                 if ((rc = launch_wgrad_unstage(tr->wstage(), O.C, Ct, kk, gw, st))) return rc;
                 tr->launches += 3;
                 tr->tc_wgrads++;
-            } else {
+            } else if (gw) {
                 WgradArgs wa{};
                 wa.x1 = A.d; wa.x2 = hasB ? Bt.d : nullptr; wa.C1 = A.C; wa.C2 = hasB ? Bt.C : 0; wa.N = Bn; wa.H = A.H; wa.W = A.W; wa.Cout = O.C;
                 wa.ksize = k; wa.stride = stride; wa.pad = pad; wa.Ho = O.H; wa.Wo = O.W; wa.dy = O.g; wa.dw = gw; wa.scale = 1.f;
@@ -426,6 +436,7 @@ struct Walk {
         pd_train* tr = t;
         bwd([=](cudaStream_t st) {
             int rc = 0;
+            if (!tr->param_grads()) return 0;     // the embedding branch only reaches parameters (timesteps / labels carry no gradient)
             if ((rc = launch_silu_bwd(emb, dact, (size_t)Bn * D, demb, st))) return rc;
             if (gcls && (rc = launch_scatter_rows(demb, labels, Bn, D, 1.f, gcls, st))) return rc;
             if ((rc = launch_colsum(demb, Bn, D, Bn, 1.f, gb2, st))) return rc;
@@ -455,6 +466,7 @@ struct Walk {
         pd_train* tr = t;
         bwd([=](cudaStream_t st) {
             int rc = 0;
+            if (!tr->param_grads()) return 0;
             if ((rc = launch_colsum(dt, Bn, co, Bn, 1.f, gtb, st))) return rc;
             if ((rc = launch_sgemm(1, 0, co, D, Bn, 1.f, dt, co, actp, D, gtw, D, 1, st))) return rc;     // dW_r += dtemb^T act
             if ((rc = launch_sgemm(0, 0, Bn, D, co, 1.f, dt, co, tw, D, dact, D, 1, st))) return rc;      // dact += dtemb W_r
@@ -519,20 +531,23 @@ struct Walk {
             const float* pws[3] = {pw0, pw1, pw2};
             float* gws[3] = {gw0, gw1, gw2};
             float* gbs[3] = {gb0, gb1, gb2};
-            PD_CHECK_CUDA(cudaMemsetAsync(btmp, 0, (size_t)C3 * sizeof(float), st));
-            if ((rc = launch_colsum_cast(dt, O.g, Bn, HW, C3, btmp, nullptr, tr->scr_a(), st))) return rc;
-            for (int j = 0; j < 3; ++j)
-                if ((rc = launch_add_inplace(gbs[j], btmp + j * C, 1.0f, (size_t)C, st))) return rc;
-            PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)C3 * C * sizeof(float), st));
-            WgradTcDesc wd{};
-            wd.dt = dt; wd.x1 = X.h; wd.C1 = C; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = C3; wd.ksize = 1; wd.dy = tr->scr_a(); wd.stage = tr->wstage();
-            WgradTcPlan* wp = tr->wg_plan(wg_idx, wd, &rc);
-            if (!wp) return rc;
-            if ((rc = wgrad_tc_launch(wp, st))) return rc;
-            for (int j = 0; j < 3; ++j) {
-                if ((rc = launch_wgrad_unstage(tr->wstage() + (size_t)j * C * C, C, C, 1, gws[j], st))) return rc;
-                if ((rc = launch_relayout_tc_dgrad(dt, pws[j], C, C, 1, 0, C, wd16, st, C3, j * C))) return rc;
+            const bool pg = gw0 != nullptr;
+            if (pg) PD_CHECK_CUDA(cudaMemsetAsync(btmp, 0, (size_t)C3 * sizeof(float), st));
+            if ((rc = launch_colsum_cast(dt, O.g, Bn, HW, C3, pg ? btmp : nullptr, nullptr, tr->scr_a(), st))) return rc;
+            if (pg) {
+                for (int j = 0; j < 3; ++j)
+                    if ((rc = launch_add_inplace(gbs[j], btmp + j * C, 1.0f, (size_t)C, st))) return rc;
+                PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)C3 * C * sizeof(float), st));
+                WgradTcDesc wd{};
+                wd.dt = dt; wd.x1 = X.h; wd.C1 = C; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = C3; wd.ksize = 1; wd.dy = tr->scr_a(); wd.stage = tr->wstage();
+                WgradTcPlan* wp = tr->wg_plan(wg_idx, wd, &rc);
+                if (!wp) return rc;
+                if ((rc = wgrad_tc_launch(wp, st))) return rc;
+                for (int j = 0; j < 3; ++j)
+                    if ((rc = launch_wgrad_unstage(tr->wstage() + (size_t)j * C * C, C, C, 1, gws[j], st))) return rc;
             }
+            for (int j = 0; j < 3; ++j)
+                if ((rc = launch_relayout_tc_dgrad(dt, pws[j], C, C, 1, 0, C, wd16, st, C3, j * C))) return rc;
             ConvTcDesc g{};
             g.dt = dt; g.x = tr->scr_a(); g.C = C3; g.N = Bn; g.H = H; g.W = W; g.ksize = 1; g.stride = 1; g.pad = 0; g.Ho = H; g.Wo = W; g.Cout = C;
             g.wmat = wd16; g.out_scale = 1.f; g.out = X.g16 ? X.g16 : tr->scr_b(); g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
@@ -636,8 +651,20 @@ struct Walk {
             need_scratch((size_t)B * H * W * C0 * 2);
             if ((size_t)9 * CP * C0 * sizeof(float) > t->wstage_max) t->wstage_max = (size_t)9 * CP * C0 * sizeof(float);
         }
-        const size_t in_wg_idx = t->wg_cursor, out_wg_idx = t->wg_cursor + 1, out_dg_idx = t->conv_cursor;
-        t->wg_cursor += 2; t->conv_cursor += 1;
+        const size_t in_wg_idx = t->wg_cursor, out_wg_idx = t->wg_cursor + 1, out_dg_idx = t->conv_cursor, in_dg_idx = t->conv_cursor + 1;
+        t->wg_cursor += 2; t->conv_cursor += 2;
+        // input gradient of conv_in (f4: torch.autograd.grad(losses, images), utils_Img2Img.py:741): on the halo kernel with the 3 input
+        // channels padded to 64 output columns in mixed-precision mode, by the gather kernel on the fp32 path
+        bool tc_in_dg = false;
+        if (t->dt != DT_F32 && (t->tc_mask & 2) && Cin <= 64) {
+            ConvTcDesc g{};
+            g.dt = t->dt; g.C = C0; g.N = B; g.H = H; g.W = W; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = H; g.Wo = W; g.Cout = 64; g.mode = TC_MODE_STD;
+            g.stats_cw = m->stats_cw;
+            tc_in_dg = conv_halo_supported(g, nullptr);
+        }
+        void* wd16_in = tc_in_dg ? aux((size_t)64 * 9 * C0 * 2) : nullptr;
+        void* dxin = aux((size_t)B * H * W * (tc_in_dg ? 64 * 2 : Cin * sizeof(float)));      // NHWC staging of the input gradient
+        if (tc_in_dg) need_scratch((size_t)B * H * W * C0 * 2);
         if (!dry()) {
             run(launch_relayout_simt(p(m->conv_in.w), C0, Cin, 3, w_in, s()));
             run(launch_conv_in(DT_F32, noisy, w_in, p(m->conv_in.b), B, Cin, H, W, C0, x->d, s()));
@@ -647,8 +674,30 @@ struct Walk {
             float *gw = gr(m->conv_in.w), *gb = gr(m->conv_in.b);
             const int Bn = B;
             pd_train* tr = t;
+            const float* pw_in = p(m->conv_in.w);
             bwd([=](cudaStream_t st) {
                 int rc = 0;
+                if (tr->d_input) {
+                    const int dt = tr->dt;
+                    if (tc_in_dg) {
+                        if ((rc = launch_f2h(dt, X.g, tr->scr_a(), (size_t)Bn * H * W * C0, st))) return rc;
+                        PD_CHECK_CUDA(cudaMemsetAsync(wd16_in, 0, (size_t)64 * 9 * C0 * 2, st));
+                        if ((rc = launch_relayout_tc_dgrad(dt, pw_in, C0, Cin, 3, 0, Cin, wd16_in, st))) return rc;
+                        ConvTcDesc g{};
+                        g.dt = dt; g.x = tr->scr_a(); g.C = C0; g.N = Bn; g.H = H; g.W = W; g.ksize = 3; g.stride = 1; g.pad = 1; g.Ho = H; g.Wo = W; g.Cout = 64;
+                        g.wmat = wd16_in; g.out_scale = 1.f; g.out = dxin; g.mode = TC_MODE_STD; g.stats_cw = tr->m->stats_cw;
+                        ConvTcPlan* gp = tr->conv_plan(in_dg_idx, g, &rc);
+                        if (!gp) return rc;
+                        if ((rc = conv_tc_launch(gp, st))) return rc;
+                        if ((rc = launch_nhwc_to_nchw_f32(dt, dxin, Bn, Cin, H * W, 64, tr->d_input, st))) return rc;
+                    } else {
+                        PD_CHECK_CUDA(cudaMemsetAsync(dxin, 0, (size_t)Bn * H * W * Cin * sizeof(float), st));
+                        if ((rc = launch_conv_dgrad_gather(X.g, C0, pw_in, Bn, H, W, Cin, H, W, C0, 1, 1, (float*)dxin, st))) return rc;
+                        if ((rc = launch_nhwc_to_nchw_f32(DT_F32, dxin, Bn, Cin, H * W, Cin, tr->d_input, st))) return rc;
+                    }
+                    tr->launches += 4;
+                }
+                if (!tr->param_grads()) return 0;
                 if (tc_in) {
                     const int dt = tr->dt;
                     if ((rc = launch_colsum_cast(dt, X.g, Bn, H * W, C0, gb, nullptr, tr->scr_a(), st))) return rc;
@@ -669,7 +718,7 @@ struct Walk {
                 wa.x1 = xin; wa.C1 = 4; wa.N = Bn; wa.H = H; wa.W = W; wa.Cout = C0; wa.ksize = 3; wa.stride = 1; wa.pad = 1; wa.Ho = H; wa.Wo = W;
                 wa.dy = X.g; wa.dw = gw; wa.scale = 1.f; wa.Iw = Cin;
                 tr->launches += 2;
-                return launch_conv_wgrad(wa, st);
+                return launch_conv_wgrad(wa, st);   // (reached only with parameter gradients on)
             });
         }
         std::vector<TT*> skips{x};
@@ -722,17 +771,19 @@ struct Walk {
             bwd([=](cudaStream_t st) {
                 int rc = launch_nchw_to_nhwc_pad(dm, Bn, Cout, H * W, 4, dy4, st);
                 if (rc) return rc;
-                if ((rc = launch_colsum(dy4, Bn * H * W, 4, Bn * H * W, 1.f, gb, st, Cout))) return rc;
+                if (gb && (rc = launch_colsum(dy4, Bn * H * W, 4, Bn * H * W, 1.f, gb, st, Cout))) return rc;
                 if (tc_out) {
                     const int dt = tr->dt;
                     if ((rc = launch_nchw_to_nhwc16_pad(dt, dm, Bn, Cout, H * W, CP, pad16, st))) return rc;
-                    PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)9 * CP * C0 * sizeof(float), st));
-                    WgradTcDesc wd{};
-                    wd.dt = dt; wd.x1 = XN.h; wd.C1 = C0; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = CP; wd.ksize = 3; wd.dy = pad16; wd.stage = tr->wstage();
-                    WgradTcPlan* wp = tr->wg_plan(out_wg_idx, wd, &rc);
-                    if (!wp) return rc;
-                    if ((rc = wgrad_tc_launch(wp, st))) return rc;
-                    if ((rc = launch_wgrad_unstage(tr->wstage(), Cout, C0, 9, gw, st, CP, C0))) return rc;
+                    if (gw) {
+                        PD_CHECK_CUDA(cudaMemsetAsync(tr->wstage(), 0, (size_t)9 * CP * C0 * sizeof(float), st));
+                        WgradTcDesc wd{};
+                        wd.dt = dt; wd.x1 = XN.h; wd.C1 = C0; wd.N = Bn; wd.H = H; wd.W = W; wd.Cout = CP; wd.ksize = 3; wd.dy = pad16; wd.stage = tr->wstage();
+                        WgradTcPlan* wp = tr->wg_plan(out_wg_idx, wd, &rc);
+                        if (!wp) return rc;
+                        if ((rc = wgrad_tc_launch(wp, st))) return rc;
+                        if ((rc = launch_wgrad_unstage(tr->wstage(), Cout, C0, 9, gw, st, CP, C0))) return rc;
+                    }
                     PD_CHECK_CUDA(cudaMemsetAsync(wd16_out, 0, (size_t)C0 * 9 * CP * 2, st));
                     if ((rc = launch_relayout_tc_dgrad(dt, pw, Cout, C0, 3, 0, C0, wd16_out, st, 9 * CP, 0, CP))) return rc;
                     ConvTcDesc g{};
@@ -748,7 +799,7 @@ struct Walk {
                 WgradArgs wa{};
                 wa.x1 = XN.d; wa.C1 = C0; wa.N = Bn; wa.H = H; wa.W = W; wa.Cout = Cout; wa.ksize = 3; wa.stride = 1; wa.pad = 1; wa.Ho = H; wa.Wo = W;
                 wa.dy = dy4; wa.dy_pitch = 4; wa.dw = gw; wa.scale = 1.f;
-                if ((rc = launch_conv_wgrad(wa, st))) return rc;
+                if (gw && (rc = launch_conv_wgrad(wa, st))) return rc;
                 tr->launches += 4;
                 return launch_conv_dgrad_gather(dy4, 4, pw, Bn, H, W, C0, H, W, Cout, 1, 1, XN.g, st);
             });
@@ -857,7 +908,7 @@ int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const f
     PD_CHECK_CUDA(cudaGetDevice(&dev));
     PD_REQUIRE(dev == t->m->device, "the current CUDA device is not the one this handle was created on");
     cudaStream_t s = (cudaStream_t)stream;
-    t->P = params; t->G = grads; t->s = s;
+    t->P = params; t->G = grads; t->s = s; t->d_input = nullptr; t->forward_pending = false;
     // gradients of the activations start at zero (every backward operator accumulates)
     PD_CHECK_CUDA(cudaMemsetAsync(t->ws + t->act_bytes, 0, t->act_bytes, s));
     float *mo = nullptr, *dm = nullptr;
@@ -872,6 +923,49 @@ int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const f
     t->tape.clear();
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int pd_train_forward(pd_train_t* t, const float* params, const float* x, const float* timesteps, const int64_t* labels, float* model_out,
+                     pd_stream_t stream) {
+    PD_REQUIRE(t && params && x && timesteps && model_out, "null argument");
+    PD_REQUIRE(t->ws, "pd_train_bind must be called first");
+    int dev = -1;
+    PD_CHECK_CUDA(cudaGetDevice(&dev));
+    PD_REQUIRE(dev == t->m->device, "the current CUDA device is not the one this handle was created on");
+    cudaStream_t s = (cudaStream_t)stream;
+    t->P = params; t->G = nullptr; t->s = s; t->d_input = nullptr; t->forward_pending = false;
+    PD_CHECK_CUDA(cudaMemsetAsync(t->ws + t->act_bytes, 0, t->act_bytes, s));
+    float *mo = nullptr, *dm = nullptr;
+    int rc = walk(t, false, x, timesteps, labels, &mo, &dm);
+    if (rc) return rc;
+    PD_REQUIRE(t->act_bump <= t->act_bytes && t->aux_bump + 2 * t->scr_max + t->wstage_max <= t->aux_bytes, "internal: training workspace plan mismatch");
+    const size_t per = (size_t)t->m->cfg.out_channels * t->H * t->W;
+    PD_CHECK_CUDA(cudaMemcpyAsync(model_out, mo, (size_t)t->B * per * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    t->pending_mo = mo; t->pending_dm = dm; t->forward_pending = true;
+    return 0;
+}
+
+int pd_train_backward_input(pd_train_t* t, const float* d_model_out, float* d_input, pd_stream_t stream) {
+    PD_REQUIRE(t && d_model_out && d_input, "null argument");
+    PD_REQUIRE(t->forward_pending, "pd_train_backward_input needs a preceding pd_train_forward on this handle");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t per = (size_t)t->m->cfg.out_channels * t->H * t->W;
+    PD_CHECK_CUDA(cudaMemcpyAsync(t->pending_dm, d_model_out, (size_t)t->B * per * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    t->d_input = d_input; t->s = s;
+    int rc = 0;
+    for (auto it = t->tape.rbegin(); it != t->tape.rend(); ++it)
+        if ((rc = (*it)(s))) break;
+    t->tape.clear();
+    t->d_input = nullptr; t->forward_pending = false;
+    if (rc) return rc;
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pd_guidance_lp_grad(const pd_step_coeffs_t* step, const float* x, const float* model_out, const float* ref, int32_t batch, int64_t per,
+                        float p, float* scratch, float* losses, float* d_model_out, float* d_x, pd_stream_t stream) {
+    PD_REQUIRE(step && x && model_out && ref && scratch && d_model_out && d_x && batch > 0 && per > 0, "bad argument");
+    return launch_guidance_lp_grad(*step, x, model_out, ref, batch, (size_t)per, p, scratch, losses, d_model_out, d_x, (cudaStream_t)stream);
 }
 
 int pd_train_launch_count(pd_train_t* t, int64_t* n) {

@@ -58,6 +58,11 @@ int launch_mse_loss(const float* m, const float* target, const float* weight, in
 int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float b1, float b2, float eps, float wd,
                  int step, float max_norm, float ema_decay, float* scratch_sumsq, float* norm_out, cudaStream_t s);
 
+// gradient-guided generation (f4): loss_i = || pred_original_sample(x, m) - ref ||_p per image and its gradients w.r.t. m and (directly) x
+int launch_guidance_lp_grad(const pd_step_coeffs_t& c, const float* x, const float* m, const float* ref, int B, size_t per, float p, float* sums,
+                            float* losses, float* dm, float* dx, cudaStream_t s);
+int launch_nhwc_to_nchw_f32(int dt, const void* x, int N, int C, int HW, int Cp, float* out, cudaStream_t s);
+
 // ---- mixed-precision path (bf16 tensor-core convolutions; pd_train_wgrad_tc.cu) -------------------------------------------------
 int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0, int Isub, void* out, cudaStream_t s, int ktot = 0, int koff = 0,
                              int ostride = 0);
@@ -82,9 +87,10 @@ int launch_attn8_mma_bwd(const float* q, const float* k, const float* v, int pit
 struct WgradTcDesc {
     int dt;
     const void *x1, *x2;
-    int C1, C2, N, H, W, Cout, ksize;
+    int C1, C2, N, H, W, Cout, ksize;      // H, W: extent of X
     const void* dy;
     float* stage;          // (k*k, Cout, C1 + C2) fp32, accumulated with vector reductions (zeroed by the caller)
+    int stride;            // 0 / 1, or 2: 3x3 stride-2 padding-1 convolution (dY is (N, H/2, W/2, Cout))
 };
 struct WgradTcPlan;
 bool wgrad_tc_supported(const WgradTcDesc& d, std::string* why);

@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GNBwdArgs a, int rows_per_b
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int g = (c + j) / cpg;
-                    atomicAdd(a.dbeta + c + j, sa[j] * a.scale);
-                    atomicAdd(a.dgamma + c + j, sb[j] * a.scale);
+                    if (a.dbeta) atomicAdd(a.dbeta + c + j, sa[j] * a.scale);      // null: input-gradient-only backward
+                    if (a.dgamma) atomicAdd(a.dgamma + c + j, sb[j] * a.scale);
                     atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2, ga[j] * sa[j]);
                     atomicAdd(a.gsum + ((size_t)n * a.groups + g) * 2 + 1, ga[j] * sb[j]);
                 }
@@ -329,7 +329,9 @@ int launch_gn_bwd(const GNBwdArgs& a, cudaStream_t s) {
     PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
     PD_REQUIRE(C % 4 == 0 && a.C1 % 4 == 0, "GroupNorm backward: channel counts must be multiples of 4");
     PD_CHECK_CUDA(cudaMemsetAsync(a.gsum, 0, (size_t)a.N * a.groups * 2 * sizeof(float), s));
-    const int rpb = std::max(8, std::min(a.HW, 128));
+    // rows per block: at least ~8 blocks per SM in flight (small feature maps), at most 128 rows (prologue amortisation)
+    int rpb = (int)std::min<size_t>(128, std::max<size_t>(16, ((size_t)a.N * a.HW) / (148 * 8)));
+    rpb = std::max(8, std::min(a.HW, rpb));
     dim3 grid((a.HW + rpb - 1) / rpb, a.N);
     const size_t smem = (size_t)4 * a.groups * sizeof(float) + 2 * 256 * sizeof(float4);
     if (a.dy_dt == DT_BF16) {
@@ -952,6 +954,96 @@ int launch_nchw_to_nhwc16_pad(int dt, const float* x, int N, int C, int HW, int 
     const size_t total8 = (size_t)N * HW * (Cp / 8);
     const int grid = (int)std::min<size_t>((total8 + 255) / 256, 148 * 16);
     PD_DISPATCH_HALF(dt, T, (nchw_to_nhwc16_pad_kernel<T><<<grid, 256, 0, s>>>(x, C, (size_t)HW, Cp, (T*)out, total8)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// gradient-guided generation (reference _custom_guided_generation, src/utils_Img2Img.py:716-745):
+//   x0 = pred_original_sample(x_t, m)  (DDIMScheduler.step: by prediction type, clipped);  loss_i = || x0_i - ref_i ||_p  (Lp_loss, :245-270)
+// pass 1 reduces sum |d|^p per image, pass 2 writes the loss and its gradients w.r.t. the model output (the upstream gradient of the
+// UNet's backward) and w.r.t. x_t directly (the path that does not go through the UNet).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float guidance_x0(const pd_step_coeffs_t& c, float x, float m, float* dx0_dx, float* dx0_dm) {
+    float x0;
+    if (c.pred_type == PD_PRED_EPSILON) { x0 = (x - c.sqrt_beta * m) / c.sqrt_alpha; *dx0_dx = 1.0f / c.sqrt_alpha; *dx0_dm = -c.sqrt_beta / c.sqrt_alpha; }
+    else if (c.pred_type == PD_PRED_SAMPLE) { x0 = m; *dx0_dx = 0.f; *dx0_dm = 1.f; }
+    else { x0 = c.sqrt_alpha * x - c.sqrt_beta * m; *dx0_dx = c.sqrt_alpha; *dx0_dm = -c.sqrt_beta; }
+    if (c.clip) {
+        // torch.clamp: the gradient passes where -r <= x0 <= r (bounds included)
+        if (!(x0 >= -c.clip_range && x0 <= c.clip_range)) { *dx0_dx = 0.f; *dx0_dm = 0.f; }
+        x0 = (x0 < -c.clip_range) ? -c.clip_range : ((x0 > c.clip_range) ? c.clip_range : x0);
+    }
+    return x0;
+}
+__global__ void __launch_bounds__(256) guidance_lp_reduce_kernel(pd_step_coeffs_t c, const float* __restrict__ x, const float* __restrict__ m,
+                                                                 const float* __restrict__ ref, size_t per, float p, float* __restrict__ sums) {
+    __shared__ float red[8];
+    const int img = blockIdx.y;
+    const size_t base = (size_t)img * per;
+    float acc = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+        float a, b;
+        const float d = fabsf(guidance_x0(c, x[base + i], m[base + i], &a, &b) - ref[base + i]);
+        acc += p == 2.f ? d * d : (p == 1.f ? d : powf(d, p));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(sums + img, t);
+    }
+}
+__global__ void __launch_bounds__(256) guidance_lp_grad_kernel(pd_step_coeffs_t c, const float* __restrict__ x, const float* __restrict__ m,
+                                                               const float* __restrict__ ref, size_t per, float p, const float* __restrict__ sums,
+                                                               float* __restrict__ losses, float* __restrict__ dm, float* __restrict__ dx) {
+    const int img = blockIdx.y;
+    const size_t base = (size_t)img * per;
+    const float sum = sums[img];
+    const float loss = p == 2.f ? sqrtf(sum) : (p == 1.f ? sum : powf(sum, 1.0f / p));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && losses) losses[img] = loss;
+    // d loss / d d_j = sign(d_j) |d_j|^(p-1) / loss^(p-1)   (0 where the norm is 0)
+    const float inv = loss > 0.f ? (p == 2.f ? 1.0f / loss : (p == 1.f ? 1.0f : powf(loss, 1.0f - p))) : 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+        float a, b;
+        const float d = guidance_x0(c, x[base + i], m[base + i], &a, &b) - ref[base + i];
+        const float ad = fabsf(d);
+        const float mag = p == 2.f ? ad : (p == 1.f ? (ad > 0.f ? 1.f : 0.f) : (ad > 0.f ? powf(ad, p - 1.0f) : 0.f));
+        const float g = (d < 0.f ? -mag : mag) * inv;
+        dm[base + i] = g * b;
+        dx[base + i] = g * a;
+    }
+}
+int launch_guidance_lp_grad(const pd_step_coeffs_t& c, const float* x, const float* m, const float* ref, int B, size_t per, float p, float* sums,
+                            float* losses, float* dm, float* dx, cudaStream_t s) {
+    PD_REQUIRE(p > 0.f && isfinite(p), "guidance loss: p must be a finite positive number (the 'inf' norms are not implemented)");
+    PD_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * sizeof(float), s));
+    dim3 grid((unsigned)std::min<size_t>((per + 255) / 256, 64), B);
+    guidance_lp_reduce_kernel<<<grid, 256, 0, s>>>(c, x, m, ref, per, p, sums);
+    guidance_lp_grad_kernel<<<grid, 256, 0, s>>>(c, x, m, ref, per, p, sums, losses, dm, dx);
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// (N, HW, Cp) 16-bit or fp32 NHWC -> first C channels as NCHW fp32 (the input gradient of conv_in leaves the library in the boundary layout)
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ x, int C, size_t HW, int Cp, float* __restrict__ out, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i % HW;
+        const size_t nc = i / HW;
+        const int c = nc % C;
+        const size_t n = nc / C;
+        out[i] = to_f(x[(n * HW + p) * Cp + c]);
+    }
+}
+int launch_nhwc_to_nchw_f32(int dt, const void* x, int N, int C, int HW, int Cp, float* out, cudaStream_t s) {
+    const size_t total = (size_t)N * C * HW;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    if (dt == DT_F32) nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, s>>>((const float*)x, C, (size_t)HW, Cp, out, total);
+    else if (dt == DT_BF16) nhwc_to_nchw_f32_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, C, (size_t)HW, Cp, out, total);
+    else nhwc_to_nchw_f32_kernel<f16><<<grid, 256, 0, s>>>((const f16*)x, C, (size_t)HW, Cp, out, total);
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,11 @@
 // (j, w) meets X(j + r - 1, w + s - 1); the products that would wrap around a row end hit a zero dY row.  The K extent is rounded
 // up to 144 rows; the tail rows of every ring slot are zeroed once and never written by TMA.
 // 1x1: one accumulator, K blocks of 128 flat pixels.
+// 3x3 stride 2 (Downsample2D, padding 1): dY pixel (oh, ow) meets X(2 oh + r - 1, 2 ow + s - 1).  X is viewed as (2C, W/2, 2, H/2, N): the
+// column parity rides in the channel index, the row parity is its own dimension.  Kernel row r fixes the row parity and a row offset
+// (r = 0: parity 1, row oh - 1; r = 1: parity 0, row oh; r = 2: parity 1, row oh); the three taps of the row need BOTH column-parity
+// tiles, each loaded from column -1: s = 0 -> parity-1 tile + 0 rows, s = 1 -> parity-0 tile + 1 row, s = 2 -> parity-1 tile + 1 row
+// (6 boxes per ring slot, 2 slots).
 //
 // Split-K over pixel blocks fills the machine (a 128 -> 128 layer has 3 tiles): every CTA adds its partial tile to the staging
 // buffer with 16-byte vector reductions; launch_wgrad_unstage folds it into the OIHW gradient.
@@ -51,6 +56,8 @@ struct WgParams {
     int ksplit, nkb;     // K blocks in total, split into ksplit contiguous ranges
     int blocks_per_img;  // 3x3: H / R
     int R;
+    int stride2;         // 3x3 stride-2 (padding 1) convolution: X is addressed through its (row parity, column parity) phase view
+    int nslots, slot_bytes;
     float* stage;        // (taps_total, Cout, Ctot)
 };
 
@@ -75,7 +82,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
                 const __grid_constant__ CUtensorMap tm_x2, const WgParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(sm + WG_SLOTS * WG_SLOT_BYTES + WG_SLACK);
+    uint64_t* full = (uint64_t*)(sm + WG_SLOTS * WG_SLOT_BYTES + WG_SLACK);     // (3 slots x 4 boxes = 2 slots x 6 boxes)
     uint64_t* empty = full + WG_SLOTS;
     uint64_t* accum = empty + WG_SLOTS;
     uint32_t* tmem_slot = (uint32_t*)(accum + 1);
@@ -107,14 +114,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx = 4u * (uint32_t)p.box_rows * 128u;
+            const uint32_t tx = (p.stride2 ? 6u : 4u) * (uint32_t)p.box_rows * 128u;
             const int co0 = tm * 128, ci0 = tn * 128;
             for (int kb = kb0; kb < kb1; ++kb) {
-                const int it = kb - kb0, slot = it % WG_SLOTS;
-                if (it >= WG_SLOTS) mbar_wait(&empty[slot], (uint32_t)((it / WG_SLOTS) - 1) & 1u);
-                uint8_t* base = sm + slot * WG_SLOT_BYTES;
+                const int it = kb - kb0, slot = it % p.nslots;
+                if (it >= p.nslots) mbar_wait(&empty[slot], (uint32_t)((it / p.nslots) - 1) & 1u);
+                uint8_t* base = sm + slot * p.slot_bytes;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[slot])), "r"(tx) : "memory");
-                if (p.taps == 3) {
+                if (p.stride2) {
+                    const int n = kb / p.blocks_per_img, y0 = (kb % p.blocks_per_img) * p.R;
+                    const int hp = rg == 1 ? 0 : 1, hh0 = y0 + (rg == 0 ? -1 : 0);
+                    for (int b = 0; b < 2; ++b) tma_load_4d(&tm_dy, &full[slot], base + b * WG_BOX_BYTES, co0 + 64 * b, 0, y0, n);
+                    for (int wp = 0; wp < 2; ++wp)
+                        for (int b = 0; b < 2; ++b)
+                            tma_load_5d(&tm_x1, &full[slot], base + (2 + 2 * wp + b) * WG_BOX_BYTES, ci0 + 64 * b + wp * p.C1, -1, hp, hh0, n);
+                } else if (p.taps == 3) {
                     const int n = kb / p.blocks_per_img, y0 = (kb % p.blocks_per_img) * p.R;
                     for (int b = 0; b < 2; ++b) tma_load_4d(&tm_dy, &full[slot], base + b * WG_BOX_BYTES, co0 + 64 * b, 0, y0, n);
                     for (int b = 0; b < 2; ++b) {
@@ -141,19 +155,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
         const uint32_t hi = (uint32_t)(dproto >> 32), lo_flags = (uint32_t)dproto;   // lo word: LBO field (bits 16..29), address added below
         const int ksteps = p.ksteps, taps = p.taps;
         for (int kb = kb0; kb < kb1; ++kb) {
-            const int it = kb - kb0, slot = it % WG_SLOTS;
-            mbar_wait(&full[slot], (uint32_t)(it / WG_SLOTS) & 1u);
+            const int it = kb - kb0, slot = it % p.nslots;
+            mbar_wait(&full[slot], (uint32_t)(it / p.nslots) & 1u);
             tc_fence_after();
-            const uint32_t a0 = lo_flags + ((sm0 + (uint32_t)slot * WG_SLOT_BYTES) >> 4);
+            const uint32_t a0 = lo_flags + ((sm0 + (uint32_t)slot * (uint32_t)p.slot_bytes) >> 4);
             const uint32_t b0 = a0 + ((2u * WG_BOX_BYTES) >> 4);
+            // B start of the three taps relative to b0 (16-byte units): stride 1: the same tile 0 / 1 / 2 rows further; stride 2: the
+            // column-parity-1 tile (2 boxes further), the parity-0 tile + 1 row, the parity-1 tile + 1 row
+            const uint32_t o0 = p.stride2 ? ((2u * WG_BOX_BYTES) >> 4) : 0u;
+            const uint32_t o1 = 128u >> 4;
+            const uint32_t o2 = p.stride2 ? ((2u * WG_BOX_BYTES + 128u) >> 4) : (256u >> 4);
             for (int ks = 0; ks < ksteps; ++ks) {
                 const uint32_t acc = (it | ks) ? 1u : 0u;
                 const uint32_t a_lo = a0 + (uint32_t)ks * (2048u >> 4), b_lo = b0 + (uint32_t)ks * (2048u >> 4);
                 if (elect_one()) {
-                    umma_f16kind(tmem, desc64(hi, a_lo), desc64(hi, b_lo), idesc, acc);
                     if (taps == 3) {
-                        umma_f16kind(tmem + 128u, desc64(hi, a_lo), desc64(hi, b_lo + (128u >> 4)), idesc, acc);
-                        umma_f16kind(tmem + 256u, desc64(hi, a_lo), desc64(hi, b_lo + (256u >> 4)), idesc, acc);
+                        umma_f16kind(tmem, desc64(hi, a_lo), desc64(hi, b_lo + o0), idesc, acc);
+                        umma_f16kind(tmem + 128u, desc64(hi, a_lo), desc64(hi, b_lo + o1), idesc, acc);
+                        umma_f16kind(tmem + 256u, desc64(hi, a_lo), desc64(hi, b_lo + o2), idesc, acc);
+                    } else {
+                        umma_f16kind(tmem, desc64(hi, a_lo), desc64(hi, b_lo), idesc, acc);
                     }
                 }
                 __syncwarp();
@@ -204,6 +225,12 @@ bool wgrad_tc_supported(const WgradTcDesc& d, std::string* why) {
     if (d.dt != DT_BF16 && d.dt != DT_F16) return no("tensor-core wgrad takes 16-bit operands");
     if (d.ksize != 1 && d.ksize != 3) return no("kernel size must be 1 or 3");
     if (d.Cout % 128 != 0 || (d.C1 + d.C2) % 128 != 0 || d.C1 % 64 != 0 || d.C2 % 64 != 0) return no("channel counts must tile into 128 x 128 (sources in 64s)");
+    if (d.stride == 2) {
+        if (d.ksize != 3 || d.C2 != 0 || d.H % 2 || d.W % 2) return no("stride 2: 3x3 over one source with even extents");
+        const int Wo = d.W / 2, Ho = d.H / 2;
+        if (Wo > 128 || Wo < 16 || 128 % Wo != 0 || Ho % (128 / Wo) != 0) return no("stride 2: output row width must divide 128");
+        return true;
+    }
     if (d.ksize == 3) {
         if (d.W > 128 || d.W < 16 || 128 % d.W != 0) return no("3x3: row width must divide 128");
         const int R = 128 / d.W;
@@ -235,7 +262,26 @@ int wgrad_tc_plan_create(const WgradTcDesc& d, WgradTcPlan** out) {
         uint32_t box[2] = {64, 128};
         return tc_encode_map(tm, d.dt, base, 2, dims, st, box, true);
     };
-    if (d.ksize == 3) {
+    p.nslots = WG_SLOTS; p.slot_bytes = WG_SLOT_BYTES;
+    if (d.stride == 2) {
+        const uint64_t Wo = W / 2, Ho = H / 2, C = d.C1;
+        const int R = 128 / (int)Wo;
+        p.stride2 = 1; p.nslots = 2; p.slot_bytes = 6 * WG_BOX_BYTES;
+        p.taps = 3; p.rgroups = 3; p.ksteps = 9; p.R = R; p.box_rows = R * ((int)Wo + 2); p.blocks_per_img = (int)Ho / R; p.nkb = d.N * p.blocks_per_img;
+        {
+            uint64_t dims[4] = {(uint64_t)d.Cout, Wo, Ho, N};
+            uint64_t st[3] = {(uint64_t)d.Cout * 2, Wo * d.Cout * 2, Ho * Wo * d.Cout * 2};
+            uint32_t box[4] = {64, (uint32_t)(Wo + 2), (uint32_t)R, 1};
+            if ((rc = tc_encode_map(&pl->tm_dy, d.dt, d.dy, 4, dims, st, box, true))) return rc;
+        }
+        {
+            uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
+            uint64_t st[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+            uint32_t box[5] = {64, (uint32_t)(Wo + 2), 1, (uint32_t)R, 1};
+            if ((rc = tc_encode_map(&pl->tm_x1, d.dt, d.x1, 5, dims, st, box, true))) return rc;
+            pl->tm_x2 = pl->tm_x1;
+        }
+    } else if (d.ksize == 3) {
         const int R = 128 / d.W;
         p.taps = 3; p.rgroups = 3; p.ksteps = 9; p.R = R; p.box_rows = R * (d.W + 2); p.blocks_per_img = d.H / R; p.nkb = d.N * p.blocks_per_img;
         if ((rc = map4(&pl->tm_dy, d.dy, d.Cout, R))) return rc;

@@ -206,6 +206,31 @@ class DenoiserTrainer:
         loss = self._loss.clone()
         return (loss, mo) if return_model_output else loss
 
+    # ---- input-gradient-only use (gradient-guided generation) --------------------------------------------------------
+    def forward_only(self, sample: torch.Tensor, timesteps: torch.Tensor, class_labels: Optional[torch.Tensor]) -> torch.Tensor:
+        """UNet forward that keeps the activations for a following `input_gradient` (no parameter gradients are produced)."""
+        if self.model._handle is not self._h:
+            raise _lib.PhenDiffB200Error("the model's library handle was re-created after this engine was built: build a new one")
+        with torch.cuda.device(self.device):
+            x = sample.contiguous().float()
+            tf = timesteps.to(device=self.device, dtype=torch.float32).reshape(-1)
+            if tf.numel() == 1:
+                tf = tf.expand(self.batch_size)
+            tf = tf.contiguous()
+            labels = None if class_labels is None else class_labels.to(device=self.device, dtype=torch.int64).contiguous()
+            out = torch.empty_like(x)
+            _lib.check(_lib.lib().pd_train_forward(self._t, _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(tf), _lib.ptr(labels), _lib.ptr(out),
+                                                  _lib.current_stream()))
+        return out
+
+    def input_gradient(self, d_model_output: torch.Tensor) -> torch.Tensor:
+        """d(sum_i loss_i)/d(sample) through the UNet for the upstream gradient `d_model_output` (after `forward_only`)."""
+        with torch.cuda.device(self.device):
+            g = d_model_output.contiguous().float()
+            out = torch.empty_like(g)
+            _lib.check(_lib.lib().pd_train_backward_input(self._t, _lib.ptr(g), _lib.ptr(out), _lib.current_stream()))
+        return out
+
     def all_reduce_gradients(self, group=None):
         """Average the flat gradient vector over the data-parallel ranks: one collective (NCCL over NVLink on the GPU box)."""
         average_gradients(self.grads, group)

@@ -103,3 +103,81 @@ def _classifier_free_guidance_forward_start(pipe: ConditionalDDIMPipeline, clean
         raise NotImplementedError("only the pixel-space ConditionalDDIMPipeline path is implemented (SURVEY §8)")
     return pipe(class_labels=target_class_labels, w=guidance_scale, num_inference_steps=num_inference_steps,
                 start_image=clean_images, frac_diffusion_skipped=frac_diffusion_skipped).images
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# gradient-guided transfer (reference utils_Img2Img.py:651-760)
+# ---------------------------------------------------------------------------------------------------------------------
+def _guidance_engine(pipe: ConditionalDDIMPipeline, batch: int, resolution: int, mixed_precision: Optional[str] = None):
+    """The forward + input-gradient engine of the UNet for this batch shape (workspace of the training walk), cached on the pipeline.
+    mixed_precision: "bf16" (tensor-core convolutions) or "no" (fp32 validation path); default: "no" for an fp32 model, else "bf16"."""
+    from .training import DenoiserTrainer
+
+    if mixed_precision is None:
+        mixed_precision = "no" if pipe.unet.precision == "fp32" else "bf16"
+    key = (batch, resolution, mixed_precision)
+    cache = pipe.__dict__.setdefault("_guidance_engines", {})
+    eng = cache.get(key)
+    if eng is None or eng.model._handle is not eng._h:
+        cache.clear()     # one workspace at a time
+        eng = DenoiserTrainer(pipe.unet, pipe.scheduler, batch, resolution, mixed_precision=mixed_precision)
+        cache[key] = eng
+    return eng
+
+
+def _custom_guided_generation(pipe: ConditionalDDIMPipeline, input_images: Tensor, target_class_labels: Tensor, cfg,
+                              num_inference_steps: int, mixed_precision: Optional[str] = None) -> Tensor:
+    """Generation guided by the gradient of || x0_pred - input_images ||_p w.r.t. the current images (utils_Img2Img.py:701-760).
+    Per step: UNet forward with saved activations, per-image loss and its gradients w.r.t. the model output and x_t
+    (`pd_guidance_lp_grad`), input-gradient-only backward (`pd_train_backward_input`), the gradient step on the images, then the
+    scheduler update with the model output computed before the gradient step — the reference's order."""
+    import ctypes as C
+
+    this_cfg = _cfg_lookup(cfg, "class_transfer_method", "linear_interp_custom_guidance_inverted_start")
+    p = _cfg_lookup(this_cfg, "p")
+    guidance_loss_scale = float(_cfg_lookup(this_cfg, "guidance_loss_scale"))
+    if isinstance(p, str):
+        raise NotImplementedError("Lp_loss with p = 'inf' / '-inf' is not implemented (finite p only)")
+    _lib.require_cuda(input_images, "input_images")
+    dev = pipe.unet.device
+    ref = input_images.detach().to(dev).contiguous().float()
+    images = ref.clone()
+    labels = target_class_labels.to(dev)
+    B, per = images.shape[0], images[0].numel()
+    eng = _guidance_engine(pipe, B, images.shape[-1], mixed_precision)
+    pipe.scheduler.set_timesteps(num_inference_steps)
+    scratch = torch.zeros(B, device=dev)
+    losses = torch.zeros(B, device=dev)
+    dm, dx = torch.empty_like(images), torch.empty_like(images)
+    one, neg_scale = _ones(B, dev), _ones(B, dev, -guidance_loss_scale)     # per-sample coefficient vectors of the axpby kernel
+    L = _lib.lib()
+    for t in pipe.scheduler.timesteps:
+        tt = torch.full((B,), float(t), device=dev)
+        model_output = eng.forward_only(images, tt, labels)
+        co = pipe.scheduler.step_coeffs(t)
+        _lib.check(L.pd_guidance_lp_grad(C.byref(co), _lib.ptr(images), _lib.ptr(model_output), _lib.ptr(ref), B, per, float(p),
+                                         _lib.ptr(scratch), _lib.ptr(losses), _lib.ptr(dm), _lib.ptr(dx), _lib.current_stream()))
+        guidance_grad = eng.input_gradient(dm)
+        # images <- images - scale * (direct + through-the-UNet gradient); then x_t -> x_{t-1} with the pre-step model output
+        _lib.check(L.pd_axpby_per_sample(_lib.ptr(guidance_grad), _lib.ptr(dx), _lib.ptr(one), _lib.ptr(one), _lib.ptr(guidance_grad), B, per,
+                                         _lib.current_stream()))
+        _lib.check(L.pd_axpby_per_sample(_lib.ptr(images), _lib.ptr(guidance_grad), _lib.ptr(one), _lib.ptr(neg_scale), _lib.ptr(images), B, per,
+                                         _lib.current_stream()))
+        images = pipe.scheduler.step(model_output, t, images).prev_sample
+    return images
+
+
+def _ones(B, dev, value=1.0):
+    return torch.full((B,), float(value), device=dev, dtype=torch.float32)
+
+
+def _linear_interp_custom_guidance_inverted_start(pipe: ConditionalDDIMPipeline, clean_images: Tensor, orig_class_labels: Tensor,
+                                                  target_class_labels: Tensor, cfg, num_inference_steps: int,
+                                                  mixed_precision: Optional[str] = None) -> List:
+    """Inversion with the source class, then gradient-guided generation with the target class (utils_Img2Img.py:651-698);
+    returns PIL images like the reference (`tensor_to_PIL`)."""
+    if not isinstance(pipe, ConditionalDDIMPipeline):
+        raise NotImplementedError("only the pixel-space ConditionalDDIMPipeline path is implemented (SURVEY §8)")
+    inverted_gauss = _inversion(pipe, clean_images, orig_class_labels, num_inference_steps, None)
+    image = _custom_guided_generation(pipe, inverted_gauss, target_class_labels, cfg, num_inference_steps, mixed_precision)
+    return pipe.numpy_to_pil(pipe.postprocess(image))

@@ -1,0 +1,116 @@
+"""Gradient-guided generation (reference `_custom_guided_generation`, src/utils_Img2Img.py:701-760) against the oracle,
+whose restatement uses torch.autograd exactly as the reference does (`torch.autograd.grad(losses, images)`, :741)."""
+import math
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+from phendiff_b200.reference_configs import SCHEDULER_CONFIGS
+from tests.util import make_pair, psnr, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(p, scale):
+    return NS(class_transfer_method=NS(linear_interp_custom_guidance_inverted_start=NS(p=p, guidance_loss_scale=scale)))
+
+
+def _pipes(denoiser, size, precision, sched="3k_steps_clipping_rescaling"):
+    from oracle import OracleDDIMScheduler, OraclePipeline
+    from phendiff_b200 import ConditionalDDIMPipeline, DDIMScheduler
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, model = make_pair(denoiser, size, precision)
+    opipe = OraclePipeline(oracle.cuda(), OracleDDIMScheduler.from_config(SCHEDULER_CONFIGS[sched]))
+    pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(SCHEDULER_CONFIGS[sched]))
+    return opipe, pipe
+
+
+@pytest.mark.parametrize("p", [2, 1, 3])
+def test_lp_loss_gradient_kernel_matches_autograd(p):
+    """pd_guidance_lp_grad vs autograd on the scheduler's x0 formula (v-prediction and epsilon, with clipping)."""
+    import ctypes as C
+
+    from phendiff_b200 import DDIMScheduler, _lib
+
+    for sched_name in ("3k_steps_clipping_rescaling", "1k_epsilon_pred"):
+        sched = DDIMScheduler.from_config(SCHEDULER_CONFIGS[sched_name])
+        sched.set_timesteps(10)
+        t = sched.timesteps[4]
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(3, 3, 16, 16, generator=g).cuda()
+        m = torch.randn(3, 3, 16, 16, generator=g).cuda()
+        ref = torch.randn(3, 3, 16, 16, generator=g).cuda() * 0.5
+        from oracle import OracleDDIMScheduler
+
+        osched = OracleDDIMScheduler.from_config(SCHEDULER_CONFIGS[sched_name])
+        osched.set_timesteps(10)
+        xr, mr = x.clone().requires_grad_(), m.clone().requires_grad_()
+        x0 = osched.step(mr, t, xr).pred_original_sample
+        losses_ref = torch.linalg.vector_norm(x0 - ref, dim=(1, 2, 3), ord=p)
+        gx, gm = torch.autograd.grad([losses_ref[i] for i in range(3)], [xr, mr])
+        co = sched.step_coeffs(t)
+        scratch, losses = torch.zeros(3, device="cuda"), torch.zeros(3, device="cuda")
+        dm, dx = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(_lib.lib().pd_guidance_lp_grad(C.byref(co), _lib.ptr(x), _lib.ptr(m), _lib.ptr(ref), 3, x[0].numel(), float(p), _lib.ptr(scratch),
+                                                 _lib.ptr(losses), _lib.ptr(dm), _lib.ptr(dx), _lib.current_stream()))
+        assert torch.allclose(losses, losses_ref, rtol=1e-5, atol=1e-6), (sched_name, losses, losses_ref)
+        assert (dm - gm).abs().max().item() <= 1e-5 * max(1.0, gm.abs().max().item()), sched_name
+        assert (dx - gx).abs().max().item() <= 1e-5 * max(1.0, gx.abs().max().item()), sched_name
+
+
+@pytest.mark.parametrize("denoiser,size,precision,tol", [("super_small", 32, "fp32", 2e-4), ("small_denoiser_config", 64, "fp32", 2e-4),
+                                                          ("small_denoiser_config", 64, "bf16", 3e-2)])
+def test_guidance_gradient_first_steps_match_oracle(denoiser, size, precision, tol):
+    """Teacher-forced: at the oracle's own images of each step, loss and guidance gradient (direct + through the UNet) vs autograd."""
+    import ctypes as C
+
+    from oracle import oracle_custom_guided_generation
+    from phendiff_b200 import _lib
+    from phendiff_b200.utils_img2img import _guidance_engine
+
+    B, n = 2, 3
+    opipe, pipe = _pipes(denoiser, size, "fp32" if precision == "fp32" else "fp16")
+    x, labels = synth_images(B, size, seed=21)
+    start = torch.randn(B, 3, size, size, generator=torch.Generator().manual_seed(5)).cuda()
+    labels = labels.cuda()
+    trace = []
+    oracle_custom_guided_generation(opipe, start, labels, 2, 1e-3, n, trace=trace)
+    eng = _guidance_engine(pipe, B, size, "no" if precision == "fp32" else "bf16")
+    pipe.scheduler.set_timesteps(n)
+    for (t, images, m_ref, losses_ref, grad_ref) in trace:
+        m = eng.forward_only(images, torch.full((B,), float(t), device="cuda"), labels)
+        co = pipe.scheduler.step_coeffs(t)
+        scratch, losses = torch.zeros(B, device="cuda"), torch.zeros(B, device="cuda")
+        dm, dx = torch.empty_like(images), torch.empty_like(images)
+        _lib.check(_lib.lib().pd_guidance_lp_grad(C.byref(co), _lib.ptr(images), _lib.ptr(m), _lib.ptr(start), B, images[0].numel(), 2.0,
+                                                 _lib.ptr(scratch), _lib.ptr(losses), _lib.ptr(dm), _lib.ptr(dx), _lib.current_stream()))
+        grad = dx + eng.input_gradient(dm)
+        e_m = (m - m_ref).abs().max().item() / m_ref.abs().max().item()
+        e_l = ((losses - losses_ref).abs() / losses_ref).max().item()
+        e_g = ((grad - grad_ref).norm() / grad_ref.norm()).item()
+        print(f"[{denoiser} {precision}] t={t}: model output {e_m:.2e}, loss {e_l:.2e}, guidance gradient rel L2 {e_g:.2e}")
+        assert e_m <= tol and e_l <= tol and e_g <= tol
+
+
+@pytest.mark.parametrize("denoiser,size,precision,bar_db", [("super_small", 32, "fp32", 80.0), ("small_denoiser_config", 64, "bf16", 40.0)])
+def test_guided_transfer_matches_oracle(denoiser, size, precision, bar_db):
+    """The whole f4 call (inversion + guided generation, utils_Img2Img.py:651-698) free-running against the oracle."""
+    from oracle import oracle_linear_interp_custom_guidance_inverted_start
+    from phendiff_b200 import _custom_guided_generation, _inversion, _linear_interp_custom_guidance_inverted_start
+
+    B, n = 2, 5
+    opipe, pipe = _pipes(denoiser, size, "fp32" if precision == "fp32" else "fp16")
+    x, src = synth_images(B, size, seed=33)
+    x, src = x.cuda(), src.cuda()
+    cfg = _cfg(2, 1e-3)
+    ref = oracle_linear_interp_custom_guidance_inverted_start(opipe, x, src, 1 - src, 2, 1e-3, n)
+    inv = _inversion(pipe, x, src, n)
+    out = _custom_guided_generation(pipe, inv, 1 - src, cfg, n, mixed_precision="no" if precision == "fp32" else "bf16")
+    db = psnr(out.clamp(-1, 1), ref.clamp(-1, 1))
+    print(f"[{denoiser} {precision}] guided transfer {n}+{n} steps: PSNR vs oracle {db:.1f} dB")
+    assert db >= bar_db
+    pil = _linear_interp_custom_guidance_inverted_start(pipe, x, src, 1 - src, cfg, n, mixed_precision="no" if precision == "fp32" else "bf16")
+    assert len(pil) == B and pil[0].size == (size, size)
