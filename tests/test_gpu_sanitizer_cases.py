@@ -59,3 +59,44 @@ def test_san_unet_forward_and_ddib(build_lib, precision):
     pipe = ConditionalDDIMPipeline(model, DDIMScheduler.from_config(SCHEDULER_CONFIGS["3k_steps_clipping_rescaling"]))
     out = ddib_transfer(pipe, x, labels, 1 - labels, 2)
     assert out.shape == (2, 3, 32, 32) and bool(torch.isfinite(out).all())
+
+
+def test_san_training_step_tensor_core(build_lib):
+    """One bf16 mixed-precision training step + one input-gradient backward on a two-level 128-channel UNet at 32x32: every kernel of
+    the training path the sanitizer has not seen above — the tcgen05 weight-gradient kernel (3x3, 1x1, stride-2 phase view), the halo
+    kernel as dgrad (incl. the sub-pixel phase mode), the mma.sync attention forward / backward, GroupNorm backward, casts."""
+    from oracle import OracleCondUNet2D
+    from phendiff_b200 import CustomCondUNet2DModel, DDIMScheduler
+    from phendiff_b200.reference_configs import DENOISER_CONFIGS, SCHEDULER_CONFIGS
+    from phendiff_b200.training import DenoiserTrainer
+
+    cfg = dict(DENOISER_CONFIGS["small_denoiser_config"], sample_size=32, block_out_channels=(128, 128), layers_per_block=1,
+               down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    torch.manual_seed(0)
+    oracle = OracleCondUNet2D(**cfg)
+    model = CustomCondUNet2DModel.from_config(cfg, precision="fp16")
+    model.load_state_dict(oracle.state_dict())
+    model = model.cuda()
+    for p in oracle.parameters():          # the oracle stays on the CPU: under the sanitizer its cuDNN kernels would be instrumented too
+        p.requires_grad_(True)
+    sched = DDIMScheduler.from_config(SCHEDULER_CONFIGS["1k_epsilon_pred"])
+    B = 1
+    x, labels = synth_images(B, 32)
+    g = torch.Generator().manual_seed(2)
+    noise, t = torch.randn(x.shape, generator=g).cuda(), torch.tensor([321]).cuda()
+    x, labels = x.cuda(), labels.cuda()
+    trainer = DenoiserTrainer(model, sched, B, 32, mixed_precision="bf16", use_ema=True)
+    loss = trainer.diffusion_and_backward(x, labels, noise=noise, timesteps=t)
+    counts = trainer.tensor_core_counts()
+    assert counts["conv_wgrad"] >= 8, counts
+    noisy = sched.add_noise(x, noise, t)
+    ref_loss = torch.nn.functional.mse_loss(oracle(noisy.cpu(), t.cpu(), class_labels=labels.cpu()).sample, noise.cpu())
+    ref_loss.backward()
+    num = sum((gr.cpu() - dict(oracle.named_parameters())[n].grad).double().pow(2).sum().item() for n, gr in trainer.named_gradients())
+    den = sum(p.grad.double().pow(2).sum().item() for p in oracle.parameters())
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * ref_loss.item()
+    assert (num / den) ** 0.5 <= 1e-2
+    trainer.optimizer_step()
+    m = trainer.forward_only(noisy, t.float(), labels)
+    gin = trainer.input_gradient(torch.ones_like(m))
+    assert torch.isfinite(gin).all() and gin.abs().max().item() > 0

@@ -14,6 +14,7 @@
 #   train2                the same at 2 GPUs (torchrun; run under `gpurun --gpus 2`)
 #   strong                strong-scaling line: total batch 256 over --gpus N ranks is not applicable at N=1; runs --batch 32 (the per-GPU share of 8)
 #   launches              ncu launch list of one forward window;  dram: ncu DRAM bytes per launch
+#   ncutrain:<regex>[:skip]  the same for a kernel of the training step (bench.py --workload train --batch 32)
 #   ncu:<regex>[:<env>]   one ncu --set full capture of kernels matching <regex> (optionally with ENV=VAL,... set)
 tag="$1"; shift
 mkdir -p gpurun_out
@@ -91,6 +92,13 @@ PY
         timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base $base -k "regex:$rx" -s ${NCU_KSKIP:-6} -c ${NCU_KCOUNT:-2} \
           -o gpurun_out/prof_${rx//[^a-zA-Z0-9_]/_}_${tag} -f $SHORT --num-inference-steps 1 --steps 1 --warmup 1 > gpurun_out/ncu_${rx//[^a-zA-Z0-9_]/_}_${tag}.log 2>&1 )
       echo "ncu $rx exit=$?"; tail -2 gpurun_out/ncu_${rx//[^a-zA-Z0-9_]/_}_${tag}.log;;
+    ncutrain)   # ncu --set full capture of a training-step kernel: ncutrain:<regex>[:<skip>]
+      rx="${arg%%:*}"; skip=4; [[ "$arg" == *:* ]] && skip="${arg#*:}"
+      base=function; [[ "$rx" == *"<"* ]] && base=demangled
+      timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base $base -k "regex:$rx" -s $skip -c ${NCU_KCOUNT:-2} \
+          -o gpurun_out/prof_train_${rx//[^a-zA-Z0-9_]/_}_${tag} -f python bench.py --workload train --batch 32 --steps 1 --warmup 1 --e2e-steps 0 \
+          > gpurun_out/ncu_train_${rx//[^a-zA-Z0-9_]/_}_${tag}.log 2>&1
+      echo "ncutrain $rx exit=$?"; tail -2 gpurun_out/ncu_train_${rx//[^a-zA-Z0-9_]/_}_${tag}.log;;
     *) echo "unknown stage $stage";;
   esac
   echo "[stage $stage took $((SECONDS - t0)) s]"
