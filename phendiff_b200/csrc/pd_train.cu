@@ -115,6 +115,9 @@ struct Walk {
         if (!dry()) {
             tt->d = (float*)(t->ws + t->act_bump);
             tt->g = (float*)(t->ws + t->act_bytes + t->act_bump);
+            // every backward operator accumulates into fp32 gradients: they start at zero (16-bit-only tensors are written, not
+            // accumulated, and are not cleared)
+            cu(cudaMemsetAsync(tt->g, 0, bytes, s()));
         }
         t->act_bump += bytes;
         TT* r = tt.get();
@@ -909,8 +912,6 @@ int pd_train_step_grad(pd_train_t* t, const float* params, float* grads, const f
     PD_REQUIRE(dev == t->m->device, "the current CUDA device is not the one this handle was created on");
     cudaStream_t s = (cudaStream_t)stream;
     t->P = params; t->G = grads; t->s = s; t->d_input = nullptr; t->forward_pending = false;
-    // gradients of the activations start at zero (every backward operator accumulates)
-    PD_CHECK_CUDA(cudaMemsetAsync(t->ws + t->act_bytes, 0, t->act_bytes, s));
     float *mo = nullptr, *dm = nullptr;
     int rc = walk(t, false, noisy, timesteps, labels, &mo, &dm);
     if (rc) return rc;
@@ -934,7 +935,6 @@ int pd_train_forward(pd_train_t* t, const float* params, const float* x, const f
     PD_REQUIRE(dev == t->m->device, "the current CUDA device is not the one this handle was created on");
     cudaStream_t s = (cudaStream_t)stream;
     t->P = params; t->G = nullptr; t->s = s; t->d_input = nullptr; t->forward_pending = false;
-    PD_CHECK_CUDA(cudaMemsetAsync(t->ws + t->act_bytes, 0, t->act_bytes, s));
     float *mo = nullptr, *dm = nullptr;
     int rc = walk(t, false, x, timesteps, labels, &mo, &dm);
     if (rc) return rc;

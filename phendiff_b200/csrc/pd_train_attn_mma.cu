@@ -23,6 +23,9 @@ constexpr float kScale8 = 0.35355339059327373f;       // 1 / sqrt(8)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int AT_THREADS = 256, AT_ROWS = 128;
+#ifndef AT_KB
+#define AT_KB 64          // keys (queries) per iteration of the backward kernels: independent MMA / ex2 chains in flight per warp
+#endif
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -150,10 +153,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_q_kernel(const float
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
     const uint32_t* Kw = reinterpret_cast<const uint32_t*>(Ks);
     const uint32_t* Vw = reinterpret_cast<const uint32_t*>(Vs);
-    for (int k0 = 0; k0 < S; k0 += 32) {
-        float c[4][4], p[4][4];
+    for (int k0 = 0; k0 < S; k0 += AT_KB) {
+        float c[AT_KB / 8][4], p[AT_KB / 8][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < AT_KB / 8; ++j) {
             c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
             p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
             const size_t w = (size_t)(k0 + 8 * j + g) * 4 + t;
@@ -161,12 +164,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_q_kernel(const float
             mma_k8(p[j], ga0, ga1, Vw[w]);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < AT_KB / 8; ++j) {
             c[j][0] = ex2(c[j][0] - L0) * (p[j][0] - d0); c[j][1] = ex2(c[j][1] - L0) * (p[j][1] - d0);
             c[j][2] = ex2(c[j][2] - L1) * (p[j][2] - d1); c[j][3] = ex2(c[j][3] - L1) * (p[j][3] - d1);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j += 2) {
+        for (int j = 0; j < AT_KB / 8; j += 2) {
             uint32_t b0, b1;
             ldsm_t2(b0, b1, Ks, k0 + 8 * j, lane);
             mma_k16(dq, pack_bf16(c[j][0], c[j][1]), pack_bf16(c[j][2], c[j][3]), pack_bf16(c[j + 1][0], c[j + 1][1]),
@@ -202,10 +205,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_kv_kernel(const floa
     float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
     const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Qs);
     const uint32_t* Gw = reinterpret_cast<const uint32_t*>(Gs);
-    for (int q0 = 0; q0 < S; q0 += 32) {
-        float c[4][4], p[4][4];     // c: S^T (rows = keys g / g + 8, cols = queries 2t, 2t + 1), p: dP^T
+    for (int q0 = 0; q0 < S; q0 += AT_KB) {
+        float c[AT_KB / 8][4], p[AT_KB / 8][4];     // c: S^T (rows = keys g / g + 8, cols = queries 2t, 2t + 1), p: dP^T
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < AT_KB / 8; ++j) {
             c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
             p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
             const size_t w = (size_t)(q0 + 8 * j + g) * 4 + t;
@@ -213,14 +216,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_kv_kernel(const floa
             mma_k8(p[j], va0, va1, Gw[w]);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < AT_KB / 8; ++j) {
             const float4 ld = *reinterpret_cast<const float4*>(LD + q0 + 8 * j + 2 * t);   // (L, delta) of queries 2t, 2t + 1
             const float p0 = ex2(c[j][0] - ld.x), p1 = ex2(c[j][1] - ld.z), p2 = ex2(c[j][2] - ld.x), p3 = ex2(c[j][3] - ld.z);
             c[j][0] = p0; c[j][1] = p1; c[j][2] = p2; c[j][3] = p3;
             p[j][0] = p0 * (p[j][0] - ld.y); p[j][1] = p1 * (p[j][1] - ld.w); p[j][2] = p2 * (p[j][2] - ld.y); p[j][3] = p3 * (p[j][3] - ld.w);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j += 2) {
+        for (int j = 0; j < AT_KB / 8; j += 2) {
             uint32_t b0, b1;
             ldsm_t2(b0, b1, Gs, q0 + 8 * j, lane);
             mma_k16(dv, pack_bf16(c[j][0], c[j][1]), pack_bf16(c[j][2], c[j][3]), pack_bf16(c[j + 1][0], c[j + 1][1]),
