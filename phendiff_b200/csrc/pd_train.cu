@@ -48,8 +48,9 @@ struct pd_train {
     int64_t launches = 0;
     // mixed precision (pd_train_set_precision): 16-bit operands for the convolutions on the tcgen05 kernels, everything else fp32
     int dt = DT_F32;
-    unsigned tc_mask = 63;         // 1 conv forward, 2 dgrad, 4 wgrad, 8 attention, 16 16-bit-only GroupNorm outputs + fused q/k/v, 32 padded
-                                   // tensor-core GEMMs for conv_in / conv_out gradients (PHENDIFF_B200_TRAIN_TC)
+    unsigned tc_mask = 127;        // 1 conv forward, 2 dgrad, 4 wgrad, 8 attention, 16 16-bit-only GroupNorm outputs + fused q/k/v, 32 padded
+                                   // tensor-core GEMMs for conv_in / conv_out gradients, 64 GroupNorm statistics from the conv's forward
+                                   // epilogue (PHENDIFF_B200_TRAIN_TC)
     size_t scr_max = 0, wstage_max = 0;          // shared scratch: two 16-bit activation-sized buffers + the wgrad staging tile
     struct ConvSlot { ConvTcDesc d; ConvTcPlan* pl = nullptr; };
     struct WgSlot { WgradTcDesc d; WgradTcPlan* pl = nullptr; };
@@ -224,7 +225,7 @@ struct Walk {
 
     // out = (conv(concat(a, b)) + bias + addvec[n] + residual) * out_scale; d_addvec (B, Cout) receives the per-image column sums
     TT* conv(const Param* w, const Param* bias, int cout, int k, int stride, int pad, TT* a, TT* b, const float* addvec, float* d_addvec,
-             TT* residual, float out_scale) {
+             TT* residual, float out_scale, bool want_stats = true) {
         const int Ct = a->C + (b ? b->C : 0);
         const int Ho = stride == 2 ? a->H / 2 : a->H, Wo = stride == 2 ? a->W / 2 : a->W;
         TT* o = act(cout, Ho, Wo);
@@ -279,6 +280,12 @@ struct Walk {
         if (tc_wg && (size_t)kk * cout * Ct * sizeof(float) > t->wstage_max) t->wstage_max = (((size_t)kk * cout * Ct * sizeof(float)) + 255) & ~(size_t)255;
         const size_t fwd_idx = t->conv_cursor, dg_idx = t->conv_cursor + 1, wg_idx = t->wg_cursor;
         t->conv_cursor += 3; t->wg_cursor += 1;
+        // the GroupNorm that consumes this output needs its chunk statistics: produced by the forward epilogue instead of a separate pass
+        const bool fuse_stats = tc_fwd && want_stats && (t->tc_mask & 64) && cout % 8 == 0 && cout / 8 <= 256 && (cout / m->cfg.norm_num_groups) % m->stats_cw == 0;
+        if (fuse_stats) {
+            o->stats = (double*)aux((size_t)B * (cout / m->stats_cw) * 2 * sizeof(double), true);
+            if (dry()) o->stats = reinterpret_cast<double*>(uintptr_t(8));
+        }
         if (dry()) return o;
         if ((size_t)cout * Ct * kk != w->numel) { set_error("internal: training conv shape mismatch for " + w->name); run(1); return o; }
         if (tc_fwd) {
@@ -291,7 +298,9 @@ struct Walk {
             ConvTcPlan* pl = t->conv_plan(fwd_idx, d, &prc);
             if (!pl) { run(prc); return o; }
             run(conv_tc_launch(pl, s()));
-            run(launch_h2f_epilogue(t->dt, t->scr_a(), addvec, residual ? residual->d : nullptr, out_scale, o->d, B, Ho * Wo, cout, s()));
+            if (fuse_stats) run(launch_h2f_epilogue_stats(t->dt, t->scr_a(), addvec, residual ? residual->d : nullptr, out_scale, o->d, B, Ho * Wo, cout,
+                                                          m->stats_cw, o->stats, s()));
+            else run(launch_h2f_epilogue(t->dt, t->scr_a(), addvec, residual ? residual->d : nullptr, out_scale, o->d, B, Ho * Wo, cout, s()));
             count(3);
             t->tc_convs++;
         } else {
@@ -580,9 +589,9 @@ struct Walk {
             qg = qkv->g; kg = qkv->g ? qkv->g + C : nullptr; vg = qkv->g ? qkv->g + 2 * C : nullptr;
             pitch = 3 * C;
         } else {
-            TT* q = conv(A.qw, A.qb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
-            TT* k = conv(A.kw, A.kb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
-            TT* v = conv(A.vw, A.vb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f);
+            TT* q = conv(A.qw, A.qb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f, false);
+            TT* k = conv(A.kw, A.kb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f, false);
+            TT* v = conv(A.vw, A.vb, C, 1, 1, 0, xn, nullptr, nullptr, nullptr, nullptr, 1.f, false);
             qd = q->d; kd = k->d; vd = v->d; qg = q->g; kg = k->g; vg = v->g;
         }
         TT* o = act(C, x->H, x->W);

@@ -69,6 +69,9 @@ int launch_relayout_tc_dgrad(int dt, const float* w, int O, int I, int k, int i0
 int launch_f2h(int dt, const float* x, void* out, size_t n, cudaStream_t s);
 int launch_h2f_epilogue(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
                         cudaStream_t s);
+// the same fused with the chunk statistics (N, C/cw, 2) of the fp32 result (zeroed by the caller)
+int launch_h2f_epilogue_stats(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
+                              int cw, double* stats, cudaStream_t s);
 int launch_h2f_accumulate(int dt, const void* y16, float* out, size_t n, cudaStream_t s);
 int launch_relayout_tc_dgrad_s2(int dt, const float* w, int O, int I, void* out, cudaStream_t s);
 // one pass over dY: column sums per tensor (out_all) and / or per image (out_img), optional 16-bit copy (dt: DT_BF16 / DT_F16)

@@ -1050,4 +1050,79 @@ int launch_nhwc_to_nchw_f32(int dt, const void* x, int N, int C, int HW, int Cp,
     return 0;
 }
 
+// forward epilogue of a tensor-core conv fused with the GroupNorm chunk statistics of its fp32 result (the consumer's GroupNorm would
+// otherwise re-read the tensor): out = (float(y16) + addvec[img] + residual) * scale, stats[img][chunk] += (sum, sum of squares) of out.
+// Same thread mapping and pivoted fp32 partials -> fp64 atomics as gn_chunk_stats_kernel (pd_kernels_simt.cu).
+template <typename T>
+__global__ void __launch_bounds__(256) h2f_stats_kernel(const Half8<T>* __restrict__ y, const float* __restrict__ addvec, const float* __restrict__ residual,
+                                                        float scale, float* __restrict__ out, int HW, int C, int cw, int rows_per_block,
+                                                        double* __restrict__ stats) {
+    const int ncv = C / 8;
+    const int n = blockIdx.y;
+    const int cv = threadIdx.x % ncv, r0 = threadIdx.x / ncv, rstep = blockDim.x / ncv;
+    if (r0 >= rstep) return;
+    const int row_begin = blockIdx.x * rows_per_block, row_end = min(row_begin + rows_per_block, HW);
+    const size_t base = (size_t)n * HW;
+    float av[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) av[i] = addvec ? addvec[(size_t)n * C + cv * 8 + i] : 0.f;
+    float s[8], q[8], pv[8];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; pv[i] = 0.f; }
+#pragma unroll 2
+    for (int r = row_begin + r0; r < row_end; r += rstep) {
+        const size_t e = (base + r) * C + cv * 8;
+        const Half8<T> h = y[e / 8];
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = to_f(h.v[i]) + av[i];
+        if (residual) {
+            const float4 a = *reinterpret_cast<const float4*>(residual + e), b = *reinterpret_cast<const float4*>(residual + e + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= scale;
+        *reinterpret_cast<float4*>(out + e) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(out + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        if (cnt == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = v[i];
+        }
+        ++cnt;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - pv[i]; s[i] += d; q[i] += d * d; }
+    }
+    if (cnt == 0) return;
+    double S[8], Q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double pd_ = (double)pv[i], nn = (double)cnt;
+        S[i] = nn * pd_ + (double)s[i];
+        Q[i] = (double)q[i] + 2.0 * pd_ * (double)s[i] + nn * pd_ * pd_;
+    }
+    double* dst = stats + ((size_t)n * (C / cw) + (cv * 8) / cw) * 2;
+    if (cw == 4) {
+        atomicAdd(dst + 0, (S[0] + S[1]) + (S[2] + S[3])); atomicAdd(dst + 1, (Q[0] + Q[1]) + (Q[2] + Q[3]));
+        atomicAdd(dst + 2, (S[4] + S[5]) + (S[6] + S[7])); atomicAdd(dst + 3, (Q[4] + Q[5]) + (Q[6] + Q[7]));
+    } else if (cw == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { atomicAdd(dst + 2 * j, S[2 * j] + S[2 * j + 1]); atomicAdd(dst + 2 * j + 1, Q[2 * j] + Q[2 * j + 1]); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, S[j]); atomicAdd(dst + 2 * j + 1, Q[j]); }
+    }
+}
+int launch_h2f_epilogue_stats(int dt, const void* y16, const float* addvec, const float* residual, float scale, float* out, int B, int HW, int C,
+                              int cw, double* stats, cudaStream_t s) {
+    PD_REQUIRE(C % 8 == 0 && C / 8 <= 256 && (cw == 4 || cw == 2 || cw == 1), "h2f_stats: channel count must be a multiple of 8 (<= 2048)");
+    const int ncv = C / 8, rstep = 256 / ncv;
+    int rows = rstep * 16;
+    if (rows > HW) rows = HW;
+    dim3 grid((HW + rows - 1) / rows, B);
+    PD_DISPATCH_HALF(dt, T, (h2f_stats_kernel<T><<<grid, 256, 0, s>>>((const Half8<T>*)y16, addvec, residual, scale, out, HW, C, cw, rows, stats)));
+    PD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace pd

@@ -198,15 +198,16 @@ def _rel_l2(g, r):
     return ((g - r).norm() / r.norm().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("tc_mask,B,size", [(1, 2, 64), (2, 2, 64), (4, 2, 64), (8, 2, 64), (15, 2, 64), (31, 2, 64), (63, 2, 64), (63, 1, 128)])
+@pytest.mark.parametrize("tc_mask,B,size", [(1, 2, 64), (2, 2, 64), (4, 2, 64), (8, 2, 64), (15, 2, 64), (31, 2, 64), (63, 2, 64), (127, 2, 64), (127, 1, 128)])
 def test_bf16_tensor_core_gradients(tc_mask, B, size, monkeypatch):
     """mixed_precision="bf16": convolutions on the tcgen05 kernels with bf16 operands (forward = 1, dgrad = 2, wgrad = 4; 8 = attention on mma.sync; 16 = GroupNorm outputs in bf16 only + fused
-    q/k/v GEMM; 32 = conv_in / conv_out gradients as zero-padded tensor-core GEMMs; all = 63)
+    q/k/v GEMM; 32 = conv_in / conv_out gradients as zero-padded tensor-core GEMMs; 64 = GroupNorm statistics
+    from the conv's forward epilogue; all = 127)
     against fp32 autograd on the oracle.  bf16 operand rounding is 2^-9 relative per element; a gradient tensor is a sum of many
     such products, so the bar is on the tensor as a whole: relative L2 error <= 3e-2 per parameter tensor (measured ~5e-3) and
     <= 1e-2 over the whole gradient vector (the VERDICT's "bf16 <= 1e-2 rel")."""
     monkeypatch.setenv("PHENDIFF_B200_TRAIN_TC", str(tc_mask))
-    # (63, 1, 128): the resolution of the headline / training configs — 128-pixel rows are one K block of the weight-gradient kernel
+    # (127, 1, 128): the resolution of the headline / training configs — 128-pixel rows are one K block of the weight-gradient kernel
     # (130-row boxes), the stride-2 phase view at 64-pixel output rows, conv_in / conv_out padded GEMMs at full width
     oracle, model, osched, sched, Trainer = _setup("small_denoiser_config", size, B, "1k_epsilon_pred")
     x, labels, noise, timesteps = _inputs(B, size, seed=9)
