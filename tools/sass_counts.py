@@ -22,6 +22,7 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+            cur = cur.replace("(anonymous namespace)::", "")
             cur = re.sub(r"\(.*", "", cur).replace("void pd::", "").replace("pd::", "")
             counts.setdefault(cur, collections.Counter())
             continue
