@@ -196,6 +196,62 @@ def cpu_config0(args):
             "seconds": dt, "images_per_s": 4 / dt, "cores": torch.get_num_threads(), "cpu": cpu_model()}
 
 
+def cpu_train_sample(args, images=4, steps=2):
+    """CPU baseline of the training step: the oracle UNet under torch.autograd + torch.optim.AdamW + clip, fp32, all host
+    threads — the reference's own step (utils_training.py:374-456) minus accelerate — on a bounded batch."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import OracleCondUNet2D, OracleDDIMScheduler
+    from phendiff_b200.reference_configs import DENOISER_CONFIGS, SCHEDULER_CONFIGS
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    unet = OracleCondUNet2D(**dict(DENOISER_CONFIGS[args.denoiser], sample_size=args.size))
+    sched = OracleDDIMScheduler.from_config(SCHEDULER_CONFIGS[args.scheduler])
+    opt = torch.optim.AdamW(unet.parameters(), lr=1e-4, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8)
+    x, labels, _ = make_inputs(images, args.size, 0)
+    g = torch.Generator().manual_seed(7)
+
+    def step():
+        noise = torch.randn(x.shape, generator=g)
+        t = torch.randint(0, sched.config.num_train_timesteps, (images,), generator=g)
+        noisy = sched.add_noise(x, noise, t)
+        target = noise if sched.config.prediction_type == "epsilon" else sched.get_velocity(x, noise, t)
+        loss = F.mse_loss(unet(noisy, t, class_labels=labels).sample, target)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(unet.parameters(), 1.0)
+        opt.step()
+        return float(loss)
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": images * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} training steps of batch {images} at {args.size}x{args.size} fp32 on the CPU oracle (autograd + clip + AdamW; {dt:.1f} s)",
+            "seconds": dt, "cpu": cpu_model()}
+
+
+def run_reference_train(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, secs = [], 0.0
+    for _ in range(max(1, args.steps)):
+        r = cpu_train_sample(args)
+        vals.append(r["value"]); secs += r["seconds"]
+    v = sum(vals) / len(vals)
+    r["value"] = v
+    line = {"impl": "reference", "metric": f"images/sec, training step {args.size}x{args.size} (forward + backward + gradient all-reduce + clip + AdamW + EMA)",
+            "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic", "config": {"workload": f"CondUNet2D {args.denoiser} {args.size}x{args.size} RGB, 2 classes, training step (CPU sample: batch 4)"},
+            "cpu_baseline": r, "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  diffusers 0.18.2 (where its arithmetic lives) is
     not installable here, so this is the oracle port; every 'step' is a bounded sample of the workload."""
@@ -538,6 +594,8 @@ def run_train(args, pipe, unet, x_host, x_dev, labels, labels_d, dev, rank, worl
                 "e2e": {"value": total * e2e_steps / float(t_e2e.item()), "unit": "images/s",
                         "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
                         "api": "phendiff_b200.training.DenoiserTrainer.step(pinned_host_images.to(dev), labels) -> loss.item()"}}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_train_sample(args)
         if gf:
             tf = value / world * 3 * gf / 1e3     # forward + dgrad + wgrad = 3 x the forward's algorithmic FLOPs
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf / pk["tflops"],
@@ -552,7 +610,7 @@ def run_train(args, pipe, unet, x_host, x_dev, labels, labels_d, dev, rank, worl
 def main():
     args = parse()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference_train(args) if args.workload == "train" else run_reference(args)
     else:
         run_ours(args)
 
