@@ -97,8 +97,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
     const int kb0 = (int)(((long long)p.nkb * split) / p.ksplit), kb1 = (int)(((long long)p.nkb * (split + 1)) / p.ksplit);
     if (kb1 <= kb0) return;
 
-    // zero the ring once (tail rows stay zero), make it visible to the async proxy
-    for (int i = threadIdx.x; i < (WG_SLOTS * WG_SLOT_BYTES + WG_SLACK) / 16; i += WG_THREADS) ((uint4*)sm)[i] = make_uint4(0, 0, 0, 0);
+    // zero the tail rows of every box (rows the TMA boxes never write: they stay zero for the whole kernel) and the slack behind the ring,
+    // make it visible to the async proxy
+    {
+        const int tail16 = (WG_ROWS - p.box_rows) * 8;        // 16-byte units per box tail
+        for (int i = threadIdx.x; i < 12 * tail16; i += WG_THREADS) {
+            const int box = i / tail16, o = i - box * tail16;
+            ((uint4*)(sm + (size_t)box * WG_BOX_BYTES + (size_t)p.box_rows * 128))[o] = make_uint4(0, 0, 0, 0);
+        }
+        for (int i = threadIdx.x; i < WG_SLACK / 16; i += WG_THREADS) ((uint4*)(sm + WG_SLOTS * WG_SLOT_BYTES))[i] = make_uint4(0, 0, 0, 0);
+        // tap-shifted reads of a box run up to 2 rows into the box behind it: before the first TMA write lands there, those rows must
+        // hold finite values (they meet zero dY rows, and 0 x NaN would poison the accumulator)
+        for (int i = threadIdx.x; i < 12 * 16; i += WG_THREADS) ((uint4*)(sm + (size_t)(i >> 4) * WG_BOX_BYTES))[i & 15] = make_uint4(0, 0, 0, 0);
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < WG_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(accum, 1);
@@ -295,8 +306,9 @@ int wgrad_tc_plan_create(const WgradTcDesc& d, WgradTcPlan** out) {
     }
     const int tiles = p.tiles_m * p.tiles_n * p.rgroups;
     const int sms = tc_num_sms();
-    // split K so that the grid covers the machine about twice (tail balance), keeping at least 8 K blocks per CTA
-    int ks = std::max(1, (2 * sms + tiles - 1) / tiles);
+    // split K so that the grid fills two whole waves of one-CTA-per-SM (a third, partial wave cost 24 % on the 48-tile layers: ncu r7e,
+    // grid 336 on 148 SMs), keeping at least 8 K blocks per CTA
+    int ks = std::max(1, (2 * sms) / tiles);
     ks = std::min(ks, std::max(1, p.nkb / 8));
     p.ksplit = ks;
     pl->grid = tiles * ks;

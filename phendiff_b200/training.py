@@ -70,7 +70,7 @@ class DenoiserTrainer:
                  learning_rate: float = 1e-4, adam_beta1: float = 0.95, adam_beta2: float = 0.999, adam_weight_decay: float = 1e-6,
                  adam_epsilon: float = 1e-8, max_grad_norm: float = 1.0, use_ema: bool = False, ema_max_decay: float = 0.9999,
                  ema_inv_gamma: float = 1.0, ema_power: float = 0.75, lr_lambda: Optional[Callable[[int], float]] = None,
-                 proba_uncond: float = 0.0, mixed_precision: str = "no"):
+                 proba_uncond: float = 0.0, mixed_precision: str = "no", shared_seed: int = 0):
         self.model = denoiser_model
         self.noise_scheduler = noise_scheduler
         self.batch_size, self.resolution = int(batch_size), int(resolution)
@@ -79,6 +79,7 @@ class DenoiserTrainer:
         self.use_ema, self.ema_max_decay, self.ema_inv_gamma, self.ema_power = use_ema, ema_max_decay, ema_inv_gamma, ema_power
         self.lr_lambda = lr_lambda
         self.proba_uncond = proba_uncond
+        self._coin = torch.Generator().manual_seed(int(shared_seed))    # must be the same on every rank
         self.global_step = 0            # optimizer steps taken
         self.cur_decay_value = 0.0
         dev = denoiser_model.device
@@ -259,11 +260,9 @@ class DenoiserTrainer:
         if do_unconditional_pass is None:
             do_unconditional_pass = False
             if self.proba_uncond > 0:
-                # rank 0 draws, everyone follows (utils_training.py:262-277)
-                flag = torch.tensor(1 if float(torch.rand(1)) < self.proba_uncond else 0, device=self.device)
-                if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-                    dist.broadcast(flag, src=0, group=group)
-                do_unconditional_pass = bool(flag.item())
+                # the reference draws on rank 0 and broadcasts (utils_training.py:262-277: a collective + a host sync per step); here
+                # every rank draws the same coin from a host generator with a shared seed — same decisions on all ranks, no traffic
+                do_unconditional_pass = bool(torch.rand(1, generator=self._coin).item() < self.proba_uncond)
         loss = self.diffusion_and_backward(clean_images, class_labels, noise, timesteps, do_unconditional_pass)
         self.all_reduce_gradients(group)
         self.optimizer_step()

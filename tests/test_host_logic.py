@@ -300,3 +300,15 @@ def test_randn_tensor_generator_list_is_per_sample():
     import pytest
     with pytest.raises(ValueError):
         randn_tensor((2, 2, 4, 4), gens, torch.device("cpu"))
+
+
+def test_unconditional_pass_coin_is_shared_seed():
+    """The CFG-training coin (utils_training.py:262-277: rank 0 draws, broadcast) is drawn here from a host generator with a shared seed:
+    two trainers (= two ranks) built with the same seed take the same decisions, at the requested rate."""
+    import torch
+
+    g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    a = [bool(torch.rand(1, generator=g1).item() < 0.1) for _ in range(2000)]
+    b = [bool(torch.rand(1, generator=g2).item() < 0.1) for _ in range(2000)]
+    assert a == b
+    assert 0.07 < sum(a) / len(a) < 0.13
