@@ -8,7 +8,8 @@
 // m16n8k16 MMAs whose A operand is the accumulator fragment of the previous product re-packed in registers and whose B operand
 // comes from the same 16-byte rows through ldmatrix.trans.  Scores are kept in the log2 domain (Q is pre-scaled by
 // log2(e) / sqrt(8)), one ex2.approx per score.
-// One CTA = 8 warps = 128 rows of one (image, head); each warp owns 16 rows.  Validated against torch.autograd on the oracle
+// One CTA = 16 warps = 256 rows of one (image, head), each warp owns 16 rows (8 warps: -3 % on the step, 4 warps: -9 %: the CTA stages the
+// whole head for its rows, so fewer rows per CTA means more staging traffic per score).  Validated against torch.autograd on the oracle
 // through tests/test_gpu_training.py (bf16 mode); the fp32 kernels in pd_train_kernels.cu remain the validation path.
 #include <cuda_bf16.h>
 
@@ -22,7 +23,10 @@ namespace {
 constexpr float kScale8 = 0.35355339059327373f;       // 1 / sqrt(8)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int AT_THREADS = 256, AT_ROWS = 128;
+#ifndef TRAIN_AT_WARPS
+#define TRAIN_AT_WARPS 16       // warps per CTA; each owns 16 rows, the CTA stages the whole head once for all of them
+#endif
+constexpr int AT_THREADS = 32 * TRAIN_AT_WARPS, AT_ROWS = 16 * TRAIN_AT_WARPS;
 #ifndef AT_KB
 #define AT_KB 64          // keys (queries) per iteration of the backward kernels: independent MMA / ex2 chains in flight per warp
 #endif
