@@ -191,7 +191,9 @@ int pd_guidance_lp_grad(const pd_step_coeffs_t* step, const float* x, const floa
                         float p, float* scratch, float* losses, float* d_model_out, float* d_x, pd_stream_t stream);
 /* accelerator.clip_grad_norm_(params, max_grad_norm) (utils_training.py:439; <= 0: no clipping) + torch.optim.AdamW.step
  * (train.py:279-285; `step` counts from 1) + diffusers EMAModel.step with the given decay (utils_training.py:224-241; ema NULL:
- * none) over flat fp32 vectors, in place.  scratch: one fp32 on the device; grad_norm_out (optional): the pre-clip global norm. */
+ * none) over flat fp32 vectors, in place.  scratch: PD_ADAMW_SCRATCH_FLOATS fp32 on the device (per-block partials of the gradient norm,
+ * summed in a fixed order: data-parallel replicas get bit-identical clip coefficients); grad_norm_out (optional): the pre-clip global norm. */
+#define PD_ADAMW_SCRATCH_FLOATS 1185
 int pd_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float ema_decay, float* scratch,
                   float* grad_norm_out, pd_stream_t stream);

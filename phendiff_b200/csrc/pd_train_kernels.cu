@@ -700,11 +700,34 @@ int launch_mse_loss(const float* m, const float* target, const float* weight, in
 // ---------------------------------------------------------------------------------------------------------------------
 // clip_grad_norm_(max_norm) + AdamW (torch.optim.AdamW semantics, decoupled weight decay) + EMA over flat fp32 vectors
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+// global gradient norm, DETERMINISTIC (fixed summation tree, no atomics): data-parallel replicas must compute bit-identical clip
+// coefficients or their parameters drift apart in the last bits (tools/check_ddp_train.py).  Stage 1: one partial per block in
+// partial[1 + block]; stage 2: one block folds them in a fixed order into partial[0].
+constexpr int kSumsqBlocks = 148 * 8;
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
+    __shared__ float red[8];
     float acc = 0.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc = fmaf(g[i], g[i], acc);
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[1 + blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) sumsq_final_kernel(float* __restrict__ partial, int nblocks) {
+    __shared__ double red[1024];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 1024) acc += (double)partial[1 + i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[0] = (float)red[0];
 }
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                      float* __restrict__ v, float* __restrict__ ema, size_t n, float lr, float b1, float b2,
@@ -726,9 +749,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 }
 int launch_adamw(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float b1, float b2, float eps, float wd,
                  int step, float max_norm, float ema_decay, float* scratch_sumsq, float* norm_out, cudaStream_t s) {
-    PD_CHECK_CUDA(cudaMemsetAsync(scratch_sumsq, 0, sizeof(float), s));
-    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    const int grid = (int)std::min<size_t>((n + 255) / 256, kSumsqBlocks);
     sumsq_kernel<<<grid, 256, 0, s>>>(g, n, scratch_sumsq);
+    sumsq_final_kernel<<<1, 1024, 0, s>>>(scratch_sumsq, grid);
     const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
     adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, ema, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), max_norm, scratch_sumsq, ema_decay, norm_out);
     PD_CHECK_CUDA(cudaGetLastError());

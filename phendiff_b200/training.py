@@ -126,7 +126,7 @@ class DenoiserTrainer:
             self._ws_ptr = (base + 255) // 256 * 256
             _lib.check(L.pd_train_bind(t, C.c_void_p(self._ws_ptr), ws.value))
             self._loss = torch.zeros(1, device=dev, dtype=torch.float32)
-            self._scratch = torch.zeros(1, device=dev, dtype=torch.float32)
+            self._scratch = torch.zeros(1185, device=dev, dtype=torch.float32)      # PD_ADAMW_SCRATCH_FLOATS
             self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
             self._acp = noise_scheduler.alphas_cumprod.to(device=dev, dtype=torch.float32)
         denoiser_model.mark_dirty()     # the inference handle re-reads the (moved) parameters on its next use

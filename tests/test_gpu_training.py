@@ -140,7 +140,7 @@ def test_clip_adamw_ema_matches_torch(max_norm, use_ema):
     ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.AdamW([ref], lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, eps=1e-8)
     ref_ema = p0.clone()
-    scratch, norm = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    scratch, norm = torch.zeros(1185, device="cuda"), torch.zeros(1, device="cuda")      # PD_ADAMW_SCRATCH_FLOATS
     for step in range(1, 6):
         g = torch.randn(n, device="cuda") * (0.1 * step)
         ref.grad = g.clone()

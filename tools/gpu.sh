@@ -11,6 +11,7 @@
 #   bench[:<args>]        bench.py (default workload) -> bench_<tag>.json + per-op table
 #   cfg                   bench.py --workload cfg
 #   train[:<args>]        bench.py --workload train (one training step, batch 64/GPU);  trainlaunches[:batch]: its ncu launch list by kernel
+#   ddpcheck              2-GPU NCCL check of the data-parallel training step (all-reduced gradient = mean of shard gradients; identical parameters)
 #   train2                the same at 2 GPUs (torchrun; run under `gpurun --gpus 2`)
 #   strong                strong-scaling line: total batch 256 over --gpus N ranks is not applicable at N=1; runs --batch 32 (the per-GPU share of 8)
 #   launches              ncu launch list of one forward window;  dram: ncu DRAM bytes per launch
@@ -77,6 +78,9 @@ PY
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
           --workload train --batch 64 --steps 3 --warmup 3 $arg > gpurun_out/bench_train_n2_${tag}.json 2> gpurun_out/bench_train_n2_${tag}.err; echo "train2 exit=$?"
       tail -c 1500 gpurun_out/bench_train_n2_${tag}.json; tail -3 gpurun_out/bench_train_n2_${tag}.err;;
+    ddpcheck)  # needs `gpurun --gpus 2`
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/check_ddp_train.py \
+          > gpurun_out/ddpcheck_${tag}.log 2>&1; echo "ddpcheck exit=$?"; grep ddpcheck gpurun_out/ddpcheck_${tag}.log;;
     strong)
       python bench.py --batch 32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_strong32_${tag}.json 2> gpurun_out/bench_strong32_${tag}.err; echo "strong exit=$?"; tail -c 1200 gpurun_out/bench_strong32_${tag}.json;;
     launches)
