@@ -78,6 +78,10 @@ PY
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
           --workload train --batch 64 --steps 3 --warmup 3 $arg > gpurun_out/bench_train_n2_${tag}.json 2> gpurun_out/bench_train_n2_${tag}.err; echo "train2 exit=$?"
       tail -c 1500 gpurun_out/bench_train_n2_${tag}.json; tail -3 gpurun_out/bench_train_n2_${tag}.err;;
+    trainN)    # trainN:<N> under `gpurun --gpus N`
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${arg:-8} --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus ${arg:-8} \
+          --workload train --batch 64 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_train_n${arg:-8}_${tag}.json 2> gpurun_out/bench_train_n${arg:-8}_${tag}.err; echo "trainN exit=$?"
+      tail -c 600 gpurun_out/bench_train_n${arg:-8}_${tag}.json; tail -2 gpurun_out/bench_train_n${arg:-8}_${tag}.err;;
     ddpcheck)  # needs `gpurun --gpus 2`
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/check_ddp_train.py \
           > gpurun_out/ddpcheck_${tag}.log 2>&1; echo "ddpcheck exit=$?"; grep ddpcheck gpurun_out/ddpcheck_${tag}.log;;
