@@ -122,7 +122,7 @@ int launch_temb_proj(const float* emb_act, const float* wcat, const float* bcat,
 // =====================================================================================================================
 // chunk statistics (N, C/cw, 2): sum and sum of squares over H*W of every cw-channel chunk (cw = 4, 2 or 1)
 template <typename T>
-__global__ void __launch_bounds__(256) gn_chunk_stats_kernel(const T* __restrict__ x, int HW, int C, int cw, int rows_per_block,
+__global__ void __launch_bounds__(512) gn_chunk_stats_kernel(const T* __restrict__ x, int HW, int C, int cw, int rows_per_block,
                                                               double* __restrict__ stats) {
     const int ncv = C / 8;
     const int n = blockIdx.y;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) gn_chunk_stats_kernel(const T* __restrict
     }
 }
 
-static int gn_block(int C) {
+static int gn_block(int C) {      // one 8-channel column per thread; up to 512 columns (the SD-2.1-width config concatenates to 2560 channels)
     int ncv = C / 8;
     int rpp = 256 / ncv;
     if (rpp < 1) rpp = 1;
@@ -176,7 +176,7 @@ static int gn_block(int C) {
 }
 
 int launch_gn_chunk_stats(int dt, const void* x, int N, int HW, int C, int cw, double* stats, cudaStream_t s) {
-    PD_REQUIRE(C % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
+    PD_REQUIRE(C % 8 == 0 && C / 8 <= 512, "GroupNorm channel count must be a multiple of 8 and <= 4096");
     PD_REQUIRE(cw == 4 || cw == 2 || cw == 1, "statistics chunk width must be 4, 2 or 1");
     const int block = gn_block(C);
     const int rstep = block / (C / 8);
@@ -197,7 +197,7 @@ template <typename T> __device__ __forceinline__ uint4 ld_raw8(const T* p) { ret
 template <typename T> __device__ __forceinline__ void unpack_raw8(const uint4& r, float v[8]) { unpack8<T>(r, v); }
 template <> __device__ __forceinline__ void unpack_raw8<float>(const uint4&, float v[8]) { for (int i = 0; i < 8; ++i) v[i] = 0.f; }   // fp32 rows are not prefetched
 template <typename T, bool kPrecise>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_block) {
+__global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int rows_per_block) {
     extern __shared__ float sm[];   // scale[C], shift[C], mean[groups], rstd[groups]
     const int C = a.C1 + a.C2, ncv = C / 8;
     float* s_sc = sm;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GNArgs a, int rows_per_bl
 
 int launch_gn_apply(int dt, bool precise, const GNArgs& a, cudaStream_t s) {
     const int C = a.C1 + a.C2;
-    PD_REQUIRE(C % 8 == 0 && a.C1 % 8 == 0 && C / 8 <= 256, "GroupNorm channel count must be a multiple of 8 and <= 2048");
+    PD_REQUIRE(C % 8 == 0 && a.C1 % 8 == 0 && C / 8 <= 512, "GroupNorm channel count must be a multiple of 8 and <= 4096");
     PD_REQUIRE(C % a.groups == 0, "channels not divisible by groups");
     const int cw = a.stats_cw;
     PD_REQUIRE((cw == 4 || cw == 2 || cw == 1) && (C / a.groups) % cw == 0 && a.C1 % cw == 0, "statistics chunk width must divide the group width");
@@ -626,11 +626,50 @@ __global__ void __launch_bounds__(256) conv_out_kernel(ConvOutArgs a, pd_step_co
     }
 }
 
+// any channel count (the register-tiled kernel above takes 32 / 64 / 128 / 256): one warp per output pixel, lanes stride over the input
+// channels, weights through L1.  Only the fp32 validation mode of unusual widths (e.g. the 320-channel SD-2.1-width config) lands here.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_out_generic_kernel(ConvOutArgs a, pd_step_coeffs_t st, int has_step) {
+    const int lane = threadIdx.x & 31;
+    const size_t gwarp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t first = (size_t)a.img_begin * HW, total = first + (size_t)(a.img_count > 0 ? a.img_count : a.N) * HW;
+    for (size_t p = first + gwarp; p < total; p += nwarps) {
+        const int n = p / HW;
+        const size_t hw = p - (size_t)n * HW;
+        const int h = hw / a.W, w = hw - (size_t)h * a.W;
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+            if (ih < 0 || ih >= a.H || iw < 0 || iw >= a.W) continue;
+            const T* src = (const T*)a.act + (((size_t)n * a.H + ih) * a.W + iw) * a.Cin;
+            for (int c = lane; c < a.Cin; c += 32) {
+                const float v = to_f(src[c]);
+                const float4 w4 = *reinterpret_cast<const float4*>(a.w + ((size_t)tap * a.Cin + c) * 4);
+                acc[0] += v * w4.x; acc[1] += v * w4.y; acc[2] += v * w4.z;
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) acc[co] = warp_sum(acc[co]);
+        if (lane == 0) {
+            const int no = n - a.img_begin;
+            for (int co = 0; co < 3 && co < a.Cout; ++co) {
+                float m = acc[co] + a.bias[co];
+                const size_t idx = ((size_t)no * a.Cout + co) * HW + hw;
+                if (a.cfg.uncond) {
+                    const float u = a.cfg.uncond[idx];
+                    m = (a.cfg.eqn == 0 ? u : m) + a.cfg.w[no] * (m - u);
+                }
+                if (a.model_out) a.model_out[idx] = m;
+                if (has_step) a.x[idx] = ddim_update(st, a.x[idx], m, 0.f, nullptr);
+            }
+        }
+    }
+}
+
 int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s) {
     PD_REQUIRE(a.Cout <= 3, "conv_out supports out_channels <= 3");
-    PD_REQUIRE(a.Cin % 32 == 0, "conv_out needs block_out_channels[0] % 32 == 0");
-    const int cpl = a.Cin / 32;
-    PD_REQUIRE(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8, "conv_out: block_out_channels[0] must be 32, 64, 128 or 256");
+    const int cpl = a.Cin % 32 == 0 ? a.Cin / 32 : 0;
     pd_step_coeffs_t st{};
     int has = 0;
     if (a.step) { st = *a.step; has = 1; PD_REQUIRE(st.sigma == 0.f, "fused conv_out update requires eta == 0"); }
@@ -638,6 +677,11 @@ int launch_conv_out(int dt, const ConvOutArgs& a, cudaStream_t s) {
     size_t total = (size_t)(a.img_count > 0 ? a.img_count : a.N) * a.H * a.W;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 8);
     if (grid < 1) grid = 1;
+    if (!(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8)) {
+        PD_DISPATCH_DT(dt, T, (conv_out_generic_kernel<T><<<grid, 256, 0, s>>>(a, st, has)));
+        PD_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     PD_DISPATCH_DT(dt, T, {
         if (cpl == 1) conv_out_kernel<T, 1><<<grid, 256, 0, s>>>(a, st, has);
         else if (cpl == 2) conv_out_kernel<T, 2><<<grid, 256, 0, s>>>(a, st, has);

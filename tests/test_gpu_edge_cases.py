@@ -168,3 +168,24 @@ def test_single_head_unconditional_config(build_lib, precision, bar):
     p = psnr(ref[ok], got[ok])
     print(f"[single-head {precision}] DDIB 3+3 steps PSNR {p:.1f} dB")
     assert p >= 40.0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 1e-2)])
+def test_sd21_width_denoiser_config(precision, tol):
+    """models_configs/denoiser/SD_2-1_config.json: the fourth shipped denoiser JSON — the same CondUNet2D class at SD-2.1 widths (320 / 640 /
+    1280 / 1280: 64-channel N tiles, 10-channel GroupNorm groups with a 2-channel statistics chunk, attention at three levels incl.
+    the input resolution; 642 M parameters).  Forward vs the oracle at 32x32 (the tcgen05 kernels take the 32- and 16-pixel levels, the
+    8- and 4-pixel levels fall back to the CUDA-core kernels)."""
+    oracle, model = make_pair("SD_2-1_config", 32, precision)
+    oracle = oracle.cuda()
+    x, labels = synth_images(1, 32)
+    x, labels = x.cuda(), labels.cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for t in (3, 999):
+        with torch.no_grad():
+            ref = oracle(x, torch.tensor(t, device="cuda"), labels).sample
+        got = model(x, torch.tensor(t), labels).sample
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        print(f"[SD-2.1 widths {precision}] t={t}: max err / max|ref| = {err:.3e}; plan {model.plan_info()}")
+        assert err <= tol
