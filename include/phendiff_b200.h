@@ -84,6 +84,8 @@ typedef struct pd_step_coeffs {
 
 const char* pd_last_error(void);
 int pd_version(void);
+/* launches of the opt-in cta_group::2 kernel for 1x1 layers (PHENDIFF_B200_LIN2CTA=1) since load: test support */
+long long pd_debug_pair_kernel_launches(void);
 
 /* ---- lifetime (replaces CustomCondUNet2DModel.__init__ / from_config / load_state_dict, cond_unet_2d.py:73-242,
  *      utils_models.py:158-182) ---- */

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "pd_guidance_lp_grad": (C.c_int, [C.POINTER(StepCoeffs), _P, _P, _P, C.c_int32, C.c_int64, C.c_float, _P, _P, _P, _P, _P]),
     "pd_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                  C.c_float, C.c_float, _P, _P, _P]),
+    "pd_debug_pair_kernel_launches": (C.c_longlong, []),
     "pd_unet_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "pd_unet_plan_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pd_unet_profile_begin": (C.c_int, [_P, C.c_int32, C.c_int32]),

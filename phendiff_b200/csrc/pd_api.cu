@@ -773,6 +773,9 @@ static int copy_padded(void* dst, const void* src, size_t item, int n, int mb, c
 extern "C" {
 
 const char* pd_last_error(void) { return g_err.c_str(); }
+/* launches of the opt-in 2-CTA 1x1 kernel (PHENDIFF_B200_LIN2CTA=1) since the library was loaded: lets a test prove it ran */
+long long pd_debug_pair_kernel_launches(void) { return conv_pair_launch_count(); }
+
 int pd_version(void) { return 100; }
 
 int pd_unet_create(const pd_unet_config_t* cfg, pd_unet_t** out) {

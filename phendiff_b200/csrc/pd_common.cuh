@@ -257,6 +257,11 @@ __device__ __forceinline__ void tma_load_5d(const void* tmap, uint64_t* bar, voi
 }
 
 // TMA stores (shared -> global), bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(tmap)),

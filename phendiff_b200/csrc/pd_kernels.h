@@ -215,6 +215,7 @@ bool conv_tc_can_emit_stats(const ConvTcDesc& d);                   // v1 only: 
 int conv_tc_plan_create(const ConvTcDesc& d, ConvTcPlan** out);     // picks the halo kernel when it supports the shape
 void conv_tc_plan_destroy(ConvTcPlan* p);
 int conv_tc_launch(const ConvTcPlan* p, cudaStream_t s, const ConvTcLaunch* extra = nullptr);
+long long conv_pair_launch_count();   // launches of the 2-CTA (cta_group::2) 1x1 kernel since the library was loaded (tests)
 // OIHW fp32 (O,I,3,3) -> (4*O, 4*I) 16-bit sub-pixel phase weights (row = phase*O + o, k = (dr*2+dc)*I + i)
 int launch_relayout_upsample(int dt, const float* w, int O, int I, void* out, cudaStream_t s);
 

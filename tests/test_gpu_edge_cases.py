@@ -189,3 +189,24 @@ def test_sd21_width_denoiser_config(precision, tol):
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         print(f"[SD-2.1 widths {precision}] t={t}: max err / max|ref| = {err:.3e}; plan {model.plan_info()}")
         assert err <= tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-2), ("bf16", 4e-2)])
+def test_pair_kernel_for_linear_layers(precision, tol, monkeypatch):
+    """PHENDIFF_B200_LIN2CTA=1: the q/k/v and out-proj projections on the cta_group::2 kernel (thread-block cluster of two SMs, M = 256
+    per MMA, each CTA loading half of the weight tile, multicast commits, remote mbarrier arrivals).  Same parity bar as the default
+    route, and the launch counter proves the kernel ran."""
+    from phendiff_b200 import _lib
+
+    monkeypatch.setenv("PHENDIFF_B200_LIN2CTA", "1")
+    before = _lib.lib().pd_debug_pair_kernel_launches()
+    oracle, model = make_pair("small_denoiser_config", 64, precision)
+    x, labels = synth_images(4, 64)
+    with torch.no_grad():
+        ref = oracle(x, torch.tensor(1500), labels).sample
+    got = model(x.cuda(), torch.tensor(1500), labels.cuda()).sample.cpu()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    ran = _lib.lib().pd_debug_pair_kernel_launches() - before
+    print(f"[pair kernel {precision}] max err / max|ref| = {err:.3e}; cta_group::2 launches {ran}")
+    assert ran >= 12       # 6 attention blocks x (qkv + out-proj)
+    assert err <= tol
