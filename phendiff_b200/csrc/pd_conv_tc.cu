@@ -517,7 +517,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) con
 
 bool conv_pair_supported(const ConvTcDesc& d) {
     // opt-in (PHENDIFF_B200_LIN2CTA=1, read at plan time): measured on par with the halo kernel's 1x1 mode (out-proj -8 %, qkv +6 %,
-    // profiles/r8b_pair_kernel.md) — both are bound by the L2 -> SM stream of the activation tile, re-read once per N tile
+    // profiles/r8b_pair_kernel.md) — these layers are bound on the output side (epilogue), not by the operand port
     const char* e = getenv("PHENDIFF_B200_LIN2CTA");
     if (!e || atoi(e) == 0) return false;
     if (d.ksize != 1 || d.stride != 1 || d.upsample || d.gn_coef || d.x2 || d.C2 || d.Csc1 || d.Csc2 || d.mode != TC_MODE_STD) return false;
