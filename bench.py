@@ -51,9 +51,10 @@ def parse():
     p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="ddib", choices=["ddib", "cfg", "train"],
+    p.add_argument("--workload", default="ddib", choices=["ddib", "cfg", "train", "guided"],
                    help="ddib (default, the BASELINE.json metric); cfg: SURVEY §8 row f1, classifier-free-guidance forward start; "
-                        "train: SURVEY §8 row f2, one training step (BASELINE.json configs[3]; default --batch 64 there)")
+                        "train: SURVEY §8 row f2, one training step (BASELINE.json configs[3]; default --batch 64 there); "
+                        "guided: SURVEY §8 row f4, inversion + gradient-guided generation (use --batch 64)")
     p.add_argument("--train-precision", default="bf16", choices=["bf16", "no"],
                    help="train workload: accelerate-style mixed precision (bf16 tensor-core convolutions) or the fp32 validation path")
     p.add_argument("--guidance-scale", type=float, default=2.5)
@@ -325,6 +326,8 @@ def run_ours(args):
         return run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local)
     if args.workload == "train":
         return run_train(args, pipe, unet, x_host, x_dev, src, src_d, dev, rank, world, local)
+    if args.workload == "guided":
+        return run_guided(args, pipe, unet, x_host, x_dev, src, src_d, tgt, tgt_d, dev, rank, world, local)
 
     def step():
         out = ddib_transfer(pipe, x_dev, src_d, tgt_d, n)
@@ -511,6 +514,70 @@ def run_cfg(args, pipe, unet, x_host, x_dev, tgt, tgt_d, dev, rank, world, local
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tf / pk["tflops"],
                                 "traffic": None, "kernel": "whole path (2 x kept UNet forwards per image, SURVEY §8d algorithmic FLOPs)",
                                 "peak_source": pk["src"] + " sustained bf16 cuBLAS"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_guided(args, pipe, unet, x_host, x_dev, src, src_d, tgt, tgt_d, dev, rank, world, local):
+    """`_linear_interp_custom_guidance_inverted_start` (utils_Img2Img.py:651-760) with the example config's p = 2,
+    guidance_loss_scale = 1e-3: n inversion steps on the fused route, then n guided steps, each = UNet forward with saved activations +
+    Lp-loss gradient + input-gradient-only backward (bf16 tensor-core mode) + gradient step + scheduler update."""
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace as NS
+
+    from phendiff_b200 import _linear_interp_custom_guidance_inverted_start as guided
+
+    n = args.num_inference_steps
+    cfg = NS(class_transfer_method=NS(linear_interp_custom_guidance_inverted_start=NS(p=2, guidance_loss_scale=1e-3)))
+    total = args.batch * world
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(min(args.warmup, 1)):
+        guided(pipe, x_dev, src_d, tgt_d, cfg, 2)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        imgs = guided(pipe, x_dev, src_d, tgt_d, cfg, n)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total * args.steps / (ms / 1000.0)
+    sync()
+    t0 = time.perf_counter()
+    imgs = guided(pipe, x_host, src, tgt, cfg, n)
+    sync()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        assert len(imgs) == args.batch
+        line = {"metric": f"images/sec, inversion + gradient-guided generation {args.size}x{args.size}, {n}+{n} steps",
+                "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp16 (inversion) + bf16 mixed precision (guided steps: forward + input-gradient backward)", "data": "synthetic",
+                "config": {"workload": f"CondUNet2D {args.denoiser} {args.size}x{args.size} RGB, 2 classes, linear_interp_custom_guidance_inverted_start "
+                                       f"(p = 2, guidance_loss_scale = 1e-3), {n}+{n} steps, batch {args.batch}/GPU (SURVEY §8 row f4)",
+                           "scheduler": args.scheduler, "global_batch": total},
+                "clocks": clocks, "gpu_launches": None,
+                "e2e": {"value": total / float(t_e2e.item()), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + src.numel() * 16,
+                        "d2h_bytes_per_step": args.batch * args.size * args.size * 3 * 4, "steps": 1,
+                        "api": "phendiff_b200._linear_interp_custom_guidance_inverted_start(pipe, pinned_host_images, src, tgt, cfg, n) -> PIL images"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

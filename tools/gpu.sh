@@ -12,6 +12,7 @@
 #   cfg                   bench.py --workload cfg
 #   train[:<args>]        bench.py --workload train (one training step, batch 64/GPU);  trainlaunches[:batch]: its ncu launch list by kernel
 #   ddpcheck              2-GPU NCCL check of the data-parallel training step (all-reduced gradient = mean of shard gradients; identical parameters)
+#   guided                bench.py --workload guided (inversion + gradient-guided generation, batch 64)
 #   train2                the same at 2 GPUs (torchrun; run under `gpurun --gpus 2`)
 #   strong                strong-scaling line: total batch 256 over --gpus N ranks is not applicable at N=1; runs --batch 32 (the per-GPU share of 8)
 #   launches              ncu launch list of one forward window;  dram: ncu DRAM bytes per launch
@@ -74,6 +75,8 @@ PY
     trainlaunches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_${tag}.csv \
           python bench.py --workload train --batch ${arg:-16} --steps 1 --warmup 1 --e2e-steps 0 > gpurun_out/ncu_launches_train_${tag}.log 2>&1; echo "trainlaunches exit=$?";;   # then here: python tools/summarize_profile.py train_<tag>
+    guided)
+      timeout 600 python bench.py --workload guided --batch 64 --steps 1 --warmup 1 $arg > gpurun_out/bench_guided_${tag}.json 2> gpurun_out/bench_guided_${tag}.err; echo "guided exit=$?"; tail -c 1200 gpurun_out/bench_guided_${tag}.json; tail -3 gpurun_out/bench_guided_${tag}.err;;
     train2)   # needs `gpurun --gpus 2`: data-parallel training step over NCCL (one all-reduce of the flat gradient vector per step)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
           --workload train --batch 64 --steps 3 --warmup 3 $arg > gpurun_out/bench_train_n2_${tag}.json 2> gpurun_out/bench_train_n2_${tag}.err; echo "train2 exit=$?"
