@@ -240,3 +240,25 @@ def test_bf16_tensor_core_gradients(tc_mask, B, size, monkeypatch):
     assert abs(loss.item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
     assert total <= 1e-2
     assert worst[0] <= 3e-2, worst
+
+
+def test_trainer_step_with_cfg_coin_and_ema_copy():
+    """`DenoiserTrainer.step` as the reference's loop body runs it for classifier-free-guidance training (proba_uncond > 0, bf16 mixed
+    precision, EMA): the shared-seed coin takes both branches, the loss stays finite and decreases on a fixed batch, and
+    `copy_ema_to_model` (EMAModel.copy_to, utils_training.py:674-676) swaps the module's parameters for the shadow ones."""
+    B, size = 4, 64
+    oracle, model, osched, sched, Trainer = _setup("small_denoiser_config", size, B, "3k_steps_clipping_rescaling")
+    x, labels, noise, timesteps = _inputs(B, size, seed=17)
+    trainer = Trainer(model, sched, B, size, learning_rate=5e-4, use_ema=True, proba_uncond=0.5, mixed_precision="bf16", shared_seed=3)
+    coin = torch.Generator().manual_seed(3)
+    expected = [bool(torch.rand(1, generator=coin).item() < 0.5) for _ in range(8)]
+    assert any(expected) and not all(expected)
+    losses = [trainer.step(x, labels, noise=noise, timesteps=timesteps).item() for _ in range(8)]
+    assert all(math.isfinite(v) for v in losses) and min(losses[4:]) < losses[0], losses
+    assert trainer.global_step == 8 and 0.0 < trainer.cur_decay_value < 1.0
+    before = model.conv_in.weight.detach().clone()
+    trainer.copy_ema_to_model()
+    assert (model.conv_in.weight - before).abs().max().item() > 0
+    assert torch.equal(trainer.params, trainer.ema)
+    out = model(x, torch.full((B,), 500, device="cuda"), class_labels=labels).sample     # the inference route re-reads the swapped weights
+    assert torch.isfinite(out).all()
