@@ -262,3 +262,24 @@ def test_trainer_step_with_cfg_coin_and_ema_copy():
     assert torch.equal(trainer.params, trainer.ema)
     out = model(x, torch.full((B,), 500, device="cuda"), class_labels=labels).sample     # the inference route re-reads the swapped weights
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("mixed", ["no", "bf16"])
+def test_gradients_sd21_width_config(mixed):
+    """The fourth shipped denoiser JSON (SD-2.1 widths: 320 / 640 / 1280 / 1280, attention at three levels, 642 M parameters) through the
+    training step at 32x32: channel counts that are multiples of 64 but not of 128 (the weight-gradient kernel falls back to CUDA cores
+    for them), 2560-channel GroupNorms, S = 1024 / 256 / 64 attention."""
+    B, size = 1, 32
+    oracle, model, osched, sched, Trainer = _setup("SD_2-1_config", size, B, "1k_epsilon_pred")
+    x, labels, noise, timesteps = _inputs(B, size, seed=4)
+    loss_ref, _ = _oracle_loss(oracle, osched, x, labels, noise, timesteps, "epsilon", False)
+    loss_ref.backward()
+    trainer = Trainer(model, sched, B, size, mixed_precision=mixed)
+    loss = trainer.diffusion_and_backward(x, labels, noise=noise, timesteps=timesteps)
+    ref = {n: p.grad for n, p in oracle.named_parameters()}
+    num = sum((g - ref[n]).double().pow(2).sum().item() for n, g in trainer.named_gradients())
+    den = sum(r.double().pow(2).sum().item() for r in ref.values())
+    rel = math.sqrt(num / den)
+    print(f"[SD-2.1 widths, mixed_precision={mixed}] loss {loss.item():.6f} vs {loss_ref.item():.6f}; whole-gradient rel L2 {rel:.2e}; {trainer.tensor_core_counts()}")
+    assert abs(loss.item() - loss_ref.item()) <= (1e-4 if mixed == "no" else 1e-2) * abs(loss_ref.item())
+    assert rel <= (1e-4 if mixed == "no" else 1e-2)
