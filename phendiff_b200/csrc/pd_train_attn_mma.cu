@@ -188,10 +188,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_q_kernel(const float
 }
 
 // ---- backward, key-stationary: dK, dV ----------------------------------------------------------------------------------------------
+// RT = 16-key row tiles per warp: with RT = 2 every staged Q / dO fragment, (lse, delta) pair and ldmatrix feeds two tiles (half the
+// shared-memory reads per score, two independent MMA / ex2 chains per warp); the key block per iteration shrinks to keep the registers.
+template <int RT>
 __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_kv_kernel(const float* __restrict__ qp, const float* __restrict__ kp, const float* __restrict__ vp,
                                                                        int pitch, const float* __restrict__ dout, const float* __restrict__ lse,
                                                                        const float* __restrict__ delta, int S, int C, float* __restrict__ dk_out,
                                                                        float* __restrict__ dv_out) {
+    constexpr int KB = AT_KB / RT;                                   // queries per iteration
     extern __shared__ uint4 sm4[];
     uint4 *Qs = sm4, *Gs = sm4 + S;                                  // Q pre-scaled by log2(e) / sqrt(8); dO
     float2* LD = reinterpret_cast<float2*>(sm4 + 2 * (size_t)S);     // per query: (lse in log2 units, delta)
@@ -201,53 +205,74 @@ __global__ void __launch_bounds__(AT_THREADS) attn8_mma_bwd_kv_kernel(const floa
     stage_rows(Gs, dout + (size_t)n * S * C + head * 8, C, S, 1.f);
     const size_t lrow = ((size_t)n * (C / 8) + head) * S;
     for (int r = threadIdx.x; r < S; r += AT_THREADS) LD[r] = make_float2(lse[lrow + r] * kLog2e, delta[lrow + r]);
-    const int key0 = blockIdx.x * AT_ROWS + warp * 16;
-    uint32_t ka0, ka1, va0, va1;
-    load_a_frag(ka0, ka1, kp + off, pitch, key0, g, t, 1.f);
-    load_a_frag(va0, va1, vp + off, pitch, key0, g, t, 1.f);
+    const int key0 = blockIdx.x * (AT_ROWS * RT) + warp * (16 * RT);
+    uint32_t ka0[RT], ka1[RT], va0[RT], va1[RT];
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt) {
+        load_a_frag(ka0[rt], ka1[rt], kp + off, pitch, key0 + 16 * rt, g, t, 1.f);
+        load_a_frag(va0[rt], va1[rt], vp + off, pitch, key0 + 16 * rt, g, t, 1.f);
+    }
     __syncthreads();
-    float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+    float dk[RT][4], dv[RT][4];
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dk[rt][i] = 0.f; dv[rt][i] = 0.f; }
     const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Qs);
     const uint32_t* Gw = reinterpret_cast<const uint32_t*>(Gs);
-    for (int q0 = 0; q0 < S; q0 += AT_KB) {
-        float c[AT_KB / 8][4], p[AT_KB / 8][4];     // c: S^T (rows = keys g / g + 8, cols = queries 2t, 2t + 1), p: dP^T
+    for (int q0 = 0; q0 < S; q0 += KB) {
+        float c[RT][KB / 8][4], p[RT][KB / 8][4];     // c: S^T (rows = keys g / g + 8, cols = queries 2t, 2t + 1), p: dP^T
 #pragma unroll
-        for (int j = 0; j < AT_KB / 8; ++j) {
-            c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
-            p[j][0] = p[j][1] = p[j][2] = p[j][3] = 0.f;
+        for (int j = 0; j < KB / 8; ++j) {
             const size_t w = (size_t)(q0 + 8 * j + g) * 4 + t;
-            mma_k8(c[j], ka0, ka1, Qw[w]);
-            mma_k8(p[j], va0, va1, Gw[w]);
+            const uint32_t qb = Qw[w], gb = Gw[w];
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                c[rt][j][0] = c[rt][j][1] = c[rt][j][2] = c[rt][j][3] = 0.f;
+                p[rt][j][0] = p[rt][j][1] = p[rt][j][2] = p[rt][j][3] = 0.f;
+                mma_k8(c[rt][j], ka0[rt], ka1[rt], qb);
+                mma_k8(p[rt][j], va0[rt], va1[rt], gb);
+            }
         }
 #pragma unroll
-        for (int j = 0; j < AT_KB / 8; ++j) {
+        for (int j = 0; j < KB / 8; ++j) {
             const float4 ld = *reinterpret_cast<const float4*>(LD + q0 + 8 * j + 2 * t);   // (L, delta) of queries 2t, 2t + 1
-            const float p0 = ex2(c[j][0] - ld.x), p1 = ex2(c[j][1] - ld.z), p2 = ex2(c[j][2] - ld.x), p3 = ex2(c[j][3] - ld.z);
-            c[j][0] = p0; c[j][1] = p1; c[j][2] = p2; c[j][3] = p3;
-            p[j][0] = p0 * (p[j][0] - ld.y); p[j][1] = p1 * (p[j][1] - ld.w); p[j][2] = p2 * (p[j][2] - ld.y); p[j][3] = p3 * (p[j][3] - ld.w);
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                const float p0 = ex2(c[rt][j][0] - ld.x), p1 = ex2(c[rt][j][1] - ld.z), p2 = ex2(c[rt][j][2] - ld.x), p3 = ex2(c[rt][j][3] - ld.z);
+                c[rt][j][0] = p0; c[rt][j][1] = p1; c[rt][j][2] = p2; c[rt][j][3] = p3;
+                p[rt][j][0] = p0 * (p[rt][j][0] - ld.y); p[rt][j][1] = p1 * (p[rt][j][1] - ld.w);
+                p[rt][j][2] = p2 * (p[rt][j][2] - ld.y); p[rt][j][3] = p3 * (p[rt][j][3] - ld.w);
+            }
         }
 #pragma unroll
-        for (int j = 0; j < AT_KB / 8; j += 2) {
-            uint32_t b0, b1;
-            ldsm_t2(b0, b1, Gs, q0 + 8 * j, lane);
-            mma_k16(dv, pack_bf16(c[j][0], c[j][1]), pack_bf16(c[j][2], c[j][3]), pack_bf16(c[j + 1][0], c[j + 1][1]),
-                    pack_bf16(c[j + 1][2], c[j + 1][3]), b0, b1);
-            ldsm_t2(b0, b1, Qs, q0 + 8 * j, lane);
-            mma_k16(dk, pack_bf16(p[j][0], p[j][1]), pack_bf16(p[j][2], p[j][3]), pack_bf16(p[j + 1][0], p[j + 1][1]),
-                    pack_bf16(p[j + 1][2], p[j + 1][3]), b0, b1);
+        for (int j = 0; j < KB / 8; j += 2) {
+            uint32_t g0, g1, q0r, q1r;
+            ldsm_t2(g0, g1, Gs, q0 + 8 * j, lane);
+            ldsm_t2(q0r, q1r, Qs, q0 + 8 * j, lane);
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                mma_k16(dv[rt], pack_bf16(c[rt][j][0], c[rt][j][1]), pack_bf16(c[rt][j][2], c[rt][j][3]), pack_bf16(c[rt][j + 1][0], c[rt][j + 1][1]),
+                        pack_bf16(c[rt][j + 1][2], c[rt][j + 1][3]), g0, g1);
+                mma_k16(dk[rt], pack_bf16(p[rt][j][0], p[rt][j][1]), pack_bf16(p[rt][j][2], p[rt][j][3]), pack_bf16(p[rt][j + 1][0], p[rt][j + 1][1]),
+                        pack_bf16(p[rt][j + 1][2], p[rt][j + 1][3]), q0r, q1r);
+            }
         }
     }
     // Qs carries log2(e) / sqrt(8): dK = sum dS^T q / sqrt(8) = (sum dS^T Qs) * ln 2
-    float* dkp = dk_out + off + (size_t)(key0 + g) * pitch + 2 * t;
-    float* dvp = dv_out + off + (size_t)(key0 + g) * pitch + 2 * t;
-    float2 a = *reinterpret_cast<float2*>(dkp), b = *reinterpret_cast<float2*>(dkp + (size_t)8 * pitch);
-    a.x += dk[0] * kLn2; a.y += dk[1] * kLn2; b.x += dk[2] * kLn2; b.y += dk[3] * kLn2;
-    *reinterpret_cast<float2*>(dkp) = a;
-    *reinterpret_cast<float2*>(dkp + (size_t)8 * pitch) = b;
-    a = *reinterpret_cast<float2*>(dvp); b = *reinterpret_cast<float2*>(dvp + (size_t)8 * pitch);
-    a.x += dv[0]; a.y += dv[1]; b.x += dv[2]; b.y += dv[3];
-    *reinterpret_cast<float2*>(dvp) = a;
-    *reinterpret_cast<float2*>(dvp + (size_t)8 * pitch) = b;
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt) {
+        float* dkp = dk_out + off + (size_t)(key0 + 16 * rt + g) * pitch + 2 * t;
+        float* dvp = dv_out + off + (size_t)(key0 + 16 * rt + g) * pitch + 2 * t;
+        float2 a = *reinterpret_cast<float2*>(dkp), b = *reinterpret_cast<float2*>(dkp + (size_t)8 * pitch);
+        a.x += dk[rt][0] * kLn2; a.y += dk[rt][1] * kLn2; b.x += dk[rt][2] * kLn2; b.y += dk[rt][3] * kLn2;
+        *reinterpret_cast<float2*>(dkp) = a;
+        *reinterpret_cast<float2*>(dkp + (size_t)8 * pitch) = b;
+        a = *reinterpret_cast<float2*>(dvp); b = *reinterpret_cast<float2*>(dvp + (size_t)8 * pitch);
+        a.x += dv[rt][0]; a.y += dv[rt][1]; b.x += dv[rt][2]; b.y += dv[rt][3];
+        *reinterpret_cast<float2*>(dvp) = a;
+        *reinterpret_cast<float2*>(dvp + (size_t)8 * pitch) = b;
+    }
 }
 
 int set_smem(const void* fn, size_t bytes, bool* done) {
@@ -276,13 +301,19 @@ int launch_attn8_mma_fwd(const float* q, const float* k, const float* v, int pit
 int launch_attn8_mma_bwd(const float* q, const float* k, const float* v, int pitch, const float* o, const float* dout, const float* lse, int N,
                          int S, int C, float* dq, float* dk, float* dv, float* delta, cudaStream_t s) {
     PD_REQUIRE(attn8_mma_supported(S, C, pitch), "attn8_mma: sequence length must be a multiple of 128 (and fit shared memory)");
-    static bool done_q[PD_MAX_DEVICES] = {}, done_kv[PD_MAX_DEVICES] = {};
+    static bool done_q[PD_MAX_DEVICES] = {}, done_kv[PD_MAX_DEVICES] = {}, done_kv2[PD_MAX_DEVICES] = {};
     int rc = set_smem((const void*)attn8_mma_bwd_q_kernel, (size_t)S * 32, &done_q[pd_cur_dev()]);
     if (rc) return rc;
-    if ((rc = set_smem((const void*)attn8_mma_bwd_kv_kernel, (size_t)S * 40, &done_kv[pd_cur_dev()]))) return rc;
     const dim3 grid(S / AT_ROWS, C / 8, N);
     attn8_mma_bwd_q_kernel<<<grid, AT_THREADS, (size_t)S * 32, s>>>(q, k, v, pitch, o, dout, lse, S, C, dq, delta);
-    attn8_mma_bwd_kv_kernel<<<grid, AT_THREADS, (size_t)S * 40, s>>>(q, k, v, pitch, dout, lse, delta, S, C, dk, dv);
+    static const int rt2 = [] { const char* e = getenv("PHENDIFF_B200_TRAIN_ATTN_RT"); return e ? atoi(e) : 2; }();
+    if (rt2 == 2 && S % (2 * AT_ROWS) == 0) {      // two 16-key tiles per warp
+        if ((rc = set_smem((const void*)attn8_mma_bwd_kv_kernel<2>, (size_t)S * 40, &done_kv2[pd_cur_dev()]))) return rc;
+        attn8_mma_bwd_kv_kernel<2><<<dim3(S / (2 * AT_ROWS), C / 8, N), AT_THREADS, (size_t)S * 40, s>>>(q, k, v, pitch, dout, lse, delta, S, C, dk, dv);
+    } else {
+        if ((rc = set_smem((const void*)attn8_mma_bwd_kv_kernel<1>, (size_t)S * 40, &done_kv[pd_cur_dev()]))) return rc;
+        attn8_mma_bwd_kv_kernel<1><<<grid, AT_THREADS, (size_t)S * 40, s>>>(q, k, v, pitch, dout, lse, delta, S, C, dk, dv);
+    }
     PD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
