@@ -312,3 +312,25 @@ def test_unconditional_pass_coin_is_shared_seed():
     b = [bool(torch.rand(1, generator=g2).item() < 0.1) for _ in range(2000)]
     assert a == b
     assert 0.07 < sum(a) / len(a) < 0.13
+
+
+def test_ema_decay_schedule_host():
+    """diffusers EMAModel.get_decay as the reference configures it (train.py:229-236): warm-up 1 - (1 + step / inv_gamma)^-power after the
+    first optimizer step, capped at max_decay; pure host logic of phendiff_b200.training."""
+    import math
+
+    from phendiff_b200.training import ema_decay_at, training_target
+
+    assert ema_decay_at(0) == 0.0 and ema_decay_at(1) == 0.0
+    assert math.isclose(ema_decay_at(2, inv_gamma=1.0, power=0.75), 1 - 2 ** -0.75)
+    assert math.isclose(ema_decay_at(101, inv_gamma=2.0, power=0.5), 1 - (1 + 100 / 2.0) ** -0.5)
+    assert ema_decay_at(10 ** 9) == 0.9999
+    assert math.isclose(ema_decay_at(5, use_ema_warmup=False), 5 / 14)
+    assert ema_decay_at(3, min_decay=0.9) == 0.9
+    # regression target by prediction type (utils_training.py:415-433)
+    assert training_target("epsilon", "clean", "noise", lambda: "vel") == "noise"
+    assert training_target("sample", "clean", "noise", lambda: "vel") == "clean"
+    assert training_target("v_prediction", "clean", "noise", lambda: "vel") == "vel"
+    import pytest as _pt
+    with _pt.raises(ValueError):
+        training_target("other", 0, 0, lambda: 0)
